@@ -1,0 +1,410 @@
+/*
+ * oracle/clover_oracle.c - plain-C CPU restatement of the reference's hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see clover_oracle.h). It restates, operation by operation and in
+ * the reference's own floating-point ORDER, what the AVX2 code under /root/reference/include
+ * computes, so that it can run on a machine where the reference sources are absent (the GPU
+ * box). Parity status: PINNED against the compiled reference (oracle/_ref) and tests/golden/.
+ *
+ * Rules that make the restatement bit-exact (verified, not assumed):
+ *   - compiled with -ffp-contract=off; every fused multiply-add is an explicit fmaf()
+ *   - 7.0f/max and 127.0f/max are IEEE divisions, never reciprocal-multiplies
+ *   - float->int is truncation (cvttps), int->float is round-to-nearest-even (cvtepi32_ps)
+ *   - the fp32 dot/mvm accumulation follows the reference's 8-lane FMA chains and its
+ *     horizontal-add tree (include/CloverBase.h:149-157)
+ */
+#include "clover_oracle.h"
+#include <math.h>
+#include <string.h>
+#include <stdlib.h>
+
+#define BLOCK 64u
+
+uint64_t orc_size_pad(uint64_t n) { /* include/CloverVector.h:86-89 (CLOVER_VECTOR_SIZE_PAD = 128) */
+    return (n % 128u) ? n + 128u - (n % 128u) : n;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * PRNG. include/simdxorshift128plus.h
+ * ---------------------------------------------------------------------------------------- */
+
+/* canonical scalar xorshift128+ step, used only for seeding/jumping (:38-44) */
+static void xs_scalar_step(uint64_t *ps0, uint64_t *ps1) {
+    uint64_t s1 = *ps0;
+    const uint64_t s0 = *ps1;
+    *ps0 = s0;
+    s1 ^= s1 << 23;
+    *ps1 = s1 ^ s0 ^ (s1 >> 18) ^ (s0 >> 5);
+}
+
+/* 2^64 jump via the published jump polynomial (:47-62) */
+static void xs_scalar_jump(uint64_t in1, uint64_t in2, uint64_t *o1, uint64_t *o2) {
+    static const uint64_t JUMP[2] = { 0x8a5cd789635d2dffULL, 0x121fd2155c472f96ULL };
+    uint64_t s0 = 0, s1 = 0;
+    for (int i = 0; i < 2; ++i)
+        for (int b = 0; b < 64; ++b) {
+            if (JUMP[i] & (1ULL << b)) { s0 ^= in1; s1 ^= in2; }
+            xs_scalar_step(&in1, &in2);
+        }
+    *o1 = s0; *o2 = s1;
+}
+
+/* lane k = lane 0 jumped k * 2^64 canonical steps (:81-92) */
+void orc_xs_init(uint64_t key1, uint64_t key2, uint64_t *state) {
+    uint64_t *p1 = state, *p2 = state + 4;
+    p1[0] = key1; p2[0] = key2;
+    for (int k = 1; k < 4; ++k) xs_scalar_jump(p1[k - 1], p2[k - 1], &p1[k], &p2[k]);
+}
+
+/* The AVX step AS WRITTEN (:97-109): part1 is overwritten with part2 before use, so each
+ * 64-bit lane is the recurrence x' = t ^ x ^ (t >> 18) ^ (x >> 5), t = x ^ (x << 23), and the
+ * output is x' + x. out8[2k], out8[2k+1] = low, high half of lane k. */
+void orc_xs_next(uint64_t *state, uint32_t *out8) {
+    uint64_t *p1 = state, *p2 = state + 4;
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t s0 = p2[k];
+        const uint64_t s1 = s0 ^ (s0 << 23);
+        p1[k] = s0;
+        p2[k] = (s1 ^ s0 ^ (s1 >> 18)) ^ (s0 >> 5);
+        const uint64_t r = p2[k] + s0;
+        out8[2 * k] = (uint32_t)r;
+        out8[2 * k + 1] = (uint32_t)(r >> 32);
+    }
+}
+
+void orc_xs_skip(uint64_t *state, uint64_t ncalls) {
+    uint32_t sink[8];
+    for (uint64_t i = 0; i < ncalls; ++i) orc_xs_next(state, sink);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Generators. include/CloverVector32.h:712-783 (same body in CloverMatrix32.h:252-323)
+ * ---------------------------------------------------------------------------------------- */
+static void fill(float *x, uint64_t n, float lo, float hi, uint64_t *state, int round_int) {
+    const float step = (hi - lo) / 2147483648.0f;
+    const uint64_t n8 = (n >> 3) << 3;
+    uint32_t w[8];
+    for (uint64_t i = 0; i < n8; i += 8) {
+        orc_xs_next(state, w);
+        for (int l = 0; l < 8; ++l) {
+            int32_t v = (int32_t)w[l];
+            if (v < 0 && v != INT32_MIN) v = -v;          /* _mm256_abs_epi32: abs(INT_MIN) stays INT_MIN */
+            float f = fmaf((float)v, step, lo);
+            x[i + l] = round_int ? nearbyintf(f) : f;      /* _MM_FROUND_TO_NEAREST_INT */
+        }
+    }
+    for (uint64_t i = n8; i < n; ++i) {                    /* left-overs burn one call each */
+        orc_xs_next(state, w);
+        int32_t v = (int32_t)w[0];
+        if (v < 0 && v != INT32_MIN) v = -v;
+        float f = fmaf((float)v, step, lo);
+        x[i] = round_int ? nearbyintf(f) : f;
+    }
+}
+void orc_fill_floats(float *x, uint64_t n, float lo, float hi, uint64_t *state) { fill(x, n, lo, hi, state, 0); }
+void orc_fill_integers(float *x, uint64_t n, float lo, float hi, uint64_t *state) { fill(x, n, lo, hi, state, 1); }
+
+/* ------------------------------------------------------------------------------------------
+ * Shared pieces
+ * ---------------------------------------------------------------------------------------- */
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float absf(float f) { return u2f(f2u(f) & 0x7FFFFFFFu); }
+
+/* _mm256_max_ps(a, b) = a > b ? a : b (second operand on ties/NaN) */
+static inline float maxps(float a, float b) { return a > b ? a : b; }
+
+/* absmax of 64 floats with the zero guard of include/CloverVector4.h:656-663: a max whose BIT
+ * PATTERN is 0 becomes 1.0f (the guard is an integer compare + add of 1.0f, so -0.0 cannot
+ * occur: the inputs are already abs()). */
+static inline float guard_zero(float m) { return (f2u(m) == 0u) ? 1.0f + m : m; }
+
+/* Stochastic-rounding noise (include/CloverVector4.h:690-734): the call's eight 32-bit words
+ * `w`, element slot (g, l): float(int32((w[l] & 0x7F7F7F7F) << 8g)) * 2^-31. */
+static inline float noise(const uint32_t *w, int g, int l) {
+    const uint32_t m = w[l] & 0x7F7F7F7Fu;
+    const int32_t s = (int32_t)(m << (8 * g));
+    return (float)s * (1.0f / 2147483648.0f);
+}
+
+/* one element: q = sign(x) * trunc(fma(|x|, scale, rnd)); _mm256_sign_epi32 semantics
+ * (include/CloverVector4.h:741-772): x bit pattern < 0 -> negate, == 0 -> 0, else keep. */
+static inline int32_t quant1(float x, float scale, float rnd) {
+    const int32_t q = (int32_t)fmaf(absf(x), scale, rnd);   /* cvttps: truncation */
+    const int32_t xi = (int32_t)f2u(x);
+    return xi < 0 ? -q : (xi == 0 ? 0 : q);
+}
+
+/* Quantize one run of 64 floats with a given (already guarded) max.
+ * `transposed` selects the noise mapping: 0 = natural (vector / matrix-tile rows / all 8-bit),
+ * 1 = the 4-bit mvm re-quantizer, whose block_values are stored pre-transposed
+ * (include/CloverMatrix4.h:806-808, :911, :925-932), i.e. element e takes slot (e%8, e/8). */
+static void quant_block(const float *x, float maxv, float qmax, int32_t *q, uint64_t *state, int transposed) {
+    const float scale = qmax / maxv;                        /* IEEE divide */
+    if (!state) {
+        for (int e = 0; e < 64; ++e) q[e] = quant1(x[e], scale, 0.0f);
+        return;
+    }
+    uint32_t w[2][8];
+    orc_xs_next(state, w[0]);
+    orc_xs_next(state, w[1]);
+    for (int e = 0; e < 64; ++e) {
+        int c, g, l;
+        if (!transposed) { c = e >> 5; g = (e & 31) >> 3; l = e & 7; }
+        else             { c = (e & 7) >> 2; g = e & 3; l = e >> 3; }
+        q[e] = quant1(x[e], scale, noise(w[c], g, l));
+    }
+}
+
+static inline void pack4(const int32_t *q, int8_t *dst) {   /* 64 values -> 32 bytes, even element high */
+    for (int i = 0; i < 32; ++i)
+        dst[i] = (int8_t)(((q[2 * i] & 0xF) << 4) | (q[2 * i + 1] & 0xF));
+}
+static inline void pack8(const int32_t *q, int8_t *dst) {
+    for (int i = 0; i < 64; ++i) dst[i] = (int8_t)q[i];
+}
+static inline int32_t nib_hi(int8_t b) { return (int32_t)b >> 4; }                    /* sign-extended */
+static inline int32_t nib_lo(int8_t b) { return (int32_t)(int8_t)((uint8_t)b << 4) >> 4; }
+
+static inline float block_absmax(const float *x) {
+    float m = 0.0f;
+    for (int e = 0; e < 64; ++e) m = maxps(absf(x[e]), m);
+    return m;
+}
+
+/* horizontal add tree of include/CloverBase.h:149-157 */
+static inline float hadd8(const float *a) {
+    return ((a[4] + a[0]) + (a[6] + a[2])) + ((a[5] + a[1]) + (a[7] + a[3]));
+}
+
+/* ------------------------------------------------------------------------------------------
+ * CloverVector4
+ * ---------------------------------------------------------------------------------------- */
+void orc_v4_quantize(const float *x, uint64_t n, int8_t *values, float *scales, uint64_t *state) {
+    /* include/CloverVector4.h:605-807 */
+    const uint64_t blocks = orc_size_pad(n) / BLOCK;
+    int32_t q[64];
+    for (uint64_t b = 0; b < blocks; ++b) {
+        const float m = guard_zero(block_absmax(x + b * 64));
+        scales[b] = m;
+        quant_block(x + b * 64, m, 7.0f, q, state, 0);
+        pack4(q, values + b * 32);
+    }
+}
+
+void orc_v4_restore(const int8_t *values, const float *scales, uint64_t n, float *x) {
+    /* include/CloverVector4.h:1027-1093 */
+    const uint64_t blocks = orc_size_pad(n) / BLOCK;
+    for (uint64_t b = 0; b < blocks; ++b) {
+        const float s = scales[b] / 7.0f;
+        for (int i = 0; i < 32; ++i) {
+            x[b * 64 + 2 * i]     = (float)nib_hi(values[b * 32 + i]) * s;
+            x[b * 64 + 2 * i + 1] = (float)nib_lo(values[b * 32 + i]) * s;
+        }
+    }
+}
+
+float orc_v4_get(const int8_t *values, const float *scales, uint64_t i) {
+    /* include/CloverVector4.h:179-188 */
+    const float s = scales[i >> 6] / 7.0f;
+    const int8_t b = values[i >> 1];
+    return s * (float)((i & 1) ? nib_lo(b) : nib_hi(b));
+}
+
+/* exact int32 lane sums of one 4-bit block: lane l = bytes 4l..4l+3 = elements 8l..8l+7
+ * (include/CloverVector4.h:1134-1181; exact because |q| <= 7 never saturates maddubs) */
+static inline void lanes4(const int8_t *u, const int8_t *v, int32_t *lane) {
+    for (int l = 0; l < 8; ++l) {
+        int32_t s = 0;
+        for (int k = 0; k < 4; ++k) {
+            const int8_t a = u[4 * l + k], b = v[4 * l + k];
+            s += nib_hi(a) * nib_hi(b) + nib_lo(a) * nib_lo(b);
+        }
+        lane[l] = s;
+    }
+}
+
+/* The 16 fp32 FMA chains of the SIMD dot (include/CloverVector4.h:1103-1191): even blocks feed
+ * accumulator 1, odd blocks accumulator 2, scale = (su * (1/49)) * sv. */
+static float dot4_chains(const int8_t *u, const float *su, const int8_t *v, const float *sv, uint64_t blocks) {
+    const float rcp49 = 1.0f / 49.0f;
+    float acc[2][8];
+    int32_t lane[8];
+    memset(acc, 0, sizeof acc);
+    for (uint64_t b = 0; b < blocks; ++b) {
+        const float s = (su[b] * rcp49) * sv[b];
+        lanes4(u + b * 32, v + b * 32, lane);
+        float *a = acc[b & 1];
+        for (int l = 0; l < 8; ++l) a[l] = fmaf(s, (float)lane[l], a[l]);
+    }
+    float t[8];
+    for (int l = 0; l < 8; ++l) t[l] = acc[0][l] + acc[1][l];
+    return hadd8(t);
+}
+
+float orc_v4_dot(const int8_t *u, const float *su, const int8_t *v, const float *sv, uint64_t n) {
+    return dot4_chains(u, su, v, sv, orc_size_pad(n) / BLOCK);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * CloverVector8
+ * ---------------------------------------------------------------------------------------- */
+void orc_v8_quantize(const float *x, uint64_t n, int8_t *values, float *scales, uint64_t *state) {
+    /* include/CloverVector8.h:393-605 */
+    const uint64_t blocks = orc_size_pad(n) / BLOCK;
+    int32_t q[64];
+    for (uint64_t b = 0; b < blocks; ++b) {
+        const float m = guard_zero(block_absmax(x + b * 64));
+        scales[b] = m;
+        quant_block(x + b * 64, m, 127.0f, q, state, 0);
+        pack8(q, values + b * 64);
+    }
+}
+
+void orc_v8_restore(const int8_t *values, const float *scales, uint64_t n, float *x) {
+    /* include/CloverVector8.h:835-909 */
+    const uint64_t blocks = orc_size_pad(n) / BLOCK;
+    for (uint64_t b = 0; b < blocks; ++b) {
+        const float s = scales[b] / 127.0f;
+        for (int i = 0; i < 64; ++i) x[b * 64 + i] = (float)values[b * 64 + i] * s;
+    }
+}
+
+/* 8 chains, lane l = bytes 4l..4l+3 and 32+4l..32+4l+3 (include/CloverVector8.h:911-977) */
+static float dot8_chains(const int8_t *u, const float *su, const int8_t *v, const float *sv, uint64_t blocks) {
+    const float rcp127 = 1.0f / 127.0f;
+    float acc[8];
+    memset(acc, 0, sizeof acc);
+    for (uint64_t b = 0; b < blocks; ++b) {
+        const float s = (su[b] * rcp127) * (sv[b] * rcp127);
+        const int8_t *pu = u + b * 64, *pv = v + b * 64;
+        for (int l = 0; l < 8; ++l) {
+            int32_t d = 0;
+            for (int k = 0; k < 4; ++k)
+                d += (int32_t)pu[4 * l + k] * pv[4 * l + k] + (int32_t)pu[32 + 4 * l + k] * pv[32 + 4 * l + k];
+            acc[l] = fmaf(s, (float)d, acc[l]);
+        }
+    }
+    return hadd8(acc);
+}
+
+float orc_v8_dot(const int8_t *u, const float *su, const int8_t *v, const float *sv, uint64_t n) {
+    return dot8_chains(u, su, v, sv, orc_size_pad(n) / BLOCK);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Matrices. rows/cols are padded dimensions (include/CloverMatrix.h:48-50).
+ * Tiles are visited column-block-major (b_j outer; include/CloverMatrix4.h:524-525), which
+ * only matters for the order in which the PRNG stream is consumed (2 calls per tile row).
+ * ---------------------------------------------------------------------------------------- */
+static void quantize_matrix(const float *a, uint64_t rows, uint64_t cols, int8_t *values, float *scales,
+                            uint64_t *state, int bits) {
+    const uint64_t hb = cols >> 6, vb = rows >> 6;
+    const float qmax = bits == 4 ? 7.0f : 127.0f;
+    #pragma omp parallel for collapse(2) schedule(static) if (!state)
+    for (uint64_t bj = 0; bj < hb; ++bj)
+        for (uint64_t bi = 0; bi < vb; ++bi) {
+            const float *t = a + (bi << 6) * cols + (bj << 6);
+            float m = 0.0f;
+            for (int i = 0; i < 64; ++i) m = maxps(block_absmax(t + (uint64_t)i * cols), m);
+            m = guard_zero(m);
+            scales[bi * hb + bj] = m;
+            int32_t q[64];
+            for (int i = 0; i < 64; ++i) {
+                quant_block(t + (uint64_t)i * cols, m, qmax, q, state, 0);
+                const uint64_t off = ((bi << 6) + (uint64_t)i) * cols + (bj << 6);
+                if (bits == 4) pack4(q, values + (off >> 1)); else pack8(q, values + off);
+            }
+        }
+}
+
+void orc_m4_quantize(const float *a, uint64_t rows, uint64_t cols, int8_t *values, float *scales, uint64_t *state) {
+    quantize_matrix(a, rows, cols, values, scales, state, 4);   /* include/CloverMatrix4.h:512-766 */
+}
+void orc_m8_quantize(const float *a, uint64_t rows, uint64_t cols, int8_t *values, float *scales, uint64_t *state) {
+    quantize_matrix(a, rows, cols, values, scales, state, 8);   /* include/CloverMatrix8.h:203-479 */
+}
+
+/* mvm(V4,V4): include/CloverMatrix4.h:777-1083. 64 row dots (the inlined SIMD dot against the
+ * tile-row's scales), running absmax, then the block-64 re-quantizer with the transposed noise
+ * mapping. y32_or_null optionally receives the fp32 intermediates (`block_values`). */
+void orc_m4_mvm(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32_or_null, uint64_t *state) {
+    const uint64_t hb = cols >> 6;
+    const uint64_t rb = rows >> 6;
+    float *y32 = y32_or_null ? y32_or_null : (float *)malloc(rows * sizeof(float));
+    #pragma omp parallel for schedule(static)
+    for (uint64_t r = 0; r < rows; ++r)
+        y32[r] = dot4_chains(values + ((r * cols) >> 1), scales + (r >> 6) * hb, xv, xs, hb);
+    for (uint64_t b = 0; b < rb; ++b) {                      /* sequential: consumes the PRNG stream */
+        float m = 0.0f;
+        for (int i = 0; i < 64; ++i) m = maxps(absf(y32[b * 64 + i]), m);   /* _mm_max_ss(habs, max) */
+        m = guard_zero(m);
+        ys[b] = m;
+        int32_t q[64];
+        quant_block(y32 + b * 64, m, 7.0f, q, state, 1);
+        pack4(q, yv + b * 32);
+    }
+    if (!y32_or_null) free(y32);
+}
+
+/* mvm(V8,V8): include/CloverMatrix8.h:1002-1298. block_values are in natural order here. */
+void orc_m8_mvm(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32_or_null, uint64_t *state) {
+    const uint64_t hb = cols >> 6;
+    const uint64_t rb = rows >> 6;
+    float *y32 = y32_or_null ? y32_or_null : (float *)malloc(rows * sizeof(float));
+    #pragma omp parallel for schedule(static)
+    for (uint64_t r = 0; r < rows; ++r)
+        y32[r] = dot8_chains(values + r * cols, scales + (r >> 6) * hb, xv, xs, hb);
+    for (uint64_t b = 0; b < rb; ++b) {
+        float m = 0.0f;
+        for (int i = 0; i < 64; ++i) m = maxps(absf(y32[b * 64 + i]), m);
+        m = guard_zero(m);
+        ys[b] = m;
+        int32_t q[64];
+        quant_block(y32 + b * 64, m, 127.0f, q, state, 0);
+        pack8(q, yv + b * 64);
+    }
+    if (!y32_or_null) free(y32);
+}
+
+/* mvm(V32,V32): include/CloverMatrix4.h:1451-1547. 32 chains per row: accumulator k (0..3),
+ * lane l, fed per block by element 8k+l and then element 32+8k+l; f = float(q) * (s/7). */
+void orc_m4_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                    const float *x32, float *y32) {
+    const uint64_t hb = cols >> 6;
+    #pragma omp parallel for schedule(static)
+    for (uint64_t r = 0; r < rows; ++r) {
+        const int8_t *u = values + ((r * cols) >> 1);
+        const float *su = scales + (r >> 6) * hb;
+        float acc[4][8];
+        memset(acc, 0, sizeof acc);
+        for (uint64_t b = 0; b < hb; ++b) {
+            const float s = su[b] / 7.0f;
+            const float *x = x32 + b * 64;
+            for (int half = 0; half < 2; ++half)
+                for (int k = 0; k < 4; ++k)
+                    for (int l = 0; l < 8; ++l) {
+                        const int e = 32 * half + 8 * k + l;
+                        const int8_t byte = u[b * 32 + (e >> 1)];
+                        const float f = (float)((e & 1) ? nib_lo(byte) : nib_hi(byte)) * s;
+                        acc[k][l] = fmaf(x[e], f, acc[k][l]);
+                    }
+        }
+        float t[8];
+        for (int l = 0; l < 8; ++l) t[l] = (acc[0][l] + acc[1][l]) + (acc[2][l] + acc[3][l]);
+        y32[r] = hadd8(t);
+    }
+}
+
+/* GEMM (extension): every C[i][j] is the reference SIMD dot of two row views. */
+void orc_m4_gemm(const int8_t *av, const float *as, const int8_t *btv, const float *bts,
+                 uint64_t K, uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1, float *c, uint64_t ldc) {
+    const uint64_t kb = K >> 6;
+    #pragma omp parallel for schedule(static)
+    for (uint64_t i = i0; i < i1; ++i)
+        for (uint64_t j = j0; j < j1; ++j)
+            c[(i - i0) * ldc + (j - j0)] =
+                dot4_chains(av + ((i * K) >> 1), as + (i >> 6) * kb, btv + ((j * K) >> 1), bts + (j >> 6) * kb, kb);
+}

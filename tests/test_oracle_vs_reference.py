@@ -1,0 +1,166 @@
+"""Pins the C restatement (oracle/clover_oracle.c) to the UNMODIFIED reference (oracle/_ref).
+
+Mirrors the reference's own differential validation (test/validate/02_vector.cpp,
+03_matrix.cpp) but with a stricter bar: every output is compared BIT-FOR-BIT, in
+rounding-disabled mode and - with an explicit PRNG key - in stochastic mode.
+CPU only; runs wherever oracle/_ref was built.
+"""
+import numpy as np
+import pytest
+
+from oracle.pyoracle import size_pad
+
+VEC_SIZES = [1, 63, 64, 65, 127, 128, 129, 200, 255, 256, 257, 511, 640, 1000, 1023, 1024, 4096, 8192 + 77]
+MAT_SHAPES = [(128, 128), (128, 256), (256, 128), (256, 384), (384, 640), (200, 300), (640, 1152)]
+
+
+def _inputs(oracle, n, kind, seed_skip=0):
+    st = oracle.xs_init()
+    oracle.xs_skip(st, seed_skip)
+    if kind == "floats":
+        return oracle.fill_floats(n, -1.0, 1.0, st)
+    if kind == "ints":
+        return oracle.fill_integers(n, -10.0, 10.0, st)
+    if kind == "wide":
+        x = oracle.fill_floats(n, -1.0, 1.0, st)
+        x[:n] *= np.exp2(np.arange(n) % 40 - 20).astype(np.float32)
+        return x
+    raise ValueError(kind)
+
+
+def test_prng_known_answer(oracle, reference):
+    # lane-0 outputs of the as-written recurrence for the reference's fixed seeds
+    st = oracle.xs_init()
+    st_ref = reference.xs_init()
+    assert np.array_equal(st, st_ref)
+    expect = [0x34fdc432b801bd42, 0x17c005a764b34867, 0xd30e76c327a8ec0a, 0x678c73e394e4ac3e]
+    for e in expect:
+        w = oracle.xs_next(st)
+        wr = reference.xs_next(st_ref)
+        assert np.array_equal(w, wr)
+        assert (int(w[0]) | (int(w[1]) << 32)) == e
+    for _ in range(1000):
+        assert np.array_equal(oracle.xs_next(st), reference.xs_next(st_ref))
+    assert np.array_equal(st, st_ref)
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 100, 4096, 1000])
+def test_generators(oracle, reference, n):
+    for fn in ("fill_floats", "fill_integers"):
+        st, st_ref = oracle.xs_init(), reference.xs_init()
+        a = getattr(oracle, fn)(n, -1.0 if fn == "fill_floats" else -10.0, 1.0 if fn == "fill_floats" else 10.0, st)
+        b = getattr(reference, fn)(n, -1.0 if fn == "fill_floats" else -10.0, 1.0 if fn == "fill_floats" else 10.0, st_ref)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert np.array_equal(st, st_ref)
+
+
+@pytest.mark.parametrize("kind", ["floats", "ints", "wide"])
+@pytest.mark.parametrize("n", VEC_SIZES)
+def test_vector_quantize_restore_dot(oracle, reference, n, kind):
+    x = _inputs(oracle, n, kind)
+    y = _inputs(oracle, n, kind, seed_skip=3 * n + 1)
+    for bits in (4, 8):
+        q, r, d = (getattr(oracle, f"v{bits}_{f}") for f in ("quantize", "restore", "dot"))
+        qr, rr, dr = (getattr(reference, f"v{bits}_{f}") for f in ("quantize", "restore", "dot"))
+        xv, xs = q(x, n)
+        xv_r, xs_r = qr(x, n)
+        assert np.array_equal(xv, xv_r), f"{bits}-bit values differ"
+        assert np.array_equal(xs.view(np.uint32), xs_r.view(np.uint32)), f"{bits}-bit scales differ"
+        yv, ys = q(y, n)
+        assert np.array_equal(r(xv, xs, n).view(np.uint32), rr(xv, xs, n).view(np.uint32))
+        got, want = d(xv, xs, yv, ys, n), dr(xv, xs, yv, ys, n)
+        assert got.view(np.uint32) == want.view(np.uint32), f"{bits}-bit dot {float(got).hex()} vs {float(want).hex()}"
+
+
+def test_vector_zero_and_signed_zero_blocks(oracle, reference):
+    n = 256
+    x = np.zeros(n, np.float32)
+    x[64:128] = -0.0
+    x[130] = 3.5
+    x[131] = -0.0
+    for bits in (4, 8):
+        a = getattr(oracle, f"v{bits}_quantize")(x, n)
+        b = getattr(reference, f"v{bits}_quantize")(x, n)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+        assert a[1][0] == 1.0 and a[1][1] == 1.0  # zero guard: max==0 -> scale 1 (CloverVector4.h:661-663)
+
+
+@pytest.mark.parametrize("n", [64, 128, 1000, 4096])
+def test_vector_quantize_stochastic_with_key(oracle, reference_sr, n):
+    x = _inputs(oracle, n, "floats")
+    for bits in (4, 8):
+        st, st_ref = oracle.xs_init(7, 9), reference_sr.xs_init(7, 9)
+        a = getattr(oracle, f"v{bits}_quantize")(x, n, state=st)
+        b = getattr(reference_sr, f"v{bits}_quantize")(x, n, state=st_ref)
+        assert np.array_equal(a[0], b[0])
+        assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+        assert np.array_equal(st, st_ref), "PRNG state after quantize differs"
+
+
+@pytest.mark.parametrize("kind", ["floats", "ints"])
+@pytest.mark.parametrize("shape", MAT_SHAPES)
+def test_matrix_quantize_mvm(oracle, reference, shape, kind):
+    from oracle.pyoracle import pad_matrix
+    rows, cols = shape
+    a = _inputs(oracle, rows * cols, kind)[: rows * cols].reshape(rows, cols)
+    a = pad_matrix(a)
+    R, Cc = a.shape
+    xvec = _inputs(oracle, Cc, kind, seed_skip=11)
+    for bits in (4, 8):
+        mv, ms = getattr(oracle, f"m{bits}_quantize")(a)
+        mv_r, ms_r, h = getattr(reference, f"m{bits}_quantize")(a)
+        assert np.array_equal(mv, mv_r), f"M{bits} values"
+        assert np.array_equal(ms.view(np.uint32), ms_r.view(np.uint32)), f"M{bits} scales"
+        xv, xs = getattr(oracle, f"v{bits}_quantize")(xvec, Cc)
+        yv, ys, y32 = getattr(oracle, f"m{bits}_mvm")(mv, ms, R, Cc, xv, xs, want_f32=True)
+        yv_r, ys_r = getattr(reference, f"m{bits}_mvm")(h, xv, xs)
+        assert np.array_equal(yv, yv_r), f"M{bits} mvm values"
+        assert np.array_equal(ys.view(np.uint32), ys_r.view(np.uint32)), f"M{bits} mvm scales"
+        # the reference's own contract: SIMD == scalar == parallel exactly (03_matrix.cpp:284, :533)
+        for variant in (1, 2):
+            yv_v, ys_v = getattr(reference, f"m{bits}_mvm")(h, xv, xs, variant=variant)
+            assert np.array_equal(yv, yv_v) and np.array_equal(ys.view(np.uint32), ys_v.view(np.uint32))
+    mv, ms = oracle.m4_quantize(a)
+    _, _, h = reference.m4_quantize(a)
+    y = oracle.m4_mvm_f32(mv, ms, R, Cc, xvec)
+    y_r = reference.m4_mvm_f32(h, xvec)
+    assert np.array_equal(y.view(np.uint32), y_r.view(np.uint32)), "mvm(V32,V32)"
+
+
+@pytest.mark.parametrize("shape", [(128, 128), (256, 384)])
+def test_matrix_stochastic_with_key(oracle, reference_sr, shape):
+    from oracle.pyoracle import pad_matrix
+    rows, cols = shape
+    a = pad_matrix(_inputs(oracle, rows * cols, "floats")[: rows * cols].reshape(rows, cols))
+    xvec = _inputs(oracle, cols, "floats", seed_skip=5)
+    for bits in (4, 8):
+        st, st_ref = oracle.xs_init(123, 456), reference_sr.xs_init(123, 456)
+        mv, ms = getattr(oracle, f"m{bits}_quantize")(a, state=st)
+        mv_r, ms_r, h = getattr(reference_sr, f"m{bits}_quantize")(a, state=st_ref)
+        assert np.array_equal(mv, mv_r) and np.array_equal(ms.view(np.uint32), ms_r.view(np.uint32))
+        assert np.array_equal(st, st_ref)
+        xv, xs = getattr(oracle, f"v{bits}_quantize")(xvec, cols)
+        yv, ys = getattr(oracle, f"m{bits}_mvm")(mv, ms, rows, cols, xv, xs, state=st)
+        yv_r, ys_r = getattr(reference_sr, f"m{bits}_mvm")(h, xv, xs, state=st_ref)
+        assert np.array_equal(yv, yv_r), f"M{bits} stochastic mvm values"
+        assert np.array_equal(ys.view(np.uint32), ys_r.view(np.uint32))
+        assert np.array_equal(st, st_ref)
+
+
+def test_gemm_definition(oracle, reference):
+    from oracle.pyoracle import pad_matrix
+    M, N, K = 128, 256, 384
+    a = pad_matrix(_inputs(oracle, M * K, "floats")[: M * K].reshape(M, K))
+    b = pad_matrix(_inputs(oracle, N * K, "floats", seed_skip=999)[: N * K].reshape(N, K))
+    av, as_, ha = reference.m4_quantize(a)
+    bv, bs, hb = reference.m4_quantize(b)
+    c = oracle.m4_gemm(av, as_, bv, bs, K, 0, M, 0, N)
+    c_r = reference.m4_gemm(ha, hb, 0, M, 0, N)
+    assert np.array_equal(c.view(np.uint32), c_r.view(np.uint32))
+    # column j of C is mvm_f32-free: equals the fp32 intermediates of mvm(V4) with x = row j of Bt
+    j = 77
+    kb = K // 64
+    xv = bv[j * K // 2:(j + 1) * K // 2]
+    xs = bs[(j // 64) * kb:(j // 64 + 1) * kb]
+    _, _, y32 = oracle.m4_mvm(av, as_, M, K, xv, xs, want_f32=True)
+    assert np.array_equal(y32.view(np.uint32), c[:, j].copy().view(np.uint32))
