@@ -1,0 +1,287 @@
+"""Host-side mirror of the reference's container interface, device-resident.
+
+Same class names, method names and argument meaning as the reference's header-only containers
+(``CloverVector32/4/8``, ``CloverMatrix32/4/8``: include/CloverVector4.h, include/CloverMatrix4.h, ...);
+every arithmetic method forwards to the C ABI of ``libclover_b200.so`` (include/clover_b200.h), so tests
+written against these classes read like the reference's own validation code
+(test/validate/02_vector.cpp, 03_matrix.cpp).
+
+PyTorch is used for plumbing only: the byte buffers are ``torch`` CUDA tensors in the reference's exact
+in-memory layout (``[values | scales]`` are two tensors here), and kernels run on torch's current stream.
+
+Differences from the reference that a caller can observe:
+  * storage lives in HBM: ``getData()`` / ``getScales()`` return CUDA tensors (``.cpu().numpy()`` gives
+    the reference's bytes);
+  * size mismatches raise :class:`CloverSizeError` instead of printing and ``exit(1)``
+    (include/CloverMatrix4.h:779-782);
+  * stochastic rounding is a run-time choice: a container without a key behaves like the reference built
+    with ``CLOVER_STOCHASTIC_ROUNDING_DISABLED``; ``setRandomKeys`` (include/CloverRandom.h:90-94)
+    switches the reference's XORShift128+ stream on, bit-compatible with its sequential code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DOT_AUTO, call
+
+CLOVER_VECTOR_BLOCK = 64          # include/CloverVector.h:41
+CLOVER_VECTOR_SIZE_PAD = 128      # include/CloverVector.h:42
+
+
+class CloverSizeError(ValueError):
+    """Operands do not conform (the reference prints a message and exits)."""
+
+
+def size_pad(n: int) -> int:
+    return n + (-n) % CLOVER_VECTOR_SIZE_PAD
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("clover_b200 needs a CUDA device: there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+class _Keyed:
+    """PRNG state holder (include/CloverRandom.h): ``key`` is uint64[8] = random_key1 | random_key2."""
+
+    key = None
+
+    def setRandomKeys(self, key) -> None:
+        if key is None:
+            self.key = None
+            return
+        key = np.ascontiguousarray(key, dtype=np.uint64).reshape(-1)
+        if key.size != 8:
+            raise ValueError("a key is uint64[8] = random_key1[4] | random_key2[4]")
+        self.key = key.copy()
+
+    def seed(self, key1: int, key2: int) -> None:
+        """avx_xorshift128plus_init(key1, key2, ...) (include/simdxorshift128plus.h:81-92)."""
+        self.key = np.zeros(8, np.uint64)
+        call("clover_prng_init", C.c_uint64(key1), C.c_uint64(key2), self.key.ctypes.data_as(C.c_void_p))
+
+    def _key_ptr(self):
+        return None if self.key is None else self.key.ctypes.data_as(C.c_void_p)
+
+
+class CloverVector32(_Keyed):
+    """fp32 input/output container (include/CloverVector32.h:53-70): length padded to x128, pad zeroed."""
+
+    def __init__(self, n: int, data=None, device=None):
+        self.length = int(n)
+        self.length_pad = size_pad(self.length)
+        self.values = torch.zeros(self.length_pad, dtype=torch.float32, device=_dev(device))
+        if data is not None:
+            src = torch.as_tensor(data, dtype=torch.float32).reshape(-1)
+            if src.numel() not in (self.length, self.length_pad):
+                raise CloverSizeError("data does not match the vector length")
+            self.values[: src.numel()].copy_(src)
+
+    def size(self): return self.length
+    def size_pad(self): return self.length_pad
+    def getBitsLength(self): return 32
+    def getBytes(self): return self.length_pad * 4
+    def getData(self): return self.values
+    def get(self, i): return float(self.values[i])
+    def numpy(self): return self.values[: self.length].cpu().numpy()
+
+
+class _QVector(_Keyed):
+    BITS = 0
+
+    def __init__(self, n: int, values=None, scales=None, device=None):
+        self.length = int(n)
+        self.length_pad = size_pad(self.length)
+        dev = _dev(device)
+        nbytes = self.length_pad * self.BITS // 8
+        if values is None:
+            # pad values 0, pad scales 1 (include/CloverVector4.h:86-94)
+            self.values = torch.zeros(nbytes, dtype=torch.int8, device=dev)
+            self.scales = torch.ones(self.length_pad // 64, dtype=torch.float32, device=dev)
+        else:  # the reference's borrowing view constructor (include/CloverVector4.h:114-119)
+            self.values = torch.as_tensor(values, device=dev).view(torch.int8).reshape(-1)
+            self.scales = torch.as_tensor(scales, dtype=torch.float32, device=dev).reshape(-1)
+            if self.values.numel() < nbytes or self.scales.numel() < self.length_pad // 64:
+                raise CloverSizeError("view buffers are smaller than the padded vector")
+
+    def size(self): return self.length
+    def size_pad(self): return self.length_pad
+    def getBitsLength(self): return self.BITS
+    def getData(self): return self.values
+    def getScales(self): return self.scales
+    def getBytes(self): return self.length_pad * self.BITS // 8 + (self.length_pad // 64) * 4
+
+    def quantize(self, other: CloverVector32) -> None:
+        # the reference reads other.size_pad()/64 blocks (include/CloverVector4.h:612-613)
+        if other.size_pad() != self.length_pad:
+            raise CloverSizeError("Vectors do not have the same size.")
+        call(f"clover_v{self.BITS}_quantize", _ptr(other.values), C.c_uint64(self.length_pad), _ptr(self.values),
+             _ptr(self.scales), self._key_ptr(), _stream())
+
+    def restore(self, other: CloverVector32) -> None:
+        if other.size_pad() != self.length_pad:
+            raise CloverSizeError("Vectors do not have the same size.")
+        call(f"clover_v{self.BITS}_restore", _ptr(self.values), _ptr(self.scales), C.c_uint64(self.length_pad),
+             _ptr(other.values), _stream())
+
+    def dot(self, other, mode: int = DOT_AUTO) -> float:
+        if other.size_pad() != self.length_pad:
+            raise CloverSizeError("Vectors do not have the same size.")
+        out = torch.empty(1, dtype=torch.float32, device=self.values.device)
+        call(f"clover_v{self.BITS}_dot", _ptr(self.values), _ptr(self.scales), _ptr(other.values), _ptr(other.scales),
+             C.c_uint64(self.length_pad), _ptr(out), C.c_int(mode), _stream())
+        return float(out.item())
+
+    def dot_device(self, other, out, mode: int = DOT_AUTO) -> None:
+        """dot() without the device->host read: result lands in the 1-element CUDA tensor ``out``."""
+        call(f"clover_v{self.BITS}_dot", _ptr(self.values), _ptr(self.scales), _ptr(other.values), _ptr(other.scales),
+             C.c_uint64(self.length_pad), _ptr(out), C.c_int(mode), _stream())
+
+    def toVector32(self) -> CloverVector32:
+        out = CloverVector32(self.length, device=self.values.device)
+        self.restore(out)
+        return out
+
+
+class CloverVector4(_QVector):
+    """4-bit vector, block-64 absmax scales (include/CloverVector4.h:44-58)."""
+    BITS = 4
+
+    def getBits(self, pos: int) -> int:               # include/CloverVector4.h:154-160
+        b = int(self.values[pos >> 1])
+        nib = (b >> 4) & 0xF if pos % 2 == 0 else b & 0xF
+        return nib - 16 if nib >= 8 else nib
+
+    def get(self, pos: int) -> float:                  # include/CloverVector4.h:179-188
+        scale = np.float32(self.scales[pos >> 6].item()) / np.float32(7.0)
+        return float(scale * np.float32(self.getBits(pos)))
+
+
+class CloverVector8(_QVector):
+    """8-bit vector, block-64 absmax scales (include/CloverVector8.h:45-78)."""
+    BITS = 8
+
+    def getBits(self, pos: int) -> int:
+        return int(self.values[pos])
+
+    def get(self, pos: int) -> float:                  # include/CloverVector8.h:136-139
+        return float(np.float32(self.getBits(pos)) * np.float32(self.scales[pos >> 6].item()) / np.float32(127.0))
+
+
+class CloverMatrix32:
+    """fp32 matrix, rows and cols padded to x128 (include/CloverMatrix.h:48-50, CloverMatrix32.h:43-50)."""
+
+    def __init__(self, rows: int, cols: int, data=None, device=None):
+        self.rows, self.cols = size_pad(int(rows)), size_pad(int(cols))
+        self.values = torch.zeros(self.rows, self.cols, dtype=torch.float32, device=_dev(device))
+        if data is not None:
+            src = torch.as_tensor(data, dtype=torch.float32)
+            self.values[: src.shape[0], : src.shape[1]].copy_(src)
+
+    def getRows(self): return self.rows
+    def getCols(self): return self.cols
+    def size(self): return self.rows * self.cols
+    def getData(self): return self.values
+    def getBytes(self): return self.rows * self.cols * 4
+
+
+class _QMatrix(_Keyed):
+    BITS = 0
+    VEC = None
+
+    def __init__(self, rows: int, cols: int, values=None, scales=None, device=None):
+        self.rows, self.cols = size_pad(int(rows)), size_pad(int(cols))
+        dev = _dev(device)
+        nbytes = self.rows * self.cols * self.BITS // 8
+        nscales = (self.rows >> 6) * (self.cols >> 6)
+        if values is None:
+            self.values = torch.zeros(nbytes, dtype=torch.int8, device=dev)
+            self.scales = torch.zeros(nscales, dtype=torch.float32, device=dev)
+        else:
+            self.values = torch.as_tensor(values, device=dev).view(torch.int8).reshape(-1)
+            self.scales = torch.as_tensor(scales, dtype=torch.float32, device=dev).reshape(-1)
+            if self.values.numel() != nbytes or self.scales.numel() != nscales:
+                raise CloverSizeError("buffers do not match the padded matrix shape")
+
+    def getRows(self): return self.rows
+    def getCols(self): return self.cols
+    def size(self): return self.rows * self.cols
+    def getBitsLength(self): return self.BITS
+    def getData(self): return self.values
+    def getScales(self): return self.scales
+    def getBytes(self):                                  # include/CloverMatrix4.h:111-121
+        return self.rows * self.cols * self.BITS // 8 + (self.rows >> 6) * (self.cols >> 6) * 4
+
+    def quantize(self, m: CloverMatrix32) -> None:
+        if m.getRows() != self.rows or m.getCols() != self.cols:
+            raise CloverSizeError("Matrices do not have the same size.")
+        call(f"clover_m{self.BITS}_quantize", _ptr(m.values), C.c_uint64(self.rows), C.c_uint64(self.cols),
+             _ptr(self.values), _ptr(self.scales), self._key_ptr(), _stream())
+
+    def mvm(self, productVector, resultVector, y32=None) -> None:
+        """y = A x. (V4,V4)/(V8,V8): include/CloverMatrix4.h:777, CloverMatrix8.h:1002; (V32,V32): :1451."""
+        if isinstance(productVector, CloverVector32):
+            if self.BITS != 4:
+                raise NotImplementedError("mvm(V32,V32) is on the hot path for CloverMatrix4 only")
+            if productVector.size() != self.cols or resultVector.size_pad() < self.rows:
+                raise CloverSizeError("MVM can not be performed.")
+            call("clover_m4_mvm_f32", _ptr(self.values), _ptr(self.scales), C.c_uint64(self.rows), C.c_uint64(self.cols),
+                 _ptr(productVector.values), _ptr(resultVector.values), _stream())
+            return
+        if not isinstance(productVector, self.VEC) or not isinstance(resultVector, self.VEC):
+            raise TypeError(f"mvm expects {self.VEC.__name__} operands")
+        # the reference checks productVector.size() != getCols() (include/CloverMatrix4.h:779-782)
+        if productVector.size() != self.cols or resultVector.size_pad() != self.rows:
+            raise CloverSizeError("MVM can not be performed.")
+        call(f"clover_m{self.BITS}_mvm", _ptr(self.values), _ptr(self.scales), C.c_uint64(self.rows), C.c_uint64(self.cols),
+             _ptr(productVector.values), _ptr(productVector.scales), _ptr(resultVector.values), _ptr(resultVector.scales),
+             _ptr(y32), self._key_ptr(), _stream())
+
+
+class CloverMatrix4(_QMatrix):
+    """4-bit row-major matrix, one absmax scale per 64x64 tile (include/CloverMatrix4.h:38-93)."""
+    BITS = 4
+    VEC = CloverVector4
+
+    def get(self, i: int, j: int) -> float:              # include/CloverMatrix4.h:123-139
+        pos = i * self.cols + j
+        b = int(self.values[pos >> 1])
+        nib = (b >> 4) & 0xF if pos % 2 == 0 else b & 0xF
+        q = nib - 16 if nib >= 8 else nib
+        scale = np.float32(self.scales[(i >> 6) * (self.cols >> 6) + (j >> 6)].item()) / np.float32(7.0)
+        return float(scale * np.float32(q))
+
+    def gemm(self, Bt: "CloverMatrix4", out=None):
+        """C = A * Bt^T with C[i][j] = rowView(A,i).dot(rowView(Bt,j)) - extension, SURVEY.md 8a-10."""
+        if Bt.cols != self.cols:
+            raise CloverSizeError("GEMM can not be performed.")
+        if out is None:
+            out = torch.empty(self.rows, Bt.rows, dtype=torch.float32, device=self.values.device)
+        call("clover_m4_gemm", _ptr(self.values), _ptr(self.scales), _ptr(Bt.values), _ptr(Bt.scales),
+             C.c_uint64(self.rows), C.c_uint64(Bt.rows), C.c_uint64(self.cols), _ptr(out), C.c_uint64(out.stride(0)),
+             _stream())
+        return out
+
+
+class CloverMatrix8(_QMatrix):
+    """8-bit row-major matrix, one absmax scale per 64x64 tile (include/CloverMatrix8.h:76-92)."""
+    BITS = 8
+    VEC = CloverVector8
+
+    def get(self, i: int, j: int) -> float:              # include/CloverMatrix8.h:117-129
+        q = int(self.values[i * self.cols + j])
+        scale = np.float32(self.scales[(i >> 6) * (self.cols >> 6) + (j >> 6)].item()) / np.float32(127.0)
+        return float(scale * np.float32(q))

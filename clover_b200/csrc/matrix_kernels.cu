@@ -1,0 +1,482 @@
+// matrix_kernels.cu - CloverMatrix4 / CloverMatrix8: quantize, mvm (GEMV), mvm with fp32 vectors.
+//
+//   quantize   include/CloverMatrix4.h:512-766, include/CloverMatrix8.h:203-479
+//   mvm(V4,V4) include/CloverMatrix4.h:777-1083      mvm(V8,V8) include/CloverMatrix8.h:1002-1298
+//   mvm(V32)   include/CloverMatrix4.h:1451-1547
+//
+// The GEMVs are HBM-bound (the matrix is read exactly once: 0.5 B/elem + scales) and reproduce the
+// reference's fp32 accumulation ORDER, so the fp32 row results and therefore the re-quantized
+// 4/8-bit output vector are bit-identical to the AVX2 code.
+#include "common.cuh"
+#include "runtime.cuh"
+
+namespace clover {
+
+// =============================================================================================
+// matrix quantize: one CTA per 64x64 tile, 256 threads, thread (row i, quarter k) owns 16 elements
+// =============================================================================================
+template <int BITS, bool STOCH>
+__global__ void __launch_bounds__(256)
+k_mquantize(const float *__restrict__ a, uint64_t rows, uint64_t cols, int8_t *__restrict__ values,
+            float *__restrict__ scales, Key4 key, const uint64_t *__restrict__ tables) {
+    constexpr float kQmax = BITS == 4 ? 7.0f : 127.0f;
+    __shared__ float warp_max_s[8];
+    const uint64_t hb = cols >> 6, vb = rows >> 6;
+    const uint64_t ntiles = hb * vb;
+    const int tid = threadIdx.x, i = tid >> 2, k = tid & 3;
+
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint64_t bi = t / hb, bj = t % hb;                 // row-major tile walk (DRAM locality)
+        const uint64_t off = ((bi << 6) + i) * cols + (bj << 6) + 16 * k;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 v = ldg_stream(reinterpret_cast<const float4 *>(a + off) + j);
+            f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
+        }
+        float m = 0.f;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) m = fmaxf(m, fabsf(f[e]));
+        m = warp_max(m);
+        if ((tid & 31) == 0) warp_max_s[tid >> 5] = m;
+        __syncthreads();
+        m = warp_max_s[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, warp_max_s[w]);
+        __syncthreads();
+        m = guard_zero(m);
+        if (tid == 0) scales[bi * hb + bj] = m;
+        const float scale = quant_scale(kQmax, m);
+
+        // stochastic mode: the reference walks tiles column-block-major (b_j outer, :524-525) and
+        // draws two calls per tile row, so row i of this tile sits at call 128*(bj*vb + bi) + 2*i.
+        // This thread's 16 elements (16k .. 16k+15 of the row) all belong to call c = k/2.
+        uint32_t w8[8];
+        if (STOCH) {
+            const uint64_t call = 128 * (bj * vb + bi) + 2 * (uint64_t)i + (k >> 1);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                uint64_t lane = xs_jump(tables, key.x[p], call);
+                const uint64_t o = xs_next(lane);
+                w8[2 * p] = (uint32_t)o;
+                w8[2 * p + 1] = (uint32_t)(o >> 32);
+            }
+        }
+        int q[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            // element 16k+e of the row: byte slot g = ((16k+e)%32)/8 = 2*(k&1) + e/8, word e%8
+            const float rnd = STOCH ? noise_from_word(w8[e & 7], 2 * (k & 1) + (e >> 3)) : 0.f;
+            q[e] = quant_one(f[e], scale, rnd);
+        }
+        if (BITS == 4) {
+            uint2 o = make_uint2(pack8_nibbles(q), pack8_nibbles(q + 8));
+            *reinterpret_cast<uint2 *>(values + (off >> 1)) = o;
+        } else {
+            uint4 o = make_uint4(pack4_bytes(q), pack4_bytes(q + 4), pack4_bytes(q + 8), pack4_bytes(q + 12));
+            *reinterpret_cast<uint4 *>(values + off) = o;
+        }
+    }
+}
+
+template <int BITS>
+static int launch_mquantize(const float *a, uint64_t rows, uint64_t cols, int8_t *values, float *scales,
+                            uint64_t *key_host, cudaStream_t stream) {
+    const uint64_t ntiles = (rows >> 6) * (cols >> 6);
+    if (ntiles == 0) return CLOVER_OK;
+    const uint64_t cap = (uint64_t)sm_count() * 8;
+    const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
+    Key4 key = {};
+    if (key_host) {
+        const uint64_t *tables = device_jump_tables();
+        if (!tables) { set_error("clover: could not upload PRNG jump tables"); return CLOVER_ERR_CUDA; }
+        key = key_lanes(key_host);
+        k_mquantize<BITS, true><<<grid, 256, 0, stream>>>(a, rows, cols, values, scales, key, tables);
+        host_key_skip(key_host, 128 * ntiles);
+    } else {
+        k_mquantize<BITS, false><<<grid, 256, 0, stream>>>(a, rows, cols, values, scales, key, nullptr);
+    }
+    count_launch();
+    return launch_status("k_mquantize");
+}
+
+// =============================================================================================
+// re-quantizer shared by the mvm epilogues (include/CloverMatrix4.h:915-1080, CloverMatrix8.h:1110-1295)
+// =============================================================================================
+// Called by the first 64 threads of a CTA with y = the fp32 result of row (64*rb + i).
+// 4-bit: the reference stores block_values pre-transposed, so element i takes the noise slot
+// (call (i%8)/4, byte i%4, word i/8); 8-bit keeps the natural slot (call i/32, byte (i%32)/8, word i%8).
+template <int BITS, bool STOCH>
+__device__ __forceinline__ void requantize_block(float y, int i, uint64_t rb, int8_t *__restrict__ yv,
+                                                 float *__restrict__ ys, const Key4 &key,
+                                                 const uint64_t *__restrict__ tables, float *smem_f, int *smem_q) {
+    constexpr float kQmax = BITS == 4 ? 7.0f : 127.0f;
+    float m = warp_max(fabsf(y));
+    if ((i & 31) == 0) smem_f[i >> 5] = m;
+    asm volatile("bar.sync 1, 64;");                            // only the 64 epilogue threads
+    m = guard_zero(fmaxf(smem_f[0], smem_f[1]));
+    if (i == 0) ys[rb] = m;
+    const float scale = quant_scale(kQmax, m);
+    float rnd = 0.f;
+    if (STOCH) {
+        int c, g, l;
+        if (BITS == 4) { c = (i & 7) >> 2; g = i & 3; l = i >> 3; }
+        else           { c = i >> 5; g = (i & 31) >> 3; l = i & 7; }
+        uint64_t lane = xs_jump(tables, key.x[l >> 1], 2 * rb + c);
+        const uint64_t o = xs_next(lane);
+        rnd = noise_from_word((l & 1) ? (uint32_t)(o >> 32) : (uint32_t)o, g);
+    }
+    smem_q[i] = quant_one(y, scale, rnd);
+    asm volatile("bar.sync 1, 64;");
+    if (BITS == 4) {
+        if (i < 8) reinterpret_cast<uint32_t *>(yv + rb * 32)[i] = pack8_nibbles(smem_q + 8 * i);
+    } else {
+        if (i < 16) reinterpret_cast<uint32_t *>(yv + rb * 64)[i] = pack4_bytes(smem_q + 4 * i);
+    }
+}
+
+// =============================================================================================
+// mvm(V4,V4): exact-order 4-bit GEMV
+// =============================================================================================
+// CTA = one 64-row block (= one block of the output vector), 512 threads.
+// thread = (row pair rp, accumulator a, AVX lane l): it IS the reference's fp32 chain (a, l) for rows
+// rp and rp+32 and performs one FMA per block pair, in block order (CloverMatrix4.h:813-898).
+// Per step it loads the 4 bytes (8 nibbles) of block 2p+a, lane l of each row: 16 threads cover the
+// 64 contiguous bytes of a block pair.
+//
+// Integer part without unpacking to signed nibbles. With h' = h+8, l' = l+8 (one LOP3 each:
+// (w ^ 0x88888888) & mask) and the x operand pre-expanded ONCE per CTA and column chunk into
+//   xh = plain signed high nibbles, xl16 = 16 * signed low nibbles, cneg = -(786432 + 8*(sum xh + sum xl)),
+//   S  = dp4a.u32.s32(16*h', xh) + dp4a.u32.s32(l', xl16)  (accumulated on top of the magic 0x4B400000)
+// is 16 * sum(h'*xh + l'*xl) and  fma(as_float(S), 1/16, cneg)  is EXACTLY float(sum h*xh + l*xl):
+// no I2F, no shifts, two LOP3 + two DP4A + two FFMA per 8 nibbles.
+constexpr int kMvmThreads = 512;
+constexpr int kMvmChunkBlocks = 64;          // blocks of x staged per chunk (4096 columns)
+constexpr uint32_t kMagicBits = 0x4B400000u; // 12582912.0f = 1.5 * 2^23
+
+struct XUnit { int xh; int xl16; float cneg; float prod; };   // one (block, lane) unit, 16 B
+
+__device__ __forceinline__ int sext_nibbles(uint32_t n) {      // bytes hold 0..15 -> signed -8..7
+    return (int)__vsub4(n ^ 0x08080808u, 0x08080808u);
+}
+
+template <bool STOCH>
+__global__ void __launch_bounds__(kMvmThreads)
+k_m4_mvm(const uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t rows_local, uint64_t cols,
+         uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
+         float *__restrict__ y32, int8_t *__restrict__ yv, float *__restrict__ ys, Key4 key,
+         const uint64_t *__restrict__ tables) {
+    __shared__ __align__(16) XUnit units[kMvmChunkBlocks * 8];
+    __shared__ float ysm[64];
+    __shared__ float red_f[2];
+    __shared__ int red_q[64];
+
+    const int tid = threadIdx.x;
+    const int rp = tid >> 4, a = (tid >> 3) & 1, l = tid & 7;
+    const uint64_t hb = cols >> 6;
+    const uint64_t wpr = cols >> 3;                              // 32-bit words per row
+
+    for (uint64_t rb = blockIdx.x; rb < (rows_local >> 6); rb += gridDim.x) {
+        const uint32_t *row0 = values + (rb * 64 + rp) * wpr;
+        const uint32_t *row1 = row0 + 32 * wpr;
+        const float *su = scales + rb * hb;
+        float acc0 = 0.f, acc1 = 0.f;
+
+        for (uint64_t cb = 0; cb < hb; cb += kMvmChunkBlocks) {
+            const int nb = (int)((hb - cb) < (uint64_t)kMvmChunkBlocks ? (hb - cb) : kMvmChunkBlocks);
+            __syncthreads();                                     // previous chunk fully consumed
+            if (tid < nb * 8) {
+                const int b = tid >> 3;
+                const uint32_t w = xv[(cb + b) * 8 + (tid & 7)];
+                const int xh = sext_nibbles((w >> 4) & 0x0F0F0F0Fu);
+                const int xl = sext_nibbles(w & 0x0F0F0F0Fu);
+                XUnit u;
+                u.xh = xh;
+                u.xl16 = (int)((w << 4) & 0xF0F0F0F0u);
+                u.cneg = -(786432.0f + 8.0f * (float)(dp4a_ss(xh, 0x01010101, 0) + dp4a_ss(xl, 0x01010101, 0)));
+                u.prod = __fmul_rn(__fmul_rn(su[cb + b], 1.0f / 49.0f), xs[cb + b]);   // (:834-837)
+                units[tid] = u;
+            }
+            __syncthreads();
+
+            const uint32_t *p0 = row0 + cb * 8 + a * 8 + l;
+            const uint32_t *p1 = row1 + cb * 8 + a * 8 + l;
+            const int steps = nb >> 1;                           // nb is even (cols % 128 == 0)
+            int p = 0;
+            for (; p + 4 <= steps; p += 4) {
+                uint32_t w0[4], w1[4];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    w0[s] = ldg_stream(p0 + (p + s) * 16);
+                    w1[s] = ldg_stream(p1 + (p + s) * 16);
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const XUnit u = units[((p + s) * 2 + a) * 8 + l];
+                    const uint32_t t0 = w0[s] ^ 0x88888888u, t1 = w1[s] ^ 0x88888888u;
+                    int s0 = dp4a_us(t0 & 0xF0F0F0F0u, u.xh, (int)kMagicBits);
+                    s0 = dp4a_us(t0 & 0x0F0F0F0Fu, u.xl16, s0);
+                    int s1 = dp4a_us(t1 & 0xF0F0F0F0u, u.xh, (int)kMagicBits);
+                    s1 = dp4a_us(t1 & 0x0F0F0F0Fu, u.xl16, s1);
+                    const float i0 = __fmaf_rn(__int_as_float(s0), 0.0625f, u.cneg);
+                    const float i1 = __fmaf_rn(__int_as_float(s1), 0.0625f, u.cneg);
+                    acc0 = __fmaf_rn(u.prod, i0, acc0);          // (:896-897)
+                    acc1 = __fmaf_rn(u.prod, i1, acc1);
+                }
+            }
+            for (; p < steps; ++p) {
+                const XUnit u = units[(p * 2 + a) * 8 + l];
+                const uint32_t t0 = ldg_stream(p0 + p * 16) ^ 0x88888888u;
+                const uint32_t t1 = ldg_stream(p1 + p * 16) ^ 0x88888888u;
+                int s0 = dp4a_us(t0 & 0xF0F0F0F0u, u.xh, (int)kMagicBits);
+                s0 = dp4a_us(t0 & 0x0F0F0F0Fu, u.xl16, s0);
+                int s1 = dp4a_us(t1 & 0xF0F0F0F0u, u.xh, (int)kMagicBits);
+                s1 = dp4a_us(t1 & 0x0F0F0F0Fu, u.xl16, s1);
+                acc0 = __fmaf_rn(u.prod, __fmaf_rn(__int_as_float(s0), 0.0625f, u.cneg), acc0);
+                acc1 = __fmaf_rn(u.prod, __fmaf_rn(__int_as_float(s1), 0.0625f, u.cneg), acc1);
+            }
+        }
+        // acc_1 + acc_2, then the hadd tree (:902-907); the 16 lanes of a row are 16 consecutive threads
+        acc0 = __fadd_rn(acc0, __shfl_xor_sync(0xFFFFFFFFu, acc0, 8));
+        acc1 = __fadd_rn(acc1, __shfl_xor_sync(0xFFFFFFFFu, acc1, 8));
+        acc0 = hadd8_butterfly(acc0);
+        acc1 = hadd8_butterfly(acc1);
+        if ((tid & 15) == 0) { ysm[rp] = acc0; ysm[rp + 32] = acc1; }
+        __syncthreads();
+        if (tid < 64) {
+            const float y = ysm[tid];
+            if (y32) y32[(rowblock0 + rb) * 64 + tid] = y;
+            if (yv) requantize_block<4, STOCH>(y, tid, rowblock0 + rb, yv, ys, key, tables, red_f, red_q);
+        }
+        // ysm / red_* are rewritten only after the next row block's chunk barriers
+    }
+}
+
+// =============================================================================================
+// mvm(V8,V8): exact-order 8-bit GEMV. 8 chains per row (one accumulator, CloverMatrix8.h:1029-1095)
+// thread = (row, lane l): per block the int32 lane sum covers bytes 4l..4l+3 and 32+4l..32+4l+3.
+// =============================================================================================
+constexpr int kMvm8ChunkBlocks = 64;
+
+template <bool STOCH>
+__global__ void __launch_bounds__(512)
+k_m8_mvm(const uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t rows_local, uint64_t cols,
+         uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
+         float *__restrict__ y32, int8_t *__restrict__ yv, float *__restrict__ ys, Key4 key,
+         const uint64_t *__restrict__ tables) {
+    __shared__ uint32_t xsm[kMvm8ChunkBlocks * 16];
+    __shared__ float prod[kMvm8ChunkBlocks];
+    __shared__ float ysm[64];
+    __shared__ float red_f[2];
+    __shared__ int red_q[64];
+
+    const int tid = threadIdx.x;
+    const int r = tid >> 3, l = tid & 7;
+    const uint64_t hb = cols >> 6;
+    const uint64_t wpr = cols >> 2;
+
+    for (uint64_t rb = blockIdx.x; rb < (rows_local >> 6); rb += gridDim.x) {
+        const uint32_t *row = values + (rb * 64 + r) * wpr;
+        const float *su = scales + rb * hb;
+        float acc = 0.f;
+        for (uint64_t cb = 0; cb < hb; cb += kMvm8ChunkBlocks) {
+            const int nb = (int)((hb - cb) < (uint64_t)kMvm8ChunkBlocks ? (hb - cb) : kMvm8ChunkBlocks);
+            __syncthreads();
+            for (int i = tid; i < nb * 16; i += 512) xsm[i] = xv[cb * 16 + i];
+            if (tid < nb)
+                prod[tid] = __fmul_rn(__fmul_rn(su[cb + tid], 1.0f / 127.0f), __fmul_rn(xs[cb + tid], 1.0f / 127.0f));
+            __syncthreads();
+            const uint32_t *p = row + cb * 16 + l;
+            int b = 0;
+            for (; b + 4 <= nb; b += 4) {
+                uint32_t w0[4], w1[4];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    w0[s] = ldg_stream(p + (b + s) * 16);
+                    w1[s] = ldg_stream(p + (b + s) * 16 + 8);
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    int d = dp4a_ss((int)w0[s], (int)xsm[(b + s) * 16 + l], 0);
+                    d = dp4a_ss((int)w1[s], (int)xsm[(b + s) * 16 + 8 + l], d);
+                    acc = __fmaf_rn(prod[b + s], __int2float_rn(d), acc);
+                }
+            }
+            for (; b < nb; ++b) {
+                int d = dp4a_ss((int)ldg_stream(p + b * 16), (int)xsm[b * 16 + l], 0);
+                d = dp4a_ss((int)ldg_stream(p + b * 16 + 8), (int)xsm[b * 16 + 8 + l], d);
+                acc = __fmaf_rn(prod[b], __int2float_rn(d), acc);
+            }
+        }
+        acc = hadd8_butterfly(acc);
+        if (l == 0) ysm[r] = acc;
+        __syncthreads();
+        if (tid < 64) {
+            const float y = ysm[tid];
+            if (y32) y32[(rowblock0 + rb) * 64 + tid] = y;
+            if (yv) requantize_block<8, STOCH>(y, tid, rowblock0 + rb, yv, ys, key, tables, red_f, red_q);
+        }
+    }
+}
+
+// =============================================================================================
+// mvm(V32,V32): 4-bit matrix, fp32 vectors (CloverMatrix4.h:1451-1547). One warp per row; lane 8k+l
+// is the reference's chain (accumulator k, AVX lane l): per block element 8k+l, then 32+8k+l.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+k_m4_mvm_f32(const uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t rows, uint64_t cols,
+             const float *__restrict__ x, float *__restrict__ y) {
+    const int lane = threadIdx.x & 31, k = lane >> 3, l = lane & 7;
+    const uint64_t hb = cols >> 6, wpr = cols >> 3;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    // nibble l of a word: byte l/2, high nibble when l is even -> shift its top bit to bit 31
+    const int top = 8 * (l >> 1) + ((l & 1) ? 3 : 7);
+    for (uint64_t r = warp; r < rows; r += nwarps) {
+        const uint32_t *row = values + r * wpr;
+        const float *su = scales + (r >> 6) * hb;
+        float acc = 0.f;
+#pragma unroll 2
+        for (uint64_t b = 0; b < hb; ++b) {
+            const uint32_t wa = __ldg(row + b * 8 + k), wb = __ldg(row + b * 8 + 4 + k);
+            const float s = __fdiv_rn(__ldg(su + b), 7.0f);                       // (:1488)
+            const int qa = ((int)(wa << (31 - top))) >> 28, qb = ((int)(wb << (31 - top))) >> 28;
+            const float fa = __fmul_rn(__int2float_rn(qa), s), fb = __fmul_rn(__int2float_rn(qb), s);
+            acc = __fmaf_rn(__ldg(x + b * 64 + lane), fa, acc);                   // element 8k+l      (:1529-1532)
+            acc = __fmaf_rn(__ldg(x + b * 64 + 32 + lane), fb, acc);              // element 32+8k+l   (:1534-1537)
+        }
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, 8));               // acc_1+acc_2 | acc_3+acc_4
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, 16));              // sum_1 + sum_2
+        acc = hadd8_butterfly(acc);
+        if (lane == 0) y[r] = acc;
+    }
+}
+
+// re-quantize a full fp32 vector like the mvm tail (used after the multi-GPU exchange)
+template <int BITS, bool STOCH>
+__global__ void __launch_bounds__(64)
+k_requantize_mvm(const float *__restrict__ y32, uint64_t nblocks, int8_t *__restrict__ yv, float *__restrict__ ys,
+                 Key4 key, const uint64_t *__restrict__ tables) {
+    __shared__ float red_f[2];
+    __shared__ int red_q[64];
+    for (uint64_t rb = blockIdx.x; rb < nblocks; rb += gridDim.x) {
+        requantize_block<BITS, STOCH>(y32[rb * 64 + threadIdx.x], threadIdx.x, rb, yv, ys, key, tables, red_f, red_q);
+        asm volatile("bar.sync 1, 64;");
+    }
+}
+
+template <int BITS>
+static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_local, uint64_t cols, uint64_t row0,
+                      const int8_t *xv, const float *xs, float *y32, int8_t *yv, float *ys, const uint64_t *key_host,
+                      cudaStream_t stream) {
+    const uint64_t nrb = rows_local >> 6;
+    if (nrb == 0 || cols == 0) return CLOVER_OK;
+    const unsigned grid = (unsigned)nrb;
+    Key4 key = {};
+    const uint64_t *tables = nullptr;
+    const bool stoch = key_host != nullptr && yv != nullptr;
+    if (stoch) {
+        tables = device_jump_tables();
+        if (!tables) { set_error("clover: could not upload PRNG jump tables"); return CLOVER_ERR_CUDA; }
+        key = key_lanes(key_host);
+    }
+    const uint32_t *v32 = reinterpret_cast<const uint32_t *>(values);
+    const uint32_t *x32 = reinterpret_cast<const uint32_t *>(xv);
+    if (BITS == 4) {
+        if (stoch) k_m4_mvm<true><<<grid, kMvmThreads, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
+        else       k_m4_mvm<false><<<grid, kMvmThreads, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
+    } else {
+        if (stoch) k_m8_mvm<true><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
+        else       k_m8_mvm<false><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
+    }
+    count_launch();
+    return launch_status("k_mvm");
+}
+
+}  // namespace clover
+
+using namespace clover;
+
+#define CLOVER_CHECK_MAT(rows, cols)                                                                   \
+    CLOVER_REQUIRE((rows) % 128u == 0 && (cols) % 128u == 0, CLOVER_ERR_INVALID,                       \
+                   "rows and cols must be multiples of 128 (include/CloverMatrix.h:48-50)")
+
+extern "C" {
+
+int clover_m4_quantize(const float *a, uint64_t rows, uint64_t cols, int8_t *values, float *scales,
+                       uint64_t *key_host, void *stream) {
+    CLOVER_REQUIRE(a && values && scales, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_CHECK_MAT(rows, cols);
+    return launch_mquantize<4>(a, rows, cols, values, scales, key_host, (cudaStream_t)stream);
+}
+int clover_m8_quantize(const float *a, uint64_t rows, uint64_t cols, int8_t *values, float *scales,
+                       uint64_t *key_host, void *stream) {
+    CLOVER_REQUIRE(a && values && scales, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_CHECK_MAT(rows, cols);
+    return launch_mquantize<8>(a, rows, cols, values, scales, key_host, (cudaStream_t)stream);
+}
+
+int clover_m4_mvm(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                  const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32,
+                  uint64_t *key_host, void *stream) {
+    CLOVER_REQUIRE(values && scales && xv && xs && yv && ys, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_CHECK_MAT(rows, cols);
+    int rc = launch_mvm<4>(values, scales, rows, cols, 0, xv, xs, y32, yv, ys, key_host, (cudaStream_t)stream);
+    if (rc == CLOVER_OK && key_host) host_key_skip(key_host, 2 * (rows >> 6));   // two calls per 64 rows (:979,:999)
+    return rc;
+}
+int clover_m8_mvm(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                  const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32,
+                  uint64_t *key_host, void *stream) {
+    CLOVER_REQUIRE(values && scales && xv && xs && yv && ys, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_CHECK_MAT(rows, cols);
+    int rc = launch_mvm<8>(values, scales, rows, cols, 0, xv, xs, y32, yv, ys, key_host, (cudaStream_t)stream);
+    if (rc == CLOVER_OK && key_host) host_key_skip(key_host, 2 * (rows >> 6));
+    return rc;
+}
+
+int clover_m4_mvm_shard(const int8_t *values_local, const float *scales_local, uint64_t rows_local, uint64_t cols,
+                        uint64_t row0, const int8_t *xv, const float *xs, float *y32_full,
+                        int8_t *yv_full, float *ys_full, uint64_t *key_host, void *stream) {
+    CLOVER_REQUIRE(values_local && scales_local && xv && xs, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_REQUIRE(y32_full || (yv_full && ys_full), CLOVER_ERR_INVALID, "no output requested");
+    CLOVER_REQUIRE(rows_local % 64u == 0 && row0 % 64u == 0 && cols % 128u == 0, CLOVER_ERR_INVALID,
+                   "shards are whole 64-row blocks; cols a multiple of 128");
+    // key_host (if any) is read at the GLOBAL row-block position and NOT advanced: the caller advances
+    // it once by 2 * total_rows / 64 (clover_prng_skip), so every rank stays on the reference's stream.
+    return launch_mvm<4>(values_local, scales_local, rows_local, cols, row0, xv, xs, y32_full,
+                         yv_full, ys_full, key_host, (cudaStream_t)stream);
+}
+
+int clover_v4_requantize_mvm(const float *y32, uint64_t rows, int8_t *yv, float *ys, uint64_t *key_host, void *stream) {
+    CLOVER_REQUIRE(y32 && yv && ys, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_REQUIRE(rows % 128u == 0, CLOVER_ERR_INVALID, "rows must be a multiple of 128");
+    const uint64_t nrb = rows >> 6;
+    if (nrb == 0) return CLOVER_OK;
+    const uint64_t cap = (uint64_t)sm_count() * 16;
+    const unsigned grid = (unsigned)(nrb < cap ? nrb : cap);
+    if (key_host) {
+        const uint64_t *tables = device_jump_tables();
+        if (!tables) { set_error("clover: could not upload PRNG jump tables"); return CLOVER_ERR_CUDA; }
+        k_requantize_mvm<4, true><<<grid, 64, 0, (cudaStream_t)stream>>>(y32, nrb, yv, ys, key_lanes(key_host), tables);
+        host_key_skip(key_host, 2 * nrb);
+    } else {
+        k_requantize_mvm<4, false><<<grid, 64, 0, (cudaStream_t)stream>>>(y32, nrb, yv, ys, Key4{}, nullptr);
+    }
+    count_launch();
+    return launch_status("k_requantize_mvm");
+}
+
+int clover_m4_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                      const float *x32, float *y32, void *stream) {
+    CLOVER_REQUIRE(values && scales && x32 && y32, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_CHECK_MAT(rows, cols);
+    if (rows == 0 || cols == 0) return CLOVER_OK;
+    const uint64_t want = (rows + 7) / 8, cap = (uint64_t)sm_count() * 8;
+    k_m4_mvm_f32<<<(unsigned)(want > cap ? cap : want), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint32_t *>(values), scales, rows, cols, x32, y32);
+    count_launch();
+    return launch_status("k_m4_mvm_f32");
+}
+
+}  // extern "C"

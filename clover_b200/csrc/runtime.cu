@@ -1,0 +1,186 @@
+// runtime.cu - library state: error string, launch counter, PRNG jump tables, memory helpers.
+#include <atomic>
+#include <mutex>
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+#include "runtime.cuh"
+
+namespace clover {
+
+static thread_local char g_error[512] = "";
+static std::atomic<int> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return CLOVER_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+// ---- jump tables: level i holds L^(2^i) as 8 byte-indexed tables --------------------------------
+static std::vector<uint64_t> g_host_tables;
+static std::once_flag g_host_tables_once;
+
+static void build_host_tables() {
+    g_host_tables.resize((size_t)kJumpLevels * kJumpTableWords);
+    uint64_t *t0 = g_host_tables.data();
+    for (int p = 0; p < 8; ++p)
+        for (int v = 0; v < 256; ++v) t0[p * 256 + v] = xs_advance((uint64_t)v << (8 * p));
+    for (int level = 1; level < kJumpLevels; ++level) {
+        uint64_t *t = t0 + (size_t)level * kJumpTableWords;
+        for (int p = 0; p < 8; ++p)
+            for (int v = 0; v < 256; ++v) {
+                const uint64_t once = xs_apply_level(t0, level - 1, (uint64_t)v << (8 * p));
+                t[p * 256 + v] = xs_apply_level(t0, level - 1, once);
+            }
+    }
+}
+
+const uint64_t *host_jump_tables() {
+    std::call_once(g_host_tables_once, build_host_tables);
+    return g_host_tables.data();
+}
+
+static std::mutex g_dev_tables_mutex;
+static uint64_t *g_dev_tables[64] = {nullptr};
+
+const uint64_t *device_jump_tables() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_dev_tables_mutex);
+    if (!g_dev_tables[dev]) {
+        const uint64_t *h = host_jump_tables();
+        const size_t bytes = (size_t)kJumpLevels * kJumpTableWords * sizeof(uint64_t);
+        uint64_t *d = nullptr;
+        if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+        g_dev_tables[dev] = d;
+    }
+    return g_dev_tables[dev];
+}
+
+void host_key_skip(uint64_t *key_host, uint64_t ncalls) {
+    if (ncalls == 0) return;
+    const uint64_t *t = host_jump_tables();
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t before_last = xs_jump(t, key_host[4 + k], ncalls - 1);
+        key_host[k] = before_last;                       // part1 trails part2 by one call
+        key_host[4 + k] = xs_advance(before_last);
+    }
+}
+
+}  // namespace clover
+
+using namespace clover;
+
+extern "C" {
+
+int clover_version(void) { return 100; }
+const char *clover_last_error(void) { return g_error; }
+int clover_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int clover_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int clover_set_device(int device) { CLOVER_CUDA_CHECK(cudaSetDevice(device)); return CLOVER_OK; }
+
+uint64_t clover_size_pad(uint64_t n) { return (n % 128u) ? n + 128u - (n % 128u) : n; }
+
+int clover_malloc(void **p, size_t bytes) {
+    CLOVER_REQUIRE(p != nullptr, CLOVER_ERR_INVALID, "null output pointer");
+    CLOVER_CUDA_CHECK(cudaMalloc(p, bytes ? bytes : 1));
+    return CLOVER_OK;
+}
+int clover_free(void *p) { CLOVER_CUDA_CHECK(cudaFree(p)); return CLOVER_OK; }
+int clover_malloc_host(void **p, size_t bytes) {
+    CLOVER_REQUIRE(p != nullptr, CLOVER_ERR_INVALID, "null output pointer");
+    CLOVER_CUDA_CHECK(cudaMallocHost(p, bytes ? bytes : 1));
+    return CLOVER_OK;
+}
+int clover_free_host(void *p) { CLOVER_CUDA_CHECK(cudaFreeHost(p)); return CLOVER_OK; }
+int clover_memset(void *p, int byte, size_t bytes, void *stream) {
+    CLOVER_CUDA_CHECK(cudaMemsetAsync(p, byte, bytes, (cudaStream_t)stream));
+    return CLOVER_OK;
+}
+int clover_copy_h2d(void *d, const void *h, size_t bytes, void *stream) {
+    CLOVER_CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return CLOVER_OK;
+}
+int clover_copy_d2h(void *h, const void *d, size_t bytes, void *stream) {
+    CLOVER_CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return CLOVER_OK;
+}
+int clover_copy_d2d(void *dst, const void *src, size_t bytes, void *stream) {
+    CLOVER_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return CLOVER_OK;
+}
+int clover_stream_sync(void *stream) { CLOVER_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream)); return CLOVER_OK; }
+
+// ---- PRNG on the host --------------------------------------------------------------------------
+// canonical scalar xorshift128+ step and 2^64 jump: only used to derive lanes 1..3 from lane 0
+// (include/simdxorshift128plus.h:38-62, :81-92)
+static void scalar_step(uint64_t &s0_slot, uint64_t &s1_slot) {
+    uint64_t s1 = s0_slot;
+    const uint64_t s0 = s1_slot;
+    s0_slot = s0;
+    s1 ^= s1 << 23;
+    s1_slot = s1 ^ s0 ^ (s1 >> 18) ^ (s0 >> 5);
+}
+static void scalar_jump(uint64_t in1, uint64_t in2, uint64_t &o1, uint64_t &o2) {
+    static const uint64_t poly[2] = {0x8a5cd789635d2dffULL, 0x121fd2155c472f96ULL};
+    uint64_t a = 0, b = 0;
+    for (int i = 0; i < 2; ++i)
+        for (int bit = 0; bit < 64; ++bit) {
+            if (poly[i] & (1ULL << bit)) { a ^= in1; b ^= in2; }
+            scalar_step(in1, in2);
+        }
+    o1 = a; o2 = b;
+}
+
+int clover_prng_init(uint64_t key1, uint64_t key2, uint64_t *key_host) {
+    CLOVER_REQUIRE(key_host != nullptr, CLOVER_ERR_INVALID, "null key");
+    key_host[0] = key1; key_host[4] = key2;
+    for (int k = 1; k < 4; ++k) scalar_jump(key_host[k - 1], key_host[4 + k - 1], key_host[k], key_host[4 + k]);
+    return CLOVER_OK;
+}
+
+int clover_prng_next(uint64_t *key_host, uint32_t *out8) {
+    CLOVER_REQUIRE(key_host != nullptr && out8 != nullptr, CLOVER_ERR_INVALID, "null pointer");
+    for (int k = 0; k < 4; ++k) {
+        key_host[k] = key_host[4 + k];
+        const uint64_t r = xs_next(key_host[4 + k]);
+        out8[2 * k] = (uint32_t)r;
+        out8[2 * k + 1] = (uint32_t)(r >> 32);
+    }
+    return CLOVER_OK;
+}
+
+int clover_prng_skip(uint64_t *key_host, uint64_t ncalls) {
+    CLOVER_REQUIRE(key_host != nullptr, CLOVER_ERR_INVALID, "null key");
+    host_key_skip(key_host, ncalls);
+    return CLOVER_OK;
+}
+
+}  // extern "C"

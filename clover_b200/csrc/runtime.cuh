@@ -1,0 +1,47 @@
+// runtime.cuh - host-side plumbing shared by the ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/clover_b200.h"
+#include "prng.cuh"
+
+namespace clover {
+
+struct Key4 { uint64_t x[4]; };                      // the four live 64-bit lanes (part2)
+
+void set_error(const char *fmt, ...);
+int  cuda_fail(cudaError_t e, const char *what);     // records the message, returns CLOVER_ERR_CUDA
+void count_launch(int n = 1);
+int  sm_count();                                      // SMs of the current device (148 on B200)
+
+// device copy of the jump tables for the CURRENT device (uploaded on first use); nullptr on failure
+const uint64_t *device_jump_tables();
+const uint64_t *host_jump_tables();
+
+// host key helpers: key_host = part1[4] | part2[4]
+inline Key4 key_lanes(const uint64_t *key_host) {
+    Key4 k;
+    for (int i = 0; i < 4; ++i) k.x[i] = key_host[4 + i];
+    return k;
+}
+void host_key_skip(uint64_t *key_host, uint64_t ncalls);
+
+#define CLOVER_CUDA_CHECK(expr)                                             \
+    do {                                                                    \
+        cudaError_t _e = (expr);                                            \
+        if (_e != cudaSuccess) return ::clover::cuda_fail(_e, #expr);       \
+    } while (0)
+
+#define CLOVER_REQUIRE(cond, code, msg)                                     \
+    do {                                                                    \
+        if (!(cond)) { ::clover::set_error("%s: %s", __func__, msg); return code; } \
+    } while (0)
+
+inline int launch_status(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    return CLOVER_OK;
+}
+
+}  // namespace clover

@@ -1,0 +1,421 @@
+// vector_kernels.cu - CloverVector4 / CloverVector8: quantize, restore, dot.
+//
+//   quantize : fp32 -> {4,8}-bit + one fp32 absmax per 64 elements. HBM-bound streaming pass
+//              (4.5625 B/elem for 4-bit, 5.0625 B/elem for 8-bit).
+//              Reference: include/CloverVector4.h:605-807, include/CloverVector8.h:393-605.
+//   restore  : include/CloverVector4.h:1027-1093, include/CloverVector8.h:835-909.
+//   dot      : include/CloverVector4.h:1095-1192, include/CloverVector8.h:911-977.
+#include <map>
+#include <mutex>
+#include <utility>
+#include "common.cuh"
+#include "runtime.cuh"
+
+namespace clover {
+
+// =============================================================================================
+// quantize
+// =============================================================================================
+// One THREAD owns one block of 64 elements at a time and walks R consecutive blocks, so that
+//   * absmax, scale, all 64 roundings and the 32/64 packed output bytes are thread-local
+//     (no shuffles, no cross-thread packing), and
+//   * in stochastic mode the thread carries its own XORShift state and steps it exactly like the
+//     reference's sequential loop does (two calls per block), after one O(log n) jump to its
+//     starting block.
+// Global loads stay fully coalesced: the CTA stages its 128 blocks (128 x 256 B pieces) through
+// shared memory with a 272 B row pitch, which makes both the cooperative 16 B stores and the
+// per-thread 16 B row reads bank-conflict free.
+constexpr int kQThreads = 128;
+constexpr int kRowFloats = 68;   // 64 data + 4 pad floats -> 272 B pitch
+
+template <int BITS, bool STOCH>
+__global__ void __launch_bounds__(kQThreads)
+k_vquantize(const float *__restrict__ x, uint64_t nblocks, uint64_t R, int8_t *__restrict__ values,
+            float *__restrict__ scales, Key4 key, const uint64_t *__restrict__ tables) {
+    __shared__ __align__(16) float tile[kQThreads * kRowFloats];
+    constexpr float kQmax = BITS == 4 ? 7.0f : 127.0f;
+
+    const int tid = threadIdx.x;
+    const uint64_t cta_first = (uint64_t)blockIdx.x * kQThreads;   // first thread slot of this CTA
+    const uint64_t my_first = (cta_first + tid) * R;               // first block of this thread
+
+    uint64_t lanes[4] = {0, 0, 0, 0};
+    if (STOCH && my_first < nblocks) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lanes[k] = xs_jump(tables, key.x[k], 2 * my_first);
+    }
+
+    const int sub = tid >> 4, chunk = tid & 15;                    // half-warp per 256 B piece
+    for (uint64_t r = 0; r < R; ++r) {
+        float4 stage[16];
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const uint64_t blk = (cta_first + it * 8 + sub) * R + r;
+            stage[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (blk < nblocks) stage[it] = ldg_stream(reinterpret_cast<const float4 *>(x + blk * 64) + chunk);
+        }
+#pragma unroll
+        for (int it = 0; it < 16; ++it)
+            *reinterpret_cast<float4 *>(&tile[(it * 8 + sub) * kRowFloats + chunk * 4]) = stage[it];
+        __syncthreads();
+
+        const uint64_t blk = my_first + r;
+        if (blk < nblocks) {
+            float f[64];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 v = *reinterpret_cast<const float4 *>(&tile[tid * kRowFloats + j * 4]);
+                f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
+            }
+            float m = 0.f;
+#pragma unroll
+            for (int e = 0; e < 64; ++e) m = fmaxf(m, fabsf(f[e]));
+            m = guard_zero(m);
+            scales[blk] = m;
+            const float scale = quant_scale(kQmax, m);
+
+            uint32_t w[2][8];
+            if (STOCH) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t o = xs_next(lanes[k]);
+                        w[c][2 * k] = (uint32_t)o;
+                        w[c][2 * k + 1] = (uint32_t)(o >> 32);
+                    }
+            }
+            if (BITS == 4) {
+                uint32_t out[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    int q[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int e = 8 * j + i;   // noise slot: call e/32, byte (e%32)/8, word e%8
+                        const float rnd = STOCH ? noise_from_word(w[e >> 5][e & 7], (e & 31) >> 3) : 0.f;
+                        q[i] = quant_one(f[e], scale, rnd);
+                    }
+                    out[j] = pack8_nibbles(q);
+                }
+                uint4 *dst = reinterpret_cast<uint4 *>(values + blk * 32);
+                dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+                dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+            } else {
+                uint4 *dst = reinterpret_cast<uint4 *>(values + blk * 64);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    uint32_t out[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        int q[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int e = 16 * j4 + 4 * j + i;
+                            const float rnd = STOCH ? noise_from_word(w[e >> 5][e & 7], (e & 31) >> 3) : 0.f;
+                            q[i] = quant_one(f[e], scale, rnd);
+                        }
+                        out[j] = pack4_bytes(q);
+                    }
+                    dst[j4] = make_uint4(out[0], out[1], out[2], out[3]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int BITS>
+static int launch_vquantize(const float *x, uint64_t n_pad, int8_t *values, float *scales, uint64_t *key_host,
+                            cudaStream_t stream) {
+    const uint64_t nblocks = n_pad / kBlock;
+    if (nblocks == 0) return CLOVER_OK;
+    // enough threads for ~6 resident CTAs per SM, then R consecutive blocks per thread
+    const uint64_t max_threads = (uint64_t)sm_count() * 6 * kQThreads;
+    const uint64_t R = (nblocks + max_threads - 1) / max_threads;
+    const uint64_t threads = (nblocks + R - 1) / R;
+    const unsigned grid = (unsigned)((threads + kQThreads - 1) / kQThreads);
+    Key4 key = {};
+    if (key_host) {
+        const uint64_t *tables = device_jump_tables();
+        if (!tables) { set_error("clover: could not upload PRNG jump tables"); return CLOVER_ERR_CUDA; }
+        key = key_lanes(key_host);
+        k_vquantize<BITS, true><<<grid, kQThreads, 0, stream>>>(x, nblocks, R, values, scales, key, tables);
+        host_key_skip(key_host, 2 * nblocks);
+    } else {
+        k_vquantize<BITS, false><<<grid, kQThreads, 0, stream>>>(x, nblocks, R, values, scales, key, nullptr);
+    }
+    count_launch();
+    return launch_status("k_vquantize");
+}
+
+// =============================================================================================
+// restore
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+k_v4_restore(const uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t nwords, float *__restrict__ x) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float s = __fdiv_rn(scales[i >> 3], 7.0f);        // su[b] / 7.0f (:1050)
+        const uint32_t w = values[i];
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = (int)(int8_t)(w >> (8 * j));
+            o[2 * j] = __fmul_rn(__int2float_rn(b >> 4), s);
+            o[2 * j + 1] = __fmul_rn(__int2float_rn((int)(int8_t)(b << 4) >> 4), s);
+        }
+        float4 *dst = reinterpret_cast<float4 *>(x + i * 8);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_v8_restore(const uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t nwords, float *__restrict__ x) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float s = __fdiv_rn(scales[i >> 4], 127.0f);      // su[b] / 127.0f (:872)
+        const uint32_t w = values[i];
+        float4 o;
+        o.x = __fmul_rn(__int2float_rn((int)(int8_t)(w)), s);
+        o.y = __fmul_rn(__int2float_rn((int)(int8_t)(w >> 8)), s);
+        o.z = __fmul_rn(__int2float_rn((int)(int8_t)(w >> 16)), s);
+        o.w = __fmul_rn(__int2float_rn((int)(int8_t)(w >> 24)), s);
+        *reinterpret_cast<float4 *>(x + i * 4) = o;
+    }
+}
+
+// =============================================================================================
+// dot - exact-order mode
+// =============================================================================================
+// One warp. 4-bit: lane = 8*a + l for the reference's accumulator a (even/odd blocks) and AVX lane
+// l; each of the 16 lanes runs its fp32 FMA chain in block order, then acc1+acc2 and the hadd tree.
+// 8-bit: 8 lanes, one accumulator (CloverVector8.h:911-977).
+template <int BITS>
+__global__ void __launch_bounds__(32)
+k_vdot_exact(const uint32_t *__restrict__ u, const float *__restrict__ su, const uint32_t *__restrict__ v,
+             const float *__restrict__ sv, uint64_t nblocks, float *__restrict__ result) {
+    const int lane = threadIdx.x;
+    float acc = 0.f;
+    if (BITS == 4) {
+        const int a = (lane >> 3) & 1, l = lane & 7;
+        if (lane < 16) {
+            const float rcp49 = 1.0f / 49.0f;
+#pragma unroll 4
+            for (uint64_t b = a; b < nblocks; b += 2) {
+                const int dot = nibble_dot_word(u[b * 8 + l], v[b * 8 + l]);
+                const float s = __fmul_rn(__fmul_rn(su[b], rcp49), sv[b]);
+                acc = __fmaf_rn(s, __int2float_rn(dot), acc);
+            }
+        }
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, 8));   // acc_1 + acc_2 (:1190)
+    } else {
+        const int l = lane & 7;
+        if (lane < 8) {
+            const float rcp127 = 1.0f / 127.0f;
+#pragma unroll 4
+            for (uint64_t b = 0; b < nblocks; ++b) {
+                int dot = dp4a_ss((int)u[b * 16 + l], (int)v[b * 16 + l], 0);
+                dot = dp4a_ss((int)u[b * 16 + 8 + l], (int)v[b * 16 + 8 + l], dot);
+                const float s = __fmul_rn(__fmul_rn(su[b], rcp127), __fmul_rn(sv[b], rcp127));
+                acc = __fmaf_rn(s, __int2float_rn(dot), acc);
+            }
+        }
+    }
+    acc = hadd8_butterfly(acc);
+    if (lane == 0) *result = acc;
+}
+
+// =============================================================================================
+// dot - fast mode
+// =============================================================================================
+// Grid-stride over 16-byte chunks of both operands (HBM/L2-bound: 1.125 B/elem for 4-bit). The
+// per-block integer is exact; each block contributes (double)s_b * I_b with the reference's fp32
+// scale s_b = (su*(1/49))*sv, summed in fp64 by a fixed tree (thread -> warp -> CTA -> last CTA),
+// so the result is deterministic and equals the fp64 evaluation of the reference's own terms.
+constexpr int kDotThreads = 256;
+
+struct DotWorkspace { double *partials; unsigned int *ticket; int capacity; };
+
+template <int BITS>
+__global__ void __launch_bounds__(kDotThreads)
+k_vdot_fast(const uint4 *__restrict__ u, const float *__restrict__ su, const uint4 *__restrict__ v,
+            const float *__restrict__ sv, uint64_t nchunks, double *__restrict__ partials,
+            unsigned int *__restrict__ ticket, float *__restrict__ result) {
+    constexpr int kChunksPerBlock = BITS == 4 ? 2 : 4;      // 16 B chunks per 64-element block
+    const uint64_t stride = (uint64_t)gridDim.x * kDotThreads;
+    double acc = 0.0;
+    // all 32 lanes of a warp run the same trip count (nchunks is a multiple of 32: n_pad % 128 == 0
+    // gives nchunks % 4 == 0 only, so guard lanes individually but keep shuffles warp-uniform)
+    const uint64_t first = (uint64_t)blockIdx.x * kDotThreads + threadIdx.x;
+    const uint64_t warp_first = first - (threadIdx.x & 31);
+    for (uint64_t base = warp_first; base < nchunks; base += stride) {
+        const uint64_t i = base + (threadIdx.x & 31);
+        int part = 0;
+        if (i < nchunks) {
+            const uint4 a = ldg_stream(u + i), b = ldg_stream(v + i);
+            if (BITS == 4) {
+                part = nibble_dot_word(a.x, b.x) + nibble_dot_word(a.y, b.y) + nibble_dot_word(a.z, b.z) +
+                       nibble_dot_word(a.w, b.w);
+            } else {
+                part = dp4a_ss((int)a.x, (int)b.x, 0);
+                part = dp4a_ss((int)a.y, (int)b.y, part);
+                part = dp4a_ss((int)a.z, (int)b.z, part);
+                part = dp4a_ss((int)a.w, (int)b.w, part);
+            }
+        }
+        part += __shfl_xor_sync(0xFFFFFFFFu, part, 1);
+        if (BITS == 8) part += __shfl_xor_sync(0xFFFFFFFFu, part, 2);
+        if (i < nchunks && (i % kChunksPerBlock) == 0) {
+            const uint64_t blk = i / kChunksPerBlock;
+            float s;
+            if (BITS == 4) s = __fmul_rn(__fmul_rn(su[blk], 1.0f / 49.0f), sv[blk]);
+            else           s = __fmul_rn(__fmul_rn(su[blk], 1.0f / 127.0f), __fmul_rn(sv[blk], 1.0f / 127.0f));
+            acc += (double)s * (double)part;
+        }
+    }
+    // fixed reduction tree
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    __shared__ double warp_sums[kDotThreads / 32];
+    __shared__ bool is_last;
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kDotThreads / 32; ++w) s += warp_sums[w];
+        partials[blockIdx.x] = s;
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double s = 0.0;
+        for (unsigned int i = threadIdx.x; i < gridDim.x; i += kDotThreads) s += __ldcg(partials + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kDotThreads / 32; ++w) t += warp_sums[w];
+            *result = (float)t;
+            *ticket = 0u;                                   // self-cleaning for the next call
+        }
+    }
+}
+
+// per-(device, stream) workspace for the cross-CTA reduction
+static std::mutex g_ws_mutex;
+static std::map<std::pair<int, cudaStream_t>, DotWorkspace> g_ws;
+
+static int dot_workspace(cudaStream_t stream, int grid, DotWorkspace *out) {
+    int dev = 0;
+    CLOVER_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    DotWorkspace &ws = g_ws[std::make_pair(dev, stream)];
+    if (ws.capacity < grid) {
+        if (ws.partials) cudaFree(ws.partials);
+        if (ws.ticket) cudaFree(ws.ticket);
+        ws = DotWorkspace{nullptr, nullptr, 0};
+        CLOVER_CUDA_CHECK(cudaMalloc(&ws.partials, sizeof(double) * (size_t)grid));
+        CLOVER_CUDA_CHECK(cudaMalloc(&ws.ticket, sizeof(unsigned int)));
+        CLOVER_CUDA_CHECK(cudaMemset(ws.ticket, 0, sizeof(unsigned int)));
+        ws.capacity = grid;
+    }
+    *out = ws;
+    return CLOVER_OK;
+}
+
+constexpr uint64_t kDotExactLimit = 1ull << 16;   // AUTO: exact-order chains up to 65536 elements
+
+template <int BITS>
+static int launch_vdot(const int8_t *u, const float *su, const int8_t *v, const float *sv, uint64_t n_pad,
+                       float *result, int mode, cudaStream_t stream) {
+    const uint64_t nblocks = n_pad / kBlock;
+    if (mode == CLOVER_DOT_AUTO) mode = (n_pad <= kDotExactLimit) ? CLOVER_DOT_EXACT : CLOVER_DOT_FAST;
+    if (mode == CLOVER_DOT_EXACT || nblocks == 0) {
+        k_vdot_exact<BITS><<<1, 32, 0, stream>>>(reinterpret_cast<const uint32_t *>(u), su,
+                                                 reinterpret_cast<const uint32_t *>(v), sv, nblocks, result);
+        count_launch();
+        return launch_status("k_vdot_exact");
+    }
+    const uint64_t nchunks = BITS == 4 ? n_pad / 32 : n_pad / 16;
+    uint64_t want = (nchunks + kDotThreads * 4 - 1) / (kDotThreads * 4);       // >= 4 chunks per thread
+    const uint64_t cap = (uint64_t)sm_count() * 8;
+    const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    DotWorkspace ws;
+    int rc = dot_workspace(stream, (int)cap, &ws);
+    if (rc != CLOVER_OK) return rc;
+    k_vdot_fast<BITS><<<grid, kDotThreads, 0, stream>>>(reinterpret_cast<const uint4 *>(u), su,
+                                                        reinterpret_cast<const uint4 *>(v), sv, nchunks,
+                                                        ws.partials, ws.ticket, result);
+    count_launch();
+    return launch_status("k_vdot_fast");
+}
+
+}  // namespace clover
+
+using namespace clover;
+
+#define CLOVER_CHECK_VEC(n_pad)                                                                     \
+    CLOVER_REQUIRE((n_pad) % 128u == 0, CLOVER_ERR_INVALID, "n_pad must be a multiple of 128 (clover_size_pad)")
+
+extern "C" {
+
+uint64_t clover_dot_exact_limit(void) { return kDotExactLimit; }
+
+int clover_v4_quantize(const float *x, uint64_t n_pad, int8_t *values, float *scales, uint64_t *key_host, void *stream) {
+    CLOVER_REQUIRE(x && values && scales, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_CHECK_VEC(n_pad);
+    return launch_vquantize<4>(x, n_pad, values, scales, key_host, (cudaStream_t)stream);
+}
+int clover_v8_quantize(const float *x, uint64_t n_pad, int8_t *values, float *scales, uint64_t *key_host, void *stream) {
+    CLOVER_REQUIRE(x && values && scales, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_CHECK_VEC(n_pad);
+    return launch_vquantize<8>(x, n_pad, values, scales, key_host, (cudaStream_t)stream);
+}
+
+int clover_v4_restore(const int8_t *values, const float *scales, uint64_t n_pad, float *x, void *stream) {
+    CLOVER_REQUIRE(x && values && scales, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_CHECK_VEC(n_pad);
+    const uint64_t nwords = n_pad / 8;
+    if (nwords == 0) return CLOVER_OK;
+    const uint64_t want = (nwords + 255) / 256, cap = (uint64_t)sm_count() * 16;
+    k_v4_restore<<<(unsigned)(want > cap ? cap : want), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint32_t *>(values), scales, nwords, x);
+    count_launch();
+    return launch_status("k_v4_restore");
+}
+int clover_v8_restore(const int8_t *values, const float *scales, uint64_t n_pad, float *x, void *stream) {
+    CLOVER_REQUIRE(x && values && scales, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_CHECK_VEC(n_pad);
+    const uint64_t nwords = n_pad / 4;
+    if (nwords == 0) return CLOVER_OK;
+    const uint64_t want = (nwords + 255) / 256, cap = (uint64_t)sm_count() * 16;
+    k_v8_restore<<<(unsigned)(want > cap ? cap : want), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint32_t *>(values), scales, nwords, x);
+    count_launch();
+    return launch_status("k_v8_restore");
+}
+
+int clover_v4_dot(const int8_t *u, const float *su, const int8_t *v, const float *sv, uint64_t n_pad,
+                  float *result, int mode, void *stream) {
+    CLOVER_REQUIRE(u && su && v && sv && result, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_REQUIRE(mode >= 0 && mode <= 2, CLOVER_ERR_INVALID, "bad dot mode");
+    CLOVER_CHECK_VEC(n_pad);
+    return launch_vdot<4>(u, su, v, sv, n_pad, result, mode, (cudaStream_t)stream);
+}
+int clover_v8_dot(const int8_t *u, const float *su, const int8_t *v, const float *sv, uint64_t n_pad,
+                  float *result, int mode, void *stream) {
+    CLOVER_REQUIRE(u && su && v && sv && result, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_REQUIRE(mode >= 0 && mode <= 2, CLOVER_ERR_INVALID, "bad dot mode");
+    CLOVER_CHECK_VEC(n_pad);
+    return launch_vdot<8>(u, su, v, sv, n_pad, result, mode, (cudaStream_t)stream);
+}
+
+}  // extern "C"

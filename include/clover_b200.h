@@ -1,0 +1,144 @@
+/*
+ * clover_b200.h - the C ABI of the B200-native Clover hot path (libclover_b200.so).
+ *
+ * The reference (astojanov/Clover) has no FFI layer: its boundary is the public method surface of
+ * the header-only containers CloverVector4/8 and CloverMatrix4/8. Every entry point below replaces
+ * the BODY of one of those methods; the host containers in include/clover_b200/containers.hpp keep
+ * the reference's class and method names and forward here.
+ *
+ * Conventions
+ *   - Plain C: pointers and sizes only. All data pointers are DEVICE pointers unless the name says
+ *     `_host`. Layouts are byte-identical to the reference's in-memory layouts:
+ *       V4: values n_pad/2 bytes (element 2i in the HIGH nibble of byte i), scales n_pad/64 fp32
+ *           (include/CloverVector4.h:44-58, 68-103)
+ *       V8: values n_pad bytes, scales n_pad/64 fp32                (include/CloverVector8.h:45-78)
+ *       M4: row-major nibbles rows*cols/2 bytes, scales[(i>>6)*(cols>>6) + (j>>6)]
+ *           (include/CloverMatrix4.h:38-93);  M8: rows*cols bytes, same scales (CloverMatrix8.h:76-92)
+ *     n_pad / rows / cols are the PADDED sizes: multiples of 128 (include/CloverVector.h:86-89,
+ *     include/CloverMatrix.h:48-50). clover_size_pad() applies the reference's rule.
+ *   - Every function returns a clover_status; nothing exits or throws (the reference prints and
+ *     exit(1)s, e.g. include/CloverMatrix4.h:779-782 - the host containers keep that behaviour).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream). Calls are
+ *     asynchronous with respect to the host unless documented otherwise.
+ *   - Stochastic rounding: `key_host` points to the reference's PRNG state, uint64[8] =
+ *     random_key1[4] | random_key2[4] (include/CloverRandom.h:39-41), in HOST memory. NULL selects
+ *     the reference's CLOVER_STOCHASTIC_ROUNDING_DISABLED behaviour (CMakeLists.txt:78-80). A non-NULL
+ *     key is consumed exactly like the reference's sequential code consumes it (same XORShift128+
+ *     stream, include/simdxorshift128plus.h:97-109) and is advanced in place before the call returns.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     CLOVER_ERR_CUDA.
+ */
+#ifndef CLOVER_B200_H
+#define CLOVER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum clover_status {
+    CLOVER_OK = 0,
+    CLOVER_ERR_INVALID = 1,     /* null pointer, size not a multiple of 128, bad flag */
+    CLOVER_ERR_CUDA = 2,        /* CUDA runtime error - see clover_last_error() */
+    CLOVER_ERR_SIZE = 3,        /* operand sizes do not match (the reference would exit(1)) */
+    CLOVER_ERR_UNSUPPORTED = 4
+} clover_status;
+
+/* dot() accumulation order. EXACT reproduces the reference SIMD dot's 16 (4-bit)
+ * / 8 (8-bit) fp32 FMA chains and its horizontal-add tree bit-for-bit; it is a latency-bound
+ * single-warp walk. FAST computes the same exact per-block integers and sums the scaled blocks
+ * with a fixed pairwise tree in higher precision (deterministic, not order-identical).
+ * AUTO = EXACT up to clover_dot_exact_limit() elements, FAST beyond. */
+typedef enum clover_dot_mode { CLOVER_DOT_AUTO = 0, CLOVER_DOT_EXACT = 1, CLOVER_DOT_FAST = 2 } clover_dot_mode;
+
+/* ---- library / device --------------------------------------------------------------------------- */
+int         clover_version(void);
+const char *clover_last_error(void);                 /* thread-local message of the last failure */
+int         clover_device_count(void);
+int         clover_set_device(int device);
+uint64_t    clover_size_pad(uint64_t n);              /* include/CloverVector.h:86-89 */
+uint64_t    clover_dot_exact_limit(void);
+int         clover_kernel_launches(void);             /* kernels launched by this library since load */
+
+/* ---- device memory helpers (what the reference does with posix_memalign/free/memcpy) ------------ */
+int clover_malloc(void **dev_ptr, size_t bytes);
+int clover_free(void *dev_ptr);
+int clover_malloc_host(void **host_ptr, size_t bytes);    /* pinned */
+int clover_free_host(void *host_ptr);
+int clover_memset(void *dev_ptr, int byte, size_t bytes, void *stream);
+int clover_copy_h2d(void *dev_dst, const void *host_src, size_t bytes, void *stream);
+int clover_copy_d2h(void *host_dst, const void *dev_src, size_t bytes, void *stream);
+int clover_copy_d2d(void *dev_dst, const void *dev_src, size_t bytes, void *stream);
+int clover_stream_sync(void *stream);
+
+/* ---- PRNG state on the host (include/simdxorshift128plus.h, include/CloverRandom.h) ------------- */
+int clover_prng_init(uint64_t key1, uint64_t key2, uint64_t *key_host);   /* avx_xorshift128plus_init :81-92 */
+int clover_prng_next(uint64_t *key_host, uint32_t *out8);                 /* avx_xorshift128plus      :97-109 */
+int clover_prng_skip(uint64_t *key_host, uint64_t ncalls);                /* O(log n) GF(2) jump-ahead */
+
+/* ---- CloverVector4 ------------------------------------------------------------------------------ */
+/* CloverVector4::quantize      include/CloverVector4.h:605-807   (x: n_pad fp32) */
+int clover_v4_quantize(const float *x, uint64_t n_pad, int8_t *values, float *scales, uint64_t *key_host, void *stream);
+/* CloverVector4::restore       include/CloverVector4.h:1027-1093 */
+int clover_v4_restore(const int8_t *values, const float *scales, uint64_t n_pad, float *x, void *stream);
+/* CloverVector4::dot           include/CloverVector4.h:1095-1192 (result: one fp32 in device memory) */
+int clover_v4_dot(const int8_t *u, const float *su, const int8_t *v, const float *sv, uint64_t n_pad,
+                  float *result, int mode, void *stream);
+
+/* ---- CloverVector8 ------------------------------------------------------------------------------ */
+/* CloverVector8::quantize      include/CloverVector8.h:393-605 */
+int clover_v8_quantize(const float *x, uint64_t n_pad, int8_t *values, float *scales, uint64_t *key_host, void *stream);
+/* CloverVector8::restore       include/CloverVector8.h:835-909 */
+int clover_v8_restore(const int8_t *values, const float *scales, uint64_t n_pad, float *x, void *stream);
+/* CloverVector8::dot           include/CloverVector8.h:911-977 */
+int clover_v8_dot(const int8_t *u, const float *su, const int8_t *v, const float *sv, uint64_t n_pad,
+                  float *result, int mode, void *stream);
+
+/* ---- CloverMatrix4 ------------------------------------------------------------------------------ */
+/* CloverMatrix4::quantize      include/CloverMatrix4.h:512-766  (a: rows*cols fp32, row-major) */
+int clover_m4_quantize(const float *a, uint64_t rows, uint64_t cols, int8_t *values, float *scales,
+                       uint64_t *key_host, void *stream);
+/* CloverMatrix4::mvm(V4,V4)    include/CloverMatrix4.h:777-1083. y = requantized A*x. `y32` (optional,
+ * `rows` fp32) additionally receives the fp32 row results the reference keeps in block_values[]. */
+int clover_m4_mvm(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                  const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32,
+                  uint64_t *key_host, void *stream);
+/* CloverMatrix4::mvm(V32,V32)  include/CloverMatrix4.h:1451-1547 */
+int clover_m4_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                      const float *x32, float *y32, void *stream);
+/* Row-sharded mvm for multi-GPU (no counterpart in the reference): this rank holds rows
+ * [row0, row0 + rows_local) of the matrix. Writes the fp32 results into y32_full[row0 ...] of a
+ * full-length vector (the NCCL collective runs on that buffer) and the requantized slice into
+ * yv/ys at element/row-block offset row0 (so an all-gather of the packed slices is also possible). */
+int clover_m4_mvm_shard(const int8_t *values_local, const float *scales_local, uint64_t rows_local, uint64_t cols,
+                        uint64_t row0, const int8_t *xv, const float *xs, float *y32_full,
+                        int8_t *yv_full, float *ys_full, uint64_t *key_host, void *stream);
+/* Requantize a full-length fp32 vector exactly like the tail of mvm (include/CloverMatrix4.h:925-1080):
+ * used after the collective so that every rank holds the same CloverVector4 result. */
+int clover_v4_requantize_mvm(const float *y32, uint64_t rows, int8_t *yv, float *ys, uint64_t *key_host, void *stream);
+/* 4-bit GEMM (extension): C[i][j] = rowView(A,i).dot(rowView(Bt,j)), A: M x K, Bt: N x K,
+ * both CloverMatrix4; C fp32 row-major with leading dimension ldc. */
+int clover_m4_gemm(const int8_t *av, const float *as, const int8_t *btv, const float *bts,
+                   uint64_t M, uint64_t N, uint64_t K, float *c, uint64_t ldc, void *stream);
+
+/* ---- CloverMatrix8 ------------------------------------------------------------------------------ */
+/* CloverMatrix8::quantize      include/CloverMatrix8.h:203-479 */
+int clover_m8_quantize(const float *a, uint64_t rows, uint64_t cols, int8_t *values, float *scales,
+                       uint64_t *key_host, void *stream);
+/* CloverMatrix8::mvm(V8,V8)    include/CloverMatrix8.h:1002-1298 */
+int clover_m8_mvm(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                  const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32,
+                  uint64_t *key_host, void *stream);
+
+/* ---- host-buffer convenience (the call a reference user makes: host containers in, host out) -----
+ * Each does pinned-staging H2D, the kernels above, and D2H of the result on `stream`, then syncs. */
+int clover_host_v4_quantize(const float *x_host, uint64_t n_pad, int8_t *values_host, float *scales_host, uint64_t *key_host);
+int clover_host_v4_dot(const int8_t *u_host, const float *su_host, const int8_t *v_host, const float *sv_host,
+                       uint64_t n_pad, float *result_host, int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLOVER_B200_H */

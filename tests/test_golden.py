@@ -1,0 +1,91 @@
+"""Oracle vs the committed golden vectors (tests/golden/clover_golden.npz, generated from the unmodified
+reference by oracle/gen_golden.py). CPU only. Also re-checks SURVEY.md 8c's known-answer table."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import fnv1a64, pad_matrix
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clover_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(GOLDEN)
+
+
+def same_bits(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8))
+
+
+def test_prng_and_inputs(oracle, g):
+    st = oracle.xs_init()
+    assert np.array_equal(st, g["seed_state"])
+    p = st.copy()
+    for row in g["prng_first_16_calls"]:
+        assert np.array_equal(oracle.xs_next(p), row)
+    for name, n in (("a", 4096), ("b", 4096), ("c", 1000), ("d", 1000)):
+        assert same_bits(oracle.fill_floats(n, -1.0, 1.0, st), g[name])
+    M = oracle.fill_floats(256 * 384, -1.0, 1.0, st)
+    assert same_bits(M.reshape(256, 384), g["M"])
+    assert same_bits(oracle.fill_floats(384, -1.0, 1.0, st), g["v"])
+    assert same_bits(oracle.fill_floats(384, -1.0, 1.0, st), g["w"])
+    assert same_bits(oracle.fill_integers(1000, -10.0, 10.0, st), g["ints"])
+    assert np.array_equal(st, g["state_after_inputs"])
+
+
+def test_known_answer_table(g):
+    # SURVEY.md 8c
+    assert fnv1a64(g["a"].tobytes()) == "18dfa6095a9f4c3c"
+    assert fnv1a64(g["v4_a_values"].tobytes()) == "f0c0b3dd721cc279"
+    assert fnv1a64(g["v4_a_scales"].tobytes()) == "c42fc9d11429fbda"
+    assert fnv1a64(g["v4_a_restore"].tobytes()) == "31e6456c16611b75"
+    assert float(g["v4_dot_ab"][0]).hex() == "-0x1.ebbfb20000000p+3"            # C1
+    assert fnv1a64(g["v4_c_values"].tobytes()) == "57dd345eb93197e7"
+    assert float(g["v4_dot_cd"][0]).hex() == "0x1.47d7d00000000p+3"
+    assert fnv1a64(g["v8_a_values"].tobytes()) == "e22c3448d27023f6"
+    assert float(g["v8_dot_ab"][0]).hex() == "-0x1.4a8bf40000000p+4"
+    assert fnv1a64(g["m4_mvm_values"].tobytes()) == "b204d807ebfa1302"
+    assert fnv1a64(g["m4_mvm_f32"].tobytes()) == "71d6996935ac366d"
+    assert fnv1a64(g["m8_mvm_values"].tobytes()) == "f52d4903d9bedb6c"
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_vectors(oracle, g, bits):
+    for name, n in (("a", 4096), ("b", 4096), ("c", 1000), ("d", 1000), ("v", 384), ("ints", 1000)):
+        v, s = getattr(oracle, f"v{bits}_quantize")(g[name], n)
+        assert same_bits(v, g[f"v{bits}_{name}_values"]) and same_bits(s, g[f"v{bits}_{name}_scales"])
+        assert same_bits(getattr(oracle, f"v{bits}_restore")(v, s, n), g[f"v{bits}_{name}_restore"])
+    for p, q, n in (("a", "b", 4096), ("c", "d", 1000)):
+        d = getattr(oracle, f"v{bits}_dot")(g[f"v{bits}_{p}_values"], g[f"v{bits}_{p}_scales"],
+                                            g[f"v{bits}_{q}_values"], g[f"v{bits}_{q}_scales"], n)
+        assert same_bits(np.array([d], np.float32), g[f"v{bits}_dot_{p}{q}"])
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_matrices(oracle, g, bits):
+    M = pad_matrix(g["M"])
+    mv, ms = getattr(oracle, f"m{bits}_quantize")(M)
+    assert same_bits(mv, g[f"m{bits}_values"]) and same_bits(ms, g[f"m{bits}_scales"])
+    yv, ys = getattr(oracle, f"m{bits}_mvm")(mv, ms, 256, 384, g[f"v{bits}_v_values"], g[f"v{bits}_v_scales"])
+    assert same_bits(yv, g[f"m{bits}_mvm_values"]) and same_bits(ys, g[f"m{bits}_mvm_scales"])
+    if bits == 4:
+        assert same_bits(oracle.m4_mvm_f32(mv, ms, 256, 384, g["w"]), g["m4_mvm_f32"][:256])
+        bv, bs = oracle.m4_quantize(pad_matrix(g["M"][:128].copy()))
+        assert same_bits(oracle.m4_gemm(mv, ms, bv, bs, 384, 0, 256, 0, 128), g["m4_gemm_256x128"])
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_stochastic_with_key(oracle, g, bits):
+    key = oracle.xs_init(7, 9)
+    v, s = getattr(oracle, f"v{bits}_quantize")(g["c"], 1000, state=key)
+    assert same_bits(v, g[f"sr_v{bits}_c_values"]) and same_bits(s, g[f"sr_v{bits}_c_scales"])
+    assert np.array_equal(key, g[f"sr_v{bits}_key_after"])
+    key = oracle.xs_init(123, 456)
+    mv, ms = getattr(oracle, f"m{bits}_quantize")(pad_matrix(g["M"]), state=key)
+    assert same_bits(mv, g[f"sr_m{bits}_values"]) and same_bits(ms, g[f"sr_m{bits}_scales"])
+    assert np.array_equal(key, g[f"sr_m{bits}_key_after_quantize"])
+    yv, ys = getattr(oracle, f"m{bits}_mvm")(mv, ms, 256, 384, g[f"v{bits}_v_values"], g[f"v{bits}_v_scales"], state=key)
+    assert same_bits(yv, g[f"sr_m{bits}_mvm_values"]) and same_bits(ys, g[f"sr_m{bits}_mvm_scales"])
+    assert np.array_equal(key, g[f"sr_m{bits}_key_after_mvm"])

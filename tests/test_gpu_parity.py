@@ -1,0 +1,299 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle. Needs a B200.
+
+Structure follows the reference's own validation (test/validate/02_vector.cpp: quantization :111-144,
+restore :223-256, dot :258-295; test/validate/03_matrix.cpp: quantization :38-96, MVM :248-326,
+mvm(V32) :419-491) with a stricter bar: the reference compares `get(i)` of two implementations, these
+tests compare every packed byte and every fp32 scale BIT-FOR-BIT.
+
+The oracle (oracle/clover_oracle.c) is itself pinned bit-for-bit to the unmodified reference by
+tests/test_oracle_vs_reference.py and tests/test_golden.py.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def cb():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import clover_b200
+    clover_b200.lib()
+    from clover_b200 import containers
+    return containers
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def gen(oracle, n, kind, skip=0):
+    st = oracle.xs_init()
+    oracle.xs_skip(st, skip)
+    if kind == "ints":
+        return oracle.fill_integers(n, -10.0, 10.0, st)
+    x = oracle.fill_floats(n, -1.0, 1.0, st)
+    if kind == "wide":
+        x[:n] *= np.exp2(np.arange(n) % 40 - 20).astype(np.float32)
+    return x
+
+
+# the reference sweeps 128..1023 step 1 (02_vector.cpp:118); every residue class mod 128 behaves the
+# same after padding, so sample it and add the large / ragged cases
+VEC_SIZES = [1, 64, 127, 128, 129, 255, 640, 1000, 1023, 4096, 65536 + 3, (1 << 20) + 128]
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+@pytest.mark.parametrize("kind", ["floats", "ints", "wide"])
+@pytest.mark.parametrize("n", VEC_SIZES)
+def test_vector_quantize_restore(cb, oracle, n, kind, bits_):
+    V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
+    x = gen(oracle, n, kind)
+    q = V(n)
+    q.quantize(cb.CloverVector32(n, x))
+    ov, os_ = getattr(oracle, f"v{bits_}_quantize")(x, n)
+    assert np.array_equal(q.getData().cpu().numpy(), ov)
+    assert np.array_equal(bits(q.getScales().cpu().numpy()), bits(os_))
+    r = cb.CloverVector32(n)
+    q.restore(r)
+    assert np.array_equal(bits(r.getData().cpu().numpy()), bits(getattr(oracle, f"v{bits_}_restore")(ov, os_, n)))
+    assert q.getBytes() == ov.nbytes + os_.nbytes
+    for i in (0, n // 2, n - 1):
+        want = getattr(oracle, f"v{bits_}_restore")(ov, os_, n)[i]
+        assert np.float32(q.get(i)) == want
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+def test_vector_zero_blocks(cb, oracle, bits_):
+    V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
+    n = 384
+    x = np.zeros(n, np.float32)
+    x[64:128] = -0.0
+    x[130], x[131], x[200] = 3.5, -0.0, -1e-30
+    q = V(n)
+    q.quantize(cb.CloverVector32(n, x))
+    ov, os_ = getattr(oracle, f"v{bits_}_quantize")(x, n)
+    assert np.array_equal(q.getData().cpu().numpy(), ov)
+    assert np.array_equal(bits(q.getScales().cpu().numpy()), bits(os_))
+    assert q.getScales()[0].item() == 1.0        # zero guard (CloverVector4.h:661-663)
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+@pytest.mark.parametrize("n", [64, 128, 1000, 4096, 65536 + 3, (1 << 20) + 128])
+def test_vector_quantize_stochastic_matches_reference_stream(cb, oracle, n, bits_):
+    """With an explicit key the device consumes the XORShift128+ stream exactly like the reference's
+    sequential loop: packed bytes, scales AND the advanced key are identical."""
+    V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
+    x = gen(oracle, n, "floats")
+    st = oracle.xs_init(7, 9)
+    ov, os_ = getattr(oracle, f"v{bits_}_quantize")(x, n, state=st)
+    q = V(n)
+    q.seed(7, 9)
+    q.quantize(cb.CloverVector32(n, x))
+    assert np.array_equal(q.getData().cpu().numpy(), ov)
+    assert np.array_equal(bits(q.getScales().cpu().numpy()), bits(os_))
+    assert np.array_equal(q.key, st), "PRNG key after quantize differs from the reference's"
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+@pytest.mark.parametrize("kind", ["floats", "ints"])
+@pytest.mark.parametrize("n", [1, 128, 1000, 4096, 65536])
+def test_vector_dot_exact_order(cb, oracle, n, kind, bits_):
+    """C1 (n=4096): the fp32 result is bit-identical to the reference SIMD dot."""
+    from clover_b200 import DOT_EXACT
+    V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
+    x, y = gen(oracle, n, kind), gen(oracle, n, kind, skip=n + 17)
+    qx, qy = V(n), V(n)
+    qx.quantize(cb.CloverVector32(n, x))
+    qy.quantize(cb.CloverVector32(n, y))
+    xv, xs = getattr(oracle, f"v{bits_}_quantize")(x, n)
+    yv, ys = getattr(oracle, f"v{bits_}_quantize")(y, n)
+    want = getattr(oracle, f"v{bits_}_dot")(xv, xs, yv, ys, n)
+    got = np.float32(qx.dot(qy, DOT_EXACT))
+    assert got.view(np.uint32) == want.view(np.uint32), f"{float(got).hex()} vs {float(want).hex()}"
+    assert np.float32(qx.dot(qy)).view(np.uint32) == want.view(np.uint32)   # AUTO picks EXACT here
+
+
+def _dot_terms(xv, xs, yv, ys, n, bits_):
+    """float64 evaluation of the reference's own per-block terms s_b * I_b, and sum |s_b * I_b|."""
+    npad = n + (-n) % 128
+    if bits_ == 4:
+        def unpack(v):
+            b = v.astype(np.int16)
+            hi = b >> 4
+            lo = ((b & 0xF) ^ 8) - 8
+            return np.stack([hi, lo], 1).reshape(-1)
+        a, b = unpack(xv), unpack(yv)
+        s = (xs * np.float32(1.0 / 49.0)) * ys
+    else:
+        a, b = xv.astype(np.int32), yv.astype(np.int32)
+        s = (xs * np.float32(1.0 / 127.0)) * (ys * np.float32(1.0 / 127.0))
+    ib = (a.astype(np.int64) * b).reshape(npad // 64, 64).sum(1)
+    t = s.astype(np.float64)[: npad // 64] * ib
+    return t.sum(), np.abs(t).sum()
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+@pytest.mark.parametrize("n", [4096, 100000, 1 << 22])
+def test_vector_dot_fast_mode(cb, oracle, n, bits_):
+    """FAST mode: same exact integers, fp64 tree. Tolerance (SURVEY.md 8c rule 3):
+    |gpu - ref| <= 4 * eps32 * sum_b |s_b * I_b|; and FAST is within 1 ulp of the fp64 evaluation."""
+    from clover_b200 import DOT_FAST
+    V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
+    x, y = gen(oracle, n, "floats"), gen(oracle, n, "floats", skip=n + 17)
+    qx, qy = V(n), V(n)
+    qx.quantize(cb.CloverVector32(n, x))
+    qy.quantize(cb.CloverVector32(n, y))
+    xv, xs = getattr(oracle, f"v{bits_}_quantize")(x, n)
+    yv, ys = getattr(oracle, f"v{bits_}_quantize")(y, n)
+    ref = float(getattr(oracle, f"v{bits_}_dot")(xv, xs, yv, ys, n))
+    got = qx.dot(qy, DOT_FAST)
+    exact64, sum_abs = _dot_terms(xv, xs, yv, ys, n, bits_)
+    eps = float(np.finfo(np.float32).eps)
+    assert abs(got - exact64) <= eps * abs(exact64) + 1e-30
+    assert abs(got - ref) <= 4 * eps * sum_abs + abs(ref - exact64)
+    assert got == qx.dot(qy, DOT_FAST), "FAST mode must be deterministic"
+
+
+MAT_SHAPES = [(128, 128), (128, 256), (256, 128), (256, 384), (384, 640), (200, 300), (640, 1152), (1280, 1280),
+              (128, 8192 + 128)]
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+@pytest.mark.parametrize("kind", ["floats", "ints"])
+@pytest.mark.parametrize("shape", MAT_SHAPES)
+def test_matrix_quantize_and_mvm(cb, oracle, shape, kind, bits_):
+    """03_matrix.cpp:38-96 and :248-326 - packed matrix, its scales and the re-quantized mvm result."""
+    from oracle.pyoracle import pad_matrix
+    rows, cols = shape
+    a = pad_matrix(gen(oracle, rows * cols, kind)[: rows * cols].reshape(rows, cols))
+    R, Cc = a.shape
+    xvec = gen(oracle, Cc, kind, skip=11)
+    M = cb.CloverMatrix4 if bits_ == 4 else cb.CloverMatrix8
+    V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
+    qa = M(rows, cols)
+    qa.quantize(cb.CloverMatrix32(rows, cols, a))
+    mv, ms = getattr(oracle, f"m{bits_}_quantize")(a)
+    assert np.array_equal(qa.getData().cpu().numpy(), mv)
+    assert np.array_equal(bits(qa.getScales().cpu().numpy()), bits(ms))
+    assert qa.getBytes() == mv.nbytes + ms.nbytes
+
+    qx, qy = V(Cc), V(R)
+    qx.quantize(cb.CloverVector32(Cc, xvec))
+    y32 = torch.zeros(R, dtype=torch.float32, device="cuda")
+    qa.mvm(qx, qy, y32=y32)
+    xv, xs = getattr(oracle, f"v{bits_}_quantize")(xvec, Cc)
+    yv, ys, oy32 = getattr(oracle, f"m{bits_}_mvm")(mv, ms, R, Cc, xv, xs, want_f32=True)
+    assert np.array_equal(bits(y32.cpu().numpy()), bits(oy32)), "fp32 row results (block_values)"
+    assert np.array_equal(qy.getData().cpu().numpy(), yv)
+    assert np.array_equal(bits(qy.getScales().cpu().numpy()), bits(ys))
+    for (i, j) in ((0, 0), (R - 1, Cc - 1), (R // 2, Cc // 3)):
+        q = mv.reshape(R, -1)
+        if bits_ == 4:
+            b = int(q[i, j // 2]); nib = (b >> 4) & 0xF if j % 2 == 0 else b & 0xF
+            val = np.float32(ms[(i >> 6) * (Cc >> 6) + (j >> 6)] / np.float32(7.0)) * np.float32(nib - 16 if nib >= 8 else nib)
+        else:
+            val = np.float32(ms[(i >> 6) * (Cc >> 6) + (j >> 6)] / np.float32(127.0)) * np.float32(q[i, j])
+        assert np.float32(qa.get(i, j)) == val
+
+
+@pytest.mark.parametrize("shape", [(128, 128), (256, 384), (640, 1152)])
+def test_matrix_mvm_f32(cb, oracle, shape):
+    """mvm(V32,V32) (CloverMatrix4.h:1451-1547): bit-exact, far inside the reference's own 0.01 bound."""
+    from oracle.pyoracle import pad_matrix
+    rows, cols = shape
+    a = pad_matrix(gen(oracle, rows * cols, "floats")[: rows * cols].reshape(rows, cols))
+    xvec = gen(oracle, cols, "floats", skip=5)
+    qa = cb.CloverMatrix4(rows, cols)
+    qa.quantize(cb.CloverMatrix32(rows, cols, a))
+    y = cb.CloverVector32(rows)
+    qa.mvm(cb.CloverVector32(cols, xvec), y)
+    mv, ms = oracle.m4_quantize(a)
+    want = oracle.m4_mvm_f32(mv, ms, rows, cols, xvec)
+    assert np.array_equal(bits(y.getData().cpu().numpy()[:rows]), bits(want))
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+@pytest.mark.parametrize("shape", [(128, 128), (256, 384), (384, 1152)])
+def test_matrix_stochastic_matches_reference_stream(cb, oracle, shape, bits_):
+    from oracle.pyoracle import pad_matrix
+    rows, cols = shape
+    a = pad_matrix(gen(oracle, rows * cols, "floats")[: rows * cols].reshape(rows, cols))
+    xvec = gen(oracle, cols, "floats", skip=5)
+    M = cb.CloverMatrix4 if bits_ == 4 else cb.CloverMatrix8
+    V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
+    st = oracle.xs_init(123, 456)
+    mv, ms = getattr(oracle, f"m{bits_}_quantize")(a, state=st)
+    qa = M(rows, cols)
+    qa.seed(123, 456)
+    qa.quantize(cb.CloverMatrix32(rows, cols, a))
+    assert np.array_equal(qa.getData().cpu().numpy(), mv)
+    assert np.array_equal(bits(qa.getScales().cpu().numpy()), bits(ms))
+    assert np.array_equal(qa.key, st)
+    xv, xs = getattr(oracle, f"v{bits_}_quantize")(xvec, cols)
+    yv, ys = getattr(oracle, f"m{bits_}_mvm")(mv, ms, rows, cols, xv, xs, state=st)
+    qx, qy = V(cols), V(rows)
+    qx.quantize(cb.CloverVector32(cols, xvec))
+    qa.mvm(qx, qy)
+    assert np.array_equal(qy.getData().cpu().numpy(), yv)
+    assert np.array_equal(bits(qy.getScales().cpu().numpy()), bits(ys))
+    assert np.array_equal(qa.key, st)
+
+
+def test_mvm_size_mismatch_raises(cb):
+    qa = cb.CloverMatrix4(128, 256)
+    with pytest.raises(cb.CloverSizeError):
+        qa.mvm(cb.CloverVector4(128), cb.CloverVector4(128))
+
+
+@pytest.mark.parametrize("mnk", [(128, 128, 128), (128, 256, 384), (256, 128, 1152)])
+def test_gemm_vs_definition(cb, oracle, mnk):
+    """GEMM extension: every C[i][j] vs the reference SIMD dot of the two row views (rule 3 tolerance)."""
+    from oracle.pyoracle import pad_matrix
+    M, N, K = mnk
+    a = pad_matrix(gen(oracle, M * K, "floats")[: M * K].reshape(M, K))
+    b = pad_matrix(gen(oracle, N * K, "floats", skip=999)[: N * K].reshape(N, K))
+    qa, qb = cb.CloverMatrix4(M, K), cb.CloverMatrix4(N, K)
+    qa.quantize(cb.CloverMatrix32(M, K, a))
+    qb.quantize(cb.CloverMatrix32(N, K, b))
+    c = qa.gemm(qb).cpu().numpy()
+    av, as_ = oracle.m4_quantize(a)
+    bv, bs = oracle.m4_quantize(b)
+    want = oracle.m4_gemm(av, as_, bv, bs, K, 0, M, 0, N)
+    # bound: 4 * eps * sum_kb |s_kb * I_kb| <= 4 * eps * K * max|a| * max|b| (crude but sufficient here)
+    eps = float(np.finfo(np.float32).eps)
+    bound = 4 * eps * K * float(np.abs(a).max()) * float(np.abs(b).max())
+    assert np.max(np.abs(c.astype(np.float64) - want.astype(np.float64))) <= bound
+
+
+def test_full_size_properties_c2(cb, oracle):
+    """BASELINE config C2 (n = 2^26): size-independent properties instead of a CPU re-computation.
+    * |x - restore(quantize(x))| <= scale/7 per element (02_vector.cpp:181-221 'consistency')
+    * every block's max element quantizes to 6 or 7, and no nibble is -8
+    * dot(q, q) FAST equals the fp64 evaluation of sum s_b^2/49 * I_b from the packed bytes."""
+    n = 1 << 26
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.rand(n, generator=g, device="cuda", dtype=torch.float32) * 2 - 1
+    v32 = cb.CloverVector32(n)
+    v32.values.copy_(x)
+    q = cb.CloverVector4(n)
+    q.quantize(v32)
+    r = cb.CloverVector32(n)
+    q.restore(r)
+    scales = q.getScales()
+    err = (r.values - x).abs().view(-1, 64)
+    assert bool((err <= (scales / 7.0).unsqueeze(1) * (1 + 1e-6)).all())
+    assert bool((scales == x.abs().view(-1, 64).max(1).values).all()), "scale must be the exact block absmax"
+    b = q.getData().view(torch.uint8)
+    hi, lo = (b >> 4), (b & 0xF)
+    assert int(((hi == 8) | (lo == 8)).sum()) == 0, "nibble -8 must never be produced"
+    from clover_b200 import DOT_FAST
+    got = q.dot(q, DOT_FAST)
+    sq = lambda t: (((t.to(torch.int16) ^ 8) - 8) ** 2).to(torch.int32)
+    ib = (sq(hi) + sq(lo)).view(-1, 32).sum(1).to(torch.float64)
+    s = ((scales * np.float32(1.0 / 49.0)) * scales).to(torch.float64)
+    want = float((s * ib).sum())
+    assert abs(got - want) <= float(np.finfo(np.float32).eps) * abs(want)
