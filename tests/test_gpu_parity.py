@@ -62,7 +62,10 @@ def test_vector_quantize_restore(cb, oracle, n, kind, bits_):
     assert np.array_equal(bits(r.getData().cpu().numpy()), bits(getattr(oracle, f"v{bits_}_restore")(ov, os_, n)))
     assert q.getBytes() == ov.nbytes + os_.nbytes
     for i in (0, n // 2, n - 1):
-        want = getattr(oracle, f"v{bits_}_restore")(ov, os_, n)[i]
+        if bits_ == 4:      # get(): (scale/7) * q, same product as restore (CloverVector4.h:179-188)
+            want = getattr(oracle, f"v{bits_}_restore")(ov, os_, n)[i]
+        else:               # get(): (q * scale) / 127 (CloverVector8.h:136-139)
+            want = np.float32(ov[i]) * os_[i >> 6] / np.float32(127.0)
         assert np.float32(q.get(i)) == want
 
 
