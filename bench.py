@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""bench.py - the headline benchmark of clover_b200 (contract: see the task statement / DESIGN.md §Measurement).
+
+Workload (BASELINE.json configs[2], "C3"): CloverMatrix4::mvm, 65536 x 65536 4-bit matrix times a 65536-element
+CloverVector4, result re-quantized to a CloverVector4 (include/CloverMatrix4.h:777-1083), stochastic rounding
+disabled (the parity configuration). One "step" = one mvm over the whole matrix. The 2 GiB matrix is far larger
+than the 126 MB L2, so every step streams it from HBM ("inputs larger than L2").
+
+  value      = algorithmic bytes moved per second, all GPUs, inputs resident in HBM
+               (reference bytes model qv + qa + qr, test/performance/01_measure.h:717)
+  e2e        = same metric through the container API with the per-step operands in HOST memory: the product
+               vector is copied from pinned host memory and the result vector is read back every step; the
+               matrix stays resident in HBM like the reference's matrix object stays in RAM between calls.
+  roofline   = the GEMV kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline = the reference's own mvm_parallel (oracle/_ref, compiled from /root/reference) on this host
+  extras     = the other BASELINE.json configs (C1, C2, C4, C5), each timed with CUDA events
+
+N > 1 (torchrun, one rank per GPU): rows sharded in 64-row blocks, one NCCL allreduce of the fp32 output per step
+(north_star), total work fixed -> "scaling": "strong".
+
+`--impl reference` times the reference CPU implementation of the same path instead (rank 0 only).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS = COLS = 65536
+METRIC = "int4_gemv_effective_GBps"
+
+
+def gemv_bytes(rows, cols, bits=4):
+    """qv.getBytes() + qa.getBytes() + qr.getBytes() (test/performance/01_measure.h:717)."""
+    per = {4: 0.5, 8: 1.0}[bits]
+    vec = lambda n: int(n * per) + (n // 64) * 4
+    return vec(cols) + int(rows * cols * per) + (rows // 64) * (cols // 64) * 4 + vec(rows)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi polled every 20 ms in the background; mark()/summary() keep only the samples that
+    arrived between the two marks, i.e. DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines, self.marks = index, None, [], []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:     # wait for the first sample
+                time.sleep(0.01)
+        except OSError:
+            self.proc = None
+        return self
+
+    def mark(self):
+        self.marks.append(len(self.lines))
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        lo, hi = (self.marks + [0, len(self.lines)])[:2] if len(self.marks) >= 2 else (0, len(self.lines))
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines[lo:max(hi, lo + 1)]:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(int(f[0])); mx = max(mx, int(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# synthetic operands
+# ----------------------------------------------------------------------------------------------------------------
+def random_nibbles(torch, nbytes, gen, device):
+    """Packed 4-bit values uniform in [-7, 7] (the quantizer never produces -8)."""
+    out = torch.empty(nbytes, dtype=torch.int8, device=device)
+    step = 1 << 28
+    for o in range(0, nbytes, step):
+        n = min(step, nbytes - o)
+        hi = torch.randint(-7, 8, (n,), dtype=torch.int8, device=device, generator=gen)
+        lo = torch.randint(-7, 8, (n,), dtype=torch.int8, device=device, generator=gen)
+        out[o:o + n] = (hi << 4) | (lo & 0xF)
+        del hi, lo
+    return out
+
+
+def host_random_nibbles(rng, nbytes):
+    hi = rng.integers(-7, 8, nbytes, dtype=np.int8)
+    lo = rng.integers(-7, 8, nbytes, dtype=np.int8)
+    return ((hi.astype(np.uint8) << 4) | (lo.astype(np.uint8) & 0xF)).view(np.int8)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the reference arm / cpu baseline: Clover's own mvm_parallel on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def reference_cpu_gemv(sample_rows, cols, steps, warmup):
+    from oracle.pyoracle import Reference, aligned
+    if Reference.available(False):
+        ref, kind = Reference(False), "reference"
+    else:
+        ref, kind = None, "port"
+    rng = np.random.default_rng(1234)
+    mv = host_random_nibbles(rng, sample_rows * cols // 2)
+    ms = rng.uniform(0.25, 1.0, (sample_rows // 64) * (cols // 64)).astype(np.float32)
+    xv = aligned(cols // 2, np.int8); xv[:] = host_random_nibbles(rng, cols // 2)
+    xs = aligned(cols // 64, np.float32); xs[:] = rng.uniform(0.25, 1.0, cols // 64).astype(np.float32)
+    nbytes = gemv_bytes(sample_rows, cols)
+    times = []
+    if ref is not None:
+        m = ref.m4_from(mv, ms, sample_rows, cols)
+        threads = ref.threads()
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            ref.m4_mvm(m, xv, xs, variant=2)             # CloverMatrix4::mvm_parallel (CloverMatrix4.h:1681)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        seq = []
+        for i in range(2):                               # CloverMatrix4::mvm, one thread, for the record
+            t0 = time.perf_counter()
+            ref.m4_mvm(m, xv, xs, variant=0)
+            seq.append(time.perf_counter() - t0)
+        seq_note = f"; sequential mvm on 1 thread: {nbytes / min(seq) / 1e9:.2f} GB/s"
+    else:
+        from oracle.pyoracle import Oracle
+        orc = Oracle()
+        threads = os.cpu_count() or 1
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            orc.m4_mvm(mv, ms, sample_rows, cols, xv, xs)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": nbytes * len(times) / total / 1e9, "unit": "GB/s", "cores": threads, "kind": kind,
+            "sample": f"{sample_rows} of {ROWS} rows x {cols} cols, {len(times)} runs of CloverMatrix4::mvm_parallel "
+                      f"(median {statistics.median(times) * 1e3:.2f} ms)" + (seq_note if ref is not None else ""),
+            "ms_per_step": total / len(times) * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = {"impl": "reference", "metric": METRIC, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int4 x int4 -> int32, fp32 scale epilogue", "data": "synthetic"}
+    r = reference_cpu_gemv(args.cpu_sample_rows, args.cols, args.steps, args.warmup)
+    base.update({"value": r["value"], "ms_per_step": r["ms_per_step"],
+                 "config": {"workload": f"CloverMatrix4::mvm_parallel {args.rows}x{args.cols} x CloverVector4 (C3), "
+                                        f"CPU reference timed on a bounded row sample", "rows": args.rows,
+                            "cols": args.cols, "sample_rows": args.cpu_sample_rows},
+                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                 "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "gpu_launches": 0})
+    print(json.dumps(base), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# extras: the other BASELINE.json configs, CUDA-event timed
+# ----------------------------------------------------------------------------------------------------------------
+def cuda_time(torch, fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def extras(torch, cb, peak):
+    from clover_b200 import DOT_EXACT, DOT_FAST
+    out = {}
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev).manual_seed(99)
+    # C2: quantize + dot at n = 2^26. dot operands (75.5 MB) fit in L2, so rotate over 4 operand sets.
+    n = 1 << 26
+    xs32 = []
+    for _ in range(2):
+        v = cb.CloverVector32(n); v.values.uniform_(-1.0, 1.0, generator=g); xs32.append(v)
+    qs = [cb.CloverVector4(n) for _ in range(8)]
+    for i, q in enumerate(qs):
+        q.quantize(xs32[i % 2])
+    i = [0]
+    def quant():
+        qs[i[0] % 8].quantize(xs32[i[0] % 2]); i[0] += 1
+    t = cuda_time(torch, quant, 20)
+    b = n * 4 + qs[0].getBytes()
+    out["C2a_quantize4_n2^26"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b}
+    res = torch.empty(1, dtype=torch.float32, device=dev)
+    def dot():
+        k = i[0] % 4; qs[2 * k].dot_device(qs[2 * k + 1], res, DOT_FAST); i[0] += 1
+    t = cuda_time(torch, dot, 40)
+    b = 2 * qs[0].getBytes()
+    out["C2b_dot4_n2^26_fast_rotating4"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b}
+    q8 = [cb.CloverVector8(n) for _ in range(2)]
+    def quant8():
+        q8[i[0] % 2].quantize(xs32[i[0] % 2]); i[0] += 1
+    t = cuda_time(torch, quant8, 20)
+    b = n * 4 + q8[0].getBytes()
+    out["quantize8_n2^26"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b}
+    del xs32, qs, q8
+    # C1: dot n = 4096 exact order (latency)
+    a, b_ = cb.CloverVector4(4096), cb.CloverVector4(4096)
+    v = cb.CloverVector32(4096); v.values.uniform_(-1, 1, generator=g); a.quantize(v)
+    v.values.uniform_(-1, 1, generator=g); b_.quantize(v)
+    t = cuda_time(torch, lambda: a.dot_device(b_, res, DOT_EXACT), 200)
+    out["C1_dot4_n4096_exact"] = {"us": t * 1e6}
+    # C5: 8-bit GEMV 32768^2
+    r8 = c8 = 32768
+    m8 = cb.CloverMatrix8(r8, c8)
+    m8.values.copy_(torch.randint(-127, 128, (r8 * c8,), dtype=torch.int8, device=dev, generator=g))
+    m8.scales.uniform_(0.25, 1.0, generator=g)
+    x8, y8 = cb.CloverVector8(c8), cb.CloverVector8(r8)
+    v = cb.CloverVector32(c8); v.values.uniform_(-1, 1, generator=g); x8.quantize(v)
+    t = cuda_time(torch, lambda: m8.mvm(x8, y8), 20)
+    b = gemv_bytes(r8, c8, 8)
+    out["C5_gemv8_32768"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b}
+    del m8
+    # C4: 4-bit GEMM 16384^3
+    M = N = K = 16384
+    A, Bt = cb.CloverMatrix4(M, K), cb.CloverMatrix4(N, K)
+    for m in (A, Bt):
+        m.values.copy_(random_nibbles(torch, M * K // 2, g, dev)); m.scales.uniform_(0.25, 1.0, generator=g)
+    Cout = torch.empty(M, N, dtype=torch.float32, device=dev)
+    t = cuda_time(torch, lambda: A.gemm(Bt, out=Cout), 2, warmup=1)
+    ops = 2.0 * M * N * K
+    out["C4_gemm4_16384"] = {"ms": t * 1e3, "TOPS": ops / t / 1e12, "frac_int8_nominal_4500": ops / t / 1e12 / 4500.0}
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="clover_b200", choices=["clover_b200", "reference"])
+    ap.add_argument("--rows", type=int, default=ROWS)
+    ap.add_argument("--cols", type=int, default=COLS)
+    ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "allgather"])
+    ap.add_argument("--cpu-sample-rows", type=int, default=8192)
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "clover_b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import clover_b200
+    from clover_b200 import containers as cb
+    from clover_b200.sharded import ShardedCloverMatrix4
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = clover_b200.lib()
+    peak, peak_src = measured_peaks()
+    rows, cols = args.rows, args.cols
+
+    # ---- operands: this rank's rows of the matrix, replicated x -------------------------------------------------
+    g = torch.Generator(device=dev).manual_seed(20261017)           # same x on every rank
+    xf = cb.CloverVector32(cols)
+    xf.values.uniform_(-1.0, 1.0, generator=g)
+    x = cb.CloverVector4(cols)
+    x.quantize(xf)
+    y = cb.CloverVector4(rows)
+    A = ShardedCloverMatrix4(rows, cols, exchange=args.exchange)
+    gm = torch.Generator(device=dev).manual_seed(1000 + rank)
+    A.local.values[: A.rows_local * cols // 2].copy_(random_nibbles(torch, A.rows_local * cols // 2, gm, dev))
+    A.local.scales.uniform_(0.25, 1.0, generator=gm)
+    torch.cuda.synchronize()
+
+    def step():
+        if world == 1:
+            A.local.mvm(x, y)          # the reference-facing call: CloverMatrix4::mvm(V4, V4), one fused kernel
+        else:
+            A.mvm(x, y)                # shard kernel + NCCL exchange + re-quantize
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    total_bytes = gemv_bytes(rows, cols)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = L.clover_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        clk.mark()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+        clk.mark()
+    launches = L.clover_kernel_launches() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    secs = float(ms.item()) * 1e-3
+    value = total_bytes * args.steps / secs / 1e9
+
+    # dominant kernel alone (the GEMV shard kernel), for the roofline: its own launches, CUDA events
+    shard_bytes = gemv_bytes(A.rows_local, cols) if A.rows_local else 0
+    def kernel_only():
+        clover_b200.call("clover_m4_mvm_shard", C.c_void_p(A.local.values.data_ptr()), C.c_void_p(A.local.scales.data_ptr()),
+                         C.c_uint64(A.rows_local), C.c_uint64(cols), C.c_uint64(A.row0), C.c_void_p(x.values.data_ptr()),
+                         C.c_void_p(x.scales.data_ptr()), C.c_void_p(A.y32.data_ptr()),
+                         C.c_void_p(y.values.data_ptr()), C.c_void_p(y.scales.data_ptr()), None,
+                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    tk = cuda_time(torch, kernel_only, args.steps)
+    achieved = shard_bytes / tk / 1e9
+
+    # ---- e2e: per-step operands in pinned host memory, result read back every step -------------------------------
+    hx_v = torch.empty_like(x.values, device="cpu").pin_memory(); hx_v.copy_(x.values)
+    hx_s = torch.empty_like(x.scales, device="cpu").pin_memory(); hx_s.copy_(x.scales)
+    hy_v = torch.empty_like(y.values, device="cpu").pin_memory()
+    hy_s = torch.empty_like(y.scales, device="cpu").pin_memory()
+    h2d = hx_v.numel() + hx_s.numel() * 4
+    d2h = hy_v.numel() + hy_s.numel() * 4
+
+    def e2e_step():
+        x.values.copy_(hx_v, non_blocking=True)
+        x.scales.copy_(hx_s, non_blocking=True)
+        step()
+        hy_v.copy_(y.values, non_blocking=True)
+        hy_s.copy_(y.scales, non_blocking=True)
+        torch.cuda.current_stream().synchronize()         # the caller reads the result of every step
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = total_bytes * args.steps / (float(ms2.item()) * 1e-3) / 1e9
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "int4 x int4 -> int32 (DP4A), fp32 scale epilogue", "data": "synthetic",
+            "config": {"workload": f"CloverMatrix4::mvm {rows}x{cols} x CloverVector4 -> CloverVector4 (BASELINE C3)",
+                       "rows": rows, "cols": cols, "algorithmic_bytes_per_step": total_bytes,
+                       "rounding": "stochastic rounding disabled (parity configuration)",
+                       "l2_policy": "inputs larger than L2 (2 GiB matrix streamed per step vs 126 MB L2)",
+                       "parallelism": "1 GPU" if world == 1 else
+                                      f"rows sharded over {world} GPUs in 64-row blocks + one NCCL {args.exchange} of the fp32 output",
+                       "e2e": "x copied from pinned host memory and y read back every step; matrix resident in HBM"},
+            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(ms2.item()) / args.steps, "wall_ms_per_step": wall / args.steps * 1e3},
+            "gpu_launches": launches,
+            "clocks": clk.summary(),
+            "roofline": {"bound": "hbm", "kernel": "k_m4_mvm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "kernel_ms": tk * 1e3, "algorithmic_bytes_per_launch": shard_bytes},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = {k: v for k, v in reference_cpu_gemv(args.cpu_sample_rows, cols, 7, 2).items()
+                                        if k != "ms_per_step"}
+            except Exception as exc:  # the checker failing must not hide the GPU number
+                line["cpu_baseline"] = {"error": repr(exc)}
+        if world == 1 and not args.no_extras:
+            del A
+            torch.cuda.empty_cache()
+            try:
+                line["extras"] = extras(torch, cb, peak)
+            except Exception as exc:
+                line["extras"] = {"error": repr(exc)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""Row-sharded multi-GPU mvm - one process per GPU, torch.distributed/NCCL for the plumbing.
+
+The reference has no distributed code; this is the multi-GPU form of ``CloverMatrix4::mvm`` that
+BASELINE.json's north_star asks for: rows are sharded in whole 64-row blocks (so every re-quantization
+block is local to one rank), the product vector is replicated, every rank computes the fp32 results of its
+own rows, and ONE collective on the fp32 output makes the full vector visible everywhere:
+
+  * ``exchange="allreduce"`` (north_star): ncclAllReduce(sum) over a zero-initialised full-length fp32
+    vector in which each rank filled only its slice;
+  * ``exchange="allgather"``: ncclAllGather of the rows/G slices - same result, 1/G of the traffic.
+
+After the exchange every rank re-quantizes the full fp32 vector with the mvm epilogue
+(include/CloverMatrix4.h:925-1080), so all ranks hold the same CloverVector4 the single-GPU call returns -
+bit-for-bit, because the fp32 row results do not depend on the sharding.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from ._lib import call
+from .containers import CloverMatrix4, CloverSizeError, CloverVector4, _ptr, _stream
+
+
+def shard_rows(rows: int, world: int, rank: int):
+    """Contiguous ranges of 64-row blocks, remainder spread over the first ranks."""
+    blocks = rows // 64
+    base, extra = divmod(blocks, world)
+    b0 = rank * base + min(rank, extra)
+    nb = base + (1 if rank < extra else 0)
+    return b0 * 64, nb * 64
+
+
+class ShardedCloverMatrix4:
+    """This rank's rows [row0, row0 + rows_local) of a (rows x cols) CloverMatrix4."""
+
+    def __init__(self, rows: int, cols: int, group=None, device=None, exchange: str = "allreduce"):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.rows = rows + (-rows) % 128
+        self.cols = cols + (-cols) % 128
+        self.row0, self.rows_local = shard_rows(self.rows, self.world, self.rank)
+        self.exchange = exchange
+        self.device = device
+        if self.rows_local:
+            # a CloverMatrix4 of rows_local x cols (rows_local is a multiple of 64; pad to 128 only in storage)
+            self.local = CloverMatrix4(self.rows_local + (-self.rows_local) % 128, self.cols, device=device)
+        else:
+            self.local = None
+        dev = self.local.values.device if self.local is not None else torch.device("cuda", torch.cuda.current_device())
+        self.y32 = torch.zeros(self.rows, dtype=torch.float32, device=dev)
+        sizes = [shard_rows(self.rows, self.world, r)[1] for r in range(self.world)]
+        self._even = len(set(sizes)) == 1
+        self._sizes = sizes
+        self.key = None
+
+    def load_shard(self, values, scales) -> None:
+        """values/scales of this rank's rows in the reference layout (rows_local*cols/2 bytes, tile-row scales)."""
+        nb = self.rows_local * self.cols // 2
+        ns = (self.rows_local // 64) * (self.cols // 64)
+        self.local.values[:nb].copy_(torch.as_tensor(values).view(torch.int8).reshape(-1)[:nb])
+        self.local.scales[:ns].copy_(torch.as_tensor(scales).reshape(-1)[:ns])
+
+    def mvm(self, x: CloverVector4, y: CloverVector4) -> None:
+        if x.size() != self.cols or y.size_pad() != self.rows:
+            raise CloverSizeError("MVM can not be performed.")
+        key_ptr = None if self.key is None else self.key.ctypes.data_as(C.c_void_p)
+        if self.exchange == "allreduce":
+            self.y32.zero_()
+        if self.rows_local:
+            call("clover_m4_mvm_shard", _ptr(self.local.values), _ptr(self.local.scales), C.c_uint64(self.rows_local),
+                 C.c_uint64(self.cols), C.c_uint64(self.row0), _ptr(x.values), _ptr(x.scales), _ptr(self.y32),
+                 None, None, None, _stream())
+        if self.world > 1:
+            if self.exchange == "allreduce":
+                dist.all_reduce(self.y32, op=dist.ReduceOp.SUM, group=self.group)
+            elif self._even:
+                dist.all_gather_into_tensor(self.y32, self.y32[self.row0:self.row0 + self.rows_local].clone(),
+                                            group=self.group)
+            else:
+                parts = list(torch.split(self.y32, self._sizes))
+                dist.all_gather(parts, parts[self.rank].clone(), group=self.group)
+        call("clover_v4_requantize_mvm", _ptr(self.y32), C.c_uint64(self.rows), _ptr(y.values), _ptr(y.scales),
+             key_ptr, _stream())
