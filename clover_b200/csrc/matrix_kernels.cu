@@ -7,6 +7,9 @@
 // The GEMVs are HBM-bound (the matrix is read exactly once: 0.5 B/elem + scales) and reproduce the
 // reference's fp32 accumulation ORDER, so the fp32 row results and therefore the re-quantized
 // 4/8-bit output vector are bit-identical to the AVX2 code.
+#include <stdlib.h>
+#include <string.h>
+#include "async_copy.cuh"
 #include "common.cuh"
 #include "runtime.cuh"
 
@@ -252,6 +255,175 @@ k_m4_mvm(const uint32_t *__restrict__ values, const float *__restrict__ scales, 
     }
 }
 
+
+// =============================================================================================
+// mvm(V4,V4), pipelined: the same exact-order arithmetic as k_m4_mvm, fed by a TMA ring
+// =============================================================================================
+// Persistent grid: one CTA per SM walks 64-row blocks (CTA b takes row blocks b, b+grid, ...), so
+// 1024 row blocks on 148 SMs cost 7 rounds instead of the 4 half-empty waves of a 2-CTA/SM launch.
+//
+//   warp 16 (one elected lane)  TMA issuer: per stage two cp.async.bulk.tensor.2d boxes
+//                               (32 rows x kKC*32 B of nibbles each) into the ring slot
+//   warp 17                     expands the matching slice of x into XUnits (incl. the fp32 scale
+//                               product of the block) for the slot, one stage ahead in registers
+//   warps 0..15 (512 threads)   consumers: thread = fp32 chain (a, l) of two rows; they wait on the
+//                               slot's full-barrier, run kKC/2 FMA steps out of shared memory and
+//                               release the slot through its empty-barrier
+//
+// Memory-level parallelism comes from the ring (kGemvStages x 32 KiB in flight per SM), not from
+// registers; the matrix is streamed with an L2 evict-first policy since it is read exactly once.
+constexpr int kGemvConsumers = 512;
+constexpr int kGemvThreads = kGemvConsumers + 64;
+constexpr int kKC = 16;                               // blocks (of 64 columns) per stage
+constexpr int kGemvStages = 5;
+constexpr int kRowPitch = kKC * 32;                   // dense TMA box rows (512 B)
+
+struct __align__(128) GemvStage {
+    uint8_t rows[64 * kRowPitch];                     // box 0: rows 0..31, box 1: rows 32..63
+    XUnit units[kKC * 8];
+};
+struct GemvSmem {
+    GemvStage stage[kGemvStages];
+    uint64_t full[kGemvStages];
+    uint64_t empty[kGemvStages];
+    float ysm[64];
+    float red_f[2];
+    int red_q[64];
+};
+
+__device__ __forceinline__ void gemv4_step(const uint8_t *r0, const uint8_t *r1, const XUnit *units, int blk, int l,
+                                           float &acc0, float &acc1) {
+    const XUnit u = units[blk * 8 + l];
+    const uint32_t w0 = *reinterpret_cast<const uint32_t *>(r0 + blk * 32);
+    const uint32_t w1 = *reinterpret_cast<const uint32_t *>(r1 + blk * 32);
+    int s0 = dp4a_us(xor_and(w0, 0x88888888u, 0xF0F0F0F0u), u.xh, (int)kMagicBits);
+    s0 = dp4a_us(xor_and(w0, 0x88888888u, 0x0F0F0F0Fu), u.xl16, s0);
+    int s1 = dp4a_us(xor_and(w1, 0x88888888u, 0xF0F0F0F0u), u.xh, (int)kMagicBits);
+    s1 = dp4a_us(xor_and(w1, 0x88888888u, 0x0F0F0F0Fu), u.xl16, s1);
+    acc0 = __fmaf_rn(u.prod, __fmaf_rn(__int_as_float(s0), 0.0625f, u.cneg), acc0);     // (:896-897)
+    acc1 = __fmaf_rn(u.prod, __fmaf_rn(__int_as_float(s1), 0.0625f, u.cneg), acc1);
+}
+
+template <bool STOCH>
+__global__ void __launch_bounds__(kGemvThreads, 1)
+k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows_local,
+             uint64_t cols, uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
+             float *__restrict__ y32, int8_t *__restrict__ yv, float *__restrict__ ys, Key4 key,
+             const uint64_t *__restrict__ tables) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    GemvSmem &sm = *reinterpret_cast<GemvSmem *>(smem_raw);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t hb = cols >> 6, nrb = rows_local >> 6;
+    const uint32_t chunks = (uint32_t)((hb + kKC - 1) / kKC);
+
+    if (tid == 0) {
+        for (int s = 0; s < kGemvStages; ++s) {
+            mbar_init(&sm.full[s], 1 + 32);              // TMA issuer (posts the tx bytes) + the 32 unit lanes
+            mbar_init(&sm.empty[s], kGemvConsumers / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kGemvConsumers / 32) {
+        // ------------------------------- TMA issuer -------------------------------
+        if (lane == 0) {
+            tma_prefetch_descriptor(&tmap);
+            const uint64_t policy = policy_evict_first();
+            uint32_t it = 0;
+            for (uint64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+                for (uint32_t c = 0; c < chunks; ++c, ++it) {
+                    const int s = it % kGemvStages;
+                    mbar_wait(&sm.empty[s], ((it / kGemvStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&sm.full[s], 64 * kRowPitch);   // boxes are always written in full (OOB = 0)
+                    tma_load_2d(sm.stage[s].rows, &tmap, (int)(c * kKC * 8), (int)(rb * 64), &sm.full[s], policy);
+                    tma_load_2d(sm.stage[s].rows + 32 * kRowPitch, &tmap, (int)(c * kKC * 8), (int)(rb * 64 + 32),
+                                &sm.full[s], policy);
+                }
+            }
+        }
+    } else if (warp == kGemvConsumers / 32 + 1) {
+        // ------------------------------- x-unit warp -------------------------------
+        // lane owns units lane, lane+32, lane+64, lane+96 of a stage = (block 4j + lane/8, AVX lane lane%8)
+        uint32_t it = 0;
+        uint32_t w[4] = {0, 0, 0, 0};
+        float sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+        auto prefetch = [&](uint64_t rb, uint32_t c) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint64_t b = (uint64_t)c * kKC + 4 * j + (lane >> 3);
+                const bool ok = b < hb;
+                w[j] = ok ? __ldg(xv + b * 8 + (lane & 7)) : 0u;
+                sa[j] = ok ? __ldg(scales + rb * hb + b) : 0.f;
+                sb[j] = ok ? __ldg(xs + b) : 0.f;
+            }
+        };
+        if (blockIdx.x < nrb) prefetch(blockIdx.x, 0);
+        for (uint64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+            for (uint32_t c = 0; c < chunks; ++c, ++it) {
+                const int s = it % kGemvStages;
+                XUnit u[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int xh = sext_nibbles((w[j] >> 4) & 0x0F0F0F0Fu);
+                    const int xl = sext_nibbles(w[j] & 0x0F0F0F0Fu);
+                    u[j].xh = xh;
+                    u[j].xl16 = (int)((w[j] << 4) & 0xF0F0F0F0u);
+                    u[j].cneg = -(786432.0f + 8.0f * (float)(dp4a_ss(xh, 0x01010101, 0) + dp4a_ss(xl, 0x01010101, 0)));
+                    u[j].prod = __fmul_rn(__fmul_rn(sa[j], 1.0f / 49.0f), sb[j]);              // (:834-837)
+                }
+                // next stage's operands are requested before we block on the slot
+                uint32_t nc = c + 1; uint64_t nrbi = rb;
+                if (nc == chunks) { nc = 0; nrbi = rb + gridDim.x; }
+                if (nrbi < nrb) prefetch(nrbi, nc);
+                mbar_wait(&sm.empty[s], ((it / kGemvStages) & 1) ^ 1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sm.stage[s].units[lane + 32 * j] = u[j];
+                mbar_arrive(&sm.full[s]);
+            }
+        }
+    } else {
+        // ------------------------------- consumer warps ------------------------------
+        // warp w, half-warp h: rows (32h + w) and (32h + w + 16) of the block; a = accumulator, l = AVX lane
+        const int h = lane >> 4, a = (lane >> 3) & 1, l = lane & 7;
+        const int row_a = 32 * h + warp, row_b = row_a + 16;
+        uint32_t it = 0;
+        for (uint64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+            float acc0 = 0.f, acc1 = 0.f;
+            for (uint32_t c = 0; c < chunks; ++c, ++it) {
+                const int s = it % kGemvStages;
+                mbar_wait(&sm.full[s], (it / kGemvStages) & 1);
+                const GemvStage &st = sm.stage[s];
+                const uint8_t *r0 = st.rows + row_a * kRowPitch + 4 * l;
+                const uint8_t *r1 = st.rows + row_b * kRowPitch + 4 * l;
+                const uint64_t cb = (uint64_t)c * kKC;
+                const int nb = (int)((hb - cb) < (uint64_t)kKC ? (hb - cb) : kKC);
+                if (nb == kKC) {
+#pragma unroll
+                    for (int p = 0; p < kKC / 2; ++p) gemv4_step(r0, r1, st.units, 2 * p + a, l, acc0, acc1);
+                } else {
+                    for (int p = 0; p < nb / 2; ++p) gemv4_step(r0, r1, st.units, 2 * p + a, l, acc0, acc1);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[s]);
+            }
+            acc0 = __fadd_rn(acc0, __shfl_xor_sync(0xFFFFFFFFu, acc0, 8));       // acc_1 + acc_2, hadd tree (:902-907)
+            acc1 = __fadd_rn(acc1, __shfl_xor_sync(0xFFFFFFFFu, acc1, 8));
+            acc0 = hadd8_butterfly(acc0);
+            acc1 = hadd8_butterfly(acc1);
+            named_bar_sync(2, kGemvConsumers);                                   // previous epilogue done with ysm
+            if ((lane & 15) == 0) { sm.ysm[row_a] = acc0; sm.ysm[row_b] = acc1; }
+            named_bar_sync(2, kGemvConsumers);
+            if (tid < 64) {
+                const float y = sm.ysm[tid];
+                if (y32) y32[(rowblock0 + rb) * 64 + tid] = y;
+                if (yv) requantize_block<4, STOCH>(y, tid, rowblock0 + rb, yv, ys, key, tables, sm.red_f, sm.red_q);
+            }
+        }
+    }
+}
+
 // =============================================================================================
 // mvm(V8,V8): exact-order 8-bit GEMV. 8 chains per row (one accumulator, CloverMatrix8.h:1029-1095)
 // thread = (row, lane l): per block the int32 lane sum covers bytes 4l..4l+3 and 32+4l..32+4l+3.
@@ -383,8 +555,27 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
     const uint32_t *v32 = reinterpret_cast<const uint32_t *>(values);
     const uint32_t *x32 = reinterpret_cast<const uint32_t *>(xv);
     if (BITS == 4) {
-        if (stoch) k_m4_mvm<true><<<grid, kMvmThreads, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
-        else       k_m4_mvm<false><<<grid, kMvmThreads, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
+        static const bool force_simple = getenv("CLOVER_GEMV_IMPL") && !strcmp(getenv("CLOVER_GEMV_IMPL"), "simple");
+        // bulk copies need 16 B aligned rows; anything else takes the plain-load kernel (same arithmetic)
+        const bool simple = force_simple || (reinterpret_cast<uintptr_t>(values) & 15u) != 0;
+        if (simple) {
+            if (stoch) k_m4_mvm<true><<<grid, kMvmThreads, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
+            else       k_m4_mvm<false><<<grid, kMvmThreads, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
+        } else {
+            const int smem = (int)sizeof(GemvSmem);
+            static bool attr_set[2] = {false, false};      // per template instance (process-wide; all devices alike)
+            auto kern = stoch ? k_m4_mvm_tma<true> : k_m4_mvm_tma<false>;
+            if (!attr_set[stoch]) {
+                CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                attr_set[stoch] = true;
+            }
+            CUtensorMap tmap;
+            int rc = make_tensor_map_u32_2d(&tmap, values, rows_local, cols >> 3, cols >> 1, 32, kKC * 8);
+            if (rc != CLOVER_OK) return rc;
+            const unsigned pgrid = (unsigned)(nrb < (uint64_t)sm_count() ? nrb : (uint64_t)sm_count());
+            kern<<<pgrid, kGemvThreads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys,
+                                                        key, tables);
+        }
     } else {
         if (stoch) k_m8_mvm<true><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
         else       k_m8_mvm<false><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);

@@ -79,6 +79,32 @@ const uint64_t *device_jump_tables() {
     return g_dev_tables[dev];
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tensor_map_u32_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t row_words,
+                           uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_words) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)");
+        if (q != cudaDriverEntryPointSuccess || !fn) { set_error("cuTensorMapEncodeTiled not available in this driver"); return CLOVER_ERR_CUDA; }
+        encode = (EncodeTiledFn)fn;
+    }
+    const cuuint64_t dims[2] = {row_words, rows};
+    const cuuint64_t strides[1] = {row_pitch_bytes};
+    const cuuint32_t box[2] = {box_words, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return CLOVER_ERR_CUDA; }
+    return CLOVER_OK;
+}
+
 void host_key_skip(uint64_t *key_host, uint64_t ncalls) {
     if (ncalls == 0) return;
     const uint64_t *t = host_jump_tables();

@@ -1,5 +1,6 @@
 // runtime.cuh - host-side plumbing shared by the ABI translation units.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -26,6 +27,12 @@ inline Key4 key_lanes(const uint64_t *key_host) {
     return k;
 }
 void host_key_skip(uint64_t *key_host, uint64_t ncalls);
+
+// Row-major 2D tensor of 32-bit words: `rows` x `row_words`, pitch `row_pitch_bytes` (multiple of 16),
+// box = box_rows x box_words, no swizzle, zero fill outside. Encoded through the driver entry point
+// (cuTensorMapEncodeTiled), so the library does not link libcuda directly.
+int make_tensor_map_u32_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t row_words,
+                           uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_words);
 
 #define CLOVER_CUDA_CHECK(expr)                                             \
     do {                                                                    \
