@@ -33,6 +33,26 @@ def shard_rows(rows: int, world: int, rank: int):
     return b0 * 64, nb * 64
 
 
+def exchange_fp32(y32: torch.Tensor, row0: int, rows_local: int, sizes, mode: str = "allreduce", group=None) -> None:
+    """The ONE collective of the sharded mvm, on the full-length fp32 output (any device/backend).
+
+    On entry ``y32[row0:row0+rows_local]`` holds this rank's results; for ``allreduce`` the rest must be
+    zero. On exit every rank holds all rows. ``sizes`` = rows per rank, in rank order."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return
+    if mode == "allreduce":
+        dist.all_reduce(y32, op=dist.ReduceOp.SUM, group=group)
+    elif mode == "allgather":
+        mine = y32[row0:row0 + rows_local].clone()
+        if len(set(sizes)) == 1 and y32.is_cuda:
+            dist.all_gather_into_tensor(y32, mine, group=group)
+        else:
+            dist.all_gather(list(torch.split(y32, list(sizes))), mine, group=group)
+    else:
+        raise ValueError(f"unknown exchange {mode!r}")
+
+
 class ShardedCloverMatrix4:
     """This rank's rows [row0, row0 + rows_local) of a (rows x cols) CloverMatrix4."""
 
@@ -74,14 +94,6 @@ class ShardedCloverMatrix4:
             call("clover_m4_mvm_shard", _ptr(self.local.values), _ptr(self.local.scales), C.c_uint64(self.rows_local),
                  C.c_uint64(self.cols), C.c_uint64(self.row0), _ptr(x.values), _ptr(x.scales), _ptr(self.y32),
                  None, None, None, _stream())
-        if self.world > 1:
-            if self.exchange == "allreduce":
-                dist.all_reduce(self.y32, op=dist.ReduceOp.SUM, group=self.group)
-            elif self._even:
-                dist.all_gather_into_tensor(self.y32, self.y32[self.row0:self.row0 + self.rows_local].clone(),
-                                            group=self.group)
-            else:
-                parts = list(torch.split(self.y32, self._sizes))
-                dist.all_gather(parts, parts[self.rank].clone(), group=self.group)
+        exchange_fp32(self.y32, self.row0, self.rows_local, self._sizes, self.exchange, self.group)
         call("clover_v4_requantize_mvm", _ptr(self.y32), C.c_uint64(self.rows), _ptr(y.values), _ptr(y.scales),
              key_ptr, _stream())
