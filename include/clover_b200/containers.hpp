@@ -1,0 +1,299 @@
+// clover_b200/containers.hpp - drop-in host containers for the Clover hot path, backed by libclover_b200.so.
+//
+// Same class names, method names and argument meaning as the reference's header-only containers
+// (include/CloverVector32.h, CloverVector4.h, CloverVector8.h, CloverMatrix32.h, CloverMatrix4.h, CloverMatrix8.h),
+// so user code and the reference's own harness templates (test/validate/03_matrix.cpp:248-276,
+// test/performance/01_measure.h:699-720) compile against them unchanged for the methods on the hot path:
+//
+//     quantize / restore / dot            (vectors)         + the `_scalar` / `_parallel` spellings
+//     quantize / mvm                      (matrices)          (all three forward to the same GPU kernel)
+//     getData / getScales / get / getBits / getBytes / size / size_pad / getRows / getCols / setRandomKeys
+//
+// Where the data lives: every container owns ONE device allocation in the reference's exact byte layout
+// ([values | scales], include/CloverVector4.h:68-103) plus a host mirror of the same bytes. getData()/getScales()
+// return HOST pointers like the reference does; the mirror is synchronised lazily (device -> host before a host
+// read, host -> device before the next kernel when the host copy was handed out writable).
+//
+// Errors keep the reference's behaviour: a message on std::cout and exit(1) (include/CloverMatrix4.h:779-782).
+// Stochastic rounding is a run-time switch: containers start WITHOUT a key (= the reference built with
+// CLOVER_STOCHASTIC_ROUNDING_DISABLED); setRandomKeys()/seed() enables the reference's XORShift128+ stream.
+//
+// Not provided (outside the hot path): scaleAndAdd, threshold, transpose, 16-bit containers,
+// fp32 BLAS on CloverVector32/CloverMatrix32.
+#ifndef CLOVER_B200_CONTAINERS_HPP
+#define CLOVER_B200_CONTAINERS_HPP
+
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <vector>
+
+#include "../clover_b200.h"
+
+#define CLOVER_VECTOR_BLOCK 64
+#define CLOVER_VECTOR_SIZE_PAD (CLOVER_VECTOR_BLOCK * 2)
+
+namespace clover_b200_detail {
+
+inline void check(int status, const char *what) {
+    if (status != CLOVER_OK) {
+        std::cout << what << " failed: " << clover_last_error() << ". Exiting ..." << std::endl;
+        exit(1);
+    }
+}
+
+// One device buffer + host mirror with lazy synchronisation.
+class Mirror {
+    void *dev_ = nullptr;
+    std::vector<unsigned char> host_;
+    mutable bool host_fresh_ = true, dev_fresh_ = true;
+public:
+    explicit Mirror(size_t bytes) : host_(bytes, 0) { check(clover_malloc(&dev_, bytes), "clover_malloc"); dev_fresh_ = false; }
+    Mirror(const Mirror &o) : host_(o.host_.size()) {
+        check(clover_malloc(&dev_, host_.size()), "clover_malloc");
+        o.to_host();
+        host_ = o.host_;
+        dev_fresh_ = false;
+    }
+    Mirror &operator=(const Mirror &) = delete;
+    ~Mirror() { if (dev_) clover_free(dev_); }
+    size_t bytes() const { return host_.size(); }
+    void to_host() const {
+        if (!host_fresh_) {
+            check(clover_copy_d2h(const_cast<unsigned char *>(host_.data()), dev_, host_.size(), nullptr), "clover_copy_d2h");
+            check(clover_stream_sync(nullptr), "clover_stream_sync");
+            host_fresh_ = true;
+        }
+    }
+    // host pointer the caller may write through: the device copy becomes stale
+    unsigned char *host_rw() { to_host(); dev_fresh_ = false; return host_.data(); }
+    const unsigned char *host_ro() const { to_host(); return host_.data(); }
+    // device pointer for a kernel that READS the buffer
+    const void *dev_in() {
+        if (!dev_fresh_) { check(clover_copy_h2d(dev_, host_.data(), host_.size(), nullptr), "clover_copy_h2d"); dev_fresh_ = true; }
+        return dev_;
+    }
+    // device pointer for a kernel that OVERWRITES (part of) the buffer
+    void *dev_out() { (void)dev_in(); host_fresh_ = false; return dev_; }
+};
+
+inline uint64_t pad128(uint64_t n) { return (n % CLOVER_VECTOR_SIZE_PAD) ? n + CLOVER_VECTOR_SIZE_PAD - (n % CLOVER_VECTOR_SIZE_PAD) : n; }
+
+class Keyed {   // include/CloverRandom.h: per-object XORShift128+ state
+protected:
+    uint64_t key_[8];
+    bool has_key_ = false;
+    uint64_t *key_ptr() { return has_key_ ? key_ : nullptr; }
+public:
+    void setRandomKeys(const uint64_t key1[4], const uint64_t key2[4]) {   // include/CloverRandom.h:90-94
+        std::memcpy(key_, key1, 32); std::memcpy(key_ + 4, key2, 32); has_key_ = true;
+    }
+    void seed(uint64_t k1, uint64_t k2) { check(clover_prng_init(k1, k2, key_), "clover_prng_init"); has_key_ = true; }
+    void disableStochasticRounding() { has_key_ = false; }
+    const uint64_t *getRandomKeys() const { return has_key_ ? key_ : nullptr; }
+};
+
+}  // namespace clover_b200_detail
+
+// ---------------------------------------------------------------------------------------------------------------
+class CloverVector32 {   // include/CloverVector32.h:53-70 - fp32, length padded to x128, pad zeroed
+    uint64_t length, length_pad;
+    mutable clover_b200_detail::Mirror buf;
+public:
+    explicit CloverVector32(uint64_t s) : length(s), length_pad(clover_b200_detail::pad128(s)), buf(length_pad * sizeof(float)) {}
+    uint64_t size() const { return length; }
+    uint64_t size_pad() const { return length_pad; }
+    uint64_t getBitsLength() const { return 32; }
+    uint64_t getBytes() const { return length_pad * sizeof(float); }
+    float *getData() const { return reinterpret_cast<float *>(buf.host_rw()); }
+    float get(uint64_t i) const { return reinterpret_cast<const float *>(buf.host_ro())[i]; }
+    void set(uint64_t i, float v) { getData()[i] = v; }
+    const float *device_in() const { return static_cast<const float *>(buf.dev_in()); }
+    float *device_out() { return static_cast<float *>(buf.dev_out()); }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int BITS>
+class CloverQuantizedVector : public clover_b200_detail::Keyed {
+protected:
+    uint64_t length, length_pad;
+    mutable clover_b200_detail::Mirror buf;                 // [values | scales], one allocation (:76-79)
+    uint64_t value_bytes() const { return length_pad * BITS / 8; }
+    uint64_t scale_count() const { return length_pad / 64; }
+    void init_padding() {                                   // pad values 0 (already), pad scales 1 (:86-94)
+        float *s = reinterpret_cast<float *>(buf.host_rw() + value_bytes());
+        for (uint64_t i = length / 64; i < scale_count(); ++i) s[i] = 1.0f;
+    }
+public:
+    explicit CloverQuantizedVector(uint64_t s)
+        : length(s), length_pad(clover_b200_detail::pad128(s)), buf(length_pad * BITS / 8 + (length_pad / 64) * sizeof(float)) { init_padding(); }
+    CloverQuantizedVector(const CloverVector32 &other) : CloverQuantizedVector(other.size()) { quantize(other); }
+    uint64_t size() const { return length; }
+    uint64_t size_pad() const { return length_pad; }
+    uint64_t getBitsLength() const { return BITS; }
+    uint64_t getBytes() const { return value_bytes() + scale_count() * sizeof(float); }
+    int8_t *getData() const { return reinterpret_cast<int8_t *>(buf.host_rw()); }
+    float *getScales() const { return reinterpret_cast<float *>(buf.host_rw() + value_bytes()); }
+    const int8_t *device_values() const { return static_cast<const int8_t *>(buf.dev_in()); }
+    const float *device_scales() const { return reinterpret_cast<const float *>(static_cast<const char *>(buf.dev_in()) + value_bytes()); }
+    int8_t *device_values_out() { return static_cast<int8_t *>(buf.dev_out()); }
+    float *device_scales_out() { return reinterpret_cast<float *>(static_cast<char *>(buf.dev_out()) + value_bytes()); }
+
+    void quantize(const CloverVector32 &other) {
+        if (other.size_pad() != length_pad) { std::cout << "Vectors do not have the same size. Exiting ..." << std::endl; exit(1); }
+        int8_t *v = device_values_out();
+        float *s = device_scales_out();
+        const int rc = BITS == 4 ? clover_v4_quantize(other.device_in(), length_pad, v, s, key_ptr(), nullptr)
+                                 : clover_v8_quantize(other.device_in(), length_pad, v, s, key_ptr(), nullptr);
+        clover_b200_detail::check(rc, "quantize");
+    }
+    void quantize_scalar(const CloverVector32 &o) { quantize(o); }
+    void quantize_parallel(const CloverVector32 &o) { quantize(o); }
+
+    void restore(CloverVector32 &other) const {
+        if (other.size_pad() != length_pad) { std::cout << "Vectors do not have the same size. Exiting ..." << std::endl; exit(1); }
+        const int rc = BITS == 4 ? clover_v4_restore(device_values(), device_scales(), length_pad, other.device_out(), nullptr)
+                                 : clover_v8_restore(device_values(), device_scales(), length_pad, other.device_out(), nullptr);
+        clover_b200_detail::check(rc, "restore");
+    }
+    void restore_scalar(CloverVector32 &o) const { restore(o); }
+
+    float dot(const CloverQuantizedVector &other, int mode = CLOVER_DOT_AUTO) const {
+        if (other.length_pad != length_pad) { std::cout << "Vectors do not have the same size. Exiting ..." << std::endl; exit(1); }
+        static thread_local float *d_result = nullptr;
+        if (!d_result) clover_b200_detail::check(clover_malloc(reinterpret_cast<void **>(&d_result), sizeof(float)), "clover_malloc");
+        const int rc = BITS == 4 ? clover_v4_dot(device_values(), device_scales(), other.device_values(), other.device_scales(), length_pad, d_result, mode, nullptr)
+                                 : clover_v8_dot(device_values(), device_scales(), other.device_values(), other.device_scales(), length_pad, d_result, mode, nullptr);
+        clover_b200_detail::check(rc, "dot");
+        float h = 0.f;
+        clover_b200_detail::check(clover_copy_d2h(&h, d_result, sizeof(float), nullptr), "clover_copy_d2h");
+        clover_b200_detail::check(clover_stream_sync(nullptr), "clover_stream_sync");
+        return h;
+    }
+    float dot_scalar(const CloverQuantizedVector &o) const { return dot(o, CLOVER_DOT_EXACT); }
+    float dot_parallel(const CloverQuantizedVector &o) const { return dot(o); }
+};
+
+class CloverVector4 : public CloverQuantizedVector<4> {
+public:
+    using CloverQuantizedVector<4>::CloverQuantizedVector;
+    int8_t getBits(uint64_t pos) const {                    // include/CloverVector4.h:154-160
+        const int8_t b = reinterpret_cast<const int8_t *>(buf.host_ro())[pos >> 1];
+        return (pos & 1) ? (int8_t)((int8_t)(b << 4) >> 4) : (int8_t)(b >> 4);
+    }
+    float get(uint64_t pos) const {                         // include/CloverVector4.h:179-188
+        const float *s = reinterpret_cast<const float *>(buf.host_ro() + value_bytes());
+        return (s[pos >> 6] / 7.0f) * (float)getBits(pos);
+    }
+};
+
+class CloverVector8 : public CloverQuantizedVector<8> {
+public:
+    using CloverQuantizedVector<8>::CloverQuantizedVector;
+    int8_t getBits(uint64_t pos) const { return reinterpret_cast<const int8_t *>(buf.host_ro())[pos]; }
+    float get(uint64_t pos) const {                         // include/CloverVector8.h:136-139
+        const float *s = reinterpret_cast<const float *>(buf.host_ro() + value_bytes());
+        return getBits(pos) * s[pos >> 6] / 127.0f;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+class CloverMatrix32 {   // include/CloverMatrix32.h:43-66
+    uint64_t rows, cols;
+    mutable clover_b200_detail::Mirror buf;
+public:
+    CloverMatrix32(uint64_t h, uint64_t w) : rows(clover_b200_detail::pad128(h)), cols(clover_b200_detail::pad128(w)), buf(rows * cols * sizeof(float)) {}
+    uint64_t getRows() const { return rows; }
+    uint64_t getCols() const { return cols; }
+    uint64_t size() const { return rows * cols; }
+    uint64_t getBytes() const { return rows * cols * sizeof(float); }
+    float *getData() const { return reinterpret_cast<float *>(buf.host_rw()); }
+    const float *device_in() const { return static_cast<const float *>(buf.dev_in()); }
+};
+
+template <int BITS, class QVector>
+class CloverQuantizedMatrix : public clover_b200_detail::Keyed {
+protected:
+    uint64_t rows, cols;
+    mutable clover_b200_detail::Mirror buf;                 // [values | scales] (include/CloverMatrix4.h:77-93)
+    uint64_t value_bytes() const { return rows * cols * BITS / 8; }
+    uint64_t scale_count() const { return (rows >> 6) * (cols >> 6); }
+public:
+    CloverQuantizedMatrix(uint64_t h, uint64_t w)
+        : rows(clover_b200_detail::pad128(h)), cols(clover_b200_detail::pad128(w)),
+          buf(rows * cols * BITS / 8 + (rows >> 6) * (cols >> 6) * sizeof(float)) {}
+    uint64_t getRows() const { return rows; }
+    uint64_t getCols() const { return cols; }
+    uint64_t size() const { return rows * cols; }
+    uint64_t getBitsLength() const { return BITS; }
+    uint64_t getBytes() const { return value_bytes() + scale_count() * sizeof(float); }
+    int8_t *getData() const { return reinterpret_cast<int8_t *>(buf.host_rw()); }
+    float *getScales() const { return reinterpret_cast<float *>(buf.host_rw() + value_bytes()); }
+    const int8_t *device_values() const { return static_cast<const int8_t *>(buf.dev_in()); }
+    const float *device_scales() const { return reinterpret_cast<const float *>(static_cast<const char *>(buf.dev_in()) + value_bytes()); }
+
+    void quantize(const CloverMatrix32 &m) {
+        if (m.getRows() != rows || m.getCols() != cols) { std::cout << "Matrices do not have the same size. Exiting ..." << std::endl; exit(1); }
+        char *d = static_cast<char *>(buf.dev_out());
+        const int rc = BITS == 4 ? clover_m4_quantize(m.device_in(), rows, cols, reinterpret_cast<int8_t *>(d), reinterpret_cast<float *>(d + value_bytes()), key_ptr(), nullptr)
+                                 : clover_m8_quantize(m.device_in(), rows, cols, reinterpret_cast<int8_t *>(d), reinterpret_cast<float *>(d + value_bytes()), key_ptr(), nullptr);
+        clover_b200_detail::check(rc, "quantize");
+    }
+    void quantize_scalar(const CloverMatrix32 &m) { quantize(m); }
+
+    // include/CloverMatrix4.h:777-1083 / include/CloverMatrix8.h:1002-1298
+    void mvm(const QVector &productVector, QVector &resultVector) {
+        if (productVector.size() != getCols() || resultVector.size_pad() != getRows()) {
+            std::cout << "MVM can not be performed. Exiting ..." << std::endl;
+            exit(1);
+        }
+        int8_t *yv = resultVector.device_values_out();
+        float *ys = resultVector.device_scales_out();
+        const int rc = BITS == 4 ? clover_m4_mvm(device_values(), device_scales(), rows, cols, productVector.device_values(), productVector.device_scales(), yv, ys, nullptr, key_ptr(), nullptr)
+                                 : clover_m8_mvm(device_values(), device_scales(), rows, cols, productVector.device_values(), productVector.device_scales(), yv, ys, nullptr, key_ptr(), nullptr);
+        clover_b200_detail::check(rc, "mvm");
+    }
+    void mvm_scalar(const QVector &x, QVector &y) { mvm(x, y); }
+    void mvm_parallel(const QVector &x, QVector &y) { mvm(x, y); }
+};
+
+class CloverMatrix4 : public CloverQuantizedMatrix<4, CloverVector4> {
+public:
+    using CloverQuantizedMatrix<4, CloverVector4>::CloverQuantizedMatrix;
+    using CloverQuantizedMatrix<4, CloverVector4>::mvm;
+    float get(uint64_t i, uint64_t j) const {               // include/CloverMatrix4.h:123-139
+        const uint64_t pos = i * cols + j;
+        const int8_t b = reinterpret_cast<const int8_t *>(buf.host_ro())[pos >> 1];
+        const int8_t q = (pos & 1) ? (int8_t)((int8_t)(b << 4) >> 4) : (int8_t)(b >> 4);
+        const float *s = reinterpret_cast<const float *>(buf.host_ro() + value_bytes());
+        return (s[(i >> 6) * (cols >> 6) + (j >> 6)] / 7.0f) * (float)q;
+    }
+    // include/CloverMatrix4.h:1451-1547
+    void mvm(const CloverVector32 &productVector, CloverVector32 &resultVector) {
+        if (productVector.size() != getCols() || resultVector.size_pad() < getRows()) {
+            std::cout << "MVM can not be performed. Exiting ..." << std::endl;
+            exit(1);
+        }
+        clover_b200_detail::check(clover_m4_mvm_f32(device_values(), device_scales(), rows, cols, productVector.device_in(),
+                                                    resultVector.device_out(), nullptr), "mvm");
+    }
+    // extension: C = A * Bt^T, C[i][j] = rowView(A,i).dot(rowView(Bt,j)); c_dev: rows x Bt.rows fp32 on the device
+    void gemm(const CloverMatrix4 &Bt, float *c_dev, uint64_t ldc) const {
+        if (Bt.getCols() != getCols()) { std::cout << "GEMM can not be performed. Exiting ..." << std::endl; exit(1); }
+        clover_b200_detail::check(clover_m4_gemm(device_values(), device_scales(), Bt.device_values(), Bt.device_scales(),
+                                                 rows, Bt.getRows(), cols, c_dev, ldc, nullptr), "gemm");
+    }
+};
+
+class CloverMatrix8 : public CloverQuantizedMatrix<8, CloverVector8> {
+public:
+    using CloverQuantizedMatrix<8, CloverVector8>::CloverQuantizedMatrix;
+    float get(uint64_t i, uint64_t j) const {               // include/CloverMatrix8.h:117-129
+        const int8_t q = reinterpret_cast<const int8_t *>(buf.host_ro())[i * cols + j];
+        const float *s = reinterpret_cast<const float *>(buf.host_ro() + value_bytes());
+        return (s[(i >> 6) * (cols >> 6) + (j >> 6)] / 127.0f) * (float)q;
+    }
+};
+
+#endif  // CLOVER_B200_CONTAINERS_HPP
