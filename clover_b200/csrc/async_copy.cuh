@@ -61,6 +61,12 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tensor_m
         " [%0], [%1, {%2, %3}], [%4], %5;"
         ::"r"(smem_u32(smem_dst)), "l"(tensor_map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
+// same without a cache hint (operands that other CTAs re-read from L2)
+__device__ __forceinline__ void tma_load_2d_default(void *smem_dst, const void *tensor_map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(tensor_map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_descriptor(const void *tensor_map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tensor_map) : "memory");
 }

@@ -83,8 +83,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tensor_map_u32_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t row_words,
-                           uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_words) {
+static int tensor_map_encoder(EncodeTiledFn *out) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -94,6 +93,31 @@ int make_tensor_map_u32_2d(CUtensorMap *map, const void *base, uint64_t rows, ui
         if (q != cudaDriverEntryPointSuccess || !fn) { set_error("cuTensorMapEncodeTiled not available in this driver"); return CLOVER_ERR_CUDA; }
         encode = (EncodeTiledFn)fn;
     }
+    *out = encode;
+    return CLOVER_OK;
+}
+
+int make_tensor_map_u8_2d_sw128(CUtensorMap *map, const void *base, uint64_t rows, uint64_t row_bytes,
+                                uint32_t box_rows) {
+    EncodeTiledFn encode;
+    int rc = tensor_map_encoder(&encode);
+    if (rc != CLOVER_OK) return rc;
+    const cuuint64_t dims[2] = {row_bytes, rows};
+    const cuuint64_t strides[1] = {row_bytes};
+    const cuuint32_t box[2] = {128, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(sw128) failed with CUresult %d", (int)r); return CLOVER_ERR_CUDA; }
+    return CLOVER_OK;
+}
+
+int make_tensor_map_u32_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t row_words,
+                           uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_words) {
+    EncodeTiledFn encode;
+    int rc0 = tensor_map_encoder(&encode);
+    if (rc0 != CLOVER_OK) return rc0;
     const cuuint64_t dims[2] = {row_words, rows};
     const cuuint64_t strides[1] = {row_pitch_bytes};
     const cuuint32_t box[2] = {box_words, box_rows};

@@ -33,6 +33,10 @@ void host_key_skip(uint64_t *key_host, uint64_t ncalls);
 // (cuTensorMapEncodeTiled), so the library does not link libcuda directly.
 int make_tensor_map_u32_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t row_words,
                            uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_words);
+// Row-major 2D tensor of bytes, box = box_rows x 128 bytes with the 128-byte shared-memory swizzle that
+// tcgen05 K-major operand descriptors (layout type SWIZZLE_128B) expect.
+int make_tensor_map_u8_2d_sw128(CUtensorMap *map, const void *base, uint64_t rows, uint64_t row_bytes,
+                                uint32_t box_rows);
 
 #define CLOVER_CUDA_CHECK(expr)                                             \
     do {                                                                    \
