@@ -49,6 +49,9 @@ _SIGNATURES = {
     "clover_m4_mvm_shard": (_int, [_vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "clover_v4_requantize_mvm": (_int, [_vp, _u64, _vp, _vp, _vp, _vp]),
     "clover_m4_gemm": (_int, [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _vp, _u64, _vp]),
+    "clover_m4_expand_e4m3": (_int, [_vp, _u64, _u64, _vp, _vp]),
+    "clover_m4_gemm_expanded": (_int, [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _vp, _u64, _vp]),
+    "clover_m4_gemm_simt": (_int, [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _vp, _u64, _vp]),
     "clover_m8_quantize": (_int, [_vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "clover_m8_mvm": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "clover_host_v4_quantize": (_int, [_vp, _u64, _vp, _vp, _vp]),

@@ -264,13 +264,32 @@ class CloverMatrix4(_QMatrix):
         scale = np.float32(self.scales[(i >> 6) * (self.cols >> 6) + (j >> 6)].item()) / np.float32(7.0)
         return float(scale * np.float32(q))
 
-    def gemm(self, Bt: "CloverMatrix4", out=None):
-        """C = A * Bt^T with C[i][j] = rowView(A,i).dot(rowView(Bt,j)) - extension, SURVEY.md 8a-10."""
+    def gemm(self, Bt: "CloverMatrix4", out=None, impl: str = "tc"):
+        """C = A * Bt^T with C[i][j] = rowView(A,i).dot(rowView(Bt,j)) - extension, SURVEY.md 8a-10.
+        impl "tc": tcgen05 tensor-core kernel (nibbles expanded to E4M3 in a workspace first);
+        impl "simt": the DP4A validation baseline. Both give the same bits."""
         if Bt.cols != self.cols:
             raise CloverSizeError("GEMM can not be performed.")
         if out is None:
             out = torch.empty(self.rows, Bt.rows, dtype=torch.float32, device=self.values.device)
-        call("clover_m4_gemm", _ptr(self.values), _ptr(self.scales), _ptr(Bt.values), _ptr(Bt.scales),
+        fn = {"tc": "clover_m4_gemm", "simt": "clover_m4_gemm_simt"}[impl]
+        call(fn, _ptr(self.values), _ptr(self.scales), _ptr(Bt.values), _ptr(Bt.scales),
+             C.c_uint64(self.rows), C.c_uint64(Bt.rows), C.c_uint64(self.cols), _ptr(out), C.c_uint64(out.stride(0)),
+             _stream())
+        return out
+
+    def expand_e4m3(self, out=None):
+        """rows*cols FP8-E4M3 bytes (natural element order) - the tensor-core GEMM's operand format."""
+        if out is None:
+            out = torch.empty(self.rows * self.cols, dtype=torch.uint8, device=self.values.device)
+        call("clover_m4_expand_e4m3", _ptr(self.values), C.c_uint64(self.rows), C.c_uint64(self.cols), _ptr(out), _stream())
+        return out
+
+    def gemm_expanded(self, a8, Bt: "CloverMatrix4", bt8, out=None):
+        """The GEMM on operands already expanded by expand_e4m3() (reused weights skip the expansion pass)."""
+        if out is None:
+            out = torch.empty(self.rows, Bt.rows, dtype=torch.float32, device=self.values.device)
+        call("clover_m4_gemm_expanded", _ptr(a8), _ptr(self.scales), _ptr(bt8), _ptr(Bt.scales),
              C.c_uint64(self.rows), C.c_uint64(Bt.rows), C.c_uint64(self.cols), _ptr(out), C.c_uint64(out.stride(0)),
              _stream())
         return out

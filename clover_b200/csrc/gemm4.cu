@@ -5,8 +5,9 @@
 // with an exact int32 partial I_kb per K-slab of 64 and a scale that is constant over each 64x64
 // output tile per slab.
 //
-// k_gemm4_simt: first, CUDA-core (DP4A) implementation - the parity baseline the tensor-core kernel
-// is validated against on the device at sizes the CPU oracle cannot reach.
+// k_gemm4_simt: CUDA-core (DP4A) implementation - the parity baseline the tensor-core kernel (gemm4_tc.cu)
+// is validated against on the device at sizes the CPU oracle cannot reach. Both accumulate the slabs
+// sequentially in fp32 with the same scale expression, so their outputs are bit-identical.
 #include "common.cuh"
 #include "runtime.cuh"
 
@@ -71,14 +72,44 @@ k_gemm4_simt(const uint32_t *__restrict__ av, const float *__restrict__ as, cons
 
 using namespace clover;
 
-extern "C" {
-
-int clover_m4_gemm(const int8_t *av, const float *as, const int8_t *btv, const float *bts,
-                   uint64_t M, uint64_t N, uint64_t K, float *c, uint64_t ldc, void *stream) {
+static int gemm_args_ok(const void *av, const void *as, const void *btv, const void *bts, uint64_t M, uint64_t N, uint64_t K,
+                        const void *c, uint64_t ldc) {
     CLOVER_REQUIRE(av && as && btv && bts && c, CLOVER_ERR_INVALID, "null pointer");
     CLOVER_REQUIRE(M % 128u == 0 && N % 128u == 0 && K % 128u == 0, CLOVER_ERR_INVALID,
                    "M, N, K must be multiples of 128 (CloverMatrix4 padding)");
     CLOVER_REQUIRE(ldc >= N && ldc % 4u == 0, CLOVER_ERR_INVALID, "ldc must be >= N and a multiple of 4");
+    CLOVER_REQUIRE(M < (1ull << 31) && N < (1ull << 31) && K < (1ull << 31), CLOVER_ERR_INVALID, "dimension too large");
+    return CLOVER_OK;
+}
+
+extern "C" {
+
+int clover_m4_gemm(const int8_t *av, const float *as, const int8_t *btv, const float *bts,
+                   uint64_t M, uint64_t N, uint64_t K, float *c, uint64_t ldc, void *stream) {
+    int rc = gemm_args_ok(av, as, btv, bts, M, N, K, c, ldc);
+    if (rc != CLOVER_OK) return rc;
+    if (M == 0 || N == 0) return CLOVER_OK;
+    return gemm4_tc(av, as, btv, bts, M, N, K, c, ldc, (cudaStream_t)stream);
+}
+
+int clover_m4_expand_e4m3(const int8_t *values, uint64_t rows, uint64_t cols, uint8_t *out, void *stream) {
+    CLOVER_REQUIRE(values && out, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_REQUIRE(rows % 128u == 0 && cols % 128u == 0, CLOVER_ERR_INVALID, "rows, cols must be multiples of 128");
+    return gemm4_expand(values, rows, cols, out, (cudaStream_t)stream);
+}
+
+int clover_m4_gemm_expanded(const uint8_t *a8, const float *as, const uint8_t *bt8, const float *bts,
+                            uint64_t M, uint64_t N, uint64_t K, float *c, uint64_t ldc, void *stream) {
+    int rc = gemm_args_ok(a8, as, bt8, bts, M, N, K, c, ldc);
+    if (rc != CLOVER_OK) return rc;
+    if (M == 0 || N == 0) return CLOVER_OK;
+    return gemm4_tc_expanded(a8, as, bt8, bts, M, N, K, c, ldc, (cudaStream_t)stream);
+}
+
+int clover_m4_gemm_simt(const int8_t *av, const float *as, const int8_t *btv, const float *bts,
+                   uint64_t M, uint64_t N, uint64_t K, float *c, uint64_t ldc, void *stream) {
+    int rc = gemm_args_ok(av, as, btv, bts, M, N, K, c, ldc);
+    if (rc != CLOVER_OK) return rc;
     if (M == 0 || N == 0) return CLOVER_OK;
     dim3 grid((unsigned)(N / 64), (unsigned)(M / 64));
     k_gemm4_simt<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t *>(av), as,

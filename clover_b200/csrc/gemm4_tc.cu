@@ -1,0 +1,288 @@
+// gemm4_tc.cu - 4-bit GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+//   C[i][j] = sum_kb (sA[i>>6][kb] * (1/49) * sB[j>>6][kb]) * I_kb[i][j]        (gemm4.cu)
+//
+// The scale changes every K-slab of 64, so the integer partial I_kb of every slab has to leave the tensor
+// core, be multiplied by its fp32 scale and be accumulated in fp32 - one FMA per output element per slab.
+// That FMA stream (M*N*K/64 of them, as many cycles on the fp32 pipe as the slab's MMAs take on the tensor
+// pipe) is the real bound of this kernel, so everything else is kept off the CUDA cores:
+//
+//   1. k_expand_e4m3 (one HBM pass, declared: +0.75 GiB of traffic at 16384^3, a few % of the GEMM):
+//      two's-complement nibbles -> FP8 E4M3 bytes. Integers -8..8 are exact in E4M3 and
+//      tcgen05.mma kind::f8f6f4 accumulates in fp32, where slab sums (<= 64*49) are exact integers:
+//      the accumulator that comes out of TMEM already IS float(I_kb) - no int->float conversion in the
+//      epilogue (kind::i8 would cost two extra fp32-pipe operations per element). Exactness of this
+//      path was verified on B200 against the integer product (tools/mma_probe.cu check).
+//   2. k_gemm4_tc: persistent, one CTA per SM, 128x256 output tile, warp-specialised:
+//        warp 0      TMA producer: A' 128x128 B and B' 256x128 B boxes (SWIZZLE_128B) into a 4-stage ring
+//        warp 1      MMA issuer: per stage 2 slabs x 2 tcgen05.mma (M128 N256 K32) into one of two
+//                    256-column TMEM buffers, tcgen05.commit -> mbarrier per slab
+//        warp 2      TMEM allocator
+//        warps 4-11  epilogue: thread = one row x 128 columns of the tile, 128 fp32 accumulators in
+//                    registers for the whole K loop; per slab 4 x tcgen05.ld.32x32b.x32 software-pipelined
+//                    against 128 FFMA with the slab's scale (s = (sA*(1/49))*sB, the reference's order).
+//      fp32 accumulation is sequential in kb - identical to k_gemm4_simt, so the two kernels agree bit for bit.
+#include "common.cuh"
+#include "runtime.cuh"
+#include "tcgen05.cuh"
+
+namespace clover {
+
+// ---------------------------------------------------------------------------------------------------------
+// nibble -> E4M3 expansion
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// w holds 8 nibbles of the reference layout (byte i: element 2i in the HIGH nibble). o0 = elements 0..3,
+// o1 = elements 4..7 as E4M3 bytes. All 16 codes are handled (-8 -> 0xD0), although quantize never emits -8.
+__device__ __forceinline__ void nib8_to_e4m3(uint32_t w, uint32_t &o0, uint32_t &o1) {
+    const uint32_t x = ((w & 0x0F0F0F0Fu) << 4) | ((w >> 4) & 0x0F0F0F0Fu);   // nibble j = element j
+    const uint32_t idx = x & 0x77777777u;
+    // byte k of the tables: E4M3(k) and E4M3(k - 8)
+    const uint32_t PL = 0x44403800u, PH = 0x4E4C4A48u, NL = 0xCACCCED0u, NH = 0xB8C0C4C8u;
+    const uint32_t p0 = prmt(PL, PH, idx), p1 = prmt(PL, PH, idx >> 16);
+    const uint32_t n0 = prmt(NL, NH, idx), n1 = prmt(NL, NH, idx >> 16);
+    const uint32_t xs = x << 4;                                                  // msb of byte k = sign of nibble 2k
+    const uint32_t m0 = prmt(xs, x, 0xD9C8u), m1 = prmt(xs, x, 0xFBEAu);        // 0xFF where the nibble is negative
+    o0 = (p0 & ~m0) | (n0 & m0);
+    o1 = (p1 & ~m1) | (n1 & m1);
+}
+
+__global__ void __launch_bounds__(256) k_expand_e4m3(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint64_t n16) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 w = ldg_stream(in + i);
+        uint4 a, b;
+        nib8_to_e4m3(w.x, a.x, a.y);
+        nib8_to_e4m3(w.y, a.z, a.w);
+        nib8_to_e4m3(w.z, b.x, b.y);
+        nib8_to_e4m3(w.w, b.z, b.w);
+        out[2 * i] = a;
+        out[2 * i + 1] = b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the GEMM
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kBM = 128, kBN = 256, kBK = 128, kStages = 4;
+constexpr int kAStage = kBM * kBK, kBStage = kBN * kBK, kStageBytes = kAStage + kBStage;
+constexpr int kGemmThreads = 384;
+constexpr int kGemmSmem = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr uint32_t kGroupM = 16;     // tiles are walked in groups of 16 tile-rows so that concurrent CTAs share A and B' panels in L2
+
+__device__ __forceinline__ void tile_coords(uint32_t t, uint32_t tiles_m, uint32_t tiles_n, uint32_t &tm, uint32_t &tn) {
+    const uint32_t group_sz = kGroupM * tiles_n;
+    const uint32_t g = t / group_sz, r = t % group_sz;
+    const uint32_t first = g * kGroupM;
+    const uint32_t gm = min(kGroupM, tiles_m - first);
+    tm = first + r % gm;
+    tn = r / gm;
+}
+
+__device__ __forceinline__ void fma32(float *acc, float s, const uint32_t *r) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = __fmaf_rn(s, __uint_as_float(r[j]), acc[j]);
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+           const float *__restrict__ as, const float *__restrict__ bs, uint32_t M, uint32_t N, uint32_t K,
+           float *__restrict__ c, uint64_t ldc) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+    uint64_t *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages, *tempty = bars + 2 * kStages + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tiles_m = M / kBM, tiles_n = (N + kBN - 1) / kBN, ntiles = tiles_m * tiles_n;
+    const uint32_t kblocks = K / kBK, KB = K >> 6, NB = N >> 6;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+        mbar_fence_init();
+        tma_prefetch_descriptor(&map_a);
+        tma_prefetch_descriptor(&map_b);
+    }
+    if (warp == 2) { tmem_alloc<1>(tmem_slot, 512); tmem_relinquish<1>(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        reg_dealloc<40>();
+        if (warp == 0 && lane == 0) {
+            // ===== TMA producer =====
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                uint32_t tm, tn;
+                tile_coords(t, tiles_m, tiles_n, tm, tn);
+                for (uint32_t kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], kStageBytes);
+                    uint8_t *sa = smem + stage * kStageBytes, *sb = sa + kAStage;
+                    tma_load_2d_default(sa, &map_a, (int)(kb * kBK), (int)(tm * kBM), &full[stage]);
+                    tma_load_2d_default(sb, &map_b, (int)(kb * kBK), (int)(tn * kBN), &full[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = umma_idesc(UMMA_E4M3, kBM, kBN);
+            uint32_t stage = 0, phase = 0, g = 0;
+            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                for (uint32_t kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                    const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + kAStage);
+#pragma unroll
+                    for (uint32_t h = 0; h < 2; ++h, ++g) {          // two K-slabs of 64 per stage
+                        const uint32_t buf = g & 1;
+                        mbar_wait(&tempty[buf], ((g >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t d = tmem + buf * 256;
+                        umma_ss<UMMA_E4M3, 1>(d, da + 4 * h, db + 4 * h, idesc, 0);
+                        umma_ss<UMMA_E4M3, 1>(d, da + 4 * h + 2, db + 4 * h + 2, idesc, 1);
+                        umma_commit<1>(&tfull[buf]);
+                    }
+                    umma_commit<1>(&empty[stage]);                    // smem stage free once its MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: warps 4..11 =====
+        reg_alloc<232>();
+        const uint32_t q = warp & 3, half = (uint32_t)(warp - 4) >> 2;
+        const uint32_t row_in_tile = q * 32 + lane;
+        const uint32_t taddr0 = tmem + ((q * 32) << 16) + half * 128;
+        float acc[128];
+        uint32_t r0[32], r1[32];
+        uint32_t g = 0;
+        for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            uint32_t tm, tn;
+            tile_coords(t, tiles_m, tiles_n, tm, tn);
+            const uint32_t jb0 = tn * 4 + half * 2;
+            const bool live = jb0 < NB;                     // N is a multiple of 128: a column half is all in or all out
+            const float *pa = as + (uint64_t)(tm * 2 + (q >> 1)) * KB;
+            const float *pb0 = bs + (uint64_t)(live ? jb0 : 0) * KB, *pb1 = pb0 + KB;
+#pragma unroll
+            for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+            float na = __ldg(pa), nb0 = __ldg(pb0), nb1 = __ldg(pb1);
+            {
+                const uint32_t buf = g & 1;
+                mbar_wait(&tfull[buf], (g >> 1) & 1);
+                tc_fence_after();
+                tmem_ld32(taddr0 + buf * 256, r0);
+            }
+            for (uint32_t kb = 0; kb < KB; ++kb) {
+                const uint32_t buf = g & 1;
+                const uint32_t ta = taddr0 + buf * 256;
+                const float sa = __fmul_rn(na, 1.0f / 49.0f);
+                const float s0 = __fmul_rn(sa, nb0), s1 = __fmul_rn(sa, nb1);
+                if (kb + 1 < KB) { na = __ldg(pa + kb + 1); nb0 = __ldg(pb0 + kb + 1); nb1 = __ldg(pb1 + kb + 1); }
+                tmem_ld_wait(r0);
+                tmem_ld32(ta + 32, r1);
+                fma32(acc, s0, r0);
+                tmem_ld_wait(r1);
+                tmem_ld32(ta + 64, r0);
+                fma32(acc + 32, s0, r1);
+                tmem_ld_wait(r0);
+                tmem_ld32(ta + 96, r1);
+                fma32(acc + 64, s1, r0);
+                tmem_ld_wait(r1);
+                tc_fence_before();                            // the buffer is drained: hand it back to the MMA warp
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]);
+                ++g;
+                if (kb + 1 < KB) {
+                    const uint32_t nbuf = g & 1;
+                    mbar_wait(&tfull[nbuf], (g >> 1) & 1);
+                    tc_fence_after();
+                    tmem_ld32(taddr0 + nbuf * 256, r0);
+                }
+                fma32(acc + 96, s1, r1);
+            }
+            if (live) {
+                float *crow = c + (uint64_t)(tm * kBM + row_in_tile) * ldc + (uint64_t)tn * kBN + half * 128;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    *reinterpret_cast<float4 *>(crow + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<1>(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+static void *g_ws[64] = {nullptr};
+static size_t g_ws_bytes[64] = {0};
+
+// grow-only per-device workspace for the expanded operands (not thread-safe; one GEMM stream per device)
+static int gemm_workspace(size_t bytes, void **out) {
+    int dev = 0;
+    CLOVER_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
+    if (g_ws_bytes[dev] < bytes) {
+        if (g_ws[dev]) { CLOVER_CUDA_CHECK(cudaDeviceSynchronize()); CLOVER_CUDA_CHECK(cudaFree(g_ws[dev])); g_ws[dev] = nullptr; g_ws_bytes[dev] = 0; }
+        CLOVER_CUDA_CHECK(cudaMalloc(&g_ws[dev], bytes));
+        g_ws_bytes[dev] = bytes;
+    }
+    *out = g_ws[dev];
+    return CLOVER_OK;
+}
+
+int gemm4_expand(const int8_t *values, uint64_t rows, uint64_t cols, uint8_t *out, cudaStream_t stream) {
+    const uint64_t n16 = rows * cols / 32;       // 16-byte input chunks
+    if (n16 == 0) return CLOVER_OK;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)sm_count() * 16);
+    k_expand_e4m3<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(values), reinterpret_cast<uint4 *>(out), n16);
+    count_launch();
+    return launch_status("k_expand_e4m3");
+}
+
+int gemm4_tc_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, const float *bs, uint64_t M, uint64_t N,
+                      uint64_t K, float *c, uint64_t ldc, cudaStream_t stream) {
+    CUtensorMap map_a, map_b;
+    int rc = make_tensor_map_u8_2d_sw128(&map_a, a8, M, K, kBM);
+    if (rc != CLOVER_OK) return rc;
+    rc = make_tensor_map_u8_2d_sw128(&map_b, b8, N, K, kBN);
+    if (rc != CLOVER_OK) return rc;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    CLOVER_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
+        CLOVER_CUDA_CHECK(cudaFuncSetAttribute(k_gemm4_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        attr_set[dev & 63] = true;
+    }
+    const uint64_t ntiles = (M / kBM) * ((N + kBN - 1) / kBN);
+    const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sm_count());
+    k_gemm4_tc<<<grid, kGemmThreads, kGemmSmem, stream>>>(map_a, map_b, as, bs, (uint32_t)M, (uint32_t)N, (uint32_t)K, c, ldc);
+    count_launch();
+    return launch_status("k_gemm4_tc");
+}
+
+int gemm4_tc(const int8_t *av, const float *as, const int8_t *btv, const float *bts, uint64_t M, uint64_t N, uint64_t K,
+             float *c, uint64_t ldc, cudaStream_t stream) {
+    void *ws = nullptr;
+    int rc = gemm_workspace((M + N) * K, &ws);
+    if (rc != CLOVER_OK) return rc;
+    uint8_t *a8 = static_cast<uint8_t *>(ws), *b8 = a8 + M * K;
+    rc = gemm4_expand(av, M, K, a8, stream);
+    if (rc != CLOVER_OK) return rc;
+    rc = gemm4_expand(btv, N, K, b8, stream);
+    if (rc != CLOVER_OK) return rc;
+    return gemm4_tc_expanded(a8, as, b8, bts, M, N, K, c, ldc, stream);
+}
+
+}  // namespace clover

@@ -38,6 +38,13 @@ int make_tensor_map_u32_2d(CUtensorMap *map, const void *base, uint64_t rows, ui
 int make_tensor_map_u8_2d_sw128(CUtensorMap *map, const void *base, uint64_t rows, uint64_t row_bytes,
                                 uint32_t box_rows);
 
+// gemm4_tc.cu: tensor-core GEMM (expand nibbles to E4M3 in a workspace, then tcgen05) and its two halves
+int gemm4_tc(const int8_t *av, const float *as, const int8_t *btv, const float *bts, uint64_t M, uint64_t N, uint64_t K,
+             float *c, uint64_t ldc, cudaStream_t stream);
+int gemm4_expand(const int8_t *values, uint64_t rows, uint64_t cols, uint8_t *out, cudaStream_t stream);
+int gemm4_tc_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, const float *bs, uint64_t M, uint64_t N,
+                      uint64_t K, float *c, uint64_t ldc, cudaStream_t stream);
+
 #define CLOVER_CUDA_CHECK(expr)                                             \
     do {                                                                    \
         cudaError_t _e = (expr);                                            \

@@ -122,6 +122,15 @@ int clover_v4_requantize_mvm(const float *y32, uint64_t rows, int8_t *yv, float 
  * both CloverMatrix4; C fp32 row-major with leading dimension ldc. */
 int clover_m4_gemm(const int8_t *av, const float *as, const int8_t *btv, const float *bts,
                    uint64_t M, uint64_t N, uint64_t K, float *c, uint64_t ldc, void *stream);
+/* The two halves of clover_m4_gemm, for callers that reuse an operand (weights): expand the nibbles of a
+ * CloverMatrix4 once into rows*cols FP8-E4M3 bytes (integers -8..7 are exact in E4M3) ... */
+int clover_m4_expand_e4m3(const int8_t *values, uint64_t rows, uint64_t cols, uint8_t *out, void *stream);
+/* ... and run the tcgen05 GEMM on expanded operands (a8: M*K bytes, bt8: N*K bytes, scales as above). */
+int clover_m4_gemm_expanded(const uint8_t *a8, const float *as, const uint8_t *bt8, const float *bts,
+                            uint64_t M, uint64_t N, uint64_t K, float *c, uint64_t ldc, void *stream);
+/* CUDA-core (DP4A) implementation of the same definition; bit-identical to clover_m4_gemm. Validation baseline. */
+int clover_m4_gemm_simt(const int8_t *av, const float *as, const int8_t *btv, const float *bts,
+                        uint64_t M, uint64_t N, uint64_t K, float *c, uint64_t ldc, void *stream);
 
 /* ---- CloverMatrix8 ------------------------------------------------------------------------------ */
 /* CloverMatrix8::quantize      include/CloverMatrix8.h:203-479 */
