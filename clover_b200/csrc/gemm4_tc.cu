@@ -18,9 +18,10 @@
 //        warp 1      MMA issuer: per stage 2 slabs x 2 tcgen05.mma (M128 N256 K32) into one of two
 //                    256-column TMEM buffers, tcgen05.commit -> mbarrier per slab
 //        warp 2      TMEM allocator
-//        warps 4-11  epilogue: thread = one row x 128 columns of the tile, 128 fp32 accumulators in
-//                    registers for the whole K loop; per slab 4 x tcgen05.ld.32x32b.x32 software-pipelined
-//                    against 128 FFMA with the slab's scale (s = (sA*(1/49))*sB, the reference's order).
+//        warps 4-19  epilogue: warp = 32 rows x 64 columns (one scale tile), thread = one row, 64 fp32
+//                    accumulators in registers for the whole K loop; per slab 2 x tcgen05.ld.32x32b.x32 and
+//                    32 packed fma.rn.f32x2 with the slab's scale (s = (sA*(1/49))*sB, the reference's order);
+//                    four warps per scheduler hide the TMEM-load and mbarrier latencies of one another.
 //      fp32 accumulation is sequential in kb - identical to k_gemm4_simt, so the two kernels agree bit for bit.
 #include "common.cuh"
 #include "runtime.cuh"
@@ -69,7 +70,8 @@ __global__ void __launch_bounds__(256) k_expand_e4m3(const uint4 *__restrict__ i
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kBM = 128, kBN = 256, kBK = 128, kStages = 4;
 constexpr int kAStage = kBM * kBK, kBStage = kBN * kBK, kStageBytes = kAStage + kBStage;
-constexpr int kGemmThreads = 384;
+constexpr int kEpiWarps = 16;                      // 4 lane quadrants x 4 column blocks of 64
+constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
 constexpr int kGemmSmem = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 constexpr uint32_t kGroupM = 16;     // tiles are walked in groups of 16 tile-rows so that concurrent CTAs share A and B' panels in L2
 
@@ -82,9 +84,21 @@ __device__ __forceinline__ void tile_coords(uint32_t t, uint32_t tiles_m, uint32
     tn = r / gm;
 }
 
-__device__ __forceinline__ void fma32(float *acc, float s, const uint32_t *r) {
+// one K-slab of one 32-lane x 64-column block: acc += s * D, D read from TMEM in two 32-column chunks
+__device__ __forceinline__ void epilogue_slab(uint64_t *acc, uint32_t *r, float s, uint32_t taddr, uint32_t tfull, uint32_t tempty,
+                                              uint32_t parity, int lane) {
+    mbar_wait_a(tfull, parity);
+    tc_fence_after();
+    tmem_ld32(taddr, r);
+    tmem_ld_wait(r);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = __fmaf_rn(s, __uint_as_float(r[j]), acc[j]);
+    for (int j = 0; j < 16; ++j) ffma2(acc[j], s, r[2 * j], r[2 * j + 1]);
+    tmem_ld32(taddr + 32, r);
+    tmem_ld_wait(r);
+    tc_fence_before();                                   // this warp's share of the buffer is drained
+    if (lane == 0) mbar_arrive_a(tempty);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ffma2(acc[16 + j], s, r[2 * j], r[2 * j + 1]);
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -92,30 +106,41 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
            const float *__restrict__ as, const float *__restrict__ bs, uint32_t M, uint32_t N, uint32_t K,
            float *__restrict__ c, uint64_t ldc) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
-    uint64_t *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages, *tempty = bars + 2 * kStages + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;             // 1024-aligned: SWIZZLE_128B atoms
+    // barrier block behind the stages: full[4] empty[4] tfull[2] tempty[2] tmem_slot
+    const uint32_t bars = smem + kStages * kStageBytes;
+    const uint32_t full = bars, empty = bars + 8 * kStages, tfull = bars + 16 * kStages, tempty = tfull + 16;
+    const uint32_t slot = tempty + 16;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_m = M / kBM, tiles_n = (N + kBN - 1) / kBN, ntiles = tiles_m * tiles_n;
     const uint32_t kblocks = K / kBK, KB = K >> 6, NB = N >> 6;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+        for (int i = 0; i < kStages; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full + 8 * i), "r"(1) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty + 8 * i), "r"(1) : "memory");
+        }
+        for (int b = 0; b < 2; ++b) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tfull + 8 * b), "r"(1) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tempty + 8 * b), "r"(kEpiWarps) : "memory");
+        }
         mbar_fence_init();
         tma_prefetch_descriptor(&map_a);
         tma_prefetch_descriptor(&map_b);
     }
-    if (warp == 2) { tmem_alloc<1>(tmem_slot, 512); tmem_relinquish<1>(); }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(512) : "memory");
+        tmem_relinquish<1>();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
 
     if (warp < 4) {
-        reg_dealloc<40>();
+        reg_dealloc<32>();   // 128*32 + 512*112 = 640*96: exactly the registers this CTA was launched with
         if (warp == 0 && lane == 0) {
             // ===== TMA producer =====
             uint32_t stage = 0, phase = 0;
@@ -123,97 +148,75 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                 uint32_t tm, tn;
                 tile_coords(t, tiles_m, tiles_n, tm, tn);
                 for (uint32_t kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], kStageBytes);
-                    uint8_t *sa = smem + stage * kStageBytes, *sb = sa + kAStage;
-                    tma_load_2d_default(sa, &map_a, (int)(kb * kBK), (int)(tm * kBM), &full[stage]);
-                    tma_load_2d_default(sb, &map_b, (int)(kb * kBK), (int)(tn * kBN), &full[stage]);
+                    mbar_wait_a(empty + 8 * stage, phase ^ 1);
+                    mbar_arrive_expect_tx_a(full + 8 * stage, kStageBytes);
+                    const uint32_t sa = smem + stage * kStageBytes;
+                    tma_load_2d_a(sa, &map_a, (int)(kb * kBK), (int)(tm * kBM), full + 8 * stage);
+                    tma_load_2d_a(sa + kAStage, &map_b, (int)(kb * kBK), (int)(tn * kBN), full + 8 * stage);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         } else if (warp == 1 && lane == 0) {
-            // ===== MMA issuer =====
+            // ===== MMA issuer: per stage, K-slab 0 -> TMEM buffer 0, K-slab 1 -> buffer 1 =====
             const uint32_t idesc = umma_idesc(UMMA_E4M3, kBM, kBN);
-            uint32_t stage = 0, phase = 0, g = 0;
+            uint32_t stage = 0, phase = 0, pair = 0;
             for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-                for (uint32_t kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                for (uint32_t kb = 0; kb < kblocks; ++kb, ++pair) {
+                    mbar_wait_a(full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                    const uint32_t sa = smem + stage * kStageBytes;
                     const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + kAStage);
 #pragma unroll
-                    for (uint32_t h = 0; h < 2; ++h, ++g) {          // two K-slabs of 64 per stage
-                        const uint32_t buf = g & 1;
-                        mbar_wait(&tempty[buf], ((g >> 1) & 1) ^ 1);
+                    for (uint32_t h = 0; h < 2; ++h) {
+                        mbar_wait_a(tempty + 8 * h, (pair & 1) ^ 1);
                         tc_fence_after();
-                        const uint32_t d = tmem + buf * 256;
+                        const uint32_t d = tmem + h * 256;
                         umma_ss<UMMA_E4M3, 1>(d, da + 4 * h, db + 4 * h, idesc, 0);
                         umma_ss<UMMA_E4M3, 1>(d, da + 4 * h + 2, db + 4 * h + 2, idesc, 1);
-                        umma_commit<1>(&tfull[buf]);
+                        umma_commit_a<1>(tfull + 8 * h);
                     }
-                    umma_commit<1>(&empty[stage]);                    // smem stage free once its MMAs retire
+                    umma_commit_a<1>(empty + 8 * stage);              // smem stage free once its MMAs retire
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else {
-        // ===== epilogue: warps 4..11 =====
-        reg_alloc<232>();
-        const uint32_t q = warp & 3, half = (uint32_t)(warp - 4) >> 2;
-        const uint32_t row_in_tile = q * 32 + lane;
-        const uint32_t taddr0 = tmem + ((q * 32) << 16) + half * 128;
-        float acc[128];
-        uint32_t r0[32], r1[32];
-        uint32_t g = 0;
+        // ===== epilogue: warps 4..19. Warp = lane quadrant q (TMEM lanes 32q..32q+31 = tile rows) x column block cb =====
+        reg_alloc<112>();
+        const uint32_t q = warp & 3, cb = (uint32_t)(warp - 4) >> 2;
+        const uint32_t taddr = tmem + ((q * 32) << 16) + cb * 64;
+        uint64_t acc[32];
+        uint32_t r[32];
+        uint32_t pair = 0;
         for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
             uint32_t tm, tn;
             tile_coords(t, tiles_m, tiles_n, tm, tn);
-            const uint32_t jb0 = tn * 4 + half * 2;
-            const bool live = jb0 < NB;                     // N is a multiple of 128: a column half is all in or all out
+            const uint32_t jb = tn * 4 + cb;
+            const bool live = jb < NB;                      // N is a multiple of 128: a 64-column block is all in or all out
             const float *pa = as + (uint64_t)(tm * 2 + (q >> 1)) * KB;
-            const float *pb0 = bs + (uint64_t)(live ? jb0 : 0) * KB, *pb1 = pb0 + KB;
+            const float *pb = bs + (uint64_t)(live ? jb : 0) * KB;
 #pragma unroll
-            for (int j = 0; j < 128; ++j) acc[j] = 0.f;
-            float na = __ldg(pa), nb0 = __ldg(pb0), nb1 = __ldg(pb1);
-            {
-                const uint32_t buf = g & 1;
-                mbar_wait(&tfull[buf], (g >> 1) & 1);
-                tc_fence_after();
-                tmem_ld32(taddr0 + buf * 256, r0);
-            }
-            for (uint32_t kb = 0; kb < KB; ++kb) {
-                const uint32_t buf = g & 1;
-                const uint32_t ta = taddr0 + buf * 256;
-                const float sa = __fmul_rn(na, 1.0f / 49.0f);
-                const float s0 = __fmul_rn(sa, nb0), s1 = __fmul_rn(sa, nb1);
-                if (kb + 1 < KB) { na = __ldg(pa + kb + 1); nb0 = __ldg(pb0 + kb + 1); nb1 = __ldg(pb1 + kb + 1); }
-                tmem_ld_wait(r0);
-                tmem_ld32(ta + 32, r1);
-                fma32(acc, s0, r0);
-                tmem_ld_wait(r1);
-                tmem_ld32(ta + 64, r0);
-                fma32(acc + 32, s0, r1);
-                tmem_ld_wait(r0);
-                tmem_ld32(ta + 96, r1);
-                fma32(acc + 64, s1, r0);
-                tmem_ld_wait(r1);
-                tc_fence_before();                            // the buffer is drained: hand it back to the MMA warp
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[buf]);
-                ++g;
-                if (kb + 1 < KB) {
-                    const uint32_t nbuf = g & 1;
-                    mbar_wait(&tfull[nbuf], (g >> 1) & 1);
-                    tc_fence_after();
-                    tmem_ld32(taddr0 + nbuf * 256, r0);
+            for (int j = 0; j < 32; ++j) acc[j] = 0ull;
+            for (uint32_t kb0 = 0; kb0 < KB; kb0 += 32) {
+                // lane l owns the scale of slab kb0 + l: s = (sA * (1/49)) * sB, the reference's order
+                const uint32_t kl = min(kb0 + lane, KB - 1);
+                const float sv = __fmul_rn(__fmul_rn(__ldg(pa + kl), 1.0f / 49.0f), __ldg(pb + kl));
+                const uint32_t n = min(32u, KB - kb0);
+                for (uint32_t k = 0; k < n; k += 2, ++pair) {
+                    const float s_even = __shfl_sync(0xFFFFFFFFu, sv, k), s_odd = __shfl_sync(0xFFFFFFFFu, sv, k + 1);
+                    epilogue_slab(acc, r, s_even, taddr, tfull, tempty, pair & 1, lane);
+                    epilogue_slab(acc, r, s_odd, taddr + 256, tfull + 8, tempty + 8, pair & 1, lane);
                 }
-                fma32(acc + 96, s1, r1);
             }
             if (live) {
-                float *crow = c + (uint64_t)(tm * kBM + row_in_tile) * ldc + (uint64_t)tn * kBN + half * 128;
+                float *crow = c + (uint64_t)(tm * kBM + q * 32 + lane) * ldc + (uint64_t)tn * kBN + cb * 64;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    *reinterpret_cast<float4 *>(crow + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                for (int j = 0; j < 16; ++j) {
+                    float4 o;
+                    o.x = __uint_as_float((uint32_t)acc[2 * j]);     o.y = __uint_as_float((uint32_t)(acc[2 * j] >> 32));
+                    o.z = __uint_as_float((uint32_t)acc[2 * j + 1]); o.w = __uint_as_float((uint32_t)(acc[2 * j + 1] >> 32));
+                    *reinterpret_cast<float4 *>(crow + 4 * j) = o;
+                }
             }
         }
     }

@@ -63,6 +63,11 @@ template <int CG> __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     else         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+template <int CG> __device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+    if (CG == 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    else         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // 32 lanes x 32 columns of 32-bit accumulators: thread t of the warp receives lane (base_lane + t),
 // columns col .. col+31. The registers are NOT valid until tmem_ld_wait() on the same array.
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
@@ -82,6 +87,13 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t *r) {
                    "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
                    "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                  :: "memory");
+}
+
+// acc.xy = s * d.xy + acc.xy, both halves rounded like a scalar fma.rn (SASS: FFMA2 with a scalar-broadcast operand)
+__device__ __forceinline__ void ffma2(uint64_t &acc, float s, uint32_t d_lo, uint32_t d_hi) {
+    const uint64_t d = ((uint64_t)d_hi << 32) | d_lo;
+    const uint64_t ss = ((uint64_t)__float_as_uint(s) << 32) | __float_as_uint(s);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ss), "l"(d));
 }
 
 template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
