@@ -23,6 +23,8 @@
 //                    32 packed fma.rn.f32x2 with the slab's scale (s = (sA*(1/49))*sB, the reference's order);
 //                    four warps per scheduler hide the TMEM-load and mbarrier latencies of one another.
 //      fp32 accumulation is sequential in kb - identical to k_gemm4_simt, so the two kernels agree bit for bit.
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "runtime.cuh"
 #include "tcgen05.cuh"
@@ -141,22 +143,25 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 
     if (warp < 4) {
         reg_dealloc<32>();   // 128*32 + 512*112 = 640*96: exactly the registers this CTA was launched with
-        if (warp == 0 && lane == 0) {
-            // ===== TMA producer =====
+        if (warp == 0) {
+            // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 uint32_t tm, tn;
                 tile_coords(t, tiles_m, tiles_n, tm, tn);
                 for (uint32_t kb = 0; kb < kblocks; ++kb) {
                     mbar_wait_a(empty + 8 * stage, phase ^ 1);
-                    mbar_arrive_expect_tx_a(full + 8 * stage, kStageBytes);
-                    const uint32_t sa = smem + stage * kStageBytes;
-                    tma_load_2d_a(sa, &map_a, (int)(kb * kBK), (int)(tm * kBM), full + 8 * stage);
-                    tma_load_2d_a(sa + kAStage, &map_b, (int)(kb * kBK), (int)(tn * kBN), full + 8 * stage);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx_a(full + 8 * stage, kStageBytes);
+                        const uint32_t sa = smem + stage * kStageBytes;
+                        tma_load_2d_a(sa, &map_a, (int)(kb * kBK), (int)(tm * kBM), full + 8 * stage);
+                        tma_load_2d_a(sa + kAStage, &map_b, (int)(kb * kBK), (int)(tn * kBN), full + 8 * stage);
+                    }
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
-        } else if (warp == 1 && lane == 0) {
+        } else if (warp == 1) {
             // ===== MMA issuer: per stage, K-slab 0 -> TMEM buffer 0, K-slab 1 -> buffer 1 =====
             const uint32_t idesc = umma_idesc(UMMA_E4M3, kBM, kBN);
             uint32_t stage = 0, phase = 0, pair = 0;
@@ -171,11 +176,14 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                         mbar_wait_a(tempty + 8 * h, (pair & 1) ^ 1);
                         tc_fence_after();
                         const uint32_t d = tmem + h * 256;
-                        umma_ss<UMMA_E4M3, 1>(d, da + 4 * h, db + 4 * h, idesc, 0);
-                        umma_ss<UMMA_E4M3, 1>(d, da + 4 * h + 2, db + 4 * h + 2, idesc, 1);
-                        umma_commit_a<1>(tfull + 8 * h);
+                        if (elect_one()) {
+                            umma_ss<UMMA_E4M3, 1>(d, da + 4 * h, db + 4 * h, idesc, 0);
+                            umma_ss<UMMA_E4M3, 1>(d, da + 4 * h + 2, db + 4 * h + 2, idesc, 1);
+                            umma_commit_a<1>(tfull + 8 * h);
+                            if (h == 1) umma_commit_a<1>(empty + 8 * stage);      // smem stage free once its MMAs retire
+                        }
+                        __syncwarp();
                     }
-                    umma_commit_a<1>(empty + 8 * stage);              // smem stage free once its MMAs retire
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -254,8 +262,14 @@ int gemm4_expand(const int8_t *values, uint64_t rows, uint64_t cols, uint8_t *ou
     return launch_status("k_expand_e4m3");
 }
 
+int gemm4_tc2_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, const float *bs, uint64_t M, uint64_t N,
+                       uint64_t K, float *c, uint64_t ldc, cudaStream_t stream, int cta_group);      // gemm4_tc2.cu
+
 int gemm4_tc_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, const float *bs, uint64_t M, uint64_t N,
                       uint64_t K, float *c, uint64_t ldc, cudaStream_t stream) {
+    // CLOVER_GEMM_KERNEL=pipe1|pair selects an experimental 4-slot pipeline (gemm4_tc2.cu); default: this file's kernel
+    static const int variant = [] { const char *e = getenv("CLOVER_GEMM_KERNEL"); return !e ? 0 : !strcmp(e, "pipe1") ? 1 : !strcmp(e, "pair") ? 2 : 0; }();
+    if (variant) return gemm4_tc2_expanded(a8, as, b8, bs, M, N, K, c, ldc, stream, variant);
     CUtensorMap map_a, map_b;
     int rc = make_tensor_map_u8_2d_sw128(&map_a, a8, M, K, kBM);
     if (rc != CLOVER_OK) return rc;

@@ -96,6 +96,16 @@ __device__ __forceinline__ void ffma2(uint64_t &acc, float s, uint32_t d_lo, uin
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ss), "l"(d));
 }
 
+// One lane of a fully converged warp. The producer / MMA warps run their loops warp-uniformly and only the
+// issue of the TMA / tcgen05 instruction is predicated on this: under `if (lane == 0)` control flow ptxas
+// cannot prove descriptors uniform and wraps every UTCQMMA / UTMALDG in an ELECT + R2UR "waterfall" loop
+// (~15 dependent instructions per MMA), which throttles the single issuing thread.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+    return p != 0;
+}
+
 template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 

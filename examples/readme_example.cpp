@@ -42,15 +42,19 @@ static void validate_mvm(uint64_t m, uint64_t n) {
     qa.mvm_parallel(qx, qy2);
     for (uint64_t k = 0; k < m; ++k)
         if (qy.get(k) != qy2.get(k)) { std::cout << "mvm mismatch at " << k << std::endl; exit(1); }
-    // consistency against a double-precision evaluation of the quantized operands (03_matrix.cpp:328-416 style)
+    // consistency against a double-precision evaluation of the quantized operands (03_matrix.cpp:328-416 style):
+    // the result is a truncating re-quantization of the fp32 row sums, so it may differ from the exact value by
+    // up to one quantum of its block (scale / 7 or scale / 127) plus the fp32 summation error
+    const double levels = qa.getBitsLength() == 4 ? 7.0 : 127.0;
     double worst = 0;
     for (uint64_t i = 0; i < m; ++i) {
         double s = 0;
         for (uint64_t j = 0; j < n; ++j) s += (double)qa.get(i, j) * (double)qx.get(j);
-        worst = std::fmax(worst, std::fabs(s - (double)qy.get(i)) / (std::fabs(s) + 1.0));
+        const double quantum = (double)qy.getScales()[i >> 6] / levels;
+        worst = std::fmax(worst, std::fabs(s - (double)qy.get(i)) / quantum);
     }
-    std::cout << "mvm " << m << "x" << n << " bits=" << qa.getBitsLength() << " max rel. error vs fp64: " << worst << std::endl;
-    if (worst > 0.2) exit(1);
+    std::cout << "mvm " << m << "x" << n << " bits=" << qa.getBitsLength() << " max error vs fp64: " << worst << " quanta" << std::endl;
+    if (worst > 1.001) exit(1);
 }
 
 int main() {
