@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256) k_lat(int iters, long long *out_cycles, u
                 uint32_t r[32];
                 tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (WITH_LD == 2 ? 192 : 0), r);   // 2: columns the MMA never writes
                 tc_wait_ld();
-                acc += r[lane & 31];
+                acc += r[0] ^ r[31];
             }
             tc_fence_before();
             t_ld += clock64() - tb;

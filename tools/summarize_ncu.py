@@ -34,12 +34,18 @@ def main():
             for k in KEYS:
                 if k in d:
                     print(f"   {k:75s} {d[k]:>18s} {units[hdr.index(k)]}")
-            rd = float(d.get("dram__bytes_read.sum", "0").replace(",", "") or 0)
-            wr = float(d.get("dram__bytes_write.sum", "0").replace(",", "") or 0)
-            u = units[hdr.index("dram__bytes_read.sum")] if "dram__bytes_read.sum" in hdr else ""
-            t = float(d.get("gpu__time_duration.sum", "0").replace(",", "") or 0)
-            tu = units[hdr.index("gpu__time_duration.sum")] if "gpu__time_duration.sum" in hdr else ""
-            print(f"   traffic(read+write) = {rd + wr:.4g} {u}; duration {t} {tu}")
+            def in_bytes(key):
+                if key not in hdr:
+                    return 0.0
+                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[units[hdr.index(key)]]
+                return float(d[key].replace(",", "") or 0) * mult
+            def in_seconds(key):
+                mult = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "second": 1.0}[units[hdr.index(key)]]
+                return float(d[key].replace(",", "") or 0) * mult
+            traffic = in_bytes("dram__bytes_read.sum") + in_bytes("dram__bytes_write.sum")
+            t = in_seconds("gpu__time_duration.sum")
+            print(f"   DRAM traffic (read+write) = {traffic:.0f} B per launch; duration {t * 1e6:.2f} us under ncu "
+                  f"-> {traffic / t / 1e9:.0f} GB/s of DRAM traffic")
 
 if __name__ == "__main__":
     main()
