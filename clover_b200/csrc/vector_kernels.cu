@@ -130,8 +130,17 @@ static int launch_vquantize(const float *x, uint64_t n_pad, int8_t *values, floa
                             cudaStream_t stream) {
     const uint64_t nblocks = n_pad / kBlock;
     if (nblocks == 0) return CLOVER_OK;
-    // enough threads for ~6 resident CTAs per SM, then R consecutive blocks per thread
-    const uint64_t max_threads = (uint64_t)sm_count() * 6 * kQThreads;
+    // exactly ONE wave: as many thread slots as can be resident (registers allow 4 CTAs per SM; asked from the
+    // occupancy calculator, not assumed), then R consecutive blocks per thread. A second, partly filled wave
+    // cost 30% at n = 2^26 (profiles/r01_quantize4_ncu_summary.txt: 1.39 waves).
+    static int ctas_per_sm[2] = {0, 0};
+    int &cps = ctas_per_sm[key_host != nullptr];
+    if (cps == 0) {
+        cudaError_t e = key_host ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vquantize<BITS, true>, kQThreads, 0)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vquantize<BITS, false>, kQThreads, 0);
+        if (e != cudaSuccess || cps < 1) cps = 1;
+    }
+    const uint64_t max_threads = (uint64_t)sm_count() * cps * kQThreads;
     const uint64_t R = (nblocks + max_threads - 1) / max_threads;
     const uint64_t threads = (nblocks + R - 1) / R;
     const unsigned grid = (unsigned)((threads + kQThreads - 1) / kQThreads);
