@@ -34,6 +34,9 @@ _SIGNATURES = {
     "clover_copy_d2h": (_int, [_vp, _vp, C.c_size_t, _vp]),
     "clover_copy_d2d": (_int, [_vp, _vp, C.c_size_t, _vp]),
     "clover_stream_sync": (_int, [_vp]),
+    "clover_ipc_export": (_int, [_vp, _vp]),
+    "clover_ipc_import": (_int, [_vp, C.POINTER(_vp)]),
+    "clover_ipc_close": (_int, [_vp]),
     "clover_prng_init": (_int, [_u64, _u64, _vp]),
     "clover_prng_next": (_int, [_vp, _vp]),
     "clover_prng_skip": (_int, [_vp, _u64]),
@@ -47,6 +50,7 @@ _SIGNATURES = {
     "clover_m4_mvm": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "clover_m4_mvm_f32": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     "clover_m4_mvm_shard": (_int, [_vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "clover_m4_mvm_shard_fused": (_int, [_vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, C.c_uint32, _vp, _vp]),
     "clover_v4_requantize_mvm": (_int, [_vp, _u64, _vp, _vp, _vp, _vp]),
     "clover_m4_gemm": (_int, [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _vp, _u64, _vp]),
     "clover_m4_expand_e4m3": (_int, [_vp, _u64, _u64, _vp, _vp]),

@@ -109,10 +109,24 @@ static int launch_mquantize(const float *a, uint64_t rows, uint64_t cols, int8_t
 // Called by the first 64 threads of a CTA with y = the fp32 result of row (64*rb + i).
 // 4-bit: the reference stores block_values pre-transposed, so element i takes the noise slot
 // (call (i%8)/4, byte i%4, word i/8); 8-bit keeps the natural slot (call i/32, byte (i%32)/8, word i%8).
+// Multi-GPU fused exchange: the peers' result vectors, mapped into this process (CUDA IPC over
+// NVLink). The re-quantizer stores each finished block to every peer as well, the last CTA of the kernel then
+// raises flags[peer][rank] = epoch on every peer and waits for the peers' flags - one kernel, no NCCL call.
+constexpr int kMaxPeers = 8;
+struct PeerOut {
+    int world = 1, rank = 0;
+    uint32_t epoch = 0;
+    unsigned int *ticket = nullptr;          // local: CTAs of this rank that are done
+    int8_t *yv[kMaxPeers] = {};              // peer p's result values / scales (entry `rank` unused: yv/ys are local)
+    float *ys[kMaxPeers] = {};
+    uint32_t *flags[kMaxPeers] = {};         // peer p's flag array, one word per source rank
+};
+
 template <int BITS, bool STOCH>
 __device__ __forceinline__ void requantize_block(float y, int i, uint64_t rb, int8_t *__restrict__ yv,
                                                  float *__restrict__ ys, const Key4 &key,
-                                                 const uint64_t *__restrict__ tables, float *smem_f, int *smem_q) {
+                                                 const uint64_t *__restrict__ tables, float *smem_f, int *smem_q,
+                                                 const PeerOut *peers = nullptr) {
     constexpr float kQmax = BITS == 4 ? 7.0f : 127.0f;
     float m = warp_max(fabsf(y));
     if ((i & 31) == 0) smem_f[i >> 5] = m;
@@ -132,10 +146,19 @@ __device__ __forceinline__ void requantize_block(float y, int i, uint64_t rb, in
     smem_q[i] = quant_one(y, scale, rnd);
     asm volatile("bar.sync 1, 64;");
     if (BITS == 4) {
-        if (i < 8) reinterpret_cast<uint32_t *>(yv + rb * 32)[i] = pack8_nibbles(smem_q + 8 * i);
+        if (i < 8) {
+            const uint32_t w = pack8_nibbles(smem_q + 8 * i);
+            reinterpret_cast<uint32_t *>(yv + rb * 32)[i] = w;
+            if (peers)
+                for (int p = 0; p < peers->world; ++p)
+                    if (p != peers->rank) reinterpret_cast<uint32_t *>(peers->yv[p] + rb * 32)[i] = w;     // NVLink store
+        }
     } else {
         if (i < 16) reinterpret_cast<uint32_t *>(yv + rb * 64)[i] = pack4_bytes(smem_q + 4 * i);
     }
+    if (peers && i == 0)
+        for (int p = 0; p < peers->world; ++p)
+            if (p != peers->rank) peers->ys[p][rb] = m;
 }
 
 // =============================================================================================
@@ -309,7 +332,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1)
 k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows_local,
              uint64_t cols, uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
              float *__restrict__ y32, int8_t *__restrict__ yv, float *__restrict__ ys, Key4 key,
-             const uint64_t *__restrict__ tables) {
+             const uint64_t *__restrict__ tables, const __grid_constant__ PeerOut peers) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     GemvSmem &sm = *reinterpret_cast<GemvSmem *>(smem_raw);
 
@@ -418,7 +441,32 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
             if (tid < 64) {
                 const float y = sm.ysm[tid];
                 if (y32) y32[(rowblock0 + rb) * 64 + tid] = y;
-                if (yv) requantize_block<4, STOCH>(y, tid, rowblock0 + rb, yv, ys, key, tables, sm.red_f, sm.red_q);
+                if (yv) requantize_block<4, STOCH>(y, tid, rowblock0 + rb, yv, ys, key, tables, sm.red_f, sm.red_q,
+                                                   peers.world > 1 ? &peers : nullptr);
+            }
+        }
+        if (peers.world > 1) {
+            // every thread that stored to a peer makes those stores visible system-wide, the CTA takes a ticket,
+            // and the LAST CTA of this rank publishes "rank done with epoch" on all peers, then waits for theirs:
+            // when this kernel has finished, the slices of all ranks have landed in the local result vector.
+            if (tid < 64) __threadfence_system();
+            named_bar_sync(2, kGemvConsumers);
+            if (tid == 0) {
+                const unsigned int t = atomicAdd(peers.ticket, 1u);
+                if (t == gridDim.x - 1) {
+                    *peers.ticket = 0u;
+                    __threadfence_system();
+                    for (int p = 0; p < peers.world; ++p)
+                        if (p != peers.rank)
+                            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.flags[p] + peers.rank), "r"(peers.epoch) : "memory");
+                    for (int q = 0; q < peers.world; ++q) {
+                        if (q == peers.rank) continue;
+                        uint32_t seen;
+                        do {
+                            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(peers.flags[peers.rank] + q) : "memory");
+                        } while ((int32_t)(seen - peers.epoch) < 0);
+                    }
+                }
             }
         }
     }
@@ -540,7 +588,7 @@ k_requantize_mvm(const float *__restrict__ y32, uint64_t nblocks, int8_t *__rest
 template <int BITS>
 static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_local, uint64_t cols, uint64_t row0,
                       const int8_t *xv, const float *xs, float *y32, int8_t *yv, float *ys, const uint64_t *key_host,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const PeerOut *peers = nullptr) {
     const uint64_t nrb = rows_local >> 6;
     if (nrb == 0 || cols == 0) return CLOVER_OK;
     const unsigned grid = (unsigned)nrb;
@@ -557,7 +605,7 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
     if (BITS == 4) {
         static const bool force_simple = getenv("CLOVER_GEMV_IMPL") && !strcmp(getenv("CLOVER_GEMV_IMPL"), "simple");
         // bulk copies need 16 B aligned rows; anything else takes the plain-load kernel (same arithmetic)
-        const bool simple = force_simple || (reinterpret_cast<uintptr_t>(values) & 15u) != 0;
+        const bool simple = (force_simple || (reinterpret_cast<uintptr_t>(values) & 15u) != 0) && !peers;
         if (simple) {
             if (stoch) k_m4_mvm<true><<<grid, kMvmThreads, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
             else       k_m4_mvm<false><<<grid, kMvmThreads, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
@@ -574,7 +622,7 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
             if (rc != CLOVER_OK) return rc;
             const unsigned pgrid = (unsigned)(nrb < (uint64_t)sm_count() ? nrb : (uint64_t)sm_count());
             kern<<<pgrid, kGemvThreads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys,
-                                                        key, tables);
+                                                        key, tables, peers ? *peers : PeerOut());
         }
     } else {
         if (stoch) k_m8_mvm<true><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
@@ -637,6 +685,28 @@ int clover_m4_mvm_shard(const int8_t *values_local, const float *scales_local, u
     // it once by 2 * total_rows / 64 (clover_prng_skip), so every rank stays on the reference's stream.
     return launch_mvm<4>(values_local, scales_local, rows_local, cols, row0, xv, xs, y32_full,
                          yv_full, ys_full, key_host, (cudaStream_t)stream);
+}
+
+int clover_m4_mvm_shard_fused(const int8_t *values_local, const float *scales_local, uint64_t rows_local, uint64_t cols,
+                              uint64_t row0, const int8_t *xv, const float *xs, int8_t *const *peer_yv_host,
+                              float *const *peer_ys_host, uint32_t *const *peer_flags_host, unsigned int *ticket,
+                              int world, int rank, uint32_t epoch, uint64_t *key_host, void *stream) {
+    CLOVER_REQUIRE(values_local && scales_local && xv && xs && peer_yv_host && peer_ys_host && peer_flags_host && ticket,
+                   CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, CLOVER_ERR_INVALID, "bad world / rank (at most 8 peers)");
+    CLOVER_REQUIRE(rows_local % 64u == 0 && row0 % 64u == 0 && cols % 128u == 0, CLOVER_ERR_INVALID,
+                   "shards are whole 64-row blocks; cols a multiple of 128");
+    CLOVER_REQUIRE(rows_local > 0, CLOVER_ERR_UNSUPPORTED, "every rank must own at least one 64-row block (a rank without work could not signal)");
+    CLOVER_REQUIRE((reinterpret_cast<uintptr_t>(values_local) & 15u) == 0, CLOVER_ERR_UNSUPPORTED, "values_local must be 16-byte aligned");
+    PeerOut peers;
+    peers.world = world; peers.rank = rank; peers.epoch = epoch; peers.ticket = ticket;
+    for (int p = 0; p < world; ++p) {
+        CLOVER_REQUIRE(peer_yv_host[p] && peer_ys_host[p] && peer_flags_host[p], CLOVER_ERR_INVALID, "null peer pointer");
+        peers.yv[p] = peer_yv_host[p]; peers.ys[p] = peer_ys_host[p]; peers.flags[p] = peer_flags_host[p];
+    }
+    // own slice goes through the ordinary local pointers; the stream position of key_host follows clover_m4_mvm_shard
+    return launch_mvm<4>(values_local, scales_local, rows_local, cols, row0, xv, xs, nullptr, peers.yv[rank], peers.ys[rank],
+                         key_host, (cudaStream_t)stream, &peers);
 }
 
 int clover_v4_requantize_mvm(const float *y32, uint64_t rows, int8_t *yv, float *ys, uint64_t *key_host, void *stream) {

@@ -233,4 +233,26 @@ int clover_prng_skip(uint64_t *key_host, uint64_t ncalls) {
     return CLOVER_OK;
 }
 
+// ---- peer memory (CUDA IPC): how one process per GPU maps the other ranks' result vectors for the fused exchange ----
+int clover_ipc_export(void *dev_ptr, unsigned char *handle64) {
+    CLOVER_REQUIRE(dev_ptr && handle64, CLOVER_ERR_INVALID, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CLOVER_CUDA_CHECK(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle64, &h, 64);
+    return CLOVER_OK;
+}
+int clover_ipc_import(const unsigned char *handle64, void **dev_ptr) {
+    CLOVER_REQUIRE(dev_ptr && handle64, CLOVER_ERR_INVALID, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CLOVER_CUDA_CHECK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CLOVER_OK;
+}
+int clover_ipc_close(void *dev_ptr) {
+    CLOVER_REQUIRE(dev_ptr, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_CUDA_CHECK(cudaIpcCloseMemHandle(dev_ptr));
+    return CLOVER_OK;
+}
+
 }  // extern "C"

@@ -12,6 +12,12 @@ own rows, and ONE collective on the fp32 output makes the full vector visible ev
 After the exchange every rank re-quantizes the full fp32 vector with the mvm epilogue
 (include/CloverMatrix4.h:925-1080), so all ranks hold the same CloverVector4 the single-GPU call returns -
 bit-for-bit, because the fp32 row results do not depend on the sharding.
+
+  * ``exchange="fused"``: no collective call at all. Re-quantization blocks are 64 rows and shards are whole
+    blocks, so each rank's GEMV kernel re-quantizes its own blocks and its epilogue stores them (36 bytes per
+    block) directly into every peer's result vector over NVLink (peer memory mapped with CUDA IPC), then
+    signals and waits on per-rank flags (``clover_m4_mvm_shard_fused``). One kernel per step and rank; the
+    same bytes as the single-GPU call.
 """
 from __future__ import annotations
 
@@ -76,6 +82,84 @@ class ShardedCloverMatrix4:
         self._even = len(set(sizes)) == 1
         self._sizes = sizes
         self.key = None
+        self._peer = None
+        if exchange == "fused":
+            self._setup_peer_memory()
+
+    # ---- fused exchange: one IPC-shared block per rank = [values x2 | scales x2 | flags | ticket] ------------------
+    @staticmethod
+    def peer_block_layout(rows: int, world: int):
+        """Byte offsets inside a rank's shared block: two result buffers (alternating by epoch), flags, ticket."""
+        al = lambda n: (n + 255) // 256 * 256
+        vb, sb = al(rows // 2), al(rows // 64 * 4)
+        off = {"yv": (0, vb), "ys": (2 * vb, 2 * vb + sb), "flags": 2 * vb + 2 * sb}
+        off["ticket"] = off["flags"] + al(4 * world)
+        off["bytes"] = off["ticket"] + 256
+        return off
+
+    def _setup_peer_memory(self) -> None:
+        from ._lib import lib
+        if self.world > 8:
+            raise ValueError("fused exchange: one node, at most 8 ranks")
+        if self.rows_local == 0:
+            raise ValueError("fused exchange: every rank needs at least one 64-row block")
+        lay = self.peer_block_layout(self.rows, self.world)
+        base = C.c_void_p()
+        call("clover_malloc", C.byref(base), C.c_size_t(lay["bytes"]))
+        call("clover_memset", base, 0, C.c_size_t(lay["bytes"]), None)
+        call("clover_stream_sync", None)
+        handle = (C.c_ubyte * 64)()
+        call("clover_ipc_export", base, handle)
+        bases = [None] * self.world
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=self.group)
+            for p, h in enumerate(handles):
+                if p == self.rank:
+                    bases[p] = base.value
+                else:
+                    ptr = C.c_void_p()
+                    call("clover_ipc_import", (C.c_ubyte * 64).from_buffer_copy(h), C.byref(ptr))
+                    bases[p] = ptr.value
+            dist.barrier(group=self.group)
+        else:
+            bases[0] = base.value
+        arr = lambda f: (C.c_void_p * self.world)(*[f(b) for b in bases])
+        self._peer = {
+            "lay": lay, "base": base.value, "bases": bases, "epoch": 0,
+            "yv": [arr(lambda b, k=k: b + lay["yv"][k]) for k in (0, 1)],
+            "ys": [arr(lambda b, k=k: b + lay["ys"][k]) for k in (0, 1)],
+            "flags": arr(lambda b: b + lay["flags"]),
+            "ticket": C.c_void_p(base.value + lay["ticket"]),
+        }
+
+    def close(self) -> None:
+        """Unmap the peers' blocks and free this rank's (collective: every rank calls it)."""
+        if self._peer is None:
+            return
+        if self.world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+        for p, b in enumerate(self._peer["bases"]):
+            if p != self.rank:
+                call("clover_ipc_close", C.c_void_p(b))
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        call("clover_free", C.c_void_p(self._peer["base"]))
+        self._peer = None
+
+    def _mvm_fused(self, x: CloverVector4, y: CloverVector4, key_ptr) -> None:
+        pr = self._peer
+        pr["epoch"] += 1
+        k = pr["epoch"] & 1
+        call("clover_m4_mvm_shard_fused", _ptr(self.local.values), _ptr(self.local.scales), C.c_uint64(self.rows_local),
+             C.c_uint64(self.cols), C.c_uint64(self.row0), _ptr(x.values), _ptr(x.scales), pr["yv"][k], pr["ys"][k],
+             pr["flags"], pr["ticket"], self.world, self.rank, C.c_uint32(pr["epoch"]), key_ptr, _stream())
+        lay = pr["lay"]
+        call("clover_copy_d2d", _ptr(y.values), C.c_void_p(pr["base"] + lay["yv"][k]), C.c_size_t(self.rows // 2), _stream())
+        call("clover_copy_d2d", _ptr(y.scales), C.c_void_p(pr["base"] + lay["ys"][k]), C.c_size_t(self.rows // 64 * 4), _stream())
+        if key_ptr is not None:      # the kernel read the key at each block's global position; advance it like the reference
+            call("clover_prng_skip", key_ptr, C.c_uint64(2 * (self.rows // 64)))
 
     def load_shard(self, values, scales) -> None:
         """values/scales of this rank's rows in the reference layout (rows_local*cols/2 bytes, tile-row scales)."""
@@ -88,6 +172,8 @@ class ShardedCloverMatrix4:
         if x.size() != self.cols or y.size_pad() != self.rows:
             raise CloverSizeError("MVM can not be performed.")
         key_ptr = None if self.key is None else self.key.ctypes.data_as(C.c_void_p)
+        if self.exchange == "fused":
+            return self._mvm_fused(x, y, key_ptr)
         if self.exchange == "allreduce":
             self.y32.zero_()
         if self.rows_local:

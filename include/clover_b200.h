@@ -73,6 +73,11 @@ int clover_copy_d2h(void *host_dst, const void *dev_src, size_t bytes, void *str
 int clover_copy_d2d(void *dev_dst, const void *dev_src, size_t bytes, void *stream);
 int clover_stream_sync(void *stream);
 
+/* ---- peer memory: map another rank's clover_malloc'ed buffer into this process (cudaIpc*), 64-byte handles ----- */
+int clover_ipc_export(void *dev_ptr, unsigned char *handle64);
+int clover_ipc_import(const unsigned char *handle64, void **dev_ptr);
+int clover_ipc_close(void *dev_ptr);
+
 /* ---- PRNG state on the host (include/simdxorshift128plus.h, include/CloverRandom.h) ------------- */
 int clover_prng_init(uint64_t key1, uint64_t key2, uint64_t *key_host);   /* avx_xorshift128plus_init :81-92 */
 int clover_prng_next(uint64_t *key_host, uint32_t *out8);                 /* avx_xorshift128plus      :97-109 */
@@ -115,6 +120,19 @@ int clover_m4_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, 
 int clover_m4_mvm_shard(const int8_t *values_local, const float *scales_local, uint64_t rows_local, uint64_t cols,
                         uint64_t row0, const int8_t *xv, const float *xs, float *y32_full,
                         int8_t *yv_full, float *ys_full, uint64_t *key_host, void *stream);
+/* Fused multi-GPU exchange ("fused NVLink-store epilogue"): like clover_m4_mvm_shard, but the kernel's
+ * epilogue stores every finished 64-row block of the re-quantized result (32 B of nibbles + one fp32 scale) straight
+ * into the result vector of EVERY rank over NVLink, then the rank's last CTA raises flags[rank] = epoch on all peers and
+ * waits for theirs. When the call has completed in stream order, the full CloverVector4 result is present on this
+ * rank - no NCCL collective, no separate re-quantize pass. peer_*_host: HOST arrays of `world` device pointers
+ * (entry p = rank p's full-length result values / scales and its `world`-word flag array, mapped with
+ * clover_ipc_import; entry `rank` = this rank's own buffers). `ticket`: one zero-initialised device word, local.
+ * `epoch` must increase by one per call; use two result buffers alternately if a rank may read its result while a
+ * faster peer already runs the next call. One node, at most 8 ranks, every rank owns >= 1 row block. */
+int clover_m4_mvm_shard_fused(const int8_t *values_local, const float *scales_local, uint64_t rows_local, uint64_t cols,
+                              uint64_t row0, const int8_t *xv, const float *xs, int8_t *const *peer_yv_host,
+                              float *const *peer_ys_host, uint32_t *const *peer_flags_host, unsigned int *ticket,
+                              int world, int rank, uint32_t epoch, uint64_t *key_host, void *stream);
 /* Requantize a full-length fp32 vector exactly like the tail of mvm (include/CloverMatrix4.h:925-1080):
  * used after the collective so that every rank holds the same CloverVector4 result. */
 int clover_v4_requantize_mvm(const float *y32, uint64_t rows, int8_t *yv, float *ys, uint64_t *key_host, void *stream);

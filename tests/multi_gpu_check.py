@@ -1,0 +1,58 @@
+"""Multi-GPU check, launched by torchrun (one rank per GPU): the row-sharded mvm with every exchange mode
+("fused" NVLink-store epilogue, "allgather", "allreduce") returns, on EVERY rank, the bytes of the single-GPU
+CloverMatrix4::mvm of the whole matrix. Several steps per mode (epochs / double buffering of the fused path),
+even and ragged shardings. Prints "multi-gpu ok" on rank 0; any mismatch raises.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import random_nibbles  # noqa: E402
+from clover_b200 import containers as cb  # noqa: E402
+from clover_b200.sharded import ShardedCloverMatrix4  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    for rows, cols in [(1024, 2048), (64 * 7 + 64, 1152), (8192, 8192)]:
+        rows += (-rows) % 128
+        g = torch.Generator(device=dev).manual_seed(7)                    # identical full matrix on every rank
+        full = cb.CloverMatrix4(rows, cols)
+        full.values.copy_(random_nibbles(torch, rows * cols // 2, g, dev))
+        full.scales.uniform_(0.05, 4.0, generator=g)
+        xs = []
+        for _ in range(5):
+            v = cb.CloverVector32(cols); v.values.uniform_(-1, 1, generator=g)
+            q = cb.CloverVector4(cols); q.quantize(v); xs.append(q)
+        want = []
+        for q in xs:
+            y = cb.CloverVector4(rows); full.mvm(q, y); want.append((y.values.clone(), y.scales.clone()))
+        for mode in ("fused", "allgather", "allreduce"):
+            A = ShardedCloverMatrix4(rows, cols, exchange=mode)
+            hb = cols // 64
+            A.load_shard(full.values[A.row0 * cols // 2:(A.row0 + A.rows_local) * cols // 2],
+                         full.scales[(A.row0 // 64) * hb:((A.row0 + A.rows_local) // 64) * hb])
+            for q, (wv, ws) in zip(xs, want):
+                y = cb.CloverVector4(rows)
+                A.mvm(q, y)
+                torch.cuda.synchronize()
+                assert torch.equal(y.values, wv), (mode, rows, cols, rank, "values")
+                assert torch.equal(y.scales.view(torch.int32)[: rows // 64], ws.view(torch.int32)[: rows // 64]), (mode, rows, cols, rank, "scales")
+            A.close()
+        dist.barrier()
+    if rank == 0:
+        print("multi-gpu ok: fused / allgather / allreduce == single-GPU mvm on", world, "ranks")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
