@@ -15,8 +15,10 @@ than the 126 MB L2, so every step streams it from HBM ("inputs larger than L2").
   cpu_baseline = the reference's own mvm_parallel (oracle/_ref, compiled from /root/reference) on this host
   extras     = the other BASELINE.json configs (C1, C2, C4, C5), each timed with CUDA events
 
-N > 1 (torchrun, one rank per GPU): rows sharded in 64-row blocks, one NCCL allreduce of the fp32 output per step
-(north_star), total work fixed -> "scaling": "strong".
+N > 1 (torchrun, one rank per GPU): rows sharded in 64-row blocks, total work fixed -> "scaling": "strong". The exchange
+step is, by default, FUSED into the GEMV kernel: its epilogue stores each re-quantized 64-row block into every peer's
+result vector over NVLink and synchronises with flags (no NCCL call, one kernel per step and rank);
+`--exchange allreduce` is north_star's single NCCL allreduce of the fp32 output, `--exchange allgather` its cheaper twin.
 
 `--impl reference` times the reference CPU implementation of the same path instead (rank 0 only).
 """
@@ -290,7 +292,7 @@ def main():
     ap.add_argument("--impl", default="clover_b200", choices=["clover_b200", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS)
     ap.add_argument("--cols", type=int, default=COLS)
-    ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "allgather"])
+    ap.add_argument("--exchange", default="fused", choices=["fused", "allgather", "allreduce"])
     ap.add_argument("--cpu-sample-rows", type=int, default=8192)
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -330,9 +332,13 @@ def main():
     A.local.scales.uniform_(0.25, 1.0, generator=gm)
     torch.cuda.synchronize()
 
+    out = {"y": y}
+
     def step():
         if world == 1:
             A.local.mvm(x, y)          # the reference-facing call: CloverMatrix4::mvm(V4, V4), one fused kernel
+        elif args.exchange == "fused":
+            out["y"] = A.mvm(x)        # one kernel: shard GEMV + NVLink-store epilogue; result = view of the shared vector
         else:
             A.mvm(x, y)                # shard kernel + NCCL exchange + re-quantize
 
@@ -387,8 +393,8 @@ def main():
         x.values.copy_(hx_v, non_blocking=True)
         x.scales.copy_(hx_s, non_blocking=True)
         step()
-        hy_v.copy_(y.values, non_blocking=True)
-        hy_s.copy_(y.scales, non_blocking=True)
+        hy_v.copy_(out["y"].values, non_blocking=True)
+        hy_s.copy_(out["y"].scales[: hy_s.numel()], non_blocking=True)
         torch.cuda.current_stream().synchronize()         # the caller reads the result of every step
 
     for _ in range(args.warmup):
@@ -417,7 +423,10 @@ def main():
                        "rounding": "stochastic rounding disabled (parity configuration)",
                        "l2_policy": "inputs larger than L2 (2 GiB matrix streamed per step vs 126 MB L2)",
                        "parallelism": "1 GPU" if world == 1 else
-                                      f"rows sharded over {world} GPUs in 64-row blocks + one NCCL {args.exchange} of the fp32 output",
+                                      (f"rows sharded over {world} GPUs in 64-row blocks; fused exchange: the GEMV epilogue stores each "
+                                       f"re-quantized block into every peer's result vector over NVLink (no NCCL call)"
+                                       if args.exchange == "fused" else
+                                       f"rows sharded over {world} GPUs in 64-row blocks + one NCCL {args.exchange} of the fp32 output"),
                        "e2e": "x copied from pinned host memory and y read back every step; matrix resident in HBM"},
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(ms2.item()) / args.steps, "wall_ms_per_step": wall / args.steps * 1e3},

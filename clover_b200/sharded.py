@@ -125,7 +125,20 @@ class ShardedCloverMatrix4:
         else:
             bases[0] = base.value
         arr = lambda f: (C.c_void_p * self.world)(*[f(b) for b in bases])
+
+        class _Raw:                      # device memory of this rank's block as a torch tensor (zero copy)
+            def __init__(self, ptr, nbytes, typestr):
+                item = 1 if typestr == "|i1" else 4
+                self.__cuda_array_interface__ = {"shape": (nbytes // item,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+        dev = self.local.values.device
+        views = []
+        for k in (0, 1):                 # the two result vectors as borrowing CloverVector4 views (CloverVector4.h:114-119)
+            v = torch.as_tensor(_Raw(base.value + lay["yv"][k], self.rows // 2, "|i1"), device=dev)
+            sc = torch.as_tensor(_Raw(base.value + lay["ys"][k], self.rows // 64 * 4, "<f4"), device=dev)
+            views.append(CloverVector4(self.rows, v, sc, device=dev))
         self._peer = {
+            "views": views,
             "lay": lay, "base": base.value, "bases": bases, "epoch": 0,
             "yv": [arr(lambda b, k=k: b + lay["yv"][k]) for k in (0, 1)],
             "ys": [arr(lambda b, k=k: b + lay["ys"][k]) for k in (0, 1)],
@@ -148,7 +161,9 @@ class ShardedCloverMatrix4:
         call("clover_free", C.c_void_p(self._peer["base"]))
         self._peer = None
 
-    def _mvm_fused(self, x: CloverVector4, y: CloverVector4, key_ptr) -> None:
+    def _mvm_fused(self, x: CloverVector4, y, key_ptr):
+        """y = None: returns a CloverVector4 VIEW of the shared result buffer of this step (valid until the step
+        after next) - no copy at all; otherwise the result is copied into the caller's vector."""
         pr = self._peer
         pr["epoch"] += 1
         k = pr["epoch"] & 1
@@ -156,10 +171,13 @@ class ShardedCloverMatrix4:
              C.c_uint64(self.cols), C.c_uint64(self.row0), _ptr(x.values), _ptr(x.scales), pr["yv"][k], pr["ys"][k],
              pr["flags"], pr["ticket"], self.world, self.rank, C.c_uint32(pr["epoch"]), key_ptr, _stream())
         lay = pr["lay"]
-        call("clover_copy_d2d", _ptr(y.values), C.c_void_p(pr["base"] + lay["yv"][k]), C.c_size_t(self.rows // 2), _stream())
-        call("clover_copy_d2d", _ptr(y.scales), C.c_void_p(pr["base"] + lay["ys"][k]), C.c_size_t(self.rows // 64 * 4), _stream())
         if key_ptr is not None:      # the kernel read the key at each block's global position; advance it like the reference
             call("clover_prng_skip", key_ptr, C.c_uint64(2 * (self.rows // 64)))
+        if y is None:
+            return pr["views"][k]
+        call("clover_copy_d2d", _ptr(y.values), C.c_void_p(pr["base"] + lay["yv"][k]), C.c_size_t(self.rows // 2), _stream())
+        call("clover_copy_d2d", _ptr(y.scales), C.c_void_p(pr["base"] + lay["ys"][k]), C.c_size_t(self.rows // 64 * 4), _stream())
+        return y
 
     def load_shard(self, values, scales) -> None:
         """values/scales of this rank's rows in the reference layout (rows_local*cols/2 bytes, tile-row scales)."""
@@ -168,9 +186,11 @@ class ShardedCloverMatrix4:
         self.local.values[:nb].copy_(torch.as_tensor(values).view(torch.int8).reshape(-1)[:nb])
         self.local.scales[:ns].copy_(torch.as_tensor(scales).reshape(-1)[:ns])
 
-    def mvm(self, x: CloverVector4, y: CloverVector4) -> None:
-        if x.size() != self.cols or y.size_pad() != self.rows:
+    def mvm(self, x: CloverVector4, y: CloverVector4 = None):
+        if x.size() != self.cols or (y is not None and y.size_pad() != self.rows):
             raise CloverSizeError("MVM can not be performed.")
+        if y is None and self.exchange != "fused":
+            y = CloverVector4(self.rows, device=self.device)
         key_ptr = None if self.key is None else self.key.ctypes.data_as(C.c_void_p)
         if self.exchange == "fused":
             return self._mvm_fused(x, y, key_ptr)
@@ -183,3 +203,4 @@ class ShardedCloverMatrix4:
         exchange_fp32(self.y32, self.row0, self.rows_local, self._sizes, self.exchange, self.group)
         call("clover_v4_requantize_mvm", _ptr(self.y32), C.c_uint64(self.rows), _ptr(y.values), _ptr(y.scales),
              key_ptr, _stream())
+        return y
