@@ -43,6 +43,8 @@ _SIGNATURES = {
     "clover_v4_quantize": (_int, [_vp, _u64, _vp, _vp, _vp, _vp]),
     "clover_v4_restore": (_int, [_vp, _vp, _u64, _vp, _vp]),
     "clover_v4_dot": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _int, _vp]),
+    "clover_v4_scale_and_add": (_int, [_vp, _vp, _vp, _vp, C.c_float, _u64, _vp, _vp, _vp, _vp]),
+    "clover_v8_scale_and_add": (_int, [_vp, _vp, _vp, _vp, C.c_float, _u64, _vp, _vp, _vp, _vp]),
     "clover_v8_quantize": (_int, [_vp, _u64, _vp, _vp, _vp, _vp]),
     "clover_v8_restore": (_int, [_vp, _vp, _u64, _vp, _vp]),
     "clover_v8_dot": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _int, _vp]),

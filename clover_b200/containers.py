@@ -145,6 +145,15 @@ class _QVector(_Keyed):
              C.c_uint64(self.length_pad), _ptr(out), C.c_int(mode), _stream())
         return float(out.item())
 
+    def scaleAndAdd(self, other, a: float, result=None) -> None:
+        """this = this + a * other (in place) or result = this + a * other, re-quantized block by block
+        (include/CloverVector4.h:1195-1218, CloverVector8.h:1063-1086). Uses THIS object's PRNG key."""
+        dst = self if result is None else result
+        if other.size_pad() != self.length_pad or dst.size_pad() != self.length_pad:
+            raise CloverSizeError("Vectors do not have the same size.")
+        call(f"clover_v{self.BITS}_scale_and_add", _ptr(self.values), _ptr(self.scales), _ptr(other.values), _ptr(other.scales),
+             C.c_float(a), C.c_uint64(self.length_pad), _ptr(dst.values), _ptr(dst.scales), self._key_ptr(), _stream())
+
     def dot_device(self, other, out, mode: int = DOT_AUTO) -> None:
         """dot() without the device->host read: result lands in the 1-element CUDA tensor ``out``."""
         call(f"clover_v{self.BITS}_dot", _ptr(self.values), _ptr(self.scales), _ptr(other.values), _ptr(other.scales),

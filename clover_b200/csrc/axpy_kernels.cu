@@ -1,0 +1,173 @@
+// axpy_kernels.cu - CloverVector4 / CloverVector8 :: scaleAndAdd, the quantized AXPY  r = requantize(u + a * v).
+//
+// Reference: include/CloverVector4.h:1222-1478, include/CloverVector8.h:1089-1357 (the step either
+// side of mvm in the IHT / gradient-descent loops, test/performance/01_measure.h:940-944). Per block of 64:
+//     su_ps = su[b] / 7,  sv_ps = (sv[b] * a) / 7                     (IEEE divides; 127 for 8-bit)
+//     value = fma(float(qv), sv_ps, float(qu) * su_ps)
+//     m = absmax(value), zero guard, scale = 7 / m, q = sign * trunc(fma(|value|, scale, noise)), pack; sr[b] = m
+// One HBM pass (1.6875 B/element for 4-bit, 3.1875 for 8-bit, the reference's getBytes() model). One thread owns one
+// block at a time (grid-stride), so r may alias u exactly like the reference's two-argument form.
+//
+// Stochastic rounding: the SIMD code peels nibbles by POSITION inside each 32-bit word, so element e of a 4-bit
+// block takes noise slot (call p / 4, byte p % 4, lane e / 8) with p = 2 * ((e / 2) % 4) + (e even); an 8-bit element
+// takes (call e / 32, byte e % 4, lane (e % 32) / 4). The thread jumps the object's XORShift stream to 2 * block.
+#include "common.cuh"
+#include "runtime.cuh"
+
+namespace clover {
+
+__device__ __forceinline__ uint32_t prmt_b(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// byte j of `biased` (a value 0..255 that encodes x + bias) -> float(x), without I2F: splice the byte under the
+// bits of 1.5 * 2^23 and subtract 12582912 + bias (exact).
+template <int J>
+__device__ __forceinline__ float byte_to_float(uint32_t biased, float magic_plus_bias) {
+    const uint32_t bits = prmt_b(biased, 0x4B400000u, 0x7650u | J);        // {magic[3], magic[2], magic[1], biased[J]}
+    return __fadd_rn(__uint_as_float(bits), -magic_plus_bias);
+}
+
+template <int BITS, bool STOCH>
+__global__ void __launch_bounds__(256)
+k_vscale_add(const uint32_t *u, const float *su, const uint32_t *__restrict__ v,       // u / su may alias r / sr (in place)
+             const float *__restrict__ sv, float a, uint64_t nblocks, uint32_t *r, float *sr, Key4 key,
+             const uint64_t *__restrict__ tables) {
+    constexpr float kQmax = BITS == 4 ? 7.0f : 127.0f;
+    constexpr int kWords = BITS == 4 ? 8 : 16;                    // 32-bit words per block
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t blk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; blk < nblocks; blk += stride) {
+        const float su_ps = __fdiv_rn(su[blk], kQmax);
+        const float sv_ps = __fdiv_rn(__fmul_rn(sv[blk], a), kQmax);
+        uint32_t wu[kWords], wv[kWords];
+#pragma unroll
+        for (int i = 0; i < kWords / 4; ++i) {
+            const uint4 x = reinterpret_cast<const uint4 *>(u + blk * kWords)[i];
+            const uint4 y = reinterpret_cast<const uint4 *>(v + blk * kWords)[i];
+            wu[4 * i] = x.x; wu[4 * i + 1] = x.y; wu[4 * i + 2] = x.z; wu[4 * i + 3] = x.w;
+            wv[4 * i] = y.x; wv[4 * i + 1] = y.y; wv[4 * i + 2] = y.z; wv[4 * i + 3] = y.w;
+        }
+        float val[64];
+        if (BITS == 4) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                // q + 8 per nibble; even elements sit in the HIGH nibbles (byte j: elements 8w+2j, 8w+2j+1)
+                const uint32_t bu = wu[w] ^ 0x88888888u, bv = wv[w] ^ 0x88888888u;
+                const uint32_t uh = (bu >> 4) & 0x0F0F0F0Fu, ul = bu & 0x0F0F0F0Fu;
+                const uint32_t vh = (bv >> 4) & 0x0F0F0F0Fu, vl = bv & 0x0F0F0F0Fu;
+#define CLOVER_AXPY4(J)                                                                                              \
+                val[8 * w + 2 * J]     = __fmaf_rn(byte_to_float<J>(vh, 12582920.0f), sv_ps,                          \
+                                                   __fmul_rn(byte_to_float<J>(uh, 12582920.0f), su_ps));             \
+                val[8 * w + 2 * J + 1] = __fmaf_rn(byte_to_float<J>(vl, 12582920.0f), sv_ps,                          \
+                                                   __fmul_rn(byte_to_float<J>(ul, 12582920.0f), su_ps));
+                CLOVER_AXPY4(0) CLOVER_AXPY4(1) CLOVER_AXPY4(2) CLOVER_AXPY4(3)
+#undef CLOVER_AXPY4
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < 16; ++w) {
+                const uint32_t bu = wu[w] ^ 0x80808080u, bv = wv[w] ^ 0x80808080u;       // q + 128 per byte
+#define CLOVER_AXPY8(J)                                                                                              \
+                val[4 * w + J] = __fmaf_rn(byte_to_float<J>(bv, 12583040.0f), sv_ps,                                  \
+                                           __fmul_rn(byte_to_float<J>(bu, 12583040.0f), su_ps));
+                CLOVER_AXPY8(0) CLOVER_AXPY8(1) CLOVER_AXPY8(2) CLOVER_AXPY8(3)
+#undef CLOVER_AXPY8
+            }
+        }
+        float m = 0.f;
+#pragma unroll
+        for (int e = 0; e < 64; ++e) m = fmaxf(m, fabsf(val[e]));
+        m = guard_zero(m);
+        sr[blk] = m;
+        const float scale = quant_scale(kQmax, m);
+
+        uint32_t nw[2][8];
+        if (STOCH) {
+            uint64_t lanes[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) lanes[k] = xs_jump(tables, key.x[k], 2 * blk);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t o = xs_next(lanes[k]);
+                    nw[c][2 * k] = (uint32_t)o;
+                    nw[c][2 * k + 1] = (uint32_t)(o >> 32);
+                }
+        }
+        uint32_t out[kWords];
+        if (BITS == 4) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                int q[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int p = 2 * ((i >> 1) & 3) + ((i & 1) ? 0 : 1);              // nibble position of element 8w+i
+                    const float rnd = STOCH ? noise_from_word(nw[p >> 2][w], p & 3) : 0.f;
+                    q[i] = quant_one(val[8 * w + i], scale, rnd);
+                }
+                out[w] = pack8_nibbles(q);
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < 16; ++w) {
+                int q[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int e = 4 * w + i;
+                    const float rnd = STOCH ? noise_from_word(nw[e >> 5][(e & 31) >> 2], e & 3) : 0.f;
+                    q[i] = quant_one(val[e], scale, rnd);
+                }
+                out[w] = pack4_bytes(q);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kWords / 4; ++i)
+            reinterpret_cast<uint4 *>(r + blk * kWords)[i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+    }
+}
+
+template <int BITS>
+static int launch_scale_add(const int8_t *u, const float *su, const int8_t *v, const float *sv, float a, uint64_t n_pad,
+                            int8_t *r, float *sr, uint64_t *key_host, cudaStream_t stream) {
+    const uint64_t nblocks = n_pad / kBlock;
+    if (nblocks == 0) return CLOVER_OK;
+    const uint64_t want = (nblocks + 255) / 256, cap = (uint64_t)sm_count() * 8;
+    const unsigned grid = (unsigned)(want > cap ? cap : want);
+    const uint32_t *u32 = reinterpret_cast<const uint32_t *>(u), *v32 = reinterpret_cast<const uint32_t *>(v);
+    uint32_t *r32 = reinterpret_cast<uint32_t *>(r);
+    Key4 key = {};
+    if (key_host) {
+        const uint64_t *tables = device_jump_tables();
+        if (!tables) { set_error("clover: could not upload PRNG jump tables"); return CLOVER_ERR_CUDA; }
+        key = key_lanes(key_host);
+        k_vscale_add<BITS, true><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, r32, sr, key, tables);
+        host_key_skip(key_host, 2 * nblocks);
+    } else {
+        k_vscale_add<BITS, false><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, r32, sr, key, nullptr);
+    }
+    count_launch();
+    return launch_status("k_vscale_add");
+}
+
+}  // namespace clover
+
+using namespace clover;
+
+extern "C" {
+
+int clover_v4_scale_and_add(const int8_t *u, const float *su, const int8_t *v, const float *sv, float a, uint64_t n_pad,
+                            int8_t *r, float *sr, uint64_t *key_host, void *stream) {
+    CLOVER_REQUIRE(u && su && v && sv && r && sr, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_REQUIRE(n_pad % 128u == 0, CLOVER_ERR_INVALID, "n_pad must be a multiple of 128 (clover_size_pad)");
+    return launch_scale_add<4>(u, su, v, sv, a, n_pad, r, sr, key_host, (cudaStream_t)stream);
+}
+int clover_v8_scale_and_add(const int8_t *u, const float *su, const int8_t *v, const float *sv, float a, uint64_t n_pad,
+                            int8_t *r, float *sr, uint64_t *key_host, void *stream) {
+    CLOVER_REQUIRE(u && su && v && sv && r && sr, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_REQUIRE(n_pad % 128u == 0, CLOVER_ERR_INVALID, "n_pad must be a multiple of 128 (clover_size_pad)");
+    return launch_scale_add<8>(u, su, v, sv, a, n_pad, r, sr, key_host, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -92,6 +92,11 @@ int clover_v4_restore(const int8_t *values, const float *scales, uint64_t n_pad,
 int clover_v4_dot(const int8_t *u, const float *su, const int8_t *v, const float *sv, uint64_t n_pad,
                   float *result, int mode, void *stream);
 
+/* CloverVector4::scaleAndAdd   include/CloverVector4.h:1222-1478: r = requantize(u + a * v), block by block.
+ * r / sr may alias u / su (the reference's two-argument, in-place form). key_host: the PRNG state of `u`'s object. */
+int clover_v4_scale_and_add(const int8_t *u, const float *su, const int8_t *v, const float *sv, float a, uint64_t n_pad,
+                            int8_t *r, float *sr, uint64_t *key_host, void *stream);
+
 /* ---- CloverVector8 ------------------------------------------------------------------------------ */
 /* CloverVector8::quantize      include/CloverVector8.h:393-605 */
 int clover_v8_quantize(const float *x, uint64_t n_pad, int8_t *values, float *scales, uint64_t *key_host, void *stream);
@@ -100,6 +105,10 @@ int clover_v8_restore(const int8_t *values, const float *scales, uint64_t n_pad,
 /* CloverVector8::dot           include/CloverVector8.h:911-977 */
 int clover_v8_dot(const int8_t *u, const float *su, const int8_t *v, const float *sv, uint64_t n_pad,
                   float *result, int mode, void *stream);
+
+/* CloverVector8::scaleAndAdd   include/CloverVector8.h:1089-1357 */
+int clover_v8_scale_and_add(const int8_t *u, const float *su, const int8_t *v, const float *sv, float a, uint64_t n_pad,
+                            int8_t *r, float *sr, uint64_t *key_host, void *stream);
 
 /* ---- CloverMatrix4 ------------------------------------------------------------------------------ */
 /* CloverMatrix4::quantize      include/CloverMatrix4.h:512-766  (a: rows*cols fp32, row-major) */

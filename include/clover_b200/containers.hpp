@@ -173,6 +173,24 @@ public:
     }
     float dot_scalar(const CloverQuantizedVector &o) const { return dot(o, CLOVER_DOT_EXACT); }
     float dot_parallel(const CloverQuantizedVector &o) const { return dot(o); }
+
+    // this = this + a * other, re-quantized (include/CloverVector4.h:1195-1204, CloverVector8.h:1063-1072)
+    void scaleAndAdd(const CloverQuantizedVector &other, float a) { scaleAndAdd(other, a, *this); }
+    // result = this + a * other (include/CloverVector4.h:1206-1218, CloverVector8.h:1074-1086)
+    void scaleAndAdd(const CloverQuantizedVector &other, float a, CloverQuantizedVector &result) {
+        if (other.length_pad != length_pad || result.length_pad != length_pad) { std::cout << "Vectors do not have the same size. Exiting ..." << std::endl; exit(1); }
+        const int8_t *u = device_values(), *v = other.device_values();
+        const float *su = device_scales(), *sv = other.device_scales();
+        int8_t *r = result.device_values_out();
+        float *sr = result.device_scales_out();
+        const int rc = BITS == 4 ? clover_v4_scale_and_add(u, su, v, sv, a, length_pad, r, sr, key_ptr(), nullptr)
+                                 : clover_v8_scale_and_add(u, su, v, sv, a, length_pad, r, sr, key_ptr(), nullptr);
+        clover_b200_detail::check(rc, "scaleAndAdd");
+    }
+    void scaleAndAdd_scalar(const CloverQuantizedVector &o, float a) { scaleAndAdd(o, a); }
+    void scaleAndAdd_parallel(const CloverQuantizedVector &o, float a) { scaleAndAdd(o, a); }
+    void scaleAndAdd_scalar(const CloverQuantizedVector &o, float a, CloverQuantizedVector &r) { scaleAndAdd(o, a, r); }
+    void scaleAndAdd_parallel(const CloverQuantizedVector &o, float a, CloverQuantizedVector &r) { scaleAndAdd(o, a, r); }
 };
 
 class CloverVector4 : public CloverQuantizedVector<4> {

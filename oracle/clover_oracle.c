@@ -211,6 +211,66 @@ float orc_v4_get(const int8_t *values, const float *scales, uint64_t i) {
     return s * (float)((i & 1) ? nib_lo(b) : nib_hi(b));
 }
 
+/* scaleAndAdd: r = requantize(u + a * v), block by block (include/CloverVector4.h:1222-1478).
+ *   su_ps = su[b] / 7, sv_ps = (sv[b] * a) / 7 (IEEE divides), value = fma(float(qv), sv_ps, float(qu) * su_ps)
+ *   absmax -> zero guard -> 7 / max -> truncating quantizer of orc_v4_quantize.
+ * The SIMD code peels nibbles by POSITION inside each 32-bit word (slli/srai, :1236-1272): nibble position p of word
+ * w is element e with w = e / 8 and p = 2 * ((e / 2) % 4) + (e even); its noise slot is call p / 4, byte p % 4,
+ * 32-bit lane w (:1363-1405) - not the slot the quantizer uses. r may alias u. */
+void orc_v4_scale_and_add(const int8_t *u, const float *su, const int8_t *v, const float *sv, float a, uint64_t n,
+                          int8_t *r, float *sr, uint64_t *state) {
+    const uint64_t blocks = orc_size_pad(n) / BLOCK;
+    for (uint64_t b = 0; b < blocks; ++b) {
+        const float su_ps = su[b] / 7.0f;
+        const float sv_ss = sv[b] * a;
+        const float sv_ps = sv_ss / 7.0f;
+        float val[64];
+        float m = 0.0f;
+        for (int i = 0; i < 32; ++i) {
+            const int8_t bu = u[b * 32 + i], bv = v[b * 32 + i];
+            val[2 * i]     = fmaf((float)nib_hi(bv), sv_ps, (float)nib_hi(bu) * su_ps);
+            val[2 * i + 1] = fmaf((float)nib_lo(bv), sv_ps, (float)nib_lo(bu) * su_ps);
+        }
+        for (int e = 0; e < 64; ++e) m = maxps(absf(val[e]), m);
+        m = guard_zero(m);
+        sr[b] = m;
+        const float scale = 7.0f / m;
+        uint32_t w[2][8];
+        if (state) { orc_xs_next(state, w[0]); orc_xs_next(state, w[1]); }
+        int32_t q[64];
+        for (int e = 0; e < 64; ++e) {
+            const int p = 2 * ((e >> 1) & 3) + ((e & 1) ? 0 : 1);
+            q[e] = quant1(val[e], scale, state ? noise(w[p >> 2], p & 3, e >> 3) : 0.0f);
+        }
+        pack4(q, r + b * 32);
+    }
+}
+
+/* 8-bit twin (include/CloverVector8.h:1089-1357): bytes 0..31 of the block use PRNG call 1, bytes 32..63 call 2;
+ * byte e of a half sits in 32-bit lane e / 4 at byte position e % 4. */
+void orc_v8_scale_and_add(const int8_t *u, const float *su, const int8_t *v, const float *sv, float a, uint64_t n,
+                          int8_t *r, float *sr, uint64_t *state) {
+    const uint64_t blocks = orc_size_pad(n) / BLOCK;
+    for (uint64_t b = 0; b < blocks; ++b) {
+        const float su_ps = su[b] / 127.0f;
+        const float sv_ss = sv[b] * a;
+        const float sv_ps = sv_ss / 127.0f;
+        float val[64];
+        float m = 0.0f;
+        for (int e = 0; e < 64; ++e) val[e] = fmaf((float)v[b * 64 + e], sv_ps, (float)u[b * 64 + e] * su_ps);
+        for (int e = 0; e < 64; ++e) m = maxps(absf(val[e]), m);
+        m = guard_zero(m);
+        sr[b] = m;
+        const float scale = 127.0f / m;
+        uint32_t w[2][8];
+        if (state) { orc_xs_next(state, w[0]); orc_xs_next(state, w[1]); }
+        int32_t q[64];
+        for (int e = 0; e < 64; ++e)
+            q[e] = quant1(val[e], scale, state ? noise(w[e >> 5], e & 3, (e & 31) >> 2) : 0.0f);
+        pack8(q, r + b * 64);
+    }
+}
+
 /* exact int32 lane sums of one 4-bit block: lane l = bytes 4l..4l+3 = elements 8l..8l+7
  * (include/CloverVector4.h:1134-1181; exact because |q| <= 7 never saturates maddubs) */
 static inline void lanes4(const int8_t *u, const int8_t *v, int32_t *lane) {

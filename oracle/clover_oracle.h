@@ -45,6 +45,13 @@ void  orc_v8_quantize(const float *x, uint64_t n, int8_t *values, float *scales,
 void  orc_v8_restore(const int8_t *values, const float *scales, uint64_t n, float *x);
 float orc_v8_dot(const int8_t *u, const float *su, const int8_t *v, const float *sv, uint64_t n);
 
+/* scaleAndAdd (quantized AXPY): r = requantize(u + a * v); r may alias u.
+ * include/CloverVector4.h:1222-1478, include/CloverVector8.h:1089-1357 */
+void orc_v4_scale_and_add(const int8_t *u, const float *su, const int8_t *v, const float *sv, float a, uint64_t n,
+                          int8_t *r, float *sr, uint64_t *state);
+void orc_v8_scale_and_add(const int8_t *u, const float *su, const int8_t *v, const float *sv, float a, uint64_t n,
+                          int8_t *r, float *sr, uint64_t *state);
+
 /* CloverMatrix4: include/CloverMatrix4.h. rows/cols are the PADDED dimensions (multiples of 128). */
 void orc_m4_quantize(const float *a, uint64_t rows, uint64_t cols, int8_t *values, float *scales, uint64_t *state);
 void orc_m4_mvm(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,

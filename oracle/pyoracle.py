@@ -149,6 +149,13 @@ class Oracle:
     def v8_dot(self, u, su, v, sv, n):
         return np.float32(self.lib.orc_v8_dot(_p(u), _p(su), _p(v), _p(sv), _u64(n)))
 
+    def scale_and_add(self, bits, u, su, v, sv, a, n, state=None):
+        """r = requantize(u + a * v) (CloverVector{4,8}::scaleAndAdd); returns (values, scales)."""
+        r, sr = (v4_alloc if bits == 4 else v8_alloc)(n)
+        getattr(self.lib, f"orc_v{bits}_scale_and_add")(_p(u), _p(su), _p(v), _p(sv), C.c_float(a), _u64(n), _p(r), _p(sr),
+                                                        _p(_state(state)))
+        return r, sr
+
     # -- matrices (a: padded fp32 [rows, cols])
     def m4_quantize(self, a, state=None):
         rows, cols = a.shape
@@ -275,6 +282,12 @@ class Reference:
 
     def v8_dot(self, u, su, v, sv, n, variant=0):
         return np.float32(self.lib.ref_v8_dot(_p(u), _p(su), _p(v), _p(sv), _u64(n), C.c_int(variant)))
+
+    def scale_and_add(self, bits, u, su, v, sv, a, n, state=None, variant=0):
+        r, sr = (v4_alloc if bits == 4 else v8_alloc)(n)
+        getattr(self.lib, f"ref_v{bits}_scale_and_add")(_p(u), _p(su), _p(v), _p(sv), C.c_float(a), _u64(n), _p(r), _p(sr),
+                                                        self._st(state), C.c_int(variant))
+        return r, sr
 
     # -- matrices: handle based (the reference's matrices own their storage)
     class _M:

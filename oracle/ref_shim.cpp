@@ -176,6 +176,28 @@ float ref_v8_dot(const int8_t *u, const float *su, const int8_t *v, const float 
     return a.dot(b);
 }
 
+/* ---- scaleAndAdd: r = u + a * v, re-quantized. variant: 0 = SIMD, 1 = _scalar, 2 = _parallel ---------------- */
+void ref_v4_scale_and_add(const int8_t *u, const float *su, const int8_t *v, const float *sv, float a, uint64_t n,
+                          int8_t *r, float *sr, uint64_t *state, int variant) {
+    silence_once();
+    V4 x(n, (int8_t *)u, (float *)su);
+    CloverVector4 y(n, (int8_t *)v, (float *)sv);
+    CloverVector4 out(n, r, sr);
+    x.set_state(state);
+    if (variant == 1) x.scaleAndAdd_scalar(y, a, out); else if (variant == 2) x.scaleAndAdd_parallel(y, a, out); else x.scaleAndAdd(y, a, out);
+    x.get_state(state);
+}
+void ref_v8_scale_and_add(const int8_t *u, const float *su, const int8_t *v, const float *sv, float a, uint64_t n,
+                          int8_t *r, float *sr, uint64_t *state, int variant) {
+    silence_once();
+    V8 x(n, (int8_t *)u, (float *)su);
+    CloverVector8 y(n, (int8_t *)v, (float *)sv);
+    CloverVector8 out(n, r, sr);
+    x.set_state(state);
+    if (variant == 1) x.scaleAndAdd_scalar(y, a, out); else if (variant == 2) x.scaleAndAdd_parallel(y, a, out); else x.scaleAndAdd(y, a, out);
+    x.get_state(state);
+}
+
 /* ---- CloverMatrix32 (input container) ------------------------------------------------ */
 void *ref_m32_create(uint64_t rows, uint64_t cols) { silence_once(); return new CloverMatrix32(rows, cols); }
 void ref_m32_destroy(void *h) { delete (CloverMatrix32 *)h; }

@@ -252,6 +252,47 @@ def test_mvm_size_mismatch_raises(cb):
         qa.mvm(cb.CloverVector4(128), cb.CloverVector4(128))
 
 
+@pytest.mark.parametrize("bits_", [4, 8])
+@pytest.mark.parametrize("a", [0.5, -1.75, 0.0])
+@pytest.mark.parametrize("n", [1, 127, 128, 640, 1000, 65536 + 3])
+def test_vector_scale_and_add(cb, oracle, n, a, bits_):
+    """scaleAndAdd (02_vector.cpp:342-394): out-of-place and in-place, every byte and scale vs the oracle."""
+    V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
+    x, y = gen(oracle, n, "floats"), gen(oracle, n, "wide", skip=321)
+    qu, qv, qr = V(n), V(n), V(n)
+    qu.quantize(cb.CloverVector32(n, x))
+    qv.quantize(cb.CloverVector32(n, y))
+    ou, osu = getattr(oracle, f"v{bits_}_quantize")(x, n)
+    ov, osv = getattr(oracle, f"v{bits_}_quantize")(y, n)
+    wr, wsr = oracle.scale_and_add(bits_, ou, osu, ov, osv, a, n)
+    qu.scaleAndAdd(qv, a, qr)
+    assert np.array_equal(qr.getData().cpu().numpy(), wr)
+    assert np.array_equal(bits(qr.getScales().cpu().numpy()), bits(wsr))
+    qu.scaleAndAdd(qv, a)                      # in place
+    assert np.array_equal(qu.getData().cpu().numpy(), wr)
+    assert np.array_equal(bits(qu.getScales().cpu().numpy()), bits(wsr))
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+def test_vector_scale_and_add_stochastic(cb, oracle, bits_):
+    """with an explicit key the noise slots and the advanced key equal the sequential reference's"""
+    V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
+    n = 4096 + 64
+    x, y = gen(oracle, n, "floats"), gen(oracle, n, "ints", skip=77)
+    qu, qv, qr = V(n), V(n), V(n)
+    qu.quantize(cb.CloverVector32(n, x))
+    qv.quantize(cb.CloverVector32(n, y))
+    ou, osu = getattr(oracle, f"v{bits_}_quantize")(x, n)
+    ov, osv = getattr(oracle, f"v{bits_}_quantize")(y, n)
+    st = oracle.xs_init(11, 22)
+    wr, wsr = oracle.scale_and_add(bits_, ou, osu, ov, osv, 0.5, n, st)
+    qu.seed(11, 22)
+    qu.scaleAndAdd(qv, 0.5, qr)
+    assert np.array_equal(qr.getData().cpu().numpy(), wr)
+    assert np.array_equal(bits(qr.getScales().cpu().numpy()), bits(wsr))
+    assert np.array_equal(qu.key, st)
+
+
 @pytest.mark.parametrize("mnk", [(128, 128, 128), (128, 256, 384), (256, 128, 1152)])
 def test_gemm_vs_definition(cb, oracle, mnk):
     """GEMM extension: every C[i][j] vs the reference SIMD dot of the two row views (rule 3 tolerance)."""

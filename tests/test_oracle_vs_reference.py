@@ -164,3 +164,41 @@ def test_gemm_definition(oracle, reference):
     xs = bs[(j // 64) * kb:(j // 64 + 1) * kb]
     _, _, y32 = oracle.m4_mvm(av, as_, M, K, xv, xs, want_f32=True)
     assert np.array_equal(y32.view(np.uint32), c[:, j].copy().view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# scaleAndAdd: quantized AXPY, include/CloverVector4.h:1222-1478, include/CloverVector8.h:1089-1357
+# the reference's own check: test/validate/02_vector.cpp:342-394 (SIMD vs _scalar, get() by get())
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bits", [4, 8])
+@pytest.mark.parametrize("a", [0.5, -1.75, 0.0, 3.0e-3])
+@pytest.mark.parametrize("n", [1, 64, 127, 128, 129, 640, 1000, 4096 + 5])
+def test_scale_and_add(oracle, reference, n, a, bits):
+    x, y = _inputs(oracle, n, "floats"), _inputs(oracle, n, "wide", seed_skip=321)
+    q = getattr(oracle, f"v{bits}_quantize")
+    (u, su), (v, sv) = q(x, n), q(y, n)
+    r0, s0 = oracle.scale_and_add(bits, u, su, v, sv, a, n)
+    r1, s1 = reference.scale_and_add(bits, u, su, v, sv, a, n)
+    assert np.array_equal(r0, r1)
+    assert np.array_equal(s0.view(np.uint32), s1.view(np.uint32))
+    # in place (the reference's two-argument form passes u as the result)
+    u2, su2 = u.copy(), su.copy()
+    getattr(oracle.lib, f"orc_v{bits}_scale_and_add")(u2.ctypes.data_as(__import__("ctypes").c_void_p), su2.ctypes.data_as(__import__("ctypes").c_void_p),
+                                                      v.ctypes.data_as(__import__("ctypes").c_void_p), sv.ctypes.data_as(__import__("ctypes").c_void_p),
+                                                      __import__("ctypes").c_float(a), __import__("ctypes").c_uint64(n),
+                                                      u2.ctypes.data_as(__import__("ctypes").c_void_p), su2.ctypes.data_as(__import__("ctypes").c_void_p), None)
+    assert np.array_equal(u2, r1) and np.array_equal(su2.view(np.uint32), s1.view(np.uint32))
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+@pytest.mark.parametrize("n", [128, 1000, 4096])
+def test_scale_and_add_stochastic(oracle, reference_sr, n, bits):
+    x, y = _inputs(oracle, n, "floats"), _inputs(oracle, n, "ints", seed_skip=77)
+    q = getattr(oracle, f"v{bits}_quantize")
+    (u, su), (v, sv) = q(x, n), q(y, n)
+    st0, st1 = oracle.xs_init(11, 22), oracle.xs_init(11, 22)
+    r0, s0 = oracle.scale_and_add(bits, u, su, v, sv, 0.5, n, st0)
+    r1, s1 = reference_sr.scale_and_add(bits, u, su, v, sv, 0.5, n, st1)
+    assert np.array_equal(r0, r1)
+    assert np.array_equal(s0.view(np.uint32), s1.view(np.uint32))
+    assert np.array_equal(st0, st1)
