@@ -50,6 +50,7 @@ _SIGNATURES = {
     "clover_v8_dot": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _int, _vp]),
     "clover_m4_quantize": (_int, [_vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "clover_m4_mvm": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "clover_m4_mvm_v8": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "clover_m4_mvm_f32": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     "clover_m4_mvm_shard": (_int, [_vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "clover_m4_mvm_shard_fused": (_int, [_vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, C.c_uint32, _vp, _vp]),

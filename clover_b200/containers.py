@@ -250,6 +250,14 @@ class _QMatrix(_Keyed):
             call("clover_m4_mvm_f32", _ptr(self.values), _ptr(self.scales), C.c_uint64(self.rows), C.c_uint64(self.cols),
                  _ptr(productVector.values), _ptr(resultVector.values), _stream())
             return
+        if self.BITS == 4 and isinstance(productVector, CloverVector8) and isinstance(resultVector, CloverVector8):
+            # mixed precision (include/CloverMatrix4.h:1093-1441)
+            if productVector.size() != self.cols or resultVector.size_pad() != self.rows:
+                raise CloverSizeError("MVM can not be performed.")
+            call("clover_m4_mvm_v8", _ptr(self.values), _ptr(self.scales), C.c_uint64(self.rows), C.c_uint64(self.cols),
+                 _ptr(productVector.values), _ptr(productVector.scales), _ptr(resultVector.values), _ptr(resultVector.scales),
+                 _ptr(y32), self._key_ptr(), _stream())
+            return
         if not isinstance(productVector, self.VEC) or not isinstance(resultVector, self.VEC):
             raise TypeError(f"mvm expects {self.VEC.__name__} operands")
         # the reference checks productVector.size() != getCols() (include/CloverMatrix4.h:779-782)

@@ -473,12 +473,22 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
 }
 
 // =============================================================================================
-// mvm(V8,V8): exact-order 8-bit GEMV. 8 chains per row (one accumulator, CloverMatrix8.h:1029-1095)
-// thread = (row, lane l): per block the int32 lane sum covers bytes 4l..4l+3 and 32+4l..32+4l+3.
+// mvm(V8,V8): exact-order GEMV with an 8-bit product vector. 8 chains per row (one accumulator,
+// CloverMatrix8.h:1029-1095); thread = (row, lane l): per block the int32 lane sum covers elements 4l..4l+3 and
+// 32+4l..32+4l+3. MBITS = 8: CloverMatrix8::mvm (CloverMatrix8.h:1002-1298). MBITS = 4: the mixed-precision
+// CloverMatrix4::mvm(V8,V8) (CloverMatrix4.h:1093-1441) - same chains on a nibble matrix, scale
+// (su * (1/7)) * (sv * (1/127)), nibbles expanded to 16*q bytes exactly like the reference and the factor 16
+// removed exactly in the int -> float step.
 // =============================================================================================
 constexpr int kMvm8ChunkBlocks = 64;
 
-template <bool STOCH>
+// two bytes (four nibbles: elements e, e+1 in byte 0, e+2, e+3 in byte 1) -> [16*q_e, 16*q_e+1, 16*q_e+2, 16*q_e+3]
+__device__ __forceinline__ uint32_t nibbles4_to_bytes16(uint32_t h) {
+    const uint32_t y = (h & 0x00FFu) | ((h & 0xFF00u) << 8);
+    return (y & 0x00F000F0u) | ((y & 0x000F000Fu) << 12);
+}
+
+template <int MBITS, bool STOCH>
 __global__ void __launch_bounds__(512)
 k_m8_mvm(const uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t rows_local, uint64_t cols,
          uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
@@ -493,7 +503,8 @@ k_m8_mvm(const uint32_t *__restrict__ values, const float *__restrict__ scales, 
     const int tid = threadIdx.x;
     const int r = tid >> 3, l = tid & 7;
     const uint64_t hb = cols >> 6;
-    const uint64_t wpr = cols >> 2;
+    const uint64_t wpr = MBITS == 8 ? cols >> 2 : cols >> 3;         // 32-bit words per matrix row
+    constexpr int kBlockWords = MBITS == 8 ? 16 : 8;
 
     for (uint64_t rb = blockIdx.x; rb < (rows_local >> 6); rb += gridDim.x) {
         const uint32_t *row = values + (rb * 64 + r) * wpr;
@@ -503,29 +514,56 @@ k_m8_mvm(const uint32_t *__restrict__ values, const float *__restrict__ scales, 
             const int nb = (int)((hb - cb) < (uint64_t)kMvm8ChunkBlocks ? (hb - cb) : kMvm8ChunkBlocks);
             __syncthreads();
             for (int i = tid; i < nb * 16; i += 512) xsm[i] = xv[cb * 16 + i];
-            if (tid < nb)
-                prod[tid] = __fmul_rn(__fmul_rn(su[cb + tid], 1.0f / 127.0f), __fmul_rn(xs[cb + tid], 1.0f / 127.0f));
-            __syncthreads();
-            const uint32_t *p = row + cb * 16 + l;
-            int b = 0;
-            for (; b + 4 <= nb; b += 4) {
-                uint32_t w0[4], w1[4];
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    w0[s] = ldg_stream(p + (b + s) * 16);
-                    w1[s] = ldg_stream(p + (b + s) * 16 + 8);
-                }
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    int d = dp4a_ss((int)w0[s], (int)xsm[(b + s) * 16 + l], 0);
-                    d = dp4a_ss((int)w1[s], (int)xsm[(b + s) * 16 + 8 + l], d);
-                    acc = __fmaf_rn(prod[b + s], __int2float_rn(d), acc);
-                }
+            if (tid < nb) {
+                if (MBITS == 8) prod[tid] = __fmul_rn(__fmul_rn(su[cb + tid], 1.0f / 127.0f), __fmul_rn(xs[cb + tid], 1.0f / 127.0f));
+                else            prod[tid] = __fmul_rn(__fmul_rn(su[cb + tid], 1.0f / 7.0f), __fmul_rn(xs[cb + tid], 1.0f / 127.0f));
             }
-            for (; b < nb; ++b) {
-                int d = dp4a_ss((int)ldg_stream(p + b * 16), (int)xsm[b * 16 + l], 0);
-                d = dp4a_ss((int)ldg_stream(p + b * 16 + 8), (int)xsm[b * 16 + 8 + l], d);
-                acc = __fmaf_rn(prod[b], __int2float_rn(d), acc);
+            __syncthreads();
+            if (MBITS == 8) {
+                const uint32_t *p = row + cb * 16 + l;
+                int b = 0;
+                for (; b + 4 <= nb; b += 4) {
+                    uint32_t w0[4], w1[4];
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        w0[s] = ldg_stream(p + (b + s) * 16);
+                        w1[s] = ldg_stream(p + (b + s) * 16 + 8);
+                    }
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        int d = dp4a_ss((int)w0[s], (int)xsm[(b + s) * 16 + l], 0);
+                        d = dp4a_ss((int)w1[s], (int)xsm[(b + s) * 16 + 8 + l], d);
+                        acc = __fmaf_rn(prod[b + s], __int2float_rn(d), acc);
+                    }
+                }
+                for (; b < nb; ++b) {
+                    int d = dp4a_ss((int)ldg_stream(p + b * 16), (int)xsm[b * 16 + l], 0);
+                    d = dp4a_ss((int)ldg_stream(p + b * 16 + 8), (int)xsm[b * 16 + 8 + l], d);
+                    acc = __fmaf_rn(prod[b], __int2float_rn(d), acc);
+                }
+            } else {
+                // block = 32 bytes of nibbles; lane l owns bytes 2l, 2l+1 (elements 4l..4l+3) and 16+2l, 17+2l
+                const uint16_t *p = reinterpret_cast<const uint16_t *>(row + cb * kBlockWords) + l;
+                int b = 0;
+                for (; b + 4 <= nb; b += 4) {
+                    uint32_t h0[4], h1[4];
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        h0[s] = __ldg(p + (b + s) * 16);
+                        h1[s] = __ldg(p + (b + s) * 16 + 8);
+                    }
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        int d = dp4a_ss((int)nibbles4_to_bytes16(h0[s]), (int)xsm[(b + s) * 16 + l], 0);
+                        d = dp4a_ss((int)nibbles4_to_bytes16(h1[s]), (int)xsm[(b + s) * 16 + 8 + l], d);
+                        acc = __fmaf_rn(prod[b + s], __int2float_rn(d >> 4), acc);      // srai 4 (:1196), exact
+                    }
+                }
+                for (; b < nb; ++b) {
+                    int d = dp4a_ss((int)nibbles4_to_bytes16(__ldg(p + b * 16)), (int)xsm[b * 16 + l], 0);
+                    d = dp4a_ss((int)nibbles4_to_bytes16(__ldg(p + b * 16 + 8)), (int)xsm[b * 16 + 8 + l], d);
+                    acc = __fmaf_rn(prod[b], __int2float_rn(d >> 4), acc);
+                }
             }
         }
         acc = hadd8_butterfly(acc);
@@ -625,8 +663,8 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
                                                         key, tables, peers ? *peers : PeerOut());
         }
     } else {
-        if (stoch) k_m8_mvm<true><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
-        else       k_m8_mvm<false><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
+        if (stoch) k_m8_mvm<8, true><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
+        else       k_m8_mvm<8, false><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
     }
     count_launch();
     return launch_status("k_mvm");
@@ -671,6 +709,30 @@ int clover_m8_mvm(const int8_t *values, const float *scales, uint64_t rows, uint
     CLOVER_CHECK_MAT(rows, cols);
     int rc = launch_mvm<8>(values, scales, rows, cols, 0, xv, xs, y32, yv, ys, key_host, (cudaStream_t)stream);
     if (rc == CLOVER_OK && key_host) host_key_skip(key_host, 2 * (rows >> 6));
+    return rc;
+}
+
+int clover_m4_mvm_v8(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                     const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32,
+                     uint64_t *key_host, void *stream) {
+    CLOVER_REQUIRE(values && scales && xv && xs && yv && ys, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_CHECK_MAT(rows, cols);
+    const uint64_t nrb = rows >> 6;
+    if (nrb == 0 || cols == 0) return CLOVER_OK;
+    Key4 key = {};
+    const uint64_t *tables = nullptr;
+    if (key_host) {
+        tables = device_jump_tables();
+        if (!tables) { set_error("clover: could not upload PRNG jump tables"); return CLOVER_ERR_CUDA; }
+        key = key_lanes(key_host);
+    }
+    const uint32_t *v32 = reinterpret_cast<const uint32_t *>(values), *x32 = reinterpret_cast<const uint32_t *>(xv);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (key_host) k_m8_mvm<4, true><<<(unsigned)nrb, 512, 0, st>>>(v32, scales, rows, cols, 0, x32, xs, y32, yv, ys, key, tables);
+    else          k_m8_mvm<4, false><<<(unsigned)nrb, 512, 0, st>>>(v32, scales, rows, cols, 0, x32, xs, y32, yv, ys, key, tables);
+    count_launch();
+    const int rc = launch_status("k_m8_mvm<4>");
+    if (rc == CLOVER_OK && key_host) host_key_skip(key_host, 2 * nrb);
     return rc;
 }
 

@@ -119,6 +119,11 @@ int clover_m4_quantize(const float *a, uint64_t rows, uint64_t cols, int8_t *val
 int clover_m4_mvm(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
                   const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32,
                   uint64_t *key_host, void *stream);
+/* CloverMatrix4::mvm(V8,V8)    include/CloverMatrix4.h:1093-1441: mixed precision - the 4-bit matrix times a
+ * CloverVector8, result re-quantized to a CloverVector8 (the reference's most accurate IHT configuration). */
+int clover_m4_mvm_v8(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                     const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32,
+                     uint64_t *key_host, void *stream);
 /* CloverMatrix4::mvm(V32,V32)  include/CloverMatrix4.h:1451-1547 */
 int clover_m4_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
                       const float *x32, float *y32, void *stream);

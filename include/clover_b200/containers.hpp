@@ -296,6 +296,19 @@ public:
         clover_b200_detail::check(clover_m4_mvm_f32(device_values(), device_scales(), rows, cols, productVector.device_in(),
                                                     resultVector.device_out(), nullptr), "mvm");
     }
+    // mixed precision, include/CloverMatrix4.h:1093-1441 (mvm_parallel :2017): 4-bit matrix x 8-bit vector -> 8-bit vector
+    void mvm(const CloverVector8 &productVector, CloverVector8 &resultVector) {
+        if (productVector.size() != getCols() || resultVector.size_pad() != getRows()) {
+            std::cout << "MVM can not be performed. Exiting ..." << std::endl;
+            exit(1);
+        }
+        int8_t *yv = resultVector.device_values_out();
+        float *ys = resultVector.device_scales_out();
+        clover_b200_detail::check(clover_m4_mvm_v8(device_values(), device_scales(), rows, cols, productVector.device_values(),
+                                                   productVector.device_scales(), yv, ys, nullptr, key_ptr(), nullptr), "mvm");
+    }
+    void mvm_parallel(const CloverVector8 &x, CloverVector8 &y) { mvm(x, y); }
+    using CloverQuantizedMatrix<4, CloverVector4>::mvm_parallel;
     // extension: C = A * Bt^T, C[i][j] = rowView(A,i).dot(rowView(Bt,j)); c_dev: rows x Bt.rows fp32 on the device
     void gemm(const CloverMatrix4 &Bt, float *c_dev, uint64_t ldc) const {
         if (Bt.getCols() != getCols()) { std::cout << "GEMM can not be performed. Exiting ..." << std::endl; exit(1); }

@@ -429,6 +429,49 @@ void orc_m8_mvm(const int8_t *values, const float *scales, uint64_t rows, uint64
     if (!y32_or_null) free(y32);
 }
 
+/* mvm(V8,V8) on a 4-bit matrix (mixed precision): include/CloverMatrix4.h:1093-1441.
+ * Per row 8 fp32 chains; lane l of block b sums elements 4l..4l+3 and 32+4l..32+4l+3 of (4-bit row) x (8-bit x)
+ * exactly (maddubs on 16*q never saturates: 2*127*128 < 32768, then >> 4), scale = (su * (1/7)) * (sv * (1/127)),
+ * acc_l = fma(scale, float(I_l), acc_l); hadd tree; 8-bit re-quantization of 64 rows, natural noise slots. */
+void orc_m4_mvm_v8(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                   const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32_or_null, uint64_t *state) {
+    const uint64_t hb = cols >> 6;
+    const uint64_t rb = rows >> 6;
+    const float rcp7 = 1.0f / 7.0f, rcp127 = 1.0f / 127.0f;
+    float *y32 = y32_or_null ? y32_or_null : (float *)malloc(rows * sizeof(float));
+    #pragma omp parallel for schedule(static)
+    for (uint64_t r = 0; r < rows; ++r) {
+        const int8_t *u = values + ((r * cols) >> 1);
+        const float *su = scales + (r >> 6) * hb;
+        float acc[8];
+        memset(acc, 0, sizeof acc);
+        for (uint64_t b = 0; b < hb; ++b) {
+            const float scale = (su[b] * rcp7) * (xs[b] * rcp127);
+            for (int l = 0; l < 8; ++l) {
+                int32_t sum = 0;
+                for (int half = 0; half < 2; ++half)
+                    for (int k = 0; k < 4; ++k) {
+                        const int e = 32 * half + 4 * l + k;
+                        const int8_t byte = u[b * 32 + (e >> 1)];
+                        sum += ((e & 1) ? nib_lo(byte) : nib_hi(byte)) * (int32_t)xv[b * 64 + e];
+                    }
+                acc[l] = fmaf(scale, (float)sum, acc[l]);
+            }
+        }
+        y32[r] = hadd8(acc);
+    }
+    for (uint64_t b = 0; b < rb; ++b) {
+        float m = 0.0f;
+        for (int i = 0; i < 64; ++i) m = maxps(absf(y32[b * 64 + i]), m);
+        m = guard_zero(m);
+        ys[b] = m;
+        int32_t q[64];
+        quant_block(y32 + b * 64, m, 127.0f, q, state, 0);
+        pack8(q, yv + b * 64);
+    }
+    if (!y32_or_null) free(y32);
+}
+
 /* mvm(V32,V32): include/CloverMatrix4.h:1451-1547. 32 chains per row: accumulator k (0..3),
  * lane l, fed per block by element 8k+l and then element 32+8k+l; f = float(q) * (s/7). */
 void orc_m4_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,

@@ -56,6 +56,9 @@ void orc_v8_scale_and_add(const int8_t *u, const float *su, const int8_t *v, con
 void orc_m4_quantize(const float *a, uint64_t rows, uint64_t cols, int8_t *values, float *scales, uint64_t *state);
 void orc_m4_mvm(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
                 const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32_or_null, uint64_t *state);
+/* mixed precision: 4-bit matrix x CloverVector8 -> CloverVector8 (include/CloverMatrix4.h:1093-1441) */
+void orc_m4_mvm_v8(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                   const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32_or_null, uint64_t *state);
 void orc_m4_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
                     const float *x32, float *y32);
 /* GEMM definition of this project: C[i][j] = rowView(A,i).dot(rowView(Bt,j)). */

@@ -178,6 +178,14 @@ class Oracle:
                             _p(_state(state)))
         return (yv, ys, y32) if want_f32 else (yv, ys)
 
+    def m4_mvm_v8(self, mv, ms, rows, cols, xv, xs, state=None, want_f32=False):
+        """mixed precision: 4-bit matrix x CloverVector8 -> CloverVector8 (CloverMatrix4.h:1093)"""
+        yv, ys = v8_alloc(rows)
+        y32 = np.zeros(rows, np.float32) if want_f32 else None
+        self.lib.orc_m4_mvm_v8(_p(mv), _p(ms), _u64(rows), _u64(cols), _p(xv), _p(xs), _p(yv), _p(ys), _p(y32),
+                               _p(_state(state)))
+        return (yv, ys, y32) if want_f32 else (yv, ys)
+
     def m8_mvm(self, mv, ms, rows, cols, xv, xs, state=None, want_f32=False):
         yv, ys = v8_alloc(rows)
         y32 = np.zeros(rows, np.float32) if want_f32 else None
@@ -353,6 +361,11 @@ class Reference:
     def m4_mvm(self, m, xv, xs, state=None, variant=0):
         yv, ys = v4_alloc(m.rows)
         self.lib.ref_m4_mvm(m.h, _p(xv), _p(xs), _p(yv), _p(ys), self._st(state), C.c_int(variant))
+        return yv, ys
+
+    def m4_mvm_v8(self, m, xv, xs, state=None, variant=0):
+        yv, ys = v8_alloc(m.rows)
+        self.lib.ref_m4_mvm_v8(m.h, _p(xv), _p(xs), _p(yv), _p(ys), self._st(state), C.c_int(variant))
         return yv, ys
 
     def m8_mvm(self, m, xv, xs, state=None, variant=0):

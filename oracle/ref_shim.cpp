@@ -239,6 +239,15 @@ void ref_m4_mvm(void *h, const int8_t *xv, const float *xs, int8_t *yv, float *y
     if (variant == 1) m->mvm_scalar(x, y); else if (variant == 2) m->mvm_parallel(x, y); else m->mvm(x, y);
     m->get_state(state);
 }
+/* mixed precision: CloverVector8 x / y on the 4-bit matrix (include/CloverMatrix4.h:1093; _parallel :2017). */
+void ref_m4_mvm_v8(void *h, const int8_t *xv, const float *xs, int8_t *yv, float *ys, uint64_t *state, int variant) {
+    M4 *m = (M4 *)h;
+    CloverVector8 x(m->getCols(), (int8_t *)xv, (float *)xs);
+    CloverVector8 y(m->getRows(), yv, ys);
+    m->set_state(state);
+    if (variant == 2) m->mvm_parallel(x, y); else m->mvm(x, y);
+    m->get_state(state);
+}
 /* fp32 x / fp32 y (include/CloverMatrix4.h:1451, :423, :2397). */
 void ref_m4_mvm_f32(void *h, const float *x32, float *y32, int variant) {
     M4 *m = (M4 *)h;

@@ -252,6 +252,36 @@ def test_mvm_size_mismatch_raises(cb):
         qa.mvm(cb.CloverVector4(128), cb.CloverVector4(128))
 
 
+@pytest.mark.parametrize("kind", ["floats", "ints"])
+@pytest.mark.parametrize("shape", [(128, 128), (256, 384), (200, 300), (640, 1152), (1024, 8192 + 128)])
+def test_matrix4_mvm_vector8(cb, oracle, shape, kind):
+    """mixed precision CloverMatrix4::mvm(V8,V8) (CloverMatrix4.h:1093-1441): packed bytes, scales and the fp32
+    row results bit-for-bit; with a key, the stochastic re-quantizer's stream position too."""
+    from oracle.pyoracle import pad_matrix
+    rows, cols = shape
+    a = pad_matrix(gen(oracle, rows * cols, kind)[: rows * cols].reshape(rows, cols))
+    R, Cc = a.shape
+    xvec = gen(oracle, Cc, kind, skip=11)
+    qa = cb.CloverMatrix4(R, Cc)
+    qa.quantize(cb.CloverMatrix32(R, Cc, a))
+    qx, qy = cb.CloverVector8(Cc), cb.CloverVector8(R)
+    qx.quantize(cb.CloverVector32(Cc, xvec))
+    y32 = torch.empty(R, dtype=torch.float32, device="cuda")
+    qa.mvm(qx, qy, y32=y32)
+    mv, ms = oracle.m4_quantize(a)
+    xv, xs = oracle.v8_quantize(xvec, Cc)
+    wv, ws, w32 = oracle.m4_mvm_v8(mv, ms, R, Cc, xv, xs, want_f32=True)
+    assert np.array_equal(bits(y32.cpu().numpy()), bits(w32))
+    assert np.array_equal(qy.getData().cpu().numpy(), wv)
+    assert np.array_equal(bits(qy.getScales().cpu().numpy()[: R // 64]), bits(ws[: R // 64]))
+    st = oracle.xs_init(5, 6)
+    wv, ws = oracle.m4_mvm_v8(mv, ms, R, Cc, xv, xs, state=st)
+    qa.seed(5, 6)
+    qa.mvm(qx, qy)
+    assert np.array_equal(qy.getData().cpu().numpy(), wv)
+    assert np.array_equal(qa.key, st)
+
+
 @pytest.mark.parametrize("bits_", [4, 8])
 @pytest.mark.parametrize("a", [0.5, -1.75, 0.0])
 @pytest.mark.parametrize("n", [1, 127, 128, 640, 1000, 65536 + 3])

@@ -202,3 +202,42 @@ def test_scale_and_add_stochastic(oracle, reference_sr, n, bits):
     assert np.array_equal(r0, r1)
     assert np.array_equal(s0.view(np.uint32), s1.view(np.uint32))
     assert np.array_equal(st0, st1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# mixed precision mvm: 4-bit matrix x CloverVector8 -> CloverVector8, include/CloverMatrix4.h:1093-1441
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["floats", "ints"])
+@pytest.mark.parametrize("shape", MAT_SHAPES)
+def test_matrix4_mvm_vector8(oracle, reference, shape, kind):
+    from oracle.pyoracle import pad_matrix
+    rows, cols = shape
+    a = pad_matrix(_inputs(oracle, rows * cols, kind)[: rows * cols].reshape(rows, cols))
+    R, Cc = a.shape
+    xvec = _inputs(oracle, Cc, kind, seed_skip=11)
+    mv, ms = oracle.m4_quantize(a)
+    _, _, h = reference.m4_quantize(a)
+    xv, xs = oracle.v8_quantize(xvec, Cc)
+    yv, ys = oracle.m4_mvm_v8(mv, ms, R, Cc, xv, xs)
+    for variant in (0, 2):                       # SIMD and _parallel
+        yv_r, ys_r = reference.m4_mvm_v8(h, xv, xs, variant=variant)
+        assert np.array_equal(yv, yv_r), f"values (variant {variant})"
+        assert np.array_equal(ys.view(np.uint32), ys_r.view(np.uint32)), f"scales (variant {variant})"
+
+
+def test_matrix4_mvm_vector8_stochastic(oracle, reference_sr):
+    from oracle.pyoracle import pad_matrix
+    rows, cols = 256, 384
+    a = pad_matrix(_inputs(oracle, rows * cols, "floats")[: rows * cols].reshape(rows, cols))
+    xvec = _inputs(oracle, cols, "floats", seed_skip=5)
+    mv, ms = oracle.m4_quantize(a)
+    _, _, h = reference_sr.m4_quantize(a)          # no state: rounding noise from whatever key; re-load the oracle's bytes
+    import ctypes as C
+    C.memmove(reference_sr.lib.ref_m4_values(h.h), mv.ctypes.data, mv.nbytes)
+    C.memmove(reference_sr.lib.ref_m4_scales(h.h), ms.ctypes.data, ms.nbytes)
+    xv, xs = oracle.v8_quantize(xvec, cols)
+    st, st_ref = oracle.xs_init(5, 6), reference_sr.xs_init(5, 6)
+    yv, ys = oracle.m4_mvm_v8(mv, ms, rows, cols, xv, xs, state=st)
+    yv_r, ys_r = reference_sr.m4_mvm_v8(h, xv, xs, state=st_ref)
+    assert np.array_equal(yv, yv_r) and np.array_equal(ys.view(np.uint32), ys_r.view(np.uint32))
+    assert np.array_equal(st, st_ref)
