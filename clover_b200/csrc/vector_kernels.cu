@@ -5,6 +5,8 @@
 //              Reference: include/CloverVector4.h:605-807, include/CloverVector8.h:393-605.
 //   restore  : include/CloverVector4.h:1027-1093, include/CloverVector8.h:835-909.
 //   dot      : include/CloverVector4.h:1095-1192, include/CloverVector8.h:911-977.
+#include <stdlib.h>
+#include <string.h>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -125,35 +127,131 @@ k_vquantize(const float *__restrict__ x, uint64_t nblocks, uint64_t R, int8_t *_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// quantize, second design: FOUR threads per block of 64 (16 contiguous elements each), no shared memory, no
+// CTA barrier. Thread s of a group loads its 64 bytes with four 16 B loads (the two halves of each 32 B sector
+// are fetched by consecutive instructions and meet in L1), the block absmax is two xor-shuffles away, and the
+// thread's 16 roundings pack into exactly the 8 (4-bit) or 16 (8-bit) contiguous bytes it stores - a warp writes
+// 256 / 512 contiguous bytes. ~45 registers => full occupancy; this is what lifted C2a from 73 % of the HBM
+// roofline (thread-per-block kernel above, kept for reference as k_vquantize) - see DESIGN.md section 3.
+// Stochastic mode: a group walks R consecutive blocks and all four threads step the same XORShift state
+// (two calls per block), so the stream is consumed exactly like the reference's sequential loop.
+// ---------------------------------------------------------------------------------------------
+constexpr int kQ4Threads = 256;
+
+template <int BITS, bool STOCH>
+__global__ void __launch_bounds__(kQ4Threads)
+k_vquantize4t(const float *__restrict__ x, uint64_t nblocks, uint64_t R, int8_t *__restrict__ values,
+              float *__restrict__ scales, Key4 key, const uint64_t *__restrict__ tables) {
+    constexpr float kQmax = BITS == 4 ? 7.0f : 127.0f;
+    const int s = threadIdx.x & 3;
+    const uint64_t group = ((uint64_t)blockIdx.x * kQ4Threads + threadIdx.x) >> 2;
+    const uint64_t ngroups = ((uint64_t)gridDim.x * kQ4Threads) >> 2;
+    // rounding disabled: grid-stride (a warp covers 8 consecutive blocks = 2 KiB); stochastic: R consecutive blocks
+    uint64_t blk = STOCH ? group * R : group;
+    const uint64_t step = STOCH ? 1 : ngroups;
+    const uint64_t end = STOCH ? min(nblocks, (group + 1) * R) : nblocks;
+    uint64_t lanes[4] = {0, 0, 0, 0};
+    if (STOCH && blk < end) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lanes[k] = xs_jump(tables, key.x[k], 2 * blk);
+    }
+    // whole warps iterate together (shuffles): the trip count is decided per GROUP, groups of a warp may differ
+    for (;; blk += step) {
+        const bool live = blk < end;
+        if (!__any_sync(0xFFFFFFFFu, live)) break;
+        float f[16];
+        if (live) {
+            const float4 *src = reinterpret_cast<const float4 *>(x + blk * 64 + 16 * s);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 v = __ldg(src + j);
+                f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = 0.f;
+        }
+        float m = 0.f;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) m = fmaxf(m, fabsf(f[e]));
+        m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 2));
+        m = guard_zero(m);
+        const float scale = quant_scale(kQmax, m);
+        uint32_t w[8];                                   // the PRNG call this thread's elements use (call s / 2)
+        if (STOCH) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t o = xs_next(lanes[k]);
+                    if (c == (s >> 1)) { w[2 * k] = (uint32_t)o; w[2 * k + 1] = (uint32_t)(o >> 32); }
+                }
+        }
+        if (!live) continue;
+        if (s == 0) scales[blk] = m;
+        int q[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            // element e = 16 s + i: noise slot (call e / 32, byte (e % 32) / 8, word e % 8)
+            const float rnd = STOCH ? noise_from_word(w[i & 7], 2 * (s & 1) + (i >> 3)) : 0.f;
+            q[i] = quant_one(f[i], scale, rnd);
+        }
+        if (BITS == 4) {
+            *reinterpret_cast<uint2 *>(values + blk * 32 + 8 * s) = make_uint2(pack8_nibbles(q), pack8_nibbles(q + 8));
+        } else {
+            *reinterpret_cast<uint4 *>(values + blk * 64 + 16 * s) =
+                make_uint4(pack4_bytes(q), pack4_bytes(q + 4), pack4_bytes(q + 8), pack4_bytes(q + 12));
+        }
+    }
+}
+
 template <int BITS>
 static int launch_vquantize(const float *x, uint64_t n_pad, int8_t *values, float *scales, uint64_t *key_host,
                             cudaStream_t stream) {
     const uint64_t nblocks = n_pad / kBlock;
     if (nblocks == 0) return CLOVER_OK;
-    // exactly ONE wave: as many thread slots as can be resident (registers allow 4 CTAs per SM; asked from the
-    // occupancy calculator, not assumed), then R consecutive blocks per thread. A second, partly filled wave
-    // cost 30% at n = 2^26 (profiles/r01_quantize4_ncu_summary.txt: 1.39 waves).
-    static int ctas_per_sm[2] = {0, 0};
-    int &cps = ctas_per_sm[key_host != nullptr];
-    if (cps == 0) {
-        cudaError_t e = key_host ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vquantize<BITS, true>, kQThreads, 0)
-                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vquantize<BITS, false>, kQThreads, 0);
-        if (e != cudaSuccess || cps < 1) cps = 1;
-    }
-    const uint64_t max_threads = (uint64_t)sm_count() * cps * kQThreads;
-    const uint64_t R = (nblocks + max_threads - 1) / max_threads;
-    const uint64_t threads = (nblocks + R - 1) / R;
-    const unsigned grid = (unsigned)((threads + kQThreads - 1) / kQThreads);
+    // CLOVER_QUANTIZE_IMPL=block selects the thread-per-block kernel (kept for A/B measurements)
+    static const bool per_block = getenv("CLOVER_QUANTIZE_IMPL") && !strcmp(getenv("CLOVER_QUANTIZE_IMPL"), "block");
     Key4 key = {};
+    const uint64_t *tables = nullptr;
     if (key_host) {
-        const uint64_t *tables = device_jump_tables();
+        tables = device_jump_tables();
         if (!tables) { set_error("clover: could not upload PRNG jump tables"); return CLOVER_ERR_CUDA; }
         key = key_lanes(key_host);
-        k_vquantize<BITS, true><<<grid, kQThreads, 0, stream>>>(x, nblocks, R, values, scales, key, tables);
-        host_key_skip(key_host, 2 * nblocks);
-    } else {
-        k_vquantize<BITS, false><<<grid, kQThreads, 0, stream>>>(x, nblocks, R, values, scales, key, nullptr);
     }
+    if (per_block) {
+        // exactly ONE wave: as many thread slots as can be resident, then R consecutive blocks per thread
+        static int ctas_per_sm[2] = {0, 0};
+        int &cps = ctas_per_sm[key_host != nullptr];
+        if (cps == 0) {
+            cudaError_t e = key_host ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vquantize<BITS, true>, kQThreads, 0)
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vquantize<BITS, false>, kQThreads, 0);
+            if (e != cudaSuccess || cps < 1) cps = 1;
+        }
+        const uint64_t max_threads = (uint64_t)sm_count() * cps * kQThreads;
+        const uint64_t R = (nblocks + max_threads - 1) / max_threads;
+        const uint64_t threads = (nblocks + R - 1) / R;
+        const unsigned grid = (unsigned)((threads + kQThreads - 1) / kQThreads);
+        if (key_host) k_vquantize<BITS, true><<<grid, kQThreads, 0, stream>>>(x, nblocks, R, values, scales, key, tables);
+        else          k_vquantize<BITS, false><<<grid, kQThreads, 0, stream>>>(x, nblocks, R, values, scales, key, nullptr);
+    } else {
+        static int ctas_per_sm[2] = {0, 0};
+        int &cps = ctas_per_sm[key_host != nullptr];
+        if (cps == 0) {
+            cudaError_t e = key_host ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vquantize4t<BITS, true>, kQ4Threads, 0)
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vquantize4t<BITS, false>, kQ4Threads, 0);
+            if (e != cudaSuccess || cps < 1) cps = 1;
+        }
+        const uint64_t max_groups = (uint64_t)sm_count() * cps * (kQ4Threads / 4);       // one resident wave
+        const uint64_t groups = nblocks < max_groups ? nblocks : max_groups;
+        const uint64_t R = (nblocks + groups - 1) / groups;
+        const unsigned grid = (unsigned)((groups * 4 + kQ4Threads - 1) / kQ4Threads);
+        if (key_host) k_vquantize4t<BITS, true><<<grid, kQ4Threads, 0, stream>>>(x, nblocks, R, values, scales, key, tables);
+        else          k_vquantize4t<BITS, false><<<grid, kQ4Threads, 0, stream>>>(x, nblocks, R, values, scales, key, nullptr);
+    }
+    if (key_host) host_key_skip(key_host, 2 * nblocks);
     count_launch();
     return launch_status("k_vquantize");
 }
