@@ -264,11 +264,15 @@ int gemm4_expand(const int8_t *values, uint64_t rows, uint64_t cols, uint8_t *ou
 
 int gemm4_tc2_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, const float *bs, uint64_t M, uint64_t N,
                        uint64_t K, float *c, uint64_t ldc, cudaStream_t stream, int cta_group);      // gemm4_tc2.cu
+int gemm4_tc3_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, const float *bs, uint64_t M, uint64_t N,
+                       uint64_t K, float *c, uint64_t ldc, cudaStream_t stream);                     // gemm4_tc3.cu
 
 int gemm4_tc_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, const float *bs, uint64_t M, uint64_t N,
                       uint64_t K, float *c, uint64_t ldc, cudaStream_t stream) {
     // CLOVER_GEMM_KERNEL=pipe1|pair selects an experimental 4-slot pipeline (gemm4_tc2.cu); default: this file's kernel
-    static const int variant = [] { const char *e = getenv("CLOVER_GEMM_KERNEL"); return !e ? 0 : !strcmp(e, "pipe1") ? 1 : !strcmp(e, "pair") ? 2 : 0; }();
+    static const int variant = [] { const char *e = getenv("CLOVER_GEMM_KERNEL");
+                                    return !e ? 0 : !strcmp(e, "pipe1") ? 1 : !strcmp(e, "pair") ? 2 : !strcmp(e, "p192") ? 3 : 0; }();
+    if (variant == 3) return gemm4_tc3_expanded(a8, as, b8, bs, M, N, K, c, ldc, stream);
     if (variant) return gemm4_tc2_expanded(a8, as, b8, bs, M, N, K, c, ldc, stream, variant);
     CUtensorMap map_a, map_b;
     int rc = make_tensor_map_u8_2d_sw128(&map_a, a8, M, K, kBM);

@@ -578,6 +578,176 @@ k_m8_mvm(const uint32_t *__restrict__ values, const float *__restrict__ scales, 
 }
 
 // =============================================================================================
+// mvm(V8,V8), pipelined (BASELINE C5): the arithmetic of k_m8_mvm<8> fed by a TMA ring, with 32-row work items
+// =============================================================================================
+// Why a second kernel: k_m8_mvm launches one CTA per 64-row block and streams with plain loads - 512 row blocks on
+// 148 SMs run as 3.46 "rounds" (86 % ceiling) and the loads of a thread are 64 bytes apart. Here
+//   * the grid is persistent (one CTA per SM) and a work item is HALF a row block (32 rows): 1024 items at
+//     32768 rows = 6.92 rounds (98.8 %). The two halves of a block may be computed by different CTAs: each writes
+//     its 32 fp32 row results to global memory, takes a ticket on the block's counter, and the second finisher
+//     re-quantizes the 64 values (threadfence + atomic "last block" pattern) and re-arms the counter;
+//   * warp 8 (one lane) issues, per stage, eight cp.async.bulk.tensor.2d boxes of 32 rows x 128 B with the
+//     128-byte shared-memory swizzle into a 5-stage ring (160 KiB in flight per SM), L2 evict-first;
+//   * warp 9 expands the matching 16 blocks of x into (xa, xb, prod) units;
+//   * warps 0-7: thread = the reference's fp32 chain (row r, AVX lane l) (CloverMatrix8.h:1029-1095). Warp =
+//     8 rows x 4 lanes (l = 4*type .. 4*type+3): the swizzle XORs the 16-byte chunk index with (row & 7), so the
+//     32 words of a warp-wide load fall into 32 different banks. Per block: 2 LDS.32 + 1 LDS.128 + 2 DP4A on top
+//     of the magic constant 1.5*2^23 (as_float(sum) - 1.5*2^23 IS float(sum): no I2F) + 1 FADD + 1 FFMA, FMAs in
+//     block order => fp32 row results and re-quantized bytes identical to k_m8_mvm and to the AVX2 code.
+constexpr int kG8Rows = 32;                 // rows per work item
+constexpr int kG8Chunks = 8;                // 128-byte column chunks per stage = 16 blocks of 64 columns
+constexpr int kG8Stages = 5;
+constexpr int kG8Consumers = 256;
+constexpr int kG8Threads = kG8Consumers + 64;
+constexpr int kG8ChunkBytes = kG8Rows * 128;
+
+struct __align__(1024) Gemv8Stage {
+    uint8_t rows[kG8Chunks][kG8ChunkBytes];   // chunk c: rows 0..31 x 128 B, SWIZZLE_128B (each 4 KiB, 1024-aligned)
+    uint4 units[kG8Chunks * 2 * 8];           // unit (block, l): x = xa, y = xb, z = bits of prod
+};
+struct Gemv8Smem {
+    Gemv8Stage stage[kG8Stages];
+    uint64_t full[kG8Stages];
+    uint64_t empty[kG8Stages];
+    float part[kG8Rows][8];
+    float ysm[64];
+    float red_f[2];
+    int red_q[64];
+    unsigned int ticket;
+};
+
+template <bool STOCH>
+__global__ void __launch_bounds__(kG8Threads, 1)
+k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows_local,
+             uint64_t cols, uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
+             float *__restrict__ ybuf, unsigned int *__restrict__ counters, int8_t *__restrict__ yv,
+             float *__restrict__ ys, Key4 key, const uint64_t *__restrict__ tables) {
+    extern __shared__ uint8_t smem_raw8[];
+    Gemv8Smem &sm = *reinterpret_cast<Gemv8Smem *>((reinterpret_cast<uintptr_t>(smem_raw8) + 1023u) & ~(uintptr_t)1023u);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t hb = cols >> 6, nitems = rows_local / kG8Rows;
+    const uint32_t nchunks128 = (uint32_t)(cols >> 7);                    // 128-byte chunks per row
+    const uint32_t steps = (nchunks128 + kG8Chunks - 1) / kG8Chunks;      // stages per work item
+
+    if (tid == 0) {
+        for (int s = 0; s < kG8Stages; ++s) {
+            mbar_init(&sm.full[s], 1 + 32);              // TMA issuer (posts the tx bytes) + the 32 unit lanes
+            mbar_init(&sm.empty[s], kG8Consumers / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kG8Consumers / 32) {
+        // ------------------------------- TMA issuer -------------------------------
+        if (lane == 0) {
+            tma_prefetch_descriptor(&tmap);
+            const uint64_t policy = policy_evict_first();
+            uint32_t it = 0;
+            for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+                for (uint32_t c = 0; c < steps; ++c, ++it) {
+                    const int s = it % kG8Stages;
+                    const uint32_t live = min((uint32_t)kG8Chunks, nchunks128 - c * kG8Chunks);
+                    mbar_wait(&sm.empty[s], ((it / kG8Stages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&sm.full[s], live * kG8ChunkBytes);
+                    for (uint32_t j = 0; j < live; ++j)
+                        tma_load_2d(sm.stage[s].rows[j], &tmap, (int)((c * kG8Chunks + j) * 128), (int)(item * kG8Rows),
+                                    &sm.full[s], policy);
+                }
+            }
+        }
+    } else if (warp == kG8Consumers / 32 + 1) {
+        // ------------------------------- x-unit warp -------------------------------
+        // lane owns units lane + 32j (j = 0..3) of a stage = (block 4j + lane/8, AVX lane lane%8)
+        uint32_t it = 0;
+        const int l = lane & 7;
+        for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const float *su = scales + (item >> 1) * hb;
+            for (uint32_t c = 0; c < steps; ++c, ++it) {
+                const int s = it % kG8Stages;
+                uint4 u[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint64_t b = (uint64_t)c * (2 * kG8Chunks) + 4 * j + (lane >> 3);
+                    const bool ok = b < hb;
+                    u[j].x = ok ? __ldg(xv + b * 16 + l) : 0u;
+                    u[j].y = ok ? __ldg(xv + b * 16 + 8 + l) : 0u;
+                    const float sa = ok ? __ldg(su + b) : 0.f, sb = ok ? __ldg(xs + b) : 0.f;
+                    u[j].z = __float_as_uint(__fmul_rn(__fmul_rn(sa, 1.0f / 127.0f), __fmul_rn(sb, 1.0f / 127.0f)));   // (CloverMatrix8.h:1042-1046)
+                    u[j].w = 0u;
+                }
+                mbar_wait(&sm.empty[s], ((it / kG8Stages) & 1) ^ 1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sm.stage[s].units[lane + 32 * j] = u[j];
+                mbar_arrive(&sm.full[s]);
+            }
+        }
+    } else {
+        // ------------------------------- consumer warps ------------------------------
+        const int ty = warp & 1, rin = lane >> 2, l = 4 * ty + (lane & 3);
+        const int r = 8 * (warp >> 1) + rin;                                 // row of the work item
+        // byte offsets of this thread's two words of block b (b = 0, 1) inside a swizzled 32 x 128 B chunk
+        const uint32_t base = (uint32_t)r * 128u + 4u * (uint32_t)(lane & 3);
+        const uint32_t oa0 = base + ((uint32_t)((0 + ty) ^ rin) << 4), ob0 = base + ((uint32_t)((2 + ty) ^ rin) << 4);
+        const uint32_t oa1 = base + ((uint32_t)((4 + ty) ^ rin) << 4), ob1 = base + ((uint32_t)((6 + ty) ^ rin) << 4);
+        uint32_t it = 0;
+        for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+            float acc = 0.f;
+            for (uint32_t c = 0; c < steps; ++c, ++it) {
+                const int s = it % kG8Stages;
+                mbar_wait(&sm.full[s], (it / kG8Stages) & 1);
+                const Gemv8Stage &st = sm.stage[s];
+                const int live = (int)min((uint32_t)kG8Chunks, nchunks128 - c * kG8Chunks);
+                auto chunk = [&](int j) {
+                    const uint8_t *p = st.rows[j];
+                    const uint32_t wa0 = *reinterpret_cast<const uint32_t *>(p + oa0), wb0 = *reinterpret_cast<const uint32_t *>(p + ob0);
+                    const uint32_t wa1 = *reinterpret_cast<const uint32_t *>(p + oa1), wb1 = *reinterpret_cast<const uint32_t *>(p + ob1);
+                    const uint4 u0 = st.units[(2 * j) * 8 + l], u1 = st.units[(2 * j + 1) * 8 + l];
+                    int d0 = dp4a_ss((int)wa0, (int)u0.x, (int)kMagicBits);
+                    d0 = dp4a_ss((int)wb0, (int)u0.y, d0);
+                    int d1 = dp4a_ss((int)wa1, (int)u1.x, (int)kMagicBits);
+                    d1 = dp4a_ss((int)wb1, (int)u1.y, d1);
+                    acc = __fmaf_rn(__uint_as_float(u0.z), __fsub_rn(__int_as_float(d0), 12582912.0f), acc);   // (:1093-1094)
+                    acc = __fmaf_rn(__uint_as_float(u1.z), __fsub_rn(__int_as_float(d1), 12582912.0f), acc);
+                };
+                if (live == kG8Chunks) {
+#pragma unroll
+                    for (int j = 0; j < kG8Chunks; ++j) chunk(j);
+                } else {
+                    for (int j = 0; j < live; ++j) chunk(j);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[s]);
+            }
+            // hadd tree ((a4+a0)+(a6+a2))+((a5+a1)+(a7+a3)) (CloverBase.h:149-157); the 8 lanes of a row sit in two warps
+            named_bar_sync(2, kG8Consumers);                                    // previous epilogue is done with part/ysm
+            sm.part[r][l] = acc;
+            named_bar_sync(2, kG8Consumers);
+            const uint64_t rb = item >> 1, grb = rowblock0 + rb;
+            if (tid < kG8Rows) {
+                const float *a = sm.part[tid];
+                const float y = __fadd_rn(__fadd_rn(__fadd_rn(a[4], a[0]), __fadd_rn(a[6], a[2])),
+                                          __fadd_rn(__fadd_rn(a[5], a[1]), __fadd_rn(a[7], a[3])));
+                ybuf[grb * 64 + (item & 1) * kG8Rows + tid] = y;
+                __threadfence();
+            }
+            named_bar_sync(2, kG8Consumers);
+            if (tid == 0) sm.ticket = yv ? atomicAdd(counters + rb, 1u) : 0u;
+            named_bar_sync(2, kG8Consumers);
+            if (sm.ticket == 1u) {                                              // both halves of the block are in ybuf
+                if (tid < 64) {
+                    __threadfence();
+                    const float y = __ldcg(ybuf + grb * 64 + tid);
+                    requantize_block<8, STOCH>(y, tid, grb, yv, ys, key, tables, sm.red_f, sm.red_q);
+                    if (tid == 0) counters[rb] = 0u;                            // re-armed for the next launch
+                }
+            }
+        }
+    }
+}
+
+// =============================================================================================
 // mvm(V32,V32): 4-bit matrix, fp32 vectors (CloverMatrix4.h:1451-1547). One warp per row; lane 8k+l
 // is the reference's chain (accumulator k, AVX lane l): per block element 8k+l, then 32+8k+l.
 // =============================================================================================
@@ -623,6 +793,32 @@ k_requantize_mvm(const float *__restrict__ y32, uint64_t nblocks, int8_t *__rest
     }
 }
 
+// grow-only per-device scratch of the pipelined 8-bit GEMV: fp32 row results (when the caller passes no y32) and one
+// zero-initialised counter per row block. Not thread-safe: one GEMV stream per device, like the GEMM workspace.
+static int mvm_scratch(uint64_t nrb_local, uint64_t nrb_global_end, float **ybuf, unsigned int **counters) {
+    static float *g_y[64] = {nullptr};
+    static uint64_t g_y_blocks[64] = {0};
+    static unsigned int *g_c[64] = {nullptr};
+    static uint64_t g_c_blocks[64] = {0};
+    int dev = 0;
+    CLOVER_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
+    if (ybuf && g_y_blocks[dev] < nrb_global_end) {
+        if (g_y[dev]) { CLOVER_CUDA_CHECK(cudaDeviceSynchronize()); CLOVER_CUDA_CHECK(cudaFree(g_y[dev])); g_y[dev] = nullptr; g_y_blocks[dev] = 0; }
+        CLOVER_CUDA_CHECK(cudaMalloc(&g_y[dev], nrb_global_end * 64 * sizeof(float)));
+        g_y_blocks[dev] = nrb_global_end;
+    }
+    if (g_c_blocks[dev] < nrb_local) {
+        if (g_c[dev]) { CLOVER_CUDA_CHECK(cudaDeviceSynchronize()); CLOVER_CUDA_CHECK(cudaFree(g_c[dev])); g_c[dev] = nullptr; g_c_blocks[dev] = 0; }
+        CLOVER_CUDA_CHECK(cudaMalloc(&g_c[dev], nrb_local * sizeof(unsigned int)));
+        CLOVER_CUDA_CHECK(cudaMemset(g_c[dev], 0, nrb_local * sizeof(unsigned int)));
+        g_c_blocks[dev] = nrb_local;
+    }
+    if (ybuf) *ybuf = g_y[dev];
+    *counters = g_c[dev];
+    return CLOVER_OK;
+}
+
 template <int BITS>
 static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_local, uint64_t cols, uint64_t row0,
                       const int8_t *xv, const float *xs, float *y32, int8_t *yv, float *ys, const uint64_t *key_host,
@@ -663,8 +859,33 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
                                                         key, tables, peers ? *peers : PeerOut());
         }
     } else {
-        if (stoch) k_m8_mvm<8, true><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
-        else       k_m8_mvm<8, false><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
+        static const bool force_simple8 = getenv("CLOVER_GEMV_IMPL") && !strcmp(getenv("CLOVER_GEMV_IMPL"), "simple");
+        const bool simple = force_simple8 || (reinterpret_cast<uintptr_t>(values) & 15u) != 0;
+        if (simple) {
+            if (stoch) k_m8_mvm<8, true><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
+            else       k_m8_mvm<8, false><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
+        } else {
+            // fp32 row results pass through global memory (the caller's y32, else a grow-only per-device scratch) and a
+            // zero-initialised counter per row block, re-armed by the kernel itself (one GEMV stream per device).
+            float *ybuf = y32;
+            unsigned int *counters = nullptr;
+            int rc = mvm_scratch(nrb, (row0 >> 6) + nrb, y32 ? nullptr : &ybuf, &counters);
+            if (rc != CLOVER_OK) return rc;
+            const int smem = (int)sizeof(Gemv8Smem) + 1024;
+            static bool attr_set8[2] = {false, false};
+            auto kern = stoch ? k_m8_mvm_tma<true> : k_m8_mvm_tma<false>;
+            if (!attr_set8[stoch]) {
+                CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                attr_set8[stoch] = true;
+            }
+            CUtensorMap tmap;
+            rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows_local, cols, kG8Rows);
+            if (rc != CLOVER_OK) return rc;
+            const uint64_t nitems = rows_local / kG8Rows;
+            const unsigned pgrid = (unsigned)(nitems < (uint64_t)sm_count() ? nitems : (uint64_t)sm_count());
+            kern<<<pgrid, kG8Threads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, ybuf, counters, yv, ys,
+                                                      key, tables);
+        }
     }
     count_launch();
     return launch_status("k_mvm");

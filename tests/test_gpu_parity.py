@@ -246,6 +246,75 @@ def test_matrix_stochastic_matches_reference_stream(cb, oracle, shape, bits_):
     assert np.array_equal(qa.key, st)
 
 
+def _random_m8(cb, rows, cols, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    m = cb.CloverMatrix8(rows, cols)
+    m.values.copy_(torch.randint(-127, 128, (rows * cols,), dtype=torch.int8, device="cuda", generator=g))
+    m.scales.uniform_(0.05, 4.0, generator=g)
+    return m
+
+
+def _random_v8(cb, n, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    v = cb.CloverVector8(n)
+    v.values.copy_(torch.randint(-127, 128, (n,), dtype=torch.int8, device="cuda", generator=g))
+    v.scales.uniform_(0.05, 4.0, generator=g)
+    return v
+
+
+@pytest.mark.parametrize("shape", [(4736 + 128, 256), (148 * 32 * 3 + 64, 2048 + 128), (8192, 1024 * 17)])
+def test_mvm8_pipelined_many_items_vs_oracle(cb, oracle, shape):
+    """CloverMatrix8::mvm through the persistent TMA-ring kernel when every CTA walks several 32-row work items, the
+    ring wraps many times and the two halves of a row block are finished by different CTAs: fp32 row results, packed
+    bytes and scales bit-for-bit against the oracle (inputs are random packed operands, not quantizer output)."""
+    rows, cols = shape
+    A, x = _random_m8(cb, rows, cols, 31), _random_v8(cb, cols, 32)
+    y = cb.CloverVector8(rows)
+    y32 = torch.zeros(rows, dtype=torch.float32, device="cuda")
+    for _ in range(2):                          # second call: the block counters must have been re-armed
+        A.mvm(x, y, y32=y32)
+    wv, ws, w32 = oracle.m8_mvm(A.values.cpu().numpy(), A.scales.cpu().numpy(), rows, cols,
+                                x.values.cpu().numpy(), x.scales.cpu().numpy(), want_f32=True)
+    assert np.array_equal(bits(y32.cpu().numpy()), bits(w32))
+    assert np.array_equal(y.getData().cpu().numpy(), wv)
+    assert np.array_equal(bits(y.getScales().cpu().numpy()[: rows // 64]), bits(ws[: rows // 64]))
+    y2 = cb.CloverVector8(rows)
+    A.mvm(x, y2)                                # without a caller-provided fp32 buffer (internal scratch)
+    assert torch.equal(y2.values, y.values) and torch.equal(y2.scales, y.scales)
+
+
+def test_full_size_properties_c5(cb):
+    """BASELINE config C5 (32768 x 32768, 8-bit): fp32 row results against an fp64 evaluation of the same exact block
+    integers (rule-3 bound), and the re-quantized vector == the reference re-quantizer applied to those fp32 values
+    (block absmax, 127/max as an IEEE divide, truncation) evaluated with torch on the same device."""
+    n = 32768
+    A, x = _random_m8(cb, n, n, 41), _random_v8(cb, n, 42)
+    y = cb.CloverVector8(n)
+    y32 = torch.zeros(n, dtype=torch.float32, device="cuda")
+    A.mvm(x, y, y32=y32)
+    torch.cuda.synchronize()
+    hb = n // 64
+    xs64 = x.values.view(hb, 64).to(torch.float16)
+    prod = ((A.scales.view(hb, hb) * np.float32(1.0 / 127.0)) * (x.scales[:hb] * np.float32(1.0 / 127.0)).unsqueeze(0))
+    ref = torch.empty(n, dtype=torch.float64, device="cuda")
+    sum_abs = torch.empty(n, dtype=torch.float64, device="cuda")
+    step = 2048
+    for r0 in range(0, n, step):                # fp16 products of int8 values accumulate exactly in fp32 (<= 64 * 127^2)
+        a = A.values.view(n, hb, 64)[r0:r0 + step].to(torch.float16)
+        ib = torch.einsum("rbk,bk->rb", a.float(), xs64.float()).to(torch.float64)
+        p = prod[r0 // 64:(r0 + step) // 64].repeat_interleave(64, dim=0).to(torch.float64)
+        ref[r0:r0 + step] = (p * ib).sum(1)
+        sum_abs[r0:r0 + step] = (p * ib).abs().sum(1)
+    eps = float(np.finfo(np.float32).eps)
+    assert bool(((y32.double() - ref).abs() <= 4 * eps * sum_abs + 1e-30).all())
+    m = y32.abs().view(-1, 64).max(1).values
+    m = torch.where(m == 0, torch.ones_like(m), m)
+    scale = (torch.full_like(m, 127.0) / m).unsqueeze(1)
+    q = torch.trunc(y32.abs().view(-1, 64) * scale) * torch.sign(y32.view(-1, 64))
+    assert torch.equal(y.values.view(-1, 64).to(torch.float32), q)
+    assert torch.equal(y.scales[: n // 64], m)
+
+
 def test_mvm_size_mismatch_raises(cb):
     qa = cb.CloverMatrix4(128, 256)
     with pytest.raises(cb.CloverSizeError):
@@ -387,7 +456,7 @@ def test_gemm_tensor_core_equals_simt(cb, mnk):
     assert bool((big[:, N:] == 7.0).all())
 
 
-@pytest.mark.parametrize("variant", ["pipe1", "pair"])
+@pytest.mark.parametrize("variant", ["pipe1", "pair", "p192"])
 def test_gemm_experimental_pipelines_equal_simt(variant):
     """The 4-slot TMEM-ring variants (gemm4_tc2.cu, CLOVER_GEMM_KERNEL) stay bit-identical to the DP4A kernel.
     The variant is read once per process, hence the subprocess."""
@@ -400,7 +469,7 @@ def test_gemm_experimental_pipelines_equal_simt(variant):
         "def mk(r, c):\n"
         "    m = cb.CloverMatrix4(r, c); m.values.copy_(random_nibbles(torch, r * c // 2, g, torch.device('cuda')))\n"
         "    m.scales.uniform_(0.05, 4.0, generator=g); return m\n"
-        "for (M, N, K) in [(128, 128, 128), (384, 640, 1152), (2176, 2048, 2048)]:\n"
+        "for (M, N, K) in [(128, 128, 128), (384, 640, 1152), (2176, 2048, 2048), (4096, 4224, 1024)]:\n"
         "    A, B = mk(M, K), mk(N, K)\n"
         "    assert torch.equal(A.gemm(B, impl='tc').view(torch.int32), A.gemm(B, impl='simt').view(torch.int32)), (M, N, K)\n"
         "print('ok')\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
