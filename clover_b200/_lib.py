@@ -61,6 +61,8 @@ _SIGNATURES = {
     "clover_m4_gemm_simt": (_int, [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _vp, _u64, _vp]),
     "clover_m8_quantize": (_int, [_vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "clover_m8_mvm": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "clover_m4_transpose": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp]),
+    "clover_m8_transpose": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     "clover_host_v4_quantize": (_int, [_vp, _u64, _vp, _vp, _vp]),
     "clover_host_v4_dot": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _int]),
 }

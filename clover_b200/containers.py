@@ -267,6 +267,15 @@ class _QMatrix(_Keyed):
              _ptr(productVector.values), _ptr(productVector.scales), _ptr(resultVector.values), _ptr(resultVector.scales),
              _ptr(y32), self._key_ptr(), _stream())
 
+    def transpose(self, other) -> None:
+        """other(j, i) = self(i, j), scales included (include/CloverMatrix4.h:1549-1663, CloverMatrix8.h:1359-1385)."""
+        if type(other) is not type(self) or other.rows != self.cols or other.cols != self.rows:
+            raise CloverSizeError("Matrix can not be transposed.")
+        call(f"clover_m{self.BITS}_transpose", _ptr(self.values), _ptr(self.scales), C.c_uint64(self.rows),
+             C.c_uint64(self.cols), _ptr(other.values), _ptr(other.scales), _stream())
+
+    transpose_scalar = transpose_parallel = transpose
+
 
 class CloverMatrix4(_QMatrix):
     """4-bit row-major matrix, one absmax scale per 64x64 tile (include/CloverMatrix4.h:38-93)."""

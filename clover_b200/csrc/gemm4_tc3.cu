@@ -63,6 +63,7 @@ __device__ __forceinline__ void cluster3_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(k3Threads, 1)
 k_gemm4_tc3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const float *__restrict__ as, const float *__restrict__ bs, uint32_t M, uint32_t N, uint32_t K,
@@ -174,35 +175,110 @@ k_gemm4_tc3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = 0ull;
             float sv = 0.f;
-            {   // first half of the tile's first slab -> ra
-                const uint32_t b = g & 1;
-                mbar_wait_a(tfull + 8 * b, (g >> 1) & 1);
-                tc_fence_after();
-                tmem_ld32(taddr + 256 * b, ra);
-            }
-            for (uint32_t kb = 0; kb < KB; ++kb) {
-                if ((kb & 31) == 0) {        // lane l owns the scale of slab kb + l: s = (sA * (1/49)) * sB, the reference's order
-                    const uint32_t kl = min(kb + lane, KB - 1);
-                    sv = __fmul_rn(__fmul_rn(__ldg(pa + kl), 1.0f / 49.0f), __ldg(pb + kl));
-                }
-                const float s = __shfl_sync(0xFFFFFFFFu, sv, kb & 31);
-                const uint32_t b = g & 1;
-                tmem_ld_wait(ra);                                        // first half of slab g has landed
-                tmem_ld32(taddr + 256 * b + 32, rb);                     // second half, lands under the FMAs below
-#pragma unroll
-                for (int j = 0; j < 16; ++j) ffma2(acc[j], s, ra[2 * j], ra[2 * j + 1]);
-                tmem_ld_wait(rb);
-                tc_fence_before();                                       // this warp's share of the buffer is drained
-                if (lane == 0) mbar3_arrive_cluster(tempty_leader + 8 * b);
-                ++g;
-                if (kb + 1 < KB) {                                       // first half of the next slab, lands under the FMAs below
-                    const uint32_t b2 = g & 1;
-                    mbar_wait_a(tfull + 8 * b2, (g >> 1) & 1);
+            if (MODE == 0) {
+                // ---- mode 0: rolling halves - one 32-column load in flight per warp ----
+                {   // first half of the tile's first slab -> ra
+                    const uint32_t b = g & 1;
+                    mbar_wait_a(tfull + 8 * b, (g >> 1) & 1);
                     tc_fence_after();
-                    tmem_ld32(taddr + 256 * b2, ra);
+                    tmem_ld32(taddr + 256 * b, ra);
                 }
+                for (uint32_t kb = 0; kb < KB; ++kb) {
+                    if ((kb & 31) == 0) {        // lane l owns the scale of slab kb + l: s = (sA * (1/49)) * sB, the reference's order
+                        const uint32_t kl = min(kb + lane, KB - 1);
+                        sv = __fmul_rn(__fmul_rn(__ldg(pa + kl), 1.0f / 49.0f), __ldg(pb + kl));
+                    }
+                    const float s = __shfl_sync(0xFFFFFFFFu, sv, kb & 31);
+                    const uint32_t b = g & 1;
+                    tmem_ld_wait(ra);                                        // first half of slab g has landed
+                    tmem_ld32(taddr + 256 * b + 32, rb);                     // second half, lands under the FMAs below
 #pragma unroll
-                for (int j = 0; j < 16; ++j) ffma2(acc[16 + j], s, rb[2 * j], rb[2 * j + 1]);
+                    for (int j = 0; j < 16; ++j) ffma2(acc[j], s, ra[2 * j], ra[2 * j + 1]);
+                    tmem_ld_wait(rb);
+                    tc_fence_before();                                       // this warp's share of the buffer is drained
+                    if (lane == 0) mbar3_arrive_cluster(tempty_leader + 8 * b);
+                    ++g;
+                    if (kb + 1 < KB) {                                       // first half of the next slab, lands under the FMAs below
+                        const uint32_t b2 = g & 1;
+                        mbar_wait_a(tfull + 8 * b2, (g >> 1) & 1);
+                        tc_fence_after();
+                        tmem_ld32(taddr + 256 * b2, ra);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) ffma2(acc[16 + j], s, rb[2 * j], rb[2 * j + 1]);
+                }
+            } else if (MODE == 1) {
+                // ---- mode 1: batch - both halves of a slab are requested together, the buffer is released before any FMA ----
+                for (uint32_t kb = 0; kb < KB; ++kb, ++g) {
+                    if ((kb & 31) == 0) {
+                        const uint32_t kl = min(kb + lane, KB - 1);
+                        sv = __fmul_rn(__fmul_rn(__ldg(pa + kl), 1.0f / 49.0f), __ldg(pb + kl));
+                    }
+                    const float s = __shfl_sync(0xFFFFFFFFu, sv, kb & 31);
+                    const uint32_t b = g & 1;
+                    mbar_wait_a(tfull + 8 * b, (g >> 1) & 1);
+                    tc_fence_after();
+                    tmem_ld32(taddr + 256 * b, ra);
+                    tmem_ld32(taddr + 256 * b + 32, rb);
+                    tmem_ld_wait(ra);
+                    tmem_ld_wait(rb);
+                    tc_fence_before();
+                    if (lane == 0) mbar3_arrive_cluster(tempty_leader + 8 * b);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) ffma2(acc[j], s, ra[2 * j], ra[2 * j + 1]);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) ffma2(acc[16 + j], s, rb[2 * j], rb[2 * j + 1]);
+                }
+            } else if (MODE == 3 || MODE == 4) {
+                // ---- measurement only (wrong results): 3 = hand-off without loads or FMAs, 4 = batch loads without FMAs ----
+                for (uint32_t kb = 0; kb < KB; ++kb, ++g) {
+                    const uint32_t b = g & 1;
+                    mbar_wait_a(tfull + 8 * b, (g >> 1) & 1);
+                    tc_fence_after();
+                    if (MODE == 4) {
+                        tmem_ld32(taddr + 256 * b, ra);
+                        tmem_ld32(taddr + 256 * b + 32, rb);
+                        tmem_ld_wait(ra);
+                        tmem_ld_wait(rb);
+                        acc[kb & 31] ^= ((uint64_t)ra[kb & 31] << 32) | rb[kb & 31];
+                    }
+                    tc_fence_before();
+                    if (lane == 0) mbar3_arrive_cluster(tempty_leader + 8 * b);
+                }
+            } else {
+                // ---- mode 2: staggered batch - ra(g+1) is requested under the FMAs of rb(g), rb(g+1) right after them;
+                //      one wait covers both, so two loads per warp overlap and the buffer is still released before its FMAs ----
+                {
+                    const uint32_t b = g & 1;
+                    mbar_wait_a(tfull + 8 * b, (g >> 1) & 1);
+                    tc_fence_after();
+                    tmem_ld32(taddr + 256 * b, ra);
+                    tmem_ld32(taddr + 256 * b + 32, rb);
+                }
+                for (uint32_t kb = 0; kb < KB; ++kb) {
+                    if ((kb & 31) == 0) {
+                        const uint32_t kl = min(kb + lane, KB - 1);
+                        sv = __fmul_rn(__fmul_rn(__ldg(pa + kl), 1.0f / 49.0f), __ldg(pb + kl));
+                    }
+                    const float s = __shfl_sync(0xFFFFFFFFu, sv, kb & 31);
+                    tmem_ld_wait(ra);
+                    tmem_ld_wait(rb);
+                    tc_fence_before();                                       // slab g is in registers
+                    if (lane == 0) mbar3_arrive_cluster(tempty_leader + 8 * (g & 1));
+                    ++g;
+                    const bool more = kb + 1 < KB;
+                    const uint32_t b2 = g & 1;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) ffma2(acc[j], s, ra[2 * j], ra[2 * j + 1]);
+                    if (more) {
+                        mbar_wait_a(tfull + 8 * b2, (g >> 1) & 1);
+                        tc_fence_after();
+                        tmem_ld32(taddr + 256 * b2, ra);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) ffma2(acc[16 + j], s, rb[2 * j], rb[2 * j + 1]);
+                    if (more) tmem_ld32(taddr + 256 * b2 + 32, rb);
+                }
             }
             if (live) {
                 float *crow = c + (uint64_t)(row0 + q * 32 + lane) * ldc + (uint64_t)jb * 64;
@@ -228,13 +304,9 @@ int gemm4_tc3_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, co
     if (rc != CLOVER_OK) return rc;
     rc = make_tensor_map_u8_2d_sw128(&map_b, b8, N, K, k3BN / 2);
     if (rc != CLOVER_OK) return rc;
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    CLOVER_CUDA_CHECK(cudaGetDevice(&dev));
-    if (!attr_set[dev & 63]) {
-        CLOVER_CUDA_CHECK(cudaFuncSetAttribute(k_gemm4_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, k3Smem));
-        attr_set[dev & 63] = true;
-    }
+    static const int mode = [] { const char *e = getenv("CLOVER_GEMM_EPI"); return e ? atoi(e) : 1; }();   // epilogue schedule, see the kernel (1 = batch: best measured)
+    auto kern = mode == 0 ? k_gemm4_tc3<0> : mode == 1 ? k_gemm4_tc3<1> : mode == 3 ? k_gemm4_tc3<3> : mode == 4 ? k_gemm4_tc3<4> : k_gemm4_tc3<2>;
+    CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k3Smem));
     const uint64_t ntiles = ((M + 2 * k3BM - 1) / (2 * k3BM)) * ((N + k3BN - 1) / k3BN);
     const unsigned groups = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sm_count() / 2);
     cudaLaunchConfig_t cfg = {};
@@ -246,7 +318,7 @@ int gemm4_tc3_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, co
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CLOVER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm4_tc3, map_a, map_b, as, bs, (uint32_t)M, (uint32_t)N, (uint32_t)K, c, ldc));
+    CLOVER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, as, bs, (uint32_t)M, (uint32_t)N, (uint32_t)K, c, ldc));
     count_launch();
     return launch_status("k_gemm4_tc3");
 }

@@ -173,6 +173,16 @@ int clover_m8_mvm(const int8_t *values, const float *scales, uint64_t rows, uint
                   const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32,
                   uint64_t *key_host, void *stream);
 
+/* ---- transpose -------------------------------------------------------------------
+ * CloverMatrix4::transpose     include/CloverMatrix4.h:1549-1663 (_scalar :435-502, _parallel :2508-2640)
+ * CloverMatrix8::transpose     include/CloverMatrix8.h:1359-1385 (_scalar :1312-1336, _parallel :1338-1357)
+ * out is the cols x rows matrix with out(j, i) = in(i, j); the 64x64-tile scales are transposed likewise
+ * (the reference calls ippiTranspose_32f_C1R for those). Out of place only, like the reference. */
+int clover_m4_transpose(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                        int8_t *out_values, float *out_scales, void *stream);
+int clover_m8_transpose(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                        int8_t *out_values, float *out_scales, void *stream);
+
 /* ---- host-buffer convenience (the call a reference user makes: host containers in, host out) -----
  * Each does pinned-staging H2D, the kernels above, and D2H of the result on `stream`, then syncs. */
 int clover_host_v4_quantize(const float *x_host, uint64_t n_pad, int8_t *values_host, float *scales_host, uint64_t *key_host);

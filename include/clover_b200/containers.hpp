@@ -274,6 +274,19 @@ public:
     }
     void mvm_scalar(const QVector &x, QVector &y) { mvm(x, y); }
     void mvm_parallel(const QVector &x, QVector &y) { mvm(x, y); }
+
+    // include/CloverMatrix4.h:1549-1663 / include/CloverMatrix8.h:1359-1385: other(j, i) = this(i, j), scales included
+    void transpose(CloverQuantizedMatrix &other) {
+        if (other.rows != cols || other.cols != rows) { std::cout << "Matrix can not be transposed. Exiting ..." << std::endl; exit(1); }
+        char *d = static_cast<char *>(other.buf.dev_out());
+        int8_t *ov = reinterpret_cast<int8_t *>(d);
+        float *os = reinterpret_cast<float *>(d + other.value_bytes());
+        const int rc = BITS == 4 ? clover_m4_transpose(device_values(), device_scales(), rows, cols, ov, os, nullptr)
+                                 : clover_m8_transpose(device_values(), device_scales(), rows, cols, ov, os, nullptr);
+        clover_b200_detail::check(rc, "transpose");
+    }
+    void transpose_scalar(CloverQuantizedMatrix &other) { transpose(other); }
+    void transpose_parallel(CloverQuantizedMatrix &other) { transpose(other); }
 };
 
 class CloverMatrix4 : public CloverQuantizedMatrix<4, CloverVector4> {

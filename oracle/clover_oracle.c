@@ -511,3 +511,35 @@ void orc_m4_gemm(const int8_t *av, const float *as, const int8_t *btv, const flo
             c[(i - i0) * ldc + (j - j0)] =
                 dot4_chains(av + ((i * K) >> 1), as + (i >> 6) * kb, btv + ((j * K) >> 1), bts + (j >> 6) * kb, kb);
 }
+
+/* transpose: include/CloverMatrix4.h:435-502 (scalar), :1549-1663 (AVX2 8x8 nibble blocks),
+ * :2508-2640 (parallel), :2649-2802 (faster scalar); include/CloverMatrix8.h:1312-1385. A pure permutation:
+ * element (i, j) of the rows x cols source becomes element (j, i) of the cols x rows result, the 64x64-tile scales
+ * are transposed likewise (the reference delegates that to ippiTranspose_32f_C1R). Nibble order inside a byte is
+ * kept (even column in the high nibble). */
+void orc_m4_transpose(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                      int8_t *out_values, float *out_scales) {
+    const uint8_t *u = (const uint8_t *)values;
+    uint8_t *v = (uint8_t *)out_values;
+    memset(v, 0, rows * cols / 2);
+    #pragma omp parallel for schedule(static)
+    for (uint64_t j = 0; j < cols; ++j)
+        for (uint64_t i = 0; i < rows; ++i) {
+            const uint8_t b = u[(i * cols + j) >> 1];
+            const uint8_t q = (j & 1) ? (b & 0x0F) : (b >> 4);
+            v[(j * rows + i) >> 1] |= (i & 1) ? q : (uint8_t)(q << 4);
+        }
+    const uint64_t vb = rows >> 6, hb = cols >> 6;
+    for (uint64_t bi = 0; bi < vb; ++bi)
+        for (uint64_t bj = 0; bj < hb; ++bj) out_scales[bj * vb + bi] = scales[bi * hb + bj];
+}
+
+void orc_m8_transpose(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                      int8_t *out_values, float *out_scales) {
+    #pragma omp parallel for schedule(static)
+    for (uint64_t j = 0; j < cols; ++j)
+        for (uint64_t i = 0; i < rows; ++i) out_values[j * rows + i] = values[i * cols + j];
+    const uint64_t vb = rows >> 6, hb = cols >> 6;
+    for (uint64_t bi = 0; bi < vb; ++bi)
+        for (uint64_t bj = 0; bj < hb; ++bj) out_scales[bj * vb + bi] = scales[bi * hb + bj];
+}

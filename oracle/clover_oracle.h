@@ -70,6 +70,13 @@ void orc_m8_quantize(const float *a, uint64_t rows, uint64_t cols, int8_t *value
 void orc_m8_mvm(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
                 const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32_or_null, uint64_t *state);
 
+
+/* transpose: include/CloverMatrix4.h:1549-1663, include/CloverMatrix8.h:1359-1385 */
+void orc_m4_transpose(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                      int8_t *out_values, float *out_scales);
+void orc_m8_transpose(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                      int8_t *out_values, float *out_scales);
+
 #ifdef __cplusplus
 }
 #endif

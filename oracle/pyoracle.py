@@ -204,6 +204,19 @@ class Oracle:
                              _p(c), _u64(j1 - j0))
         return c
 
+    def m4_transpose(self, mv, ms, rows, cols):
+        """(values, scales) of the cols x rows transpose (CloverMatrix4.h:1549-1663)"""
+        ov = np.zeros(rows * cols // 2, np.int8)
+        os_ = np.zeros((rows // 64) * (cols // 64), np.float32)
+        self.lib.orc_m4_transpose(_p(mv), _p(ms), _u64(rows), _u64(cols), _p(ov), _p(os_))
+        return ov, os_
+
+    def m8_transpose(self, mv, ms, rows, cols):
+        ov = np.zeros(rows * cols, np.int8)
+        os_ = np.zeros((rows // 64) * (cols // 64), np.float32)
+        self.lib.orc_m8_transpose(_p(mv), _p(ms), _u64(rows), _u64(cols), _p(ov), _p(os_))
+        return ov, os_
+
 
 class Reference:
     """The unmodified reference (oracle/_ref). ``stochastic`` picks the build flavour.
@@ -372,6 +385,17 @@ class Reference:
         yv, ys = v8_alloc(m.rows)
         self.lib.ref_m8_mvm(m.h, _p(xv), _p(xs), _p(yv), _p(ys), self._st(state), C.c_int(variant))
         return yv, ys
+
+    def m4_transpose(self, m, variant=0):
+        """variant: 0 SIMD, 1 scalar, 2 parallel, 3 scalar_faster"""
+        o = Reference._M(self, 4, m.cols, m.rows)
+        self.lib.ref_m4_transpose(m.h, o.h, C.c_int(variant))
+        return o.values.copy(), o.scales.copy()
+
+    def m8_transpose(self, m, variant=0):
+        o = Reference._M(self, 8, m.cols, m.rows)
+        self.lib.ref_m8_transpose(m.h, o.h, C.c_int(variant))
+        return o.values.copy(), o.scales.copy()
 
     def m4_mvm_f32(self, m, x32, variant=0):
         y = aligned(size_pad(m.rows), np.float32)

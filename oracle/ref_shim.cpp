@@ -271,6 +271,13 @@ void ref_m4_gemm_rows(void *ha, void *hbt, uint64_t i0, uint64_t i1, uint64_t j0
     }
 }
 
+/* transpose into another reference matrix (include/CloverMatrix4.h:1549 SIMD, :435 scalar, :2508 parallel, :2649 faster scalar) */
+void ref_m4_transpose(void *h, void *hout, int variant) {
+    M4 *m = (M4 *)h, *o = (M4 *)hout;
+    if (variant == 1) m->transpose_scalar(*o); else if (variant == 2) m->transpose_parallel(*o);
+    else if (variant == 3) m->transpose_scalar_faster(*o); else m->transpose(*o);
+}
+
 /* ---- CloverMatrix8 ------------------------------------------------------------------- */
 void *ref_m8_create(uint64_t rows, uint64_t cols) { silence_once(); return new M8(rows, cols); }
 void ref_m8_destroy(void *h) { delete (M8 *)h; }
@@ -292,6 +299,12 @@ void ref_m8_mvm(void *h, const int8_t *xv, const float *xs, int8_t *yv, float *y
     m->set_state(state);
     if (variant == 1) m->mvm_scalar(x, y); else if (variant == 2) m->mvm_parallel(x, y); else m->mvm(x, y);
     m->get_state(state);
+}
+
+/* include/CloverMatrix8.h:1359 (IPP), :1312 scalar, :1338 parallel */
+void ref_m8_transpose(void *h, void *hout, int variant) {
+    M8 *m = (M8 *)h, *o = (M8 *)hout;
+    if (variant == 1) m->transpose_scalar(*o); else if (variant == 2) m->transpose_parallel(*o); else m->transpose(*o);
 }
 
 } // extern "C"

@@ -262,7 +262,7 @@ def _random_v8(cb, n, seed):
     return v
 
 
-@pytest.mark.parametrize("shape", [(4736 + 128, 256), (148 * 32 * 3 + 64, 2048 + 128), (8192, 1024 * 17)])
+@pytest.mark.parametrize("shape", [(4736 + 128, 256), (148 * 32 * 3 + 128, 2048 + 128), (8192, 1024 * 17)])
 def test_mvm8_pipelined_many_items_vs_oracle(cb, oracle, shape):
     """CloverMatrix8::mvm through the persistent TMA-ring kernel when every CTA walks several 32-row work items, the
     ring wraps many times and the two halves of a row block are finished by different CTAs: fp32 row results, packed
@@ -313,6 +313,49 @@ def test_full_size_properties_c5(cb):
     q = torch.trunc(y32.abs().view(-1, 64) * scale) * torch.sign(y32.view(-1, 64))
     assert torch.equal(y.values.view(-1, 64).to(torch.float32), q)
     assert torch.equal(y.scales[: n // 64], m)
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+@pytest.mark.parametrize("shape", [(128, 128), (128, 256), (256, 128), (384, 640), (200, 300), (640, 1152), (2048 + 128, 4096 + 384)])
+def test_matrix_transpose(cb, oracle, shape, bits_):
+    """transpose (03_matrix.cpp:153-246 checks qm.get(i,j) == qt.get(j,i)): every packed byte and every scale of the
+    transposed matrix against the oracle (itself pinned to all reference variants), and get() symmetry."""
+    from oracle.pyoracle import pad_matrix
+    rows, cols = shape
+    a = pad_matrix(gen(oracle, rows * cols, "floats")[: rows * cols].reshape(rows, cols))
+    R, Cc = a.shape
+    M = cb.CloverMatrix4 if bits_ == 4 else cb.CloverMatrix8
+    qa, qt = M(R, Cc), M(Cc, R)
+    qa.quantize(cb.CloverMatrix32(R, Cc, a))
+    qa.transpose(qt)
+    tv, ts = getattr(oracle, f"m{bits_}_transpose")(qa.getData().cpu().numpy(), qa.getScales().cpu().numpy(), R, Cc)
+    assert np.array_equal(qt.getData().cpu().numpy(), tv)
+    assert np.array_equal(bits(qt.getScales().cpu().numpy()), bits(ts))
+    for (i, j) in ((0, 0), (R - 1, Cc - 1), (R // 2, Cc // 3), (1, 2), (66, 127)):
+        assert qa.get(i, j) == qt.get(j, i)
+    with pytest.raises(cb.CloverSizeError):
+        qa.transpose(M(R + 128, Cc))
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+def test_transpose_full_size_involution(cb, bits_):
+    """16384 x 16384 (the GEMM operand size): transposing twice restores every byte and scale, and the transposed
+    matrix really is the transpose (checked through an independent torch unpack on the device)."""
+    n = 16384
+    A = _random_m4(cb, n, n, 51) if bits_ == 4 else _random_m8(cb, n, n, 51)
+    M = cb.CloverMatrix4 if bits_ == 4 else cb.CloverMatrix8
+    T, B = M(n, n), M(n, n)
+    A.transpose(T)
+    T.transpose(B)
+    assert torch.equal(A.values, B.values) and torch.equal(A.scales, B.scales)
+    assert torch.equal(T.scales.view(n // 64, n // 64), A.scales.view(n // 64, n // 64).t())
+    if bits_ == 8:
+        assert torch.equal(T.values.view(n, n), A.values.view(n, n).t())
+    else:
+        def unpack(m):          # element 2i in the high nibble
+            b = m.values.view(torch.uint8).view(n, n // 2)
+            return torch.stack((b >> 4, b & 0xF), dim=2).view(n, n)
+        assert torch.equal(unpack(T), unpack(A).t())
 
 
 def test_mvm_size_mismatch_raises(cb):

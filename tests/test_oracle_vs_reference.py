@@ -241,3 +241,23 @@ def test_matrix4_mvm_vector8_stochastic(oracle, reference_sr):
     yv_r, ys_r = reference_sr.m4_mvm_v8(h, xv, xs, state=st_ref)
     assert np.array_equal(yv, yv_r) and np.array_equal(ys.view(np.uint32), ys_r.view(np.uint32))
     assert np.array_equal(st, st_ref)
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+@pytest.mark.parametrize("shape", [(128, 128), (128, 256), (256, 128), (384, 640), (200, 300), (640, 1152)])
+def test_matrix_transpose(oracle, reference, shape, bits_):
+    """transpose (03_matrix.cpp:153-246 checks get(i,j) == get(j,i)): the restatement equals every
+    variant of the reference byte-for-byte - SIMD, scalar, parallel and (4-bit) scalar_faster - scales included."""
+    from oracle.pyoracle import pad_matrix
+    rows, cols = shape
+    a = pad_matrix(_inputs(oracle, rows * cols, "floats")[: rows * cols].reshape(rows, cols))
+    R, Cc = a.shape
+    mv, ms, m = getattr(reference, f"m{bits_}_quantize")(a)
+    tv, ts = getattr(oracle, f"m{bits_}_transpose")(mv, ms, R, Cc)
+    for variant in ((0, 1, 2, 3) if bits_ == 4 else (0, 1, 2)):
+        rv, rs = getattr(reference, f"m{bits_}_transpose")(m, variant)
+        assert np.array_equal(tv, rv), variant
+        assert np.array_equal(ts.view(np.uint32), rs.view(np.uint32)), variant
+    # an involution: transposing back restores the matrix
+    bv, bs = getattr(oracle, f"m{bits_}_transpose")(tv, ts, Cc, R)
+    assert np.array_equal(bv, mv) and np.array_equal(bs.view(np.uint32), ms.view(np.uint32))
