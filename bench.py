@@ -261,6 +261,15 @@ def extras(torch, cb, peak):
     b = gemv_bytes(r8, c8, 8)
     out["C5_gemv8_32768"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b}
     del m8
+    # transpose of a 16384 x 16384 matrix (every byte read once and written once)
+    for bits_, M_ in ((4, cb.CloverMatrix4), (8, cb.CloverMatrix8)):
+        src, dst = M_(16384, 16384), M_(16384, 16384)
+        src.values.copy_(torch.randint(-128, 128, (src.values.numel(),), dtype=torch.int8, device=dev, generator=g))
+        src.scales.uniform_(0.25, 1.0, generator=g)
+        t = cuda_time(torch, lambda: src.transpose(dst), 20)
+        b = 2 * src.getBytes()
+        out[f"transpose{bits_}_16384"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b}
+        del src, dst
     # C4: 4-bit GEMM 16384^3
     M = N = K = 16384
     A, Bt = cb.CloverMatrix4(M, K), cb.CloverMatrix4(N, K)

@@ -87,32 +87,53 @@ __device__ __forceinline__ void tile_coords(uint32_t t, uint32_t tiles_m, uint32
 }
 
 // one K-slab of one 32-lane x 64-column block: acc += s * D, D read from TMEM in two 32-column chunks
+// PROBE (measurement only, wrong results): 1 = TMEM loads but no FMAs, 2 = neither (pure MMA / TMA / barrier hand-off)
+template <int PROBE>
 __device__ __forceinline__ void epilogue_slab(uint64_t *acc, uint32_t *r, float s, uint32_t taddr, uint32_t tfull, uint32_t tempty,
                                               uint32_t parity, int lane) {
     mbar_wait_a(tfull, parity);
     tc_fence_after();
+    if (PROBE == 2) {
+        tc_fence_before();
+        if (lane == 0) mbar_arrive_a(tempty);
+        return;
+    }
     tmem_ld32(taddr, r);
     tmem_ld_wait(r);
+    if (PROBE == 1) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) ffma2(acc[j], s, r[2 * j], r[2 * j + 1]);
+        for (int j = 0; j < 32; j += 8) acc[0] ^= r[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ffma2(acc[j], s, r[2 * j], r[2 * j + 1]);
+    }
     tmem_ld32(taddr + 32, r);
     tmem_ld_wait(r);
     tc_fence_before();                                   // this warp's share of the buffer is drained
     if (lane == 0) mbar_arrive_a(tempty);
+    if (PROBE == 1) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) ffma2(acc[16 + j], s, r[2 * j], r[2 * j + 1]);
+        for (int j = 0; j < 32; j += 8) acc[1] ^= r[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ffma2(acc[16 + j], s, r[2 * j], r[2 * j + 1]);
+    }
 }
 
+// SPLIT = true (CLOVER_GEMM_KERNEL=split): every slab is issued as two N=128 halves with their own full/empty barriers
+// (four 128-column TMEM buffers at the same addresses). The warps of the left and of the right half then run about
+// half a slab out of phase, so the FMA bursts of one group overlap the TMEM-load round trips of the other.
+template <bool SPLIT, int PROBE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
            const float *__restrict__ as, const float *__restrict__ bs, uint32_t M, uint32_t N, uint32_t K,
            float *__restrict__ c, uint64_t ldc) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;             // 1024-aligned: SWIZZLE_128B atoms
-    // barrier block behind the stages: full[4] empty[4] tfull[2] tempty[2] tmem_slot
+    // barrier block behind the stages: full[4] empty[4] tfull[4] tempty[4] tmem_slot (tfull/tempty: 2 used unless SPLIT)
     const uint32_t bars = smem + kStages * kStageBytes;
-    const uint32_t full = bars, empty = bars + 8 * kStages, tfull = bars + 16 * kStages, tempty = tfull + 16;
-    const uint32_t slot = tempty + 16;
+    const uint32_t full = bars, empty = bars + 8 * kStages, tfull = bars + 16 * kStages, tempty = tfull + 32;
+    const uint32_t slot = tempty + 32;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_m = M / kBM, tiles_n = (N + kBN - 1) / kBN, ntiles = tiles_m * tiles_n;
@@ -123,9 +144,9 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full + 8 * i), "r"(1) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty + 8 * i), "r"(1) : "memory");
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 4; ++b) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tfull + 8 * b), "r"(1) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tempty + 8 * b), "r"(kEpiWarps) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tempty + 8 * b), "r"(SPLIT ? kEpiWarps / 2 : kEpiWarps) : "memory");
         }
         mbar_fence_init();
         tma_prefetch_descriptor(&map_a);
@@ -163,7 +184,7 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             }
         } else if (warp == 1) {
             // ===== MMA issuer: per stage, K-slab 0 -> TMEM buffer 0, K-slab 1 -> buffer 1 =====
-            const uint32_t idesc = umma_idesc(UMMA_E4M3, kBM, kBN);
+            const uint32_t idesc = umma_idesc(UMMA_E4M3, kBM, kBN), idesc_half = umma_idesc(UMMA_E4M3, kBM, kBN / 2);
             uint32_t stage = 0, phase = 0, pair = 0;
             for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 for (uint32_t kb = 0; kb < kblocks; ++kb, ++pair) {
@@ -173,6 +194,23 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                     const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + kAStage);
 #pragma unroll
                     for (uint32_t h = 0; h < 2; ++h) {
+                        if (SPLIT) {
+#pragma unroll
+                            for (uint32_t half = 0; half < 2; ++half) {
+                                const uint32_t hb = 2 * h + half;
+                                mbar_wait_a(tempty + 8 * hb, (pair & 1) ^ 1);
+                                tc_fence_after();
+                                const uint32_t d = tmem + h * 256 + half * 128;
+                                const uint64_t dbh = db + half * ((128 * kBK) >> 4);       // rows 128..255 of the B' stage
+                                if (elect_one()) {
+                                    umma_ss<UMMA_E4M3, 1>(d, da + 4 * h, dbh + 4 * h, idesc_half, 0);
+                                    umma_ss<UMMA_E4M3, 1>(d, da + 4 * h + 2, dbh + 4 * h + 2, idesc_half, 1);
+                                    umma_commit_a<1>(tfull + 8 * hb);
+                                    if (hb == 3) umma_commit_a<1>(empty + 8 * stage);
+                                }
+                                __syncwarp();
+                            }
+                        } else {
                         mbar_wait_a(tempty + 8 * h, (pair & 1) ^ 1);
                         tc_fence_after();
                         const uint32_t d = tmem + h * 256;
@@ -183,6 +221,7 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                             if (h == 1) umma_commit_a<1>(empty + 8 * stage);      // smem stage free once its MMAs retire
                         }
                         __syncwarp();
+                        }
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -212,8 +251,13 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                 const uint32_t n = min(32u, KB - kb0);
                 for (uint32_t k = 0; k < n; k += 2, ++pair) {
                     const float s_even = __shfl_sync(0xFFFFFFFFu, sv, k), s_odd = __shfl_sync(0xFFFFFFFFu, sv, k + 1);
-                    epilogue_slab(acc, r, s_even, taddr, tfull, tempty, pair & 1, lane);
-                    epilogue_slab(acc, r, s_odd, taddr + 256, tfull + 8, tempty + 8, pair & 1, lane);
+                    if (SPLIT) {     // barriers of (slab parity, half): index 2 * parity + (cb >> 1)
+                        epilogue_slab<PROBE>(acc, r, s_even, taddr, tfull + 8 * (cb >> 1), tempty + 8 * (cb >> 1), pair & 1, lane);
+                        epilogue_slab<PROBE>(acc, r, s_odd, taddr + 256, tfull + 16 + 8 * (cb >> 1), tempty + 16 + 8 * (cb >> 1), pair & 1, lane);
+                    } else {
+                        epilogue_slab<PROBE>(acc, r, s_even, taddr, tfull, tempty, pair & 1, lane);
+                        epilogue_slab<PROBE>(acc, r, s_odd, taddr + 256, tfull + 8, tempty + 8, pair & 1, lane);
+                    }
                 }
             }
             if (live) {
@@ -271,9 +315,9 @@ int gemm4_tc_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, con
                       uint64_t K, float *c, uint64_t ldc, cudaStream_t stream) {
     // CLOVER_GEMM_KERNEL=pipe1|pair selects an experimental 4-slot pipeline (gemm4_tc2.cu); default: this file's kernel
     static const int variant = [] { const char *e = getenv("CLOVER_GEMM_KERNEL");
-                                    return !e ? 0 : !strcmp(e, "pipe1") ? 1 : !strcmp(e, "pair") ? 2 : !strcmp(e, "p192") ? 3 : 0; }();
+                                    return !e ? 0 : !strcmp(e, "pipe1") ? 1 : !strcmp(e, "pair") ? 2 : !strcmp(e, "p192") ? 3 : !strcmp(e, "split") ? 4 : 0; }();
     if (variant == 3) return gemm4_tc3_expanded(a8, as, b8, bs, M, N, K, c, ldc, stream);
-    if (variant) return gemm4_tc2_expanded(a8, as, b8, bs, M, N, K, c, ldc, stream, variant);
+    if (variant == 1 || variant == 2) return gemm4_tc2_expanded(a8, as, b8, bs, M, N, K, c, ldc, stream, variant);
     CUtensorMap map_a, map_b;
     int rc = make_tensor_map_u8_2d_sw128(&map_a, a8, M, K, kBM);
     if (rc != CLOVER_OK) return rc;
@@ -282,13 +326,15 @@ int gemm4_tc_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, con
     static bool attr_set[64] = {false};
     int dev = 0;
     CLOVER_CUDA_CHECK(cudaGetDevice(&dev));
+    static const int probe = [] { const char *e = getenv("CLOVER_GEMM_PROBE"); return e ? atoi(e) : 0; }();   // measurement only
+    auto kern = variant == 4 ? k_gemm4_tc<true, 0> : probe == 1 ? k_gemm4_tc<false, 1> : probe == 2 ? k_gemm4_tc<false, 2> : k_gemm4_tc<false, 0>;
     if (!attr_set[dev & 63]) {
-        CLOVER_CUDA_CHECK(cudaFuncSetAttribute(k_gemm4_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
         attr_set[dev & 63] = true;
     }
     const uint64_t ntiles = (M / kBM) * ((N + kBN - 1) / kBN);
     const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sm_count());
-    k_gemm4_tc<<<grid, kGemmThreads, kGemmSmem, stream>>>(map_a, map_b, as, bs, (uint32_t)M, (uint32_t)N, (uint32_t)K, c, ldc);
+    kern<<<grid, kGemmThreads, kGemmSmem, stream>>>(map_a, map_b, as, bs, (uint32_t)M, (uint32_t)N, (uint32_t)K, c, ldc);
     count_launch();
     return launch_status("k_gemm4_tc");
 }

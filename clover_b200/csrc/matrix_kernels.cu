@@ -748,6 +748,208 @@ k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
 }
 
 // =============================================================================================
+// mvm(V4,V4), second-generation pipeline (BASELINE C3 default): the arithmetic of k_m4_mvm_tma in the layout of
+// k_m8_mvm_tma - swizzled 32-row x 128-byte TMA boxes (no shared-memory bank conflicts; ncu counted 17 M conflicts
+// per launch in the dense-box kernel), 32-row work items with a last-finisher re-quantize (2048 items on 148 SMs at
+// 65536 rows; a 2-GPU shard still has 1024), one x-unit per (block, lane).
+//   warp 16 (one lane)  eight cp.async.bulk.tensor.2d boxes (32 rows x 128 B = 256 nibbles = 4 blocks) per stage
+//   warp 17             XUnits of the stage's 32 blocks
+//   warps 0-7           thread = the reference's fp32 chain (accumulator a, AVX lane l) of TWO rows (r, r + 16: one
+//                       XUnit load serves both); warp = 8 rows x 4 lanes with fixed (a, l >> 2): its two words per
+//                       row and 128-byte chunk are 16-byte chunks 2a + (l>>2) and 2a + 4 + (l>>2), XOR-swizzled by
+//                       (row & 7) -> 32 lanes, 32 banks.
+// =============================================================================================
+constexpr int kG4Rows = 32;
+constexpr int kG4Chunks = 8;                 // 128-byte chunks per stage = 32 blocks of 64 columns
+constexpr int kG4Stages = 5;
+constexpr int kG4Consumers = 256;
+constexpr int kG4Threads = kG4Consumers + 64;
+constexpr int kG4ChunkBytes = kG4Rows * 128;
+
+struct __align__(1024) Gemv4Stage {
+    uint8_t rows[kG4Chunks][kG4ChunkBytes];
+    XUnit units[kG4Chunks * 4 * 8];          // unit (block, l)
+};
+struct Gemv4Smem {
+    Gemv4Stage stage[kG4Stages];
+    uint64_t full[kG4Stages];
+    uint64_t empty[kG4Stages];
+    float part[kG4Rows][16];
+    float red_f[2];
+    int red_q[64];
+    unsigned int ticket;
+};
+
+template <bool STOCH>
+__global__ void __launch_bounds__(kG4Threads, 1)
+k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows_local,
+              uint64_t cols, uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
+              float *__restrict__ ybuf, unsigned int *__restrict__ counters, int8_t *__restrict__ yv,
+              float *__restrict__ ys, Key4 key, const uint64_t *__restrict__ tables, const __grid_constant__ PeerOut peers) {
+    extern __shared__ uint8_t smem_raw4[];
+    Gemv4Smem &sm = *reinterpret_cast<Gemv4Smem *>((reinterpret_cast<uintptr_t>(smem_raw4) + 1023u) & ~(uintptr_t)1023u);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t hb = cols >> 6, nitems = rows_local / kG4Rows;
+    const uint32_t nchunks128 = (uint32_t)((cols + 255) >> 8);            // 128-byte chunks per row (256 nibbles each); the last one may be half
+                                                                          // outside the row (cols = 128 mod 256): TMA zero-fills it, its units are zero
+    const uint32_t steps = (nchunks128 + kG4Chunks - 1) / kG4Chunks;
+
+    if (tid == 0) {
+        for (int s = 0; s < kG4Stages; ++s) {
+            mbar_init(&sm.full[s], 1 + 32);
+            mbar_init(&sm.empty[s], kG4Consumers / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kG4Consumers / 32) {
+        // ------------------------------- TMA issuer -------------------------------
+        if (lane == 0) {
+            tma_prefetch_descriptor(&tmap);
+            const uint64_t policy = policy_evict_first();
+            uint32_t it = 0;
+            for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+                for (uint32_t c = 0; c < steps; ++c, ++it) {
+                    const int s = it % kG4Stages;
+                    const uint32_t live = min((uint32_t)kG4Chunks, nchunks128 - c * kG4Chunks);
+                    mbar_wait(&sm.empty[s], ((it / kG4Stages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&sm.full[s], live * kG4ChunkBytes);
+                    for (uint32_t j = 0; j < live; ++j)
+                        tma_load_2d(sm.stage[s].rows[j], &tmap, (int)((c * kG4Chunks + j) * 128), (int)(item * kG4Rows),
+                                    &sm.full[s], policy);
+                }
+            }
+        }
+    } else if (warp == kG4Consumers / 32 + 1) {
+        // ------------------------------- x-unit warp -------------------------------
+        // lane owns units lane + 32j (j = 0..7) of a stage = (block 4j + lane/8, AVX lane lane%8)
+        uint32_t it = 0;
+        const int l = lane & 7;
+        for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const float *su = scales + (item >> 1) * hb;
+            for (uint32_t c = 0; c < steps; ++c, ++it) {
+                const int s = it % kG4Stages;
+                XUnit u[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint64_t b = (uint64_t)c * (4 * kG4Chunks) + 4 * j + (lane >> 3);
+                    const bool ok = b < hb;
+                    const uint32_t w = ok ? __ldg(xv + b * 8 + l) : 0u;
+                    const float sa = ok ? __ldg(su + b) : 0.f, sb = ok ? __ldg(xs + b) : 0.f;
+                    const int xh = sext_nibbles((w >> 4) & 0x0F0F0F0Fu);
+                    const int xl = sext_nibbles(w & 0x0F0F0F0Fu);
+                    u[j].xh = xh;
+                    u[j].xl16 = (int)((w << 4) & 0xF0F0F0F0u);
+                    u[j].cneg = -(786432.0f + 8.0f * (float)(dp4a_ss(xh, 0x01010101, 0) + dp4a_ss(xl, 0x01010101, 0)));
+                    u[j].prod = __fmul_rn(__fmul_rn(sa, 1.0f / 49.0f), sb);                       // (:834-837)
+                }
+                mbar_wait(&sm.empty[s], ((it / kG4Stages) & 1) ^ 1);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sm.stage[s].units[lane + 32 * j] = u[j];
+                mbar_arrive(&sm.full[s]);
+            }
+        }
+    } else {
+        // ------------------------------- consumer warps ------------------------------
+        // warp = (row group rg, accumulator a, lane type ty); lane = (row rin of the group, l & 3); rows r and r + 16
+        const int rg = warp >> 2, a = (warp >> 1) & 1, ty = warp & 1;
+        const int rin = lane >> 2, l = 4 * ty + (lane & 3);
+        const int r = 8 * rg + rin;
+        const uint32_t base = (uint32_t)r * 128u + 4u * (uint32_t)(lane & 3);
+        // this chain's two blocks of a 128-byte chunk: b = a and b = a + 2 -> 16-byte chunks 2b + ty, swizzled by (row & 7)
+        const uint32_t o0 = base + ((uint32_t)((2 * a + ty) ^ rin) << 4), o1 = base + ((uint32_t)((2 * a + 4 + ty) ^ rin) << 4);
+        uint32_t it = 0;
+        for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+            float acc = 0.f, acc2 = 0.f;
+            for (uint32_t c = 0; c < steps; ++c, ++it) {
+                const int s = it % kG4Stages;
+                mbar_wait(&sm.full[s], (it / kG4Stages) & 1);
+                const Gemv4Stage &st = sm.stage[s];
+                const int live = (int)min((uint32_t)kG4Chunks, nchunks128 - c * kG4Chunks);
+                auto chunk = [&](int j) {
+                    const uint8_t *p = st.rows[j];
+                    const uint32_t w0 = *reinterpret_cast<const uint32_t *>(p + o0), w1 = *reinterpret_cast<const uint32_t *>(p + o1);
+                    const uint32_t v0 = *reinterpret_cast<const uint32_t *>(p + o0 + 16 * 128), v1 = *reinterpret_cast<const uint32_t *>(p + o1 + 16 * 128);
+                    const XUnit u0 = st.units[(4 * j + a) * 8 + l], u1 = st.units[(4 * j + a + 2) * 8 + l];
+                    int s0 = dp4a_us(xor_and(w0, 0x88888888u, 0xF0F0F0F0u), u0.xh, (int)kMagicBits);
+                    s0 = dp4a_us(xor_and(w0, 0x88888888u, 0x0F0F0F0Fu), u0.xl16, s0);
+                    int t0 = dp4a_us(xor_and(v0, 0x88888888u, 0xF0F0F0F0u), u0.xh, (int)kMagicBits);
+                    t0 = dp4a_us(xor_and(v0, 0x88888888u, 0x0F0F0F0Fu), u0.xl16, t0);
+                    int s1 = dp4a_us(xor_and(w1, 0x88888888u, 0xF0F0F0F0u), u1.xh, (int)kMagicBits);
+                    s1 = dp4a_us(xor_and(w1, 0x88888888u, 0x0F0F0F0Fu), u1.xl16, s1);
+                    int t1 = dp4a_us(xor_and(v1, 0x88888888u, 0xF0F0F0F0u), u1.xh, (int)kMagicBits);
+                    t1 = dp4a_us(xor_and(v1, 0x88888888u, 0x0F0F0F0Fu), u1.xl16, t1);
+                    acc = __fmaf_rn(u0.prod, __fmaf_rn(__int_as_float(s0), 0.0625f, u0.cneg), acc);      // (:896-897), block order
+                    acc2 = __fmaf_rn(u0.prod, __fmaf_rn(__int_as_float(t0), 0.0625f, u0.cneg), acc2);
+                    acc = __fmaf_rn(u1.prod, __fmaf_rn(__int_as_float(s1), 0.0625f, u1.cneg), acc);
+                    acc2 = __fmaf_rn(u1.prod, __fmaf_rn(__int_as_float(t1), 0.0625f, u1.cneg), acc2);
+                };
+                if (live == kG4Chunks) {
+#pragma unroll
+                    for (int j = 0; j < kG4Chunks; ++j) chunk(j);
+                } else {
+                    for (int j = 0; j < live; ++j) chunk(j);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[s]);
+            }
+            named_bar_sync(2, kG4Consumers);                                    // previous epilogue is done with part
+            sm.part[r][8 * a + l] = acc;
+            sm.part[r + 16][8 * a + l] = acc2;
+            named_bar_sync(2, kG4Consumers);
+            const uint64_t rb = item >> 1, grb = rowblock0 + rb;
+            if (tid < kG4Rows) {
+                const float *pa = sm.part[tid];
+                float sl[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sl[k] = __fadd_rn(pa[k], pa[8 + k]);                   // acc_1 + acc_2 (:902)
+                const float y = __fadd_rn(__fadd_rn(__fadd_rn(sl[4], sl[0]), __fadd_rn(sl[6], sl[2])),
+                                          __fadd_rn(__fadd_rn(sl[5], sl[1]), __fadd_rn(sl[7], sl[3])));   // hadd tree (:903-907)
+                ybuf[grb * 64 + (item & 1) * kG4Rows + tid] = y;
+                __threadfence();
+            }
+            named_bar_sync(2, kG4Consumers);
+            if (tid == 0) sm.ticket = yv ? atomicAdd(counters + rb, 1u) : 0u;
+            named_bar_sync(2, kG4Consumers);
+            if (sm.ticket == 1u) {                                              // both halves of the block are in ybuf
+                if (tid < 64) {
+                    __threadfence();
+                    const float y = __ldcg(ybuf + grb * 64 + tid);
+                    requantize_block<4, STOCH>(y, tid, grb, yv, ys, key, tables, sm.red_f, sm.red_q,
+                                               peers.world > 1 ? &peers : nullptr);
+                    if (tid == 0) counters[rb] = 0u;
+                }
+            }
+        }
+        if (peers.world > 1) {
+            // as in k_m4_mvm_tma: make the peer stores visible system-wide, take a ticket, the LAST CTA of this rank
+            // publishes "rank done with epoch" on all peers and waits for theirs
+            if (tid < 64) __threadfence_system();
+            named_bar_sync(2, kG4Consumers);
+            if (tid == 0) {
+                const unsigned int t = atomicAdd(peers.ticket, 1u);
+                if (t == gridDim.x - 1) {
+                    *peers.ticket = 0u;
+                    __threadfence_system();
+                    for (int p = 0; p < peers.world; ++p)
+                        if (p != peers.rank)
+                            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.flags[p] + peers.rank), "r"(peers.epoch) : "memory");
+                    for (int q = 0; q < peers.world; ++q) {
+                        if (q == peers.rank) continue;
+                        uint32_t seen;
+                        do {
+                            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(peers.flags[peers.rank] + q) : "memory");
+                        } while ((int32_t)(seen - peers.epoch) < 0);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// =============================================================================================
 // mvm(V32,V32): 4-bit matrix, fp32 vectors (CloverMatrix4.h:1451-1547). One warp per row; lane 8k+l
 // is the reference's chain (accumulator k, AVX lane l): per block element 8k+l, then 32+8k+l.
 // =============================================================================================
@@ -837,12 +1039,41 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
     const uint32_t *v32 = reinterpret_cast<const uint32_t *>(values);
     const uint32_t *x32 = reinterpret_cast<const uint32_t *>(xv);
     if (BITS == 4) {
-        static const bool force_simple = getenv("CLOVER_GEMV_IMPL") && !strcmp(getenv("CLOVER_GEMV_IMPL"), "simple");
+        // CLOVER_GEMV_IMPL (read per call): simple = plain loads, ring64 = 64-row work items (k_m4_mvm_tma),
+        // items32 = 32-row work items (k_m4_mvm_tma2). Default: ring64 (96-99 % of the HBM roofline at 65536 rows) unless
+        // halving the work item fills the last round of the persistent grid markedly better - a 2-GPU shard of C3 has
+        // 512 row blocks = 3.46 rounds on 148 SMs, but 1024 half blocks = 6.92 (measured: 0.179 vs 0.189 ms).
+        const char *impl_env = getenv("CLOVER_GEMV_IMPL");
+        const bool force_simple = impl_env && !strcmp(impl_env, "simple");
+        const bool force_items32 = impl_env && !strcmp(impl_env, "items32");
+        auto fill = [](uint64_t items, uint64_t sms) { return (double)items / (double)(((items + sms - 1) / sms) * sms); };
+        const bool force_ring64 = (impl_env && !strcmp(impl_env, "ring64")) ||
+                                  (!force_items32 && fill(2 * nrb, (uint64_t)sm_count()) < 1.04 * fill(nrb, (uint64_t)sm_count()));
         // bulk copies need 16 B aligned rows; anything else takes the plain-load kernel (same arithmetic)
         const bool simple = (force_simple || (reinterpret_cast<uintptr_t>(values) & 15u) != 0) && !peers;
         if (simple) {
             if (stoch) k_m4_mvm<true><<<grid, kMvmThreads, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
             else       k_m4_mvm<false><<<grid, kMvmThreads, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
+        } else if (!force_ring64) {
+            // default: 32-row work items, swizzled boxes (k_m4_mvm_tma2)
+            float *ybuf = y32;
+            unsigned int *counters = nullptr;
+            int rc = mvm_scratch(nrb, (row0 >> 6) + nrb, y32 ? nullptr : &ybuf, &counters);
+            if (rc != CLOVER_OK) return rc;
+            const int smem = (int)sizeof(Gemv4Smem) + 1024;
+            static bool attr_set2[2] = {false, false};
+            auto kern = stoch ? k_m4_mvm_tma2<true> : k_m4_mvm_tma2<false>;
+            if (!attr_set2[stoch]) {
+                CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                attr_set2[stoch] = true;
+            }
+            CUtensorMap tmap;
+            rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows_local, cols >> 1, kG4Rows);
+            if (rc != CLOVER_OK) return rc;
+            const uint64_t nitems = rows_local / kG4Rows;
+            const unsigned pgrid = (unsigned)(nitems < (uint64_t)sm_count() ? nitems : (uint64_t)sm_count());
+            kern<<<pgrid, kG4Threads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, ybuf, counters, yv, ys,
+                                                      key, tables, peers ? *peers : PeerOut());
         } else {
             const int smem = (int)sizeof(GemvSmem);
             static bool attr_set[2] = {false, false};      // per template instance (process-wide; all devices alike)

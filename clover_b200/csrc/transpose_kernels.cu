@@ -8,13 +8,13 @@
 // those to ippiTranspose_32f_C1R). HBM-bound: every byte is read once and written once (0.5 + 0.5 B/element for
 // 4-bit, 1 + 1 for 8-bit, plus the scales).
 //
-// One CTA of 256 threads per tile (4-bit: 128x128 elements, 8-bit: 64x64; either way 64 bytes wide on the way in
+// One CTA of 256 threads per tile (4-bit: 256x256 elements, 8-bit: 128x128; either way 128 bytes wide on the way in
 // and on the way out):
-//   1. thread (bi, bj) loads word bj of 8 (4) consecutive rows - a warp reads two 64-byte runs per instruction;
+//   1. thread (bi, bj) loads word bj of 8 (4) consecutive rows - a warp reads one 128-byte run per instruction;
 //   2. transposes its 8x8 nibbles (three masked-swap stages) / 4x4 bytes (six PRMT) in registers;
-//   3. writes the result words into a shared-memory image of the output tile, columns rotated by bj so that the 16
-//      lanes of a half-warp hit 16 different banks;
-//   4. the CTA copies the image out row by row: a warp writes two 64-byte runs per instruction.
+//   3. writes the result words into a shared-memory image of the output tile, columns rotated by bj so that the 32
+//      lanes of a warp hit 32 different banks;
+//   4. the CTA copies the image out row by row: a warp writes one 128-byte run per instruction.
 #include "common.cuh"
 #include "runtime.cuh"
 
@@ -63,48 +63,55 @@ __device__ __forceinline__ void transpose4x4_bytes(uint32_t (&a)[4]) {
     a[3] = prmt_b32(t1, u1, 0x7632u);
 }
 
-// BITS = 4: tile 128 x 128 elements, thread block 8 x 8 nibbles. BITS = 8: tile 64 x 64, thread block 4 x 4 bytes.
-// Either way a tile is 16 x 16 thread blocks, 16 words wide, and RB rows per thread block.
+// A tile is 32 x 32 thread blocks of RB x RB elements (RB = 8 nibbles / 4 bytes = one 32-bit word wide): 256 x 256
+// elements (4-bit) or 128 x 128 (8-bit), i.e. 128-byte runs on the way in and on the way out. 256 threads, thread =
+// word column bj of four thread-block rows bi: all of its 4 * RB loads are in flight together.
 template <int BITS>
 __global__ void __launch_bounds__(256)
 k_mtranspose(const uint32_t *__restrict__ in, const float *__restrict__ in_scales, uint64_t rows, uint64_t cols,
              uint32_t *__restrict__ out, float *__restrict__ out_scales) {
     constexpr int RB = BITS == 4 ? 8 : 4;             // rows (and columns) per thread block
-    constexpr int TILE = 16 * RB;                     // 128 / 64
-    constexpr int EPW = BITS == 4 ? 8 : 4;            // elements per 32-bit word
-    __shared__ uint32_t img[TILE * 16];
+    constexpr int TILE = 32 * RB;                     // 256 / 128
+    constexpr int ST = TILE / 64;                     // scale tiles per tile edge
+    __shared__ uint32_t img[TILE * 32];
 
-    const int t = threadIdx.x, bi = t >> 4, bj = t & 15;
-    const uint64_t tiles_j = cols / TILE, ntiles = (rows / TILE) * tiles_j;
-    const uint64_t wpr_in = cols / EPW, wpr_out = rows / EPW;
+    const int t = threadIdx.x, bj = t & 31, bi0 = t >> 5;
+    const uint64_t tiles_i = (rows + TILE - 1) / TILE, tiles_j = (cols + TILE - 1) / TILE, ntiles = tiles_i * tiles_j;
+    const uint64_t wpr_in = cols / RB, wpr_out = rows / RB;      // words per row (RB elements per word)
     const uint64_t vb = rows >> 6, hb = cols >> 6;
 
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t ti = tile / tiles_j, tj = tile % tiles_j;
-        const uint32_t *src = in + (ti * TILE + (uint64_t)bi * RB) * wpr_in + tj * 16 + bj;
-        uint32_t a[RB];
+        const bool col_ok = tj * 32 + bj < wpr_in;                // rows/cols are multiples of 128: a word is all in or all out
+        uint32_t a[4][RB];
 #pragma unroll
-        for (int r = 0; r < RB; ++r) a[r] = ldg_stream(src + (uint64_t)r * wpr_in);
-        if constexpr (BITS == 4) transpose8x8_nibbles(a);
-        else                     transpose4x4_bytes(a);
-        // output row (bj * RB + c) of the tile, word bi; columns rotated by bj
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t row0 = ti * TILE + (uint64_t)(bi0 + 8 * k) * RB;
+            const bool ok = col_ok && row0 < rows;
+            const uint32_t *src = in + row0 * wpr_in + tj * 32 + bj;
 #pragma unroll
-        for (int c = 0; c < RB; ++c) img[(bj * RB + c) * 16 + ((bi + bj) & 15)] = a[c];
-        // scales of this tile: 2 x 2 entries for the 4-bit tile (128 x 128), one for the 8-bit tile (64 x 64)
-        if (BITS == 4) {
-            if (t < 4) {
-                const uint64_t si = ti * 2 + (t >> 1), sj = tj * 2 + (t & 1);
-                out_scales[sj * vb + si] = in_scales[si * hb + sj];
-            }
-        } else if (t == 0) {
-            out_scales[tj * vb + ti] = in_scales[ti * hb + tj];
+            for (int r = 0; r < RB; ++r) a[k][r] = ok ? ldg_stream(src + (uint64_t)r * wpr_in) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if constexpr (BITS == 4) transpose8x8_nibbles(a[k]);
+            else                     transpose4x4_bytes(a[k]);
+            const int bi = bi0 + 8 * k;
+            // output row (bj * RB + c) of the tile, word bi; columns rotated by bj: the 32 lanes hit 32 banks
+#pragma unroll
+            for (int c = 0; c < RB; ++c) img[(bj * RB + c) * 32 + ((bi + bj) & 31)] = a[k][c];
+        }
+        if (t < ST * ST) {                                        // the tile's 64x64-block scales
+            const uint64_t si = ti * ST + t / ST, sj = tj * ST + t % ST;
+            if (si < vb && sj < hb) out_scales[sj * vb + si] = in_scales[si * hb + sj];
         }
         __syncthreads();
-        uint32_t *dst = out + (tj * TILE) * wpr_out + ti * 16 + bj;
-#pragma unroll
-        for (int it = 0; it < TILE / 16; ++it) {
-            const int r = bi + 16 * it;                                   // output row of the tile; this thread writes word bj
-            dst[(uint64_t)r * wpr_out] = img[r * 16 + ((bj + r / RB) & 15)];
+        const bool word_ok = ti * 32 + bj < wpr_out;
+        uint32_t *dst = out + (tj * TILE) * wpr_out + ti * 32 + bj;
+#pragma unroll 8
+        for (int it = 0; it < TILE / 8; ++it) {
+            const int r = bi0 + 8 * it;                           // output row of the tile; this thread writes word bj
+            if (word_ok && tj * TILE + r < cols) __stcs(dst + (uint64_t)r * wpr_out, img[r * 32 + ((bj + r / RB) & 31)]);
         }
         __syncthreads();
     }
@@ -113,10 +120,10 @@ k_mtranspose(const uint32_t *__restrict__ in, const float *__restrict__ in_scale
 template <int BITS>
 static int launch_transpose(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols, int8_t *out_values,
                             float *out_scales, cudaStream_t stream) {
-    constexpr uint64_t TILE = BITS == 4 ? 128 : 64;
-    const uint64_t ntiles = (rows / TILE) * (cols / TILE);
+    constexpr uint64_t TILE = BITS == 4 ? 256 : 128;
+    const uint64_t ntiles = ((rows + TILE - 1) / TILE) * ((cols + TILE - 1) / TILE);
     if (ntiles == 0) return CLOVER_OK;
-    const uint64_t cap = (uint64_t)sm_count() * 8;
+    const uint64_t cap = (uint64_t)sm_count() * 16;
     const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
     k_mtranspose<BITS><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint32_t *>(values), scales, rows, cols,
                                                  reinterpret_cast<uint32_t *>(out_values), out_scales);

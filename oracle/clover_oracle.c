@@ -543,3 +543,113 @@ void orc_m8_transpose(const int8_t *values, const float *scales, uint64_t rows, 
     for (uint64_t bi = 0; bi < vb; ++bi)
         for (uint64_t bj = 0; bj < hb; ++bj) out_scales[bj * vb + bi] = scales[bi * hb + bj];
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * threshold: keep the k elements of largest magnitude, zero the rest.
+ *   include/CloverVector4.h:1913-1973 (threshold -> threshold_min_heap), include/CloverVector8.h:1680-1740,
+ *   heap helpers include/CloverBase.h:205-249. The reference builds a min-heap of the first k elements with
+ *   std::make_heap(gt_idx_t) and then replaces the root whenever a later element is STRICTLY larger, re-heapifying
+ *   with its own min_heapify. Which of several equal elements survives therefore depends on the heap layout; the
+ *   restatement below follows libstdc++'s make_heap (bits/stl_heap.h: __make_heap / __adjust_heap / __push_heap,
+ *   GCC 13) and the reference's min_heapify step by step, so it reproduces the reference bit for bit.
+ *   getAbs: 4-bit |(scale/7.0f) * (float)q| (:190-203), 8-bit |((float)q * scale) / 127.0f| (CloverVector8.h:141-147).
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct { float value; int32_t bits; uint64_t idx; } heap_item;
+
+static int heap_gt(const heap_item *a, const heap_item *b) { return (a->value > b->value) || isnan(a->value); }
+
+static void heap_push(heap_item *first, int64_t hole, int64_t top, heap_item value) {
+    int64_t parent = (hole - 1) / 2;
+    while (hole > top && heap_gt(first + parent, &value)) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+static void heap_adjust(heap_item *first, int64_t hole, int64_t len, heap_item value) {
+    const int64_t top = hole;
+    int64_t child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (heap_gt(first + child, first + (child - 1))) child--;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    heap_push(first, hole, top, value);
+}
+static void heap_make(heap_item *first, int64_t len) {
+    if (len < 2) return;
+    int64_t parent = (len - 2) / 2;
+    for (;;) {
+        heap_item v = first[parent];
+        heap_adjust(first, parent, len, v);
+        if (parent == 0) return;
+        parent--;
+    }
+}
+static void heap_min_heapify(heap_item *heap, uint32_t pos, uint32_t k) {      /* include/CloverBase.h:226-249 */
+    uint32_t smallest = pos;
+    for (;;) {
+        const uint32_t l = pos * 2 + 1, r = pos * 2 + 2;
+        if (l < k && heap[l].value < heap[smallest].value) smallest = l;
+        if (r < k && heap[r].value < heap[smallest].value) smallest = r;
+        if (smallest == pos) break;
+        heap_item t = heap[pos]; heap[pos] = heap[smallest]; heap[smallest] = t;
+        pos = smallest;
+    }
+}
+
+static int32_t v4_getbits(const int8_t *values, uint64_t i) {          /* sign-extended nibble, even index = high nibble */
+    const uint8_t b = (uint8_t)values[i >> 1];
+    const int32_t nib = (i & 1) ? (b & 0x0F) : (b >> 4);
+    return nib >= 8 ? nib - 16 : nib;
+}
+static void v4_setbits(int8_t *values, uint64_t i, int32_t q) {
+    uint8_t b = (uint8_t)values[i >> 1];
+    if (i & 1) b = (uint8_t)((b & 0xF0) | (q & 0x0F)); else b = (uint8_t)((b & 0x0F) | ((q & 0x0F) << 4));
+    values[i >> 1] = (int8_t)b;
+}
+float orc_v4_abs(const int8_t *values, const float *scales, uint64_t i) {
+    const float scale = scales[i >> 6] / 7.0f;
+    return absf(scale * (float)v4_getbits(values, i));
+}
+float orc_v8_abs(const int8_t *values, const float *scales, uint64_t i) {
+    return absf(((float)values[i] * scales[i >> 6]) / 127.0f);
+}
+
+static void threshold_impl(int bits, int8_t *values, const float *scales, uint64_t n, uint64_t k) {
+    if (k == 0 || k > n) {                                  /* the reference assumes 1 <= k <= n; k = 0 zeroes everything */
+        if (k == 0) for (uint64_t i = 0; i < n; ++i) { if (bits == 4) v4_setbits(values, i, 0); else values[i] = 0; }
+        return;
+    }
+    heap_item *heap = (heap_item *)malloc(k * sizeof(heap_item));
+    for (uint64_t i = 0; i < k; ++i) {
+        heap[i].value = bits == 4 ? orc_v4_abs(values, scales, i) : orc_v8_abs(values, scales, i);
+        heap[i].bits = bits == 4 ? v4_getbits(values, i) : values[i];
+        heap[i].idx = i;
+        if (bits == 4) v4_setbits(values, i, 0); else values[i] = 0;
+    }
+    heap_make(heap, (int64_t)k);
+    for (uint64_t i = k; i < n; ++i) {
+        const float value = bits == 4 ? orc_v4_abs(values, scales, i) : orc_v8_abs(values, scales, i);
+        if (value > heap[0].value) {
+            heap[0].bits = bits == 4 ? v4_getbits(values, i) : values[i];
+            heap[0].value = value;
+            heap[0].idx = i;
+            heap_min_heapify(heap, 0, (uint32_t)k);
+        }
+        if (bits == 4) v4_setbits(values, i, 0); else values[i] = 0;
+    }
+    for (uint64_t i = 0; i < k; ++i) {
+        if (bits == 4) v4_setbits(values, heap[i].idx, heap[i].bits); else values[heap[i].idx] = (int8_t)heap[i].bits;
+    }
+    free(heap);
+}
+void orc_v4_threshold(int8_t *values, const float *scales, uint64_t n, uint64_t k) { threshold_impl(4, values, scales, n, k); }
+void orc_v8_threshold(int8_t *values, const float *scales, uint64_t n, uint64_t k) { threshold_impl(8, values, scales, n, k); }

@@ -77,6 +77,12 @@ void orc_m4_transpose(const int8_t *values, const float *scales, uint64_t rows, 
 void orc_m8_transpose(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
                       int8_t *out_values, float *out_scales);
 
+/* threshold: include/CloverVector4.h:1913-1973, include/CloverVector8.h:1680-1740 (in place) */
+void  orc_v4_threshold(int8_t *values, const float *scales, uint64_t n, uint64_t k);
+void  orc_v8_threshold(int8_t *values, const float *scales, uint64_t n, uint64_t k);
+float orc_v4_abs(const int8_t *values, const float *scales, uint64_t i);
+float orc_v8_abs(const int8_t *values, const float *scales, uint64_t i);
+
 #ifdef __cplusplus
 }
 #endif

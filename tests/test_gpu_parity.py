@@ -262,6 +262,60 @@ def _random_v8(cb, n, seed):
     return v
 
 
+@pytest.mark.parametrize("shape", [(4736 + 128, 128), (4736 + 128, 384), (148 * 32 * 3 + 128, 4096 + 128), (8192, 2048 * 17)])
+def test_mvm4_pipelined_many_items_vs_oracle(cb, oracle, shape, monkeypatch):
+    """CloverMatrix4::mvm through the 32-row-item TMA kernel with several items per CTA, half chunks at the row end
+    (cols = 128 mod 256) and row blocks finished by two different CTAs: bit-for-bit against the oracle."""
+    monkeypatch.setenv("CLOVER_GEMV_IMPL", "items32")       # read per call by the launcher
+    rows, cols = shape
+    A = _random_m4(cb, rows, cols, 61)
+    g = torch.Generator(device="cuda").manual_seed(62)
+    x = cb.CloverVector4(cols)
+    from bench import random_nibbles
+    x.values.copy_(random_nibbles(torch, cols // 2, g, torch.device("cuda")))
+    x.scales.uniform_(0.05, 4.0, generator=g)
+    y = cb.CloverVector4(rows)
+    y32 = torch.zeros(rows, dtype=torch.float32, device="cuda")
+    for _ in range(2):
+        A.mvm(x, y, y32=y32)
+    wv, ws, w32 = oracle.m4_mvm(A.values.cpu().numpy(), A.scales.cpu().numpy(), rows, cols,
+                                x.values.cpu().numpy(), x.scales.cpu().numpy(), want_f32=True)
+    assert np.array_equal(bits(y32.cpu().numpy()), bits(w32))
+    assert np.array_equal(y.getData().cpu().numpy(), wv)
+    assert np.array_equal(bits(y.getScales().cpu().numpy()[: rows // 64]), bits(ws[: rows // 64]))
+    y2 = cb.CloverVector4(rows)
+    A.mvm(x, y2)
+    assert torch.equal(y2.values, y.values) and torch.equal(y2.scales, y.scales)
+
+
+@pytest.mark.parametrize("impl", ["ring64", "items32", "simple"])
+def test_mvm4_kernels_equal_default(impl):
+    """Every GEMV kernel selectable with CLOVER_GEMV_IMPL gives the same bytes as the default choice (fresh processes)."""
+    import os, subprocess, sys
+    code = (
+        "import torch, sys, hashlib; sys.path.insert(0, %r)\n"
+        "from clover_b200 import containers as cb\n"
+        "from bench import random_nibbles\n"
+        "g = torch.Generator(device='cuda').manual_seed(3)\n"
+        "h = hashlib.sha256()\n"
+        "for (r, c) in [(128, 128), (640, 1152), (4864, 2176), (32768, 1024)]:\n"
+        "    A = cb.CloverMatrix4(r, c); A.values.copy_(random_nibbles(torch, r * c // 2, g, torch.device('cuda'))); A.scales.uniform_(0.05, 4.0, generator=g)\n"
+        "    x = cb.CloverVector4(c); x.values.copy_(random_nibbles(torch, c // 2, g, torch.device('cuda'))); x.scales.uniform_(0.05, 4.0, generator=g)\n"
+        "    y = cb.CloverVector4(r); A.mvm(x, y); torch.cuda.synchronize()\n"
+        "    h.update(y.values.cpu().numpy().tobytes()); h.update(y.scales.cpu().numpy().tobytes())\n"
+        "print(h.hexdigest())\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = []
+    for env_impl in (None, impl):
+        env = dict(os.environ)
+        env.pop("CLOVER_GEMV_IMPL", None)
+        if env_impl:
+            env["CLOVER_GEMV_IMPL"] = env_impl
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, env=env)
+        assert out.returncode == 0, out.stdout + out.stderr
+        outs.append(out.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1]
+
+
 @pytest.mark.parametrize("shape", [(4736 + 128, 256), (148 * 32 * 3 + 128, 2048 + 128), (8192, 1024 * 17)])
 def test_mvm8_pipelined_many_items_vs_oracle(cb, oracle, shape):
     """CloverMatrix8::mvm through the persistent TMA-ring kernel when every CTA walks several 32-row work items, the
@@ -499,7 +553,7 @@ def test_gemm_tensor_core_equals_simt(cb, mnk):
     assert bool((big[:, N:] == 7.0).all())
 
 
-@pytest.mark.parametrize("variant", ["pipe1", "pair", "p192"])
+@pytest.mark.parametrize("variant", ["pipe1", "pair", "p192", "split"])
 def test_gemm_experimental_pipelines_equal_simt(variant):
     """The 4-slot TMEM-ring variants (gemm4_tc2.cu, CLOVER_GEMM_KERNEL) stay bit-identical to the DP4A kernel.
     The variant is read once per process, hence the subprocess."""

@@ -9,7 +9,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 for k in ${KERNELS:-gemv4 quantize4 dot4 gemv8 gemm4 mquantize4}; do
   case $k in
     gemv4) re=k_m4_mvm;; gemv8) re=k_m8_mvm;; quantize4|quantize8|quantize4_sr) re=k_vquantize;; dot4) re=k_vdot_fast;;
-    mquantize4) re=k_mquantize;; gemm4) re=k_gemm4_tc;;
+    mquantize4) re=k_mquantize;; gemm4) re=k_gemm4_tc;; transpose4|transpose8) re=k_mtranspose;;
   esac
   GEMM_N=${GEMM_N:-16384} ncu --set full --clock-control none --import-source on -k regex:$re -s 3 -c 1 -f -o gpurun_out/prof_${k}_${TAG} \
       python tools/profile_driver.py $k 5 > gpurun_out/prof_${k}_${TAG}.log 2>&1

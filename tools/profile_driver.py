@@ -1,6 +1,6 @@
 """Launch ONE hot-path kernel a few times at its BASELINE.json size - the command ncu wraps.
 
-usage: python tools/profile_driver.py {gemv4|gemv8|quantize4|quantize8|dot4|mquantize4|gemm4|quantize4_sr} [iters]
+usage: python tools/profile_driver.py {gemv4|gemv8|quantize4|quantize8|dot4|mquantize4|gemm4|quantize4_sr|transpose4|transpose8} [iters]
 """
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -48,6 +48,13 @@ elif what == "mquantize4":
     a = cb.CloverMatrix32(n, n); a.values.uniform_(-1, 1, generator=g)
     q = cb.CloverMatrix4(n, n)
     fn = lambda: q.quantize(a)
+elif what in ("transpose4", "transpose8"):
+    n = 16384
+    M = cb.CloverMatrix4 if what == "transpose4" else cb.CloverMatrix8
+    A, T = M(n, n), M(n, n)
+    A.values.copy_(torch.randint(-128, 128, (A.values.numel(),), dtype=torch.int8, device=dev, generator=g))
+    A.scales.uniform_(0.25, 1.0, generator=g)
+    fn = lambda: A.transpose(T)
 elif what == "gemm4":
     n = int(os.environ.get("GEMM_N", "16384"))
     A, B = cb.CloverMatrix4(n, n), cb.CloverMatrix4(n, n)
