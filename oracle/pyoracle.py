@@ -156,6 +156,18 @@ class Oracle:
                                                         _p(_state(state)))
         return r, sr
 
+    def threshold(self, bits, values, scales, n, k):
+        """keep the k largest magnitudes (CloverVector{4,8}::threshold); returns the thresholded copy of values"""
+        out = np.array(values, copy=True)
+        getattr(self.lib, f"orc_v{bits}_threshold")(_p(out), _p(scales), _u64(n), _u64(k))
+        return out
+
+    def v_abs(self, bits, values, scales, n):
+        """getAbs(i) for i < n (CloverVector4.h:190-203, CloverVector8.h:141-147)"""
+        fn = getattr(self.lib, f"orc_v{bits}_abs")
+        fn.restype = C.c_float
+        return np.array([fn(_p(values), _p(scales), _u64(i)) for i in range(n)], np.float32)
+
     # -- matrices (a: padded fp32 [rows, cols])
     def m4_quantize(self, a, state=None):
         rows, cols = a.shape
@@ -309,6 +321,12 @@ class Reference:
         getattr(self.lib, f"ref_v{bits}_scale_and_add")(_p(u), _p(su), _p(v), _p(sv), C.c_float(a), _u64(n), _p(r), _p(sr),
                                                         self._st(state), C.c_int(variant))
         return r, sr
+
+    def threshold(self, bits, values, scales, n, k, variant=0):
+        out = np.array(values, copy=True)
+        sc = np.array(scales, copy=True)
+        getattr(self.lib, f"ref_v{bits}_threshold")(_p(out), _p(sc), _u64(n), _u64(k), C.c_int(variant))
+        return out
 
     # -- matrices: handle based (the reference's matrices own their storage)
     class _M:

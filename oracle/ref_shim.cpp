@@ -198,6 +198,18 @@ void ref_v8_scale_and_add(const int8_t *u, const float *su, const int8_t *v, con
     x.get_state(state);
 }
 
+/* threshold in place (include/CloverVector4.h:1913, CloverVector8.h:1680); variant 2 = threshold_parallel */
+void ref_v4_threshold(int8_t *values, float *scales, uint64_t n, uint64_t k, int variant) {
+    silence_once();
+    CloverVector4 q(n, values, scales);
+    if (variant == 2) q.threshold_parallel(k); else q.threshold(k);
+}
+void ref_v8_threshold(int8_t *values, float *scales, uint64_t n, uint64_t k, int variant) {
+    silence_once();
+    CloverVector8 q(n, values, scales);
+    if (variant == 2) q.threshold_parallel(k); else q.threshold(k);
+}
+
 /* ---- CloverMatrix32 (input container) ------------------------------------------------ */
 void *ref_m32_create(uint64_t rows, uint64_t cols) { silence_once(); return new CloverMatrix32(rows, cols); }
 void ref_m32_destroy(void *h) { delete (CloverMatrix32 *)h; }

@@ -261,3 +261,19 @@ def test_matrix_transpose(oracle, reference, shape, bits_):
     # an involution: transposing back restores the matrix
     bv, bs = getattr(oracle, f"m{bits_}_transpose")(tv, ts, Cc, R)
     assert np.array_equal(bv, mv) and np.array_equal(bs.view(np.uint32), ms.view(np.uint32))
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+@pytest.mark.parametrize("n,k", [(128, 64), (129, 1), (1000, 64), (1000, 999), (1000, 1000), (2047, 64), (4096, 300), (8192 + 77, 2000)])
+def test_vector_threshold(oracle, reference, n, k, bits_):
+    """threshold (02_vector.cpp:450-500): the restatement - libstdc++ make_heap + the reference's
+    min_heapify - leaves exactly the bytes of the reference's sequential threshold(k), ties included."""
+    x = _inputs(oracle, n, "ints", seed_skip=k)          # integers in [-10, 10]: many equal magnitudes (worst case for ties)
+    qv, qs = getattr(reference, f"v{bits_}_quantize")(x, n)
+    want = reference.threshold(bits_, qv, qs, n, k)
+    got = oracle.threshold(bits_, qv, qs, n, k)
+    assert np.array_equal(got, want)
+    # the reference's own acceptance test: sorted magnitudes of the survivors == the k largest magnitudes
+    mags = np.sort(oracle.v_abs(bits_, qv, qs, n))[::-1]
+    kept = np.sort(oracle.v_abs(bits_, got, qs, n))[::-1]
+    assert np.array_equal(kept[:k], mags[:k]) and not kept[k:].any()
