@@ -314,8 +314,9 @@ int gemm4_tc3_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, co
 int gemm4_tc_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, const float *bs, uint64_t M, uint64_t N,
                       uint64_t K, float *c, uint64_t ldc, cudaStream_t stream) {
     // CLOVER_GEMM_KERNEL=pipe1|pair selects an experimental 4-slot pipeline (gemm4_tc2.cu); default: this file's kernel
-    static const int variant = [] { const char *e = getenv("CLOVER_GEMM_KERNEL");
-                                    return !e ? 0 : !strcmp(e, "pipe1") ? 1 : !strcmp(e, "pair") ? 2 : !strcmp(e, "p192") ? 3 : !strcmp(e, "split") ? 4 : 0; }();
+    // read on every call (cheap) so that one measurement process can walk through the variants
+    const int variant = [] { const char *e = getenv("CLOVER_GEMM_KERNEL");
+                             return !e ? 0 : !strcmp(e, "pipe1") ? 1 : !strcmp(e, "pair") ? 2 : !strcmp(e, "p192") ? 3 : !strcmp(e, "split") ? 4 : 0; }();
     if (variant == 3) return gemm4_tc3_expanded(a8, as, b8, bs, M, N, K, c, ldc, stream);
     if (variant == 1 || variant == 2) return gemm4_tc2_expanded(a8, as, b8, bs, M, N, K, c, ldc, stream, variant);
     CUtensorMap map_a, map_b;
@@ -323,15 +324,9 @@ int gemm4_tc_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, con
     if (rc != CLOVER_OK) return rc;
     rc = make_tensor_map_u8_2d_sw128(&map_b, b8, N, K, kBN);
     if (rc != CLOVER_OK) return rc;
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    CLOVER_CUDA_CHECK(cudaGetDevice(&dev));
-    static const int probe = [] { const char *e = getenv("CLOVER_GEMM_PROBE"); return e ? atoi(e) : 0; }();   // measurement only
+    const int probe = [] { const char *e = getenv("CLOVER_GEMM_PROBE"); return e ? atoi(e) : 0; }();   // measurement only
     auto kern = variant == 4 ? k_gemm4_tc<true, 0> : probe == 1 ? k_gemm4_tc<false, 1> : probe == 2 ? k_gemm4_tc<false, 2> : k_gemm4_tc<false, 0>;
-    if (!attr_set[dev & 63]) {
-        CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-        attr_set[dev & 63] = true;
-    }
+    CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     const uint64_t ntiles = (M / kBM) * ((N + kBN - 1) / kBN);
     const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sm_count());
     kern<<<grid, kGemmThreads, kGemmSmem, stream>>>(map_a, map_b, as, bs, (uint32_t)M, (uint32_t)N, (uint32_t)K, c, ldc);

@@ -304,7 +304,7 @@ int gemm4_tc3_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, co
     if (rc != CLOVER_OK) return rc;
     rc = make_tensor_map_u8_2d_sw128(&map_b, b8, N, K, k3BN / 2);
     if (rc != CLOVER_OK) return rc;
-    static const int mode = [] { const char *e = getenv("CLOVER_GEMM_EPI"); return e ? atoi(e) : 1; }();   // epilogue schedule, see the kernel (1 = batch: best measured)
+    const int mode = [] { const char *e = getenv("CLOVER_GEMM_EPI"); return e ? atoi(e) : 1; }();   // epilogue schedule, see the kernel (1 = batch: best measured)
     auto kern = mode == 0 ? k_gemm4_tc3<0> : mode == 1 ? k_gemm4_tc3<1> : mode == 3 ? k_gemm4_tc3<3> : mode == 4 ? k_gemm4_tc3<4> : k_gemm4_tc3<2>;
     CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k3Smem));
     const uint64_t ntiles = ((M + 2 * k3BM - 1) / (2 * k3BM)) * ((N + k3BN - 1) / k3BN);
