@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libclover_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_SIZE, ERR_UNSUPPORTED = range(5)
 DOT_AUTO, DOT_EXACT, DOT_FAST = 0, 1, 2
+THRESHOLD_AUTO, THRESHOLD_EXACT, THRESHOLD_FAST = 0, 1, 2
 
 _u64, _vp, _int = C.c_uint64, C.c_void_p, C.c_int
 
@@ -24,6 +25,7 @@ _SIGNATURES = {
     "clover_set_device": (_int, [_int]),
     "clover_size_pad": (_u64, [_u64]),
     "clover_dot_exact_limit": (_u64, []),
+    "clover_threshold_exact_limit": (_u64, []),
     "clover_kernel_launches": (_int, []),
     "clover_malloc": (_int, [C.POINTER(_vp), C.c_size_t]),
     "clover_free": (_int, [_vp]),
@@ -45,6 +47,8 @@ _SIGNATURES = {
     "clover_v4_dot": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _int, _vp]),
     "clover_v4_scale_and_add": (_int, [_vp, _vp, _vp, _vp, C.c_float, _u64, _vp, _vp, _vp, _vp]),
     "clover_v8_scale_and_add": (_int, [_vp, _vp, _vp, _vp, C.c_float, _u64, _vp, _vp, _vp, _vp]),
+    "clover_v4_threshold": (_int, [_vp, _vp, _u64, _u64, _int, _vp]),
+    "clover_v8_threshold": (_int, [_vp, _vp, _u64, _u64, _int, _vp]),
     "clover_v8_quantize": (_int, [_vp, _u64, _vp, _vp, _vp, _vp]),
     "clover_v8_restore": (_int, [_vp, _vp, _u64, _vp, _vp]),
     "clover_v8_dot": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _int, _vp]),

@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DOT_AUTO, call
+from ._lib import DOT_AUTO, THRESHOLD_AUTO, call
 
 CLOVER_VECTOR_BLOCK = 64          # include/CloverVector.h:41
 CLOVER_VECTOR_SIZE_PAD = 128      # include/CloverVector.h:42
@@ -153,6 +153,19 @@ class _QVector(_Keyed):
             raise CloverSizeError("Vectors do not have the same size.")
         call(f"clover_v{self.BITS}_scale_and_add", _ptr(self.values), _ptr(self.scales), _ptr(other.values), _ptr(other.scales),
              C.c_float(a), C.c_uint64(self.length_pad), _ptr(dst.values), _ptr(dst.scales), self._key_ptr(), _stream())
+
+    def threshold(self, k: int, mode: int = THRESHOLD_AUTO) -> None:
+        """Hard thresholding in place: only the k elements of largest magnitude survive
+        (include/CloverVector4.h:1913-1973, CloverVector8.h:1680-1740). mode: see clover_threshold_mode."""
+        call(f"clover_v{self.BITS}_threshold", _ptr(self.values), _ptr(self.scales), C.c_uint64(self.length), C.c_uint64(int(k)),
+             C.c_int(mode), _stream())
+
+    threshold_parallel = threshold                   # include/CloverVector4.h:1919-1925: same contract, OpenMP heaps
+
+    def clear(self) -> None:
+        """all elements 0, scales 1 (include/CloverVector4.h:306-318) - the start vector of the IHT / GD loops"""
+        self.values.zero_()
+        self.scales.fill_(1.0)
 
     def dot_device(self, other, out, mode: int = DOT_AUTO) -> None:
         """dot() without the device->host read: result lands in the 1-element CUDA tensor ``out``."""

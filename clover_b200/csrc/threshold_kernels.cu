@@ -1,0 +1,380 @@
+// threshold_kernels.cu - CloverVector4/8::threshold(k): keep the k elements of largest magnitude, zero the rest, in place
+// (include/CloverVector4.h:1913-1973, include/CloverVector8.h:1680-1740).
+//
+// The magnitude of element i is the reference's getAbs(i), reproduced bit for bit:
+//   4-bit: | (scale / 7.0f) * float(q) |          (include/CloverVector4.h:190-203)
+//   8-bit: | (float(q) * scale) / 127.0f |        (include/CloverVector8.h:141-147)
+// Magnitudes are non-negative fp32, so their bit patterns order like unsigned integers.
+//
+// Two paths (clover_threshold_mode):
+//   EXACT  the reference's own sequential walk - std::make_heap over the first k elements (libstdc++ __make_heap /
+//          __adjust_heap / __push_heap), then "replace the root if STRICTLY larger" + min_heapify
+//          (include/CloverBase.h:226-249) - executed by one thread over magnitudes a parallel kernel prepared. Which of
+//          several equal magnitudes survives depends on the heap layout; this path leaves exactly the reference's bytes.
+//          Latency-bound, meant for parity runs (n <= clover_threshold_exact_limit()).
+//   FAST   an 8-bit-digit radix select over the magnitude bits (4 histogram passes, all on the device, no host sync)
+//          finds the k-th largest magnitude t; everything above t stays, everything below goes, and of the elements equal
+//          to t the ones with the LOWEST indices stay until k survivors are reached (the reference's sequential and
+//          OpenMP variants already disagree with each other on such ties; its acceptance test - 02_vector.cpp:450-500 -
+//          compares sorted magnitudes only, which this path satisfies exactly).
+#include <algorithm>
+#include <mutex>
+#include "common.cuh"
+#include "runtime.cuh"
+
+namespace clover {
+
+constexpr int kThrThreads = 256;
+constexpr uint64_t kThrExactLimit = 1u << 16;
+
+struct ThrState {            // device-resident selection state
+    uint32_t prefix;         // magnitude bits decided so far (high digits)
+    uint32_t mask;           // which bits of `prefix` are decided
+    uint64_t k_rem;          // survivors still to be found among the elements matching prefix
+    uint32_t hist[256];
+};
+
+// magnitudes of the 8 elements of a 4-bit word (element order) / the 4 elements of an 8-bit word, as ordered bit patterns
+__device__ __forceinline__ uint32_t abs_bits4(float scale7, int q) { return __float_as_uint(fabsf(__fmul_rn(scale7, __int2float_rn(q)))); }
+__device__ __forceinline__ uint32_t abs_bits8(float scale, int q) { return __float_as_uint(fabsf(__fdiv_rn(__fmul_rn(__int2float_rn(q), scale), 127.0f))); }
+
+// element e (0..7) of a 4-bit word: byte e>>1, even elements in the HIGH nibble
+__device__ __forceinline__ int nib_of(uint32_t w, int e) {
+    const int sh = 8 * (e >> 1) + ((e & 1) ? 0 : 4);
+    return ((int)(w << (28 - sh))) >> 28;
+}
+
+template <int BITS> struct ThrWord {
+    static constexpr int kElems = BITS == 4 ? 8 : 4;     // elements per 32-bit word
+    __device__ static void mags(uint32_t w, float scale, uint64_t first, uint64_t n, uint32_t *m) {
+        const float s = BITS == 4 ? __fdiv_rn(scale, 7.0f) : scale;
+#pragma unroll
+        for (int e = 0; e < kElems; ++e) {
+            const int q = BITS == 4 ? nib_of(w, e) : (int)(int8_t)(w >> (8 * e));
+            const uint32_t b = BITS == 4 ? abs_bits4(s, q) : abs_bits8(s, q);
+            m[e] = first + e < n ? b : 0u;                // pad elements never compete
+        }
+    }
+    __device__ static uint32_t clear(uint32_t w, int e) {
+        return BITS == 4 ? w & ~(0xFu << (8 * (e >> 1) + ((e & 1) ? 0 : 4))) : w & ~(0xFFu << (8 * e));
+    }
+};
+
+// ---- FAST: one histogram pass over digit `shift` of the magnitudes that match the decided prefix -------------------
+template <int BITS>
+__global__ void __launch_bounds__(kThrThreads)
+k_thr_hist(const uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t n, uint64_t nwords, int shift,
+           ThrState *__restrict__ st) {
+    constexpr int E = ThrWord<BITS>::kElems;
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t prefix = st->prefix, mask = st->mask;
+    for (uint64_t i = (uint64_t)blockIdx.x * kThrThreads + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * kThrThreads) {
+        uint32_t m[E];
+        ThrWord<BITS>::mags(values[i], scales[(i * E) >> 6], i * E, n, m);
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (i * E + e < n && (m[e] & mask) == prefix) atomicAdd(&h[(m[e] >> shift) & 0xFF], 1u);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], h[threadIdx.x]);
+}
+
+// one block: pick the digit in which the k_rem-th largest of the matching elements falls, extend the prefix
+__global__ void __launch_bounds__(256) k_thr_pick(ThrState *st, int shift) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = st->hist[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t k = st->k_rem, above = 0;
+        int d = 255;
+        for (; d > 0; --d) {                              // descending: `above` = matching elements with a larger digit
+            if (above + h[d] >= k) break;
+            above += h[d];
+        }
+        st->prefix |= (uint32_t)d << shift;
+        st->mask |= 0xFFu << shift;
+        st->k_rem = k - above;
+    }
+    __syncthreads();
+    st->hist[threadIdx.x] = 0;
+}
+
+__global__ void k_thr_init(ThrState *st, uint64_t k) {
+    if (threadIdx.x == 0) { st->prefix = 0; st->mask = 0; st->k_rem = k; }
+    st->hist[threadIdx.x] = 0;
+}
+
+// ---- FAST: ties at the threshold. Each CTA owns one contiguous range of words (index order) ------------------------
+template <int BITS>
+__global__ void __launch_bounds__(kThrThreads)
+k_thr_count_ties(const uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t n, uint64_t nwords,
+                 uint64_t words_per_cta, const ThrState *__restrict__ st, uint32_t *__restrict__ tie_count) {
+    constexpr int E = ThrWord<BITS>::kElems;
+    const uint32_t t = st->prefix;
+    const uint64_t w0 = (uint64_t)blockIdx.x * words_per_cta, w1 = min(w0 + words_per_cta, nwords);
+    uint32_t c = 0;
+    for (uint64_t i = w0 + threadIdx.x; i < w1; i += kThrThreads) {
+        uint32_t m[E];
+        ThrWord<BITS>::mags(values[i], scales[(i * E) >> 6], i * E, n, m);
+#pragma unroll
+        for (int e = 0; e < E; ++e) c += (i * E + e < n && m[e] == t) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    __shared__ uint32_t ws[kThrThreads / 32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int w = 0; w < kThrThreads / 32; ++w) s += ws[w];
+        tie_count[blockIdx.x] = s;
+    }
+}
+
+// one block: exclusive prefix sums of the per-CTA tie counts (64-bit: n may exceed 2^32)
+__global__ void __launch_bounds__(256) k_thr_scan(const uint32_t *__restrict__ tie_count, uint64_t *__restrict__ tie_base, int nctas) {
+    __shared__ uint64_t part[256];
+    const int per = (nctas + 255) / 256, a = threadIdx.x * per, b = min(a + per, nctas);
+    uint64_t s = 0;
+    for (int i = a; i < b; ++i) s += tie_count[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        for (int i = 0; i < 256; ++i) { const uint64_t v = part[i]; part[i] = run; run += v; }
+    }
+    __syncthreads();
+    uint64_t run = part[threadIdx.x];
+    for (int i = a; i < b; ++i) { tie_base[i] = run; run += tie_count[i]; }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(kThrThreads)
+k_thr_apply(uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t n, uint64_t nwords, uint64_t words_per_cta,
+            const ThrState *__restrict__ st, const uint64_t *__restrict__ tie_base) {
+    constexpr int E = ThrWord<BITS>::kElems;
+    const uint32_t t = st->prefix;
+    const uint64_t keep_ties = st->k_rem;                    // how many elements equal to t survive (lowest indices first)
+    const uint64_t w0 = (uint64_t)blockIdx.x * words_per_cta, w1 = min(w0 + words_per_cta, nwords);
+    __shared__ uint32_t ws[kThrThreads / 32];
+    __shared__ uint64_t running;
+    if (threadIdx.x == 0) running = tie_base[blockIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t base = w0; base < w1; base += kThrThreads) {
+        const uint64_t i = base + threadIdx.x;
+        uint32_t w = 0, m[E], ties = 0;
+        if (i < w1) {
+            w = values[i];
+            ThrWord<BITS>::mags(w, scales[(i * E) >> 6], i * E, n, m);
+#pragma unroll
+            for (int e = 0; e < E; ++e) ties += (i * E + e < n && m[e] == t) ? 1u : 0u;
+        }
+        // exclusive scan of `ties` over the CTA in thread (= index) order
+        uint32_t incl = ties;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) ws[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int x = 0; x < kThrThreads / 32; ++x) { const uint32_t v = ws[x]; if (x < warp) before += v; total += v; }
+        uint64_t rank = running + before + (incl - ties);
+        if (i < w1) {
+            uint32_t out = w;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                if (i * E + e >= n) continue;
+                bool keep = m[e] > t;
+                if (m[e] == t) { keep = rank < keep_ties; ++rank; }
+                if (!keep) out = ThrWord<BITS>::clear(out, e);
+            }
+            if (out != w) values[i] = out;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) running += total;
+        __syncthreads();
+    }
+}
+
+// ---- EXACT: magnitudes + sign-extended bits in parallel, the heap walk by one thread, the mask applied in parallel --
+template <int BITS>
+__global__ void k_thr_prepare(const uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t n, uint64_t nwords,
+                              float *__restrict__ mag, uint8_t *__restrict__ keep) {
+    constexpr int E = ThrWord<BITS>::kElems;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t m[E];
+        ThrWord<BITS>::mags(values[i], scales[(i * E) >> 6], i * E, n, m);
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (i * E + e < n) { mag[i * E + e] = __uint_as_float(m[e]); keep[i * E + e] = 0; }
+    }
+}
+
+struct HeapItem { float value; uint32_t idx; };
+__device__ __forceinline__ bool heap_gt(const HeapItem &a, const HeapItem &b) { return a.value > b.value || isnan(a.value); }   // gt_idx_t, include/CloverBase.h:205-224
+
+__device__ void heap_push(HeapItem *first, long hole, long top, HeapItem value) {          // libstdc++ __push_heap
+    long parent = (hole - 1) / 2;
+    while (hole > top && heap_gt(first[parent], value)) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+__device__ void heap_adjust(HeapItem *first, long hole, long len, HeapItem value) {        // libstdc++ __adjust_heap
+    const long top = hole;
+    long child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (heap_gt(first[child], first[child - 1])) child--;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    heap_push(first, hole, top, value);
+}
+
+__global__ void k_thr_heap(const float *__restrict__ mag, uint64_t n, uint64_t k, HeapItem *__restrict__ heap, uint8_t *__restrict__ keep) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (uint64_t i = 0; i < k; ++i) heap[i] = HeapItem{mag[i], (uint32_t)i};
+    if (k >= 2) {                                                                          // std::make_heap
+        long parent = ((long)k - 2) / 2;
+        for (;;) {
+            const HeapItem v = heap[parent];
+            heap_adjust(heap, parent, (long)k, v);
+            if (parent == 0) break;
+            parent--;
+        }
+    }
+    for (uint64_t i = k; i < n; ++i) {
+        const float value = mag[i];
+        if (value > heap[0].value) {
+            heap[0] = HeapItem{value, (uint32_t)i};
+            uint32_t pos = 0;                                                              // min_heapify, include/CloverBase.h:226-249
+            for (;;) {
+                const uint32_t l = 2 * pos + 1, r = 2 * pos + 2;
+                uint32_t smallest = pos;
+                if (l < k && heap[l].value < heap[smallest].value) smallest = l;
+                if (r < k && heap[r].value < heap[smallest].value) smallest = r;
+                if (smallest == pos) break;
+                const HeapItem tmp = heap[pos]; heap[pos] = heap[smallest]; heap[smallest] = tmp;
+                pos = smallest;
+            }
+        }
+    }
+    for (uint64_t i = 0; i < k; ++i) keep[heap[i].idx] = 1;
+}
+
+template <int BITS>
+__global__ void k_thr_apply_mask(uint32_t *__restrict__ values, uint64_t n, uint64_t nwords, const uint8_t *__restrict__ keep) {
+    constexpr int E = ThrWord<BITS>::kElems;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = values[i];
+        uint32_t out = w;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (i * E + e < n && !keep[i * E + e]) out = ThrWord<BITS>::clear(out, e);
+        if (out != w) values[i] = out;
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+struct ThrWorkspace { void *p; size_t bytes; };
+static std::mutex g_thr_mutex;
+static ThrWorkspace g_thr_ws[64] = {};
+
+// grow-only per-device scratch (selection state, per-CTA tie counts, EXACT-mode magnitudes / heap / mask);
+// one threshold stream per device at a time, like the GEMM workspace
+static int thr_workspace(size_t bytes, void **out) {
+    int dev = 0;
+    CLOVER_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(g_thr_mutex);
+    ThrWorkspace &ws = g_thr_ws[dev];
+    if (ws.bytes < bytes) {
+        if (ws.p) { CLOVER_CUDA_CHECK(cudaDeviceSynchronize()); CLOVER_CUDA_CHECK(cudaFree(ws.p)); ws.p = nullptr; ws.bytes = 0; }
+        CLOVER_CUDA_CHECK(cudaMalloc(&ws.p, bytes));
+        ws.bytes = bytes;
+    }
+    *out = ws.p;
+    return CLOVER_OK;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <int BITS>
+static int launch_threshold(int8_t *values, const float *scales, uint64_t n, uint64_t k, int mode, cudaStream_t stream) {
+    constexpr int E = ThrWord<BITS>::kElems;
+    if (n == 0 || k >= n) return CLOVER_OK;                          // k == n keeps everything; the reference requires k <= n
+    const uint64_t nwords = (n + E - 1) / E;
+    uint32_t *v32 = reinterpret_cast<uint32_t *>(values);
+    const uint64_t cap = (uint64_t)sm_count() * 8;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nwords + kThrThreads - 1) / kThrThreads, cap));
+    if (k == 0) {                                                    // nothing survives (pad nibbles are zero already)
+        CLOVER_CUDA_CHECK(cudaMemsetAsync(values, 0, BITS == 4 ? (n + 1) / 2 : n, stream));
+        return CLOVER_OK;
+    }
+    const bool exact = mode == CLOVER_THRESHOLD_EXACT || (mode == CLOVER_THRESHOLD_AUTO && n <= kThrExactLimit);
+    if (exact) {
+        CLOVER_REQUIRE(n <= 0xFFFFFFFFull, CLOVER_ERR_UNSUPPORTED, "EXACT threshold is limited to 2^32 - 1 elements");
+        const size_t off_heap = align_up(n * sizeof(float), 256), off_keep = off_heap + align_up(k * sizeof(HeapItem), 256);
+        void *ws = nullptr;
+        int rc = thr_workspace(off_keep + align_up(n, 256), &ws);
+        if (rc != CLOVER_OK) return rc;
+        float *mag = static_cast<float *>(ws);
+        HeapItem *heap = reinterpret_cast<HeapItem *>(static_cast<uint8_t *>(ws) + off_heap);
+        uint8_t *keep = static_cast<uint8_t *>(ws) + off_keep;
+        k_thr_prepare<BITS><<<grid, kThrThreads, 0, stream>>>(v32, scales, n, nwords, mag, keep);
+        k_thr_heap<<<1, 32, 0, stream>>>(mag, n, k, heap, keep);
+        k_thr_apply_mask<BITS><<<grid, kThrThreads, 0, stream>>>(v32, n, nwords, keep);
+        count_launch(3);
+        return launch_status("k_thr_heap");
+    }
+    const uint64_t words_per_cta = (nwords + grid - 1) / grid;
+    const size_t off_cnt = align_up(sizeof(ThrState), 256), off_base = off_cnt + align_up(sizeof(uint32_t) * grid, 256);
+    void *ws = nullptr;
+    int rc = thr_workspace(off_base + sizeof(uint64_t) * grid, &ws);
+    if (rc != CLOVER_OK) return rc;
+    ThrState *st = static_cast<ThrState *>(ws);
+    uint32_t *tie_count = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ws) + off_cnt);
+    uint64_t *tie_base = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(ws) + off_base);
+    k_thr_init<<<1, 256, 0, stream>>>(st, k);
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        k_thr_hist<BITS><<<grid, kThrThreads, 0, stream>>>(v32, scales, n, nwords, shift, st);
+        k_thr_pick<<<1, 256, 0, stream>>>(st, shift);
+    }
+    k_thr_count_ties<BITS><<<grid, kThrThreads, 0, stream>>>(v32, scales, n, nwords, words_per_cta, st, tie_count);
+    k_thr_scan<<<1, 256, 0, stream>>>(tie_count, tie_base, (int)grid);
+    k_thr_apply<BITS><<<grid, kThrThreads, 0, stream>>>(v32, scales, n, nwords, words_per_cta, st, tie_base);
+    count_launch(12);
+    return launch_status("k_thr_apply");
+}
+
+}  // namespace clover
+
+using namespace clover;
+
+extern "C" {
+
+uint64_t clover_threshold_exact_limit(void) { return kThrExactLimit; }
+
+int clover_v4_threshold(int8_t *values, const float *scales, uint64_t n, uint64_t k, int mode, void *stream) {
+    CLOVER_REQUIRE(values && scales, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_REQUIRE(mode >= 0 && mode <= 2, CLOVER_ERR_INVALID, "bad threshold mode");
+    return launch_threshold<4>(values, scales, n, k, mode, (cudaStream_t)stream);
+}
+int clover_v8_threshold(int8_t *values, const float *scales, uint64_t n, uint64_t k, int mode, void *stream) {
+    CLOVER_REQUIRE(values && scales, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_REQUIRE(mode >= 0 && mode <= 2, CLOVER_ERR_INVALID, "bad threshold mode");
+    return launch_threshold<8>(values, scales, n, k, mode, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -53,6 +53,14 @@ typedef enum clover_status {
  * AUTO = EXACT up to clover_dot_exact_limit() elements, FAST beyond. */
 typedef enum clover_dot_mode { CLOVER_DOT_AUTO = 0, CLOVER_DOT_EXACT = 1, CLOVER_DOT_FAST = 2 } clover_dot_mode;
 
+/* threshold() tie handling. EXACT walks the reference's sequential min-heap (std::make_heap +
+ * min_heapify, include/CloverVector4.h:1929-1973) with one thread, so that of several EQUAL magnitudes exactly the
+ * reference's survivors remain; FAST is a parallel radix select that keeps all larger magnitudes and, of the elements
+ * equal to the k-th largest magnitude, those with the lowest indices. Both leave exactly k non-cleared elements holding
+ * the k largest magnitudes (the reference's acceptance test, test/validate/02_vector.cpp:450-500).
+ * AUTO = EXACT up to clover_threshold_exact_limit() elements, FAST beyond. */
+typedef enum clover_threshold_mode { CLOVER_THRESHOLD_AUTO = 0, CLOVER_THRESHOLD_EXACT = 1, CLOVER_THRESHOLD_FAST = 2 } clover_threshold_mode;
+
 /* ---- library / device --------------------------------------------------------------------------- */
 int         clover_version(void);
 const char *clover_last_error(void);                 /* thread-local message of the last failure */
@@ -60,6 +68,7 @@ int         clover_device_count(void);
 int         clover_set_device(int device);
 uint64_t    clover_size_pad(uint64_t n);              /* include/CloverVector.h:86-89 */
 uint64_t    clover_dot_exact_limit(void);
+uint64_t    clover_threshold_exact_limit(void);
 int         clover_kernel_launches(void);             /* kernels launched by this library since load */
 
 /* ---- device memory helpers (what the reference does with posix_memalign/free/memcpy) ------------ */
@@ -97,6 +106,11 @@ int clover_v4_dot(const int8_t *u, const float *su, const int8_t *v, const float
 int clover_v4_scale_and_add(const int8_t *u, const float *su, const int8_t *v, const float *sv, float a, uint64_t n_pad,
                             int8_t *r, float *sr, uint64_t *key_host, void *stream);
 
+/* CloverVector4::threshold(k)  include/CloverVector4.h:1913-1973 (threshold_parallel :1919-1925): keep the k elements
+ * of largest magnitude getAbs(i) = |scale/7.0f * q| (:190-203), clear the other nibbles, in place. n = the LOGICAL
+ * length (the reference walks `length`, :1931); k >= n leaves the vector unchanged, k = 0 clears it. */
+int clover_v4_threshold(int8_t *values, const float *scales, uint64_t n, uint64_t k, int mode, void *stream);
+
 /* ---- CloverVector8 ------------------------------------------------------------------------------ */
 /* CloverVector8::quantize      include/CloverVector8.h:393-605 */
 int clover_v8_quantize(const float *x, uint64_t n_pad, int8_t *values, float *scales, uint64_t *key_host, void *stream);
@@ -109,6 +123,9 @@ int clover_v8_dot(const int8_t *u, const float *su, const int8_t *v, const float
 /* CloverVector8::scaleAndAdd   include/CloverVector8.h:1089-1357 */
 int clover_v8_scale_and_add(const int8_t *u, const float *su, const int8_t *v, const float *sv, float a, uint64_t n_pad,
                             int8_t *r, float *sr, uint64_t *key_host, void *stream);
+
+/* CloverVector8::threshold(k)  include/CloverVector8.h:1680-1740; getAbs(i) = |(q * scale) / 127.0f| (:141-147) */
+int clover_v8_threshold(int8_t *values, const float *scales, uint64_t n, uint64_t k, int mode, void *stream);
 
 /* ---- CloverMatrix4 ------------------------------------------------------------------------------ */
 /* CloverMatrix4::quantize      include/CloverMatrix4.h:512-766  (a: rows*cols fp32, row-major) */

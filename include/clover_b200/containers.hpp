@@ -18,8 +18,7 @@
 // Stochastic rounding is a run-time switch: containers start WITHOUT a key (= the reference built with
 // CLOVER_STOCHASTIC_ROUNDING_DISABLED); setRandomKeys()/seed() enables the reference's XORShift128+ stream.
 //
-// Not provided (outside the hot path): scaleAndAdd, threshold, transpose, 16-bit containers,
-// fp32 BLAS on CloverVector32/CloverMatrix32.
+// Not provided (outside the hot path): 16-bit containers, fp32 BLAS on CloverVector32/CloverMatrix32.
 #ifndef CLOVER_B200_CONTAINERS_HPP
 #define CLOVER_B200_CONTAINERS_HPP
 
@@ -187,6 +186,14 @@ public:
                                  : clover_v8_scale_and_add(u, su, v, sv, a, length_pad, r, sr, key_ptr(), nullptr);
         clover_b200_detail::check(rc, "scaleAndAdd");
     }
+    // hard thresholding in place: only the k largest magnitudes survive (include/CloverVector4.h:1913-1973, CloverVector8.h:1680-1740)
+    void threshold(uint64_t k, int mode = CLOVER_THRESHOLD_AUTO) {
+        int8_t *v = device_values_out();
+        const int rc = BITS == 4 ? clover_v4_threshold(v, device_scales(), length, k, mode, nullptr)
+                                 : clover_v8_threshold(v, device_scales(), length, k, mode, nullptr);
+        clover_b200_detail::check(rc, "threshold");
+    }
+    void threshold_parallel(uint64_t k) { threshold(k); }
     void scaleAndAdd_scalar(const CloverQuantizedVector &o, float a) { scaleAndAdd(o, a); }
     void scaleAndAdd_parallel(const CloverQuantizedVector &o, float a) { scaleAndAdd(o, a); }
     void scaleAndAdd_scalar(const CloverQuantizedVector &o, float a, CloverQuantizedVector &r) { scaleAndAdd(o, a, r); }

@@ -618,3 +618,114 @@ def test_full_size_properties_c2(cb, oracle):
     s = ((scales * np.float32(1.0 / 49.0)) * scales).to(torch.float64)
     want = float((s * ib).sum())
     assert abs(got - want) <= float(np.finfo(np.float32).eps) * abs(want)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# threshold: include/CloverVector4.h:1913-1973, include/CloverVector8.h:1680-1740;
+# the reference's acceptance test is test/validate/02_vector.cpp:450-500 (sorted magnitudes of the survivors)
+# ---------------------------------------------------------------------------------------------------------
+def _abs_all(oracle, bits_, values, scales, n):
+    """getAbs(i) for every i < n, vectorised with the oracle's arithmetic (fp32, one rounding per operation)"""
+    v = np.asarray(values).view(np.int8)
+    if bits_ == 4:
+        b = v[: (n + 1) // 2].view(np.uint8).astype(np.int32)
+        q = np.empty(2 * b.size, np.int32)
+        q[0::2], q[1::2] = b >> 4, b & 15
+        q = np.where(q >= 8, q - 16, q)[:n].astype(np.float32)
+        s = (np.asarray(scales, np.float32) / np.float32(7.0))[np.arange(n) >> 6]
+        return np.abs(s * q)
+    q = v[:n].astype(np.float32)
+    return np.abs((q * np.asarray(scales, np.float32)[np.arange(n) >> 6]) / np.float32(127.0))
+
+
+THR_CASES = [(128, 64), (129, 1), (1000, 64), (1000, 999), (1000, 1000), (1000, 0), (2047, 64), (4096, 300), (8192 + 77, 2000),
+             (65536, 4096)]
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+@pytest.mark.parametrize("kind", ["floats", "ints"])
+@pytest.mark.parametrize("n,k", THR_CASES)
+def test_vector_threshold_exact(cb, oracle, n, k, kind, bits_):
+    """EXACT mode = the reference's sequential heap walk: every byte equals the oracle's, ties included
+    ("ints" inputs in [-10, 10] produce many equal magnitudes)."""
+    from clover_b200._lib import THRESHOLD_EXACT
+    V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
+    x = gen(oracle, n, kind, skip=k)
+    q = V(n)
+    q.quantize(cb.CloverVector32(n, x))
+    qv, qs = q.getData().cpu().numpy().copy(), q.getScales().cpu().numpy().copy()
+    want = oracle.threshold(bits_, qv, qs, n, k)
+    q.threshold(k, THRESHOLD_EXACT)
+    assert np.array_equal(q.getData().cpu().numpy(), want)
+    assert np.array_equal(bits(q.getScales().cpu().numpy()), bits(qs))          # scales are not touched
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+@pytest.mark.parametrize("kind", ["floats", "ints"])
+@pytest.mark.parametrize("n,k", THR_CASES + [((1 << 20) + 77, 50000)])
+def test_vector_threshold_fast(cb, oracle, n, k, kind, bits_):
+    """FAST mode (radix select): exactly min(k, n) survivors with unchanged bits, every magnitude above the k-th largest
+    kept, every one below cleared, ties by lowest index; its sorted magnitudes equal the oracle's (the reference's own
+    acceptance criterion), and with no tie at the threshold the bytes equal the oracle's."""
+    from clover_b200._lib import THRESHOLD_FAST
+    V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
+    x = gen(oracle, n, kind, skip=k)
+    q = V(n)
+    q.quantize(cb.CloverVector32(n, x))
+    qv, qs = q.getData().cpu().numpy().copy(), q.getScales().cpu().numpy().copy()
+    mags = _abs_all(oracle, bits_, qv, qs, n)
+    q.threshold(k, THRESHOLD_FAST)
+    got = q.getData().cpu().numpy()
+    kept = _abs_all(oracle, bits_, got, qs, n)
+    if k >= n:
+        assert np.array_equal(got, qv)
+        return
+    if k == 0:
+        assert not got.any()
+        return
+    order = np.sort(mags)[::-1]
+    t = order[k - 1]
+    changed = kept != mags                                                      # cleared elements (non-zero before)
+    assert np.all(kept[changed] == 0)                                           # an element is either untouched or cleared
+    assert np.array_equal(kept[mags > t], mags[mags > t])                       # everything above the threshold survives
+    assert not kept[mags < t].any()                                             # everything below is cleared
+    ties = np.flatnonzero(mags == t)
+    r = k - int((mags > t).sum())                                               # ties that survive: the lowest indices
+    if t > 0:
+        assert np.array_equal(kept[ties[:r]], mags[ties[:r]]) and not kept[ties[r:]].any()
+        assert int((kept > 0).sum()) == k
+    assert np.array_equal(np.sort(kept)[::-1][:k], order[:k])                   # 02_vector.cpp:450-500
+    if n <= 70000:
+        want = oracle.threshold(bits_, qv, qs, n, k)
+        assert np.array_equal(np.sort(_abs_all(oracle, bits_, want, qs, n)), np.sort(kept))
+        if len(ties) == r:                                                      # no tie-break needed: identical bytes
+            assert np.array_equal(got, want)
+    # pad nibbles / bytes stay zero
+    pad_from = (n + 1) // 2 if bits_ == 4 else n
+    assert not got[pad_from:].any()
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+def test_vector_threshold_auto_and_idempotent(cb, oracle, bits_):
+    """AUTO = EXACT up to the limit, FAST beyond; thresholding twice with the same k changes nothing (size-independent
+    property, checked at 2^22 elements)."""
+    import clover_b200
+    V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
+    limit = clover_b200.lib().clover_threshold_exact_limit()
+    assert limit == 65536
+    n, k = 4096, 100
+    x = gen(oracle, n, "ints")
+    q = V(n)
+    q.quantize(cb.CloverVector32(n, x))
+    want = oracle.threshold(bits_, q.getData().cpu().numpy().copy(), q.getScales().cpu().numpy().copy(), n, k)
+    q.threshold(k)                                                              # AUTO
+    assert np.array_equal(q.getData().cpu().numpy(), want)
+    n, k = 1 << 22, 12345
+    x = gen(oracle, n, "floats")
+    q = V(n)
+    q.quantize(cb.CloverVector32(n, x))
+    q.threshold_parallel(k)
+    once = q.getData().clone()
+    assert int((_abs_all(oracle, bits_, once.cpu().numpy(), q.getScales().cpu().numpy(), n) > 0).sum()) == k
+    q.threshold(k)
+    assert torch.equal(q.getData(), once)
