@@ -5,8 +5,10 @@ Layers:
   _lib.py          ctypes binding of include/clover_b200.h (fails loudly when the library is missing)
   containers.py    device-resident mirror of the reference containers (CloverVector4, CloverMatrix4, ...)
   sharded.py       row-sharded multi-GPU mvm over torch.distributed / NCCL
+  apps.py          the reference's application loops (Q_IHT, Q_GD) composed from the containers
 """
-from ._lib import (ABI_SYMBOLS, DOT_AUTO, DOT_EXACT, DOT_FAST, CloverError, build, call, lib)  # noqa: F401
+from ._lib import (ABI_SYMBOLS, DOT_AUTO, DOT_EXACT, DOT_FAST, THRESHOLD_AUTO, THRESHOLD_EXACT, THRESHOLD_FAST,  # noqa: F401
+                   CloverError, build, call, lib)
 
 
 def __getattr__(name):

@@ -17,6 +17,7 @@
 //          to t the ones with the LOWEST indices stay until k survivors are reached (the reference's sequential and
 //          OpenMP variants already disagree with each other on such ties; its acceptance test - 02_vector.cpp:450-500 -
 //          compares sorted magnitudes only, which this path satisfies exactly).
+#include <stdlib.h>
 #include <algorithm>
 #include <mutex>
 #include "common.cuh"
@@ -25,14 +26,48 @@
 namespace clover {
 
 constexpr int kThrThreads = 256;
-constexpr uint64_t kThrExactLimit = 1u << 16;
+constexpr int kThrSmallThreads = 1024;
+constexpr uint64_t kThrExactLimit = 1u << 12;     // AUTO: the sequential heap walk up to 4096 elements
+constexpr uint64_t kThrSmallLimit = 1u << 15;     // FAST: one CTA does the whole selection up to 32768 elements (29 us; the 7-launch path wins beyond)
 
-struct ThrState {            // device-resident selection state
+struct ThrState {            // device-resident selection state; hist[] and ticket are zero between calls
     uint32_t prefix;         // magnitude bits decided so far (high digits)
     uint32_t mask;           // which bits of `prefix` are decided
     uint64_t k_rem;          // survivors still to be found among the elements matching prefix
+    uint32_t ticket;         // CTAs that have finished the current pass
     uint32_t hist[256];
 };
+
+// Histogram update. Measured on B200 at n = 2^26 (random and all-equal inputs alike): merging equal bins across the warp
+// first (match.any / match.all) is 4-17 % SLOWER than plain shared-memory atomics - the passes are bound by the ~30
+// instructions per element that rebuild the magnitude, not by bin contention - so the atomics stay plain.
+__device__ __forceinline__ void hist_add(uint32_t *h, uint32_t digit, bool valid) {
+    if (valid) atomicAdd(&h[digit], 1u);
+}
+
+// the digit in which the k-th largest of the counted elements falls: returns it, `above` = elements with a larger digit.
+// Called by every thread of a CTA with >= 256 threads; h[] is shared memory holding the full histogram.
+__device__ __forceinline__ uint32_t pick_digit(const uint32_t *h, uint64_t k, uint64_t *scratch /* 256 */, uint64_t &above) {
+    const uint32_t d = threadIdx.x;
+    if (d < 256) scratch[d] = h[d];
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {                      // inclusive suffix sums: scratch[d] = sum_{j >= d} h[j]
+        uint64_t v = 0;
+        if (d < 256 && d + o < 256) v = scratch[d + o];
+        __syncthreads();
+        if (d < 256) scratch[d] += v;
+        __syncthreads();
+    }
+    __shared__ uint32_t picked;
+    __shared__ uint64_t picked_above;
+    if (d < 256) {
+        const uint64_t ge = scratch[d], gt = ge - h[d];
+        if (gt < k && k <= ge) { picked = d; picked_above = gt; }        // exactly one digit satisfies this
+    }
+    __syncthreads();
+    above = picked_above;
+    return picked;
+}
 
 // magnitudes of the 8 elements of a 4-bit word (element order) / the 4 elements of an 8-bit word, as ordered bit patterns
 __device__ __forceinline__ uint32_t abs_bits4(float scale7, int q) { return __float_as_uint(fabsf(__fmul_rn(scale7, __int2float_rn(q)))); }
@@ -60,50 +95,51 @@ template <int BITS> struct ThrWord {
     }
 };
 
-// ---- FAST: one histogram pass over digit `shift` of the magnitudes that match the decided prefix -------------------
-template <int BITS>
+// ---- FAST (large n): one histogram pass over digit `shift` of the magnitudes that match the decided prefix; the last
+// CTA to finish extends the prefix by the digit in which the k_rem-th largest matching element falls -------------------
+template <int BITS, bool TOP>
 __global__ void __launch_bounds__(kThrThreads)
 k_thr_hist(const uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t n, uint64_t nwords, int shift,
-           ThrState *__restrict__ st) {
+           uint64_t k, ThrState *__restrict__ st) {
     constexpr int E = ThrWord<BITS>::kElems;
     __shared__ uint32_t h[256];
+    __shared__ uint64_t scratch[256];
+    __shared__ bool is_last;
     h[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t prefix = st->prefix, mask = st->mask;
-    for (uint64_t i = (uint64_t)blockIdx.x * kThrThreads + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * kThrThreads) {
+    const uint32_t prefix = TOP ? 0u : st->prefix, mask = TOP ? 0u : st->mask;
+    const uint64_t stride = (uint64_t)gridDim.x * kThrThreads;
+    const uint64_t warp_first = (uint64_t)blockIdx.x * kThrThreads + (threadIdx.x & ~31u);
+    for (uint64_t base = warp_first; base < nwords; base += stride) {         // warp-uniform trip count (collectives inside)
+        const uint64_t i = base + (threadIdx.x & 31);
         uint32_t m[E];
-        ThrWord<BITS>::mags(values[i], scales[(i * E) >> 6], i * E, n, m);
+        if (i < nwords) ThrWord<BITS>::mags(values[i], scales[(i * E) >> 6], i * E, n, m);
 #pragma unroll
-        for (int e = 0; e < E; ++e)
-            if (i * E + e < n && (m[e] & mask) == prefix) atomicAdd(&h[(m[e] >> shift) & 0xFF], 1u);
+        for (int e = 0; e < E; ++e) {
+            const bool valid = i < nwords && i * E + e < n && (m[e] & mask) == prefix;
+            hist_add(h, valid ? (m[e] >> shift) & 0xFFu : 0u, valid);
+        }
     }
     __syncthreads();
     if (h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], h[threadIdx.x]);
-}
-
-// one block: pick the digit in which the k_rem-th largest of the matching elements falls, extend the prefix
-__global__ void __launch_bounds__(256) k_thr_pick(ThrState *st, int shift) {
-    __shared__ uint32_t h[256];
-    h[threadIdx.x] = st->hist[threadIdx.x];
+    __threadfence();
     __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    h[threadIdx.x] = __ldcg(&st->hist[threadIdx.x]);
+    __syncthreads();
+    const uint64_t k_rem = TOP ? k : st->k_rem;
+    uint64_t above;
+    const uint32_t d = pick_digit(h, k_rem, scratch, above);
+    st->hist[threadIdx.x] = 0;                                                // leave the state clean for the next pass / call
     if (threadIdx.x == 0) {
-        uint64_t k = st->k_rem, above = 0;
-        int d = 255;
-        for (; d > 0; --d) {                              // descending: `above` = matching elements with a larger digit
-            if (above + h[d] >= k) break;
-            above += h[d];
-        }
-        st->prefix |= (uint32_t)d << shift;
-        st->mask |= 0xFFu << shift;
-        st->k_rem = k - above;
+        st->prefix = prefix | (d << shift);
+        st->mask = mask | (0xFFu << shift);
+        st->k_rem = k_rem - above;
+        st->ticket = 0;
     }
-    __syncthreads();
-    st->hist[threadIdx.x] = 0;
-}
-
-__global__ void k_thr_init(ThrState *st, uint64_t k) {
-    if (threadIdx.x == 0) { st->prefix = 0; st->mask = 0; st->k_rem = k; }
-    st->hist[threadIdx.x] = 0;
 }
 
 // ---- FAST: ties at the threshold. Each CTA owns one contiguous range of words (index order) ------------------------
@@ -150,25 +186,34 @@ __global__ void __launch_bounds__(256) k_thr_scan(const uint32_t *__restrict__ t
     for (int i = a; i < b; ++i) { tie_base[i] = run; run += tie_count[i]; }
 }
 
-template <int BITS>
-__global__ void __launch_bounds__(kThrThreads)
-k_thr_apply(uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t n, uint64_t nwords, uint64_t words_per_cta,
-            const ThrState *__restrict__ st, const uint64_t *__restrict__ tie_base) {
+template <int E> __device__ __forceinline__ void load_mags(const uint32_t *__restrict__ mag, uint64_t word, uint32_t *m) {
+#pragma unroll
+    for (int j = 0; j < E / 4; ++j) {
+        const uint4 v = reinterpret_cast<const uint4 *>(mag)[word * (E / 4) + j];
+        m[4 * j] = v.x; m[4 * j + 1] = v.y; m[4 * j + 2] = v.z; m[4 * j + 3] = v.w;
+    }
+}
+
+// Clear what does not survive in words [w0, w1), walked in index order by the whole CTA (NT threads): magnitudes above t
+// stay, below t go, and an element equal to t stays while fewer than keep_ties such elements precede it (`first_rank` =
+// ties before w0).
+template <int BITS, int NT>
+__device__ __forceinline__ void apply_range(uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t n, uint64_t w0,
+                                            uint64_t w1, uint32_t t, uint64_t keep_ties, uint64_t first_rank,
+                                            const uint32_t *__restrict__ mag = nullptr /* cached magnitudes, E per word */) {
     constexpr int E = ThrWord<BITS>::kElems;
-    const uint32_t t = st->prefix;
-    const uint64_t keep_ties = st->k_rem;                    // how many elements equal to t survive (lowest indices first)
-    const uint64_t w0 = (uint64_t)blockIdx.x * words_per_cta, w1 = min(w0 + words_per_cta, nwords);
-    __shared__ uint32_t ws[kThrThreads / 32];
+    __shared__ uint32_t ws[NT / 32];
     __shared__ uint64_t running;
-    if (threadIdx.x == 0) running = tie_base[blockIdx.x];
+    if (threadIdx.x == 0) running = first_rank;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint64_t base = w0; base < w1; base += kThrThreads) {
+    for (uint64_t base = w0; base < w1; base += NT) {
         const uint64_t i = base + threadIdx.x;
         uint32_t w = 0, m[E], ties = 0;
         if (i < w1) {
             w = values[i];
-            ThrWord<BITS>::mags(w, scales[(i * E) >> 6], i * E, n, m);
+            if (mag) load_mags<E>(mag, i, m);
+            else ThrWord<BITS>::mags(w, scales[(i * E) >> 6], i * E, n, m);
 #pragma unroll
             for (int e = 0; e < E; ++e) ties += (i * E + e < n && m[e] == t) ? 1u : 0u;
         }
@@ -180,7 +225,7 @@ k_thr_apply(uint32_t *__restrict__ values, const float *__restrict__ scales, uin
         __syncthreads();
         uint32_t before = 0, total = 0;
 #pragma unroll
-        for (int x = 0; x < kThrThreads / 32; ++x) { const uint32_t v = ws[x]; if (x < warp) before += v; total += v; }
+        for (int x = 0; x < NT / 32; ++x) { const uint32_t v = ws[x]; if (x < warp) before += v; total += v; }
         uint64_t rank = running + before + (incl - ties);
         if (i < w1) {
             uint32_t out = w;
@@ -197,6 +242,61 @@ k_thr_apply(uint32_t *__restrict__ values, const float *__restrict__ scales, uin
         if (threadIdx.x == 0) running += total;
         __syncthreads();
     }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(kThrThreads)
+k_thr_apply(uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t n, uint64_t nwords, uint64_t words_per_cta,
+            const ThrState *__restrict__ st, const uint64_t *__restrict__ tie_base) {
+    const uint64_t w0 = (uint64_t)blockIdx.x * words_per_cta, w1 = min(w0 + words_per_cta, nwords);
+    apply_range<BITS, kThrThreads>(values, scales, n, w0, w1, st->prefix, st->k_rem, tie_base[blockIdx.x]);
+}
+
+// ---- FAST (n <= kThrSmallLimit, the IHT sizes): ONE CTA does the four digit passes and the ordered apply - one launch.
+// The passes are bound by the instructions that rebuild a magnitude (~30 per element: nibble extract, int->float, IEEE
+// divide / multiply), so the first pass leaves the magnitudes in an L2-resident scratch array and the other passes and the
+// apply read them back (one 16-byte load per four elements).
+template <int BITS>
+__global__ void __launch_bounds__(kThrSmallThreads)
+k_thr_small(uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t n, uint32_t nwords, uint64_t k,
+            uint32_t *__restrict__ mag) {
+    constexpr int E = ThrWord<BITS>::kElems;
+    __shared__ uint32_t h[256];
+    __shared__ uint64_t scratch[256];
+    uint32_t prefix = 0, mask = 0;
+    uint64_t k_rem = k;
+#pragma unroll 1
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        if (threadIdx.x < 256) h[threadIdx.x] = 0;
+        __syncthreads();
+        if (shift == 24) {
+            for (uint32_t i = threadIdx.x; i < nwords; i += kThrSmallThreads) {
+                uint32_t m[E];
+                ThrWord<BITS>::mags(values[i], scales[((uint64_t)i * E) >> 6], (uint64_t)i * E, n, m);
+#pragma unroll
+                for (int j = 0; j < E / 4; ++j)
+                    reinterpret_cast<uint4 *>(mag)[(uint64_t)i * (E / 4) + j] = make_uint4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
+#pragma unroll
+                for (int e = 0; e < E; ++e) hist_add(h, m[e] >> 24, (uint64_t)i * E + e < n);
+            }
+        } else {
+#pragma unroll 2
+            for (uint32_t i = threadIdx.x; i < nwords; i += kThrSmallThreads) {
+                uint32_t m[E];
+                load_mags<E>(mag, i, m);
+#pragma unroll
+                for (int e = 0; e < E; ++e) hist_add(h, (m[e] >> shift) & 0xFFu, (uint64_t)i * E + e < n && (m[e] & mask) == prefix);
+            }
+        }
+        __syncthreads();
+        uint64_t above;
+        const uint32_t d = pick_digit(h, k_rem, scratch, above);
+        prefix |= d << shift;
+        mask |= 0xFFu << shift;
+        k_rem -= above;
+        __syncthreads();
+    }
+    apply_range<BITS, kThrSmallThreads>(values, scales, n, 0, nwords, prefix, k_rem, 0, mag);
 }
 
 // ---- EXACT: magnitudes + sign-extended bits in parallel, the heap walk by one thread, the mask applied in parallel --
@@ -302,6 +402,7 @@ static int thr_workspace(size_t bytes, void **out) {
     if (ws.bytes < bytes) {
         if (ws.p) { CLOVER_CUDA_CHECK(cudaDeviceSynchronize()); CLOVER_CUDA_CHECK(cudaFree(ws.p)); ws.p = nullptr; ws.bytes = 0; }
         CLOVER_CUDA_CHECK(cudaMalloc(&ws.p, bytes));
+        CLOVER_CUDA_CHECK(cudaMemset(ws.p, 0, sizeof(ThrState)));      // hist[] / ticket start clean; every pass leaves them clean
         ws.bytes = bytes;
     }
     *out = ws.p;
@@ -325,11 +426,12 @@ static int launch_threshold(int8_t *values, const float *scales, uint64_t n, uin
     const bool exact = mode == CLOVER_THRESHOLD_EXACT || (mode == CLOVER_THRESHOLD_AUTO && n <= kThrExactLimit);
     if (exact) {
         CLOVER_REQUIRE(n <= 0xFFFFFFFFull, CLOVER_ERR_UNSUPPORTED, "EXACT threshold is limited to 2^32 - 1 elements");
-        const size_t off_heap = align_up(n * sizeof(float), 256), off_keep = off_heap + align_up(k * sizeof(HeapItem), 256);
+        const size_t off_mag = align_up(sizeof(ThrState), 256);          // the FAST path's state keeps the head of the workspace
+        const size_t off_heap = off_mag + align_up(n * sizeof(float), 256), off_keep = off_heap + align_up(k * sizeof(HeapItem), 256);
         void *ws = nullptr;
         int rc = thr_workspace(off_keep + align_up(n, 256), &ws);
         if (rc != CLOVER_OK) return rc;
-        float *mag = static_cast<float *>(ws);
+        float *mag = reinterpret_cast<float *>(static_cast<uint8_t *>(ws) + off_mag);
         HeapItem *heap = reinterpret_cast<HeapItem *>(static_cast<uint8_t *>(ws) + off_heap);
         uint8_t *keep = static_cast<uint8_t *>(ws) + off_keep;
         k_thr_prepare<BITS><<<grid, kThrThreads, 0, stream>>>(v32, scales, n, nwords, mag, keep);
@@ -337,6 +439,16 @@ static int launch_threshold(int8_t *values, const float *scales, uint64_t n, uin
         k_thr_apply_mask<BITS><<<grid, kThrThreads, 0, stream>>>(v32, n, nwords, keep);
         count_launch(3);
         return launch_status("k_thr_heap");
+    }
+    if (n <= kThrSmallLimit) {
+        const size_t off_mag = align_up(sizeof(ThrState), 256);
+        void *ws = nullptr;
+        int rc = thr_workspace(off_mag + nwords * E * sizeof(uint32_t), &ws);
+        if (rc != CLOVER_OK) return rc;
+        k_thr_small<BITS><<<1, kThrSmallThreads, 0, stream>>>(v32, scales, n, (uint32_t)nwords, k,
+                                                              reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ws) + off_mag));
+        count_launch();
+        return launch_status("k_thr_small");
     }
     const uint64_t words_per_cta = (nwords + grid - 1) / grid;
     const size_t off_cnt = align_up(sizeof(ThrState), 256), off_base = off_cnt + align_up(sizeof(uint32_t) * grid, 256);
@@ -346,15 +458,13 @@ static int launch_threshold(int8_t *values, const float *scales, uint64_t n, uin
     ThrState *st = static_cast<ThrState *>(ws);
     uint32_t *tie_count = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ws) + off_cnt);
     uint64_t *tie_base = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(ws) + off_base);
-    k_thr_init<<<1, 256, 0, stream>>>(st, k);
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        k_thr_hist<BITS><<<grid, kThrThreads, 0, stream>>>(v32, scales, n, nwords, shift, st);
-        k_thr_pick<<<1, 256, 0, stream>>>(st, shift);
-    }
+    k_thr_hist<BITS, true><<<grid, kThrThreads, 0, stream>>>(v32, scales, n, nwords, 24, k, st);
+    for (int shift = 16; shift >= 0; shift -= 8)
+        k_thr_hist<BITS, false><<<grid, kThrThreads, 0, stream>>>(v32, scales, n, nwords, shift, k, st);
     k_thr_count_ties<BITS><<<grid, kThrThreads, 0, stream>>>(v32, scales, n, nwords, words_per_cta, st, tie_count);
     k_thr_scan<<<1, 256, 0, stream>>>(tie_count, tie_base, (int)grid);
     k_thr_apply<BITS><<<grid, kThrThreads, 0, stream>>>(v32, scales, n, nwords, words_per_cta, st, tie_base);
-    count_launch(12);
+    count_launch(7);
     return launch_status("k_thr_apply");
 }
 

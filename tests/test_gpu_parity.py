@@ -706,13 +706,36 @@ def test_vector_threshold_fast(cb, oracle, n, k, kind, bits_):
 
 
 @pytest.mark.parametrize("bits_", [4, 8])
+@pytest.mark.parametrize("n,k", [(1000, 10), (32768, 777), (100000, 777), (300000, 150001)])
+def test_vector_threshold_fast_all_equal(cb, oracle, n, k, bits_):
+    """worst case for the tie rule and for histogram contention: ONE magnitude - the k lowest indices survive
+    (single-CTA path up to 32768 elements, multi-CTA path beyond)"""
+    from clover_b200._lib import THRESHOLD_FAST
+    V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
+    x = np.full(n, -0.75, np.float32)
+    x[1::2] = 0.75
+    q = V(n)
+    q.quantize(cb.CloverVector32(n, x))
+    before = q.getData().cpu().numpy().copy()
+    q.threshold(k, THRESHOLD_FAST)
+    got = q.getData().cpu().numpy()
+    nb = k // 2 if bits_ == 4 else k                     # k is even in the 4-bit cases or handled below
+    if bits_ == 4 and k % 2:
+        assert np.array_equal(got[:nb], before[:nb])
+        assert got.view(np.uint8)[nb] == (before.view(np.uint8)[nb] & 0xF0)     # element k-1 (even index) sits in the high nibble
+        assert not got[nb + 1:].any()
+    else:
+        assert np.array_equal(got[:nb], before[:nb]) and not got[nb:].any()
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
 def test_vector_threshold_auto_and_idempotent(cb, oracle, bits_):
     """AUTO = EXACT up to the limit, FAST beyond; thresholding twice with the same k changes nothing (size-independent
     property, checked at 2^22 elements)."""
     import clover_b200
     V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
     limit = clover_b200.lib().clover_threshold_exact_limit()
-    assert limit == 65536
+    assert limit == 4096
     n, k = 4096, 100
     x = gen(oracle, n, "ints")
     q = V(n)
@@ -729,3 +752,49 @@ def test_vector_threshold_auto_and_idempotent(cb, oracle, bits_):
     assert int((_abs_all(oracle, bits_, once.cpu().numpy(), q.getScales().cpu().numpy(), n) > 0).sum()) == k
     q.threshold(k)
     assert torch.equal(q.getData(), once)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the reference's application loops (test/performance/01_measure.h:924-946 Q_IHT, :1000-1020 Q_GD): the whole
+# iteration sequence - mvm, scaleAndAdd, mvm, scaleAndAdd, threshold - stays bit-identical to the oracle
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bits_", [4, 8])
+@pytest.mark.parametrize("algo", ["iht", "gd"])
+def test_application_loops(cb, oracle, bits_, algo):
+    from clover_b200 import apps
+    from clover_b200._lib import THRESHOLD_EXACT
+    M, N, K, iters, mu = 256, 512, 40, 4, np.float32(0.05)
+    V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
+    Mx = cb.CloverMatrix4 if bits_ == 4 else cb.CloverMatrix8
+    st = oracle.xs_init()
+    phi32 = oracle.fill_floats(M * N, -1.0, 1.0, st).reshape(M, N) * np.float32(0.0625)
+    y32 = oracle.fill_floats(M, -1.0, 1.0, st)
+    Phi, PhiT = Mx(M, N), Mx(N, M)
+    Phi.quantize(cb.CloverMatrix32(M, N, phi32))
+    Phi.transpose(PhiT)
+    y = V(M)
+    y.quantize(cb.CloverVector32(M, y32))
+    x, t1, t2, t3 = V(N), V(M), V(M), V(N)
+    if algo == "iht":
+        apps.Q_IHT(Phi, PhiT, x, y, t1, t2, t3, iters, K, float(mu), THRESHOLD_EXACT)
+    else:
+        apps.Q_GD(Phi, PhiT, x, y, t1, t2, t3, iters, float(mu))
+    # the same loop on the oracle
+    mq = getattr(oracle, f"m{bits_}_quantize")
+    mvm = getattr(oracle, f"m{bits_}_mvm")
+    tr = getattr(oracle, f"m{bits_}_transpose")
+    pv, ps = mq(phi32)
+    tv, ts = tr(pv, ps, M, N)
+    yv, ys = getattr(oracle, f"v{bits_}_quantize")(y32, M)
+    xv = np.zeros(N * bits_ // 8, np.int8)
+    xs = np.ones(N // 64, np.float32)
+    for _ in range(iters):
+        t1v, t1s = mvm(pv, ps, M, N, xv, xs)
+        t2v, t2s = oracle.scale_and_add(bits_, yv, ys, t1v, t1s, -1.0, M)
+        t3v, t3s = mvm(tv, ts, N, M, t2v, t2s)
+        xv, xs = oracle.scale_and_add(bits_, xv, xs, t3v, t3s, float(mu), N)
+        if algo == "iht":
+            xv = oracle.threshold(bits_, xv, xs, N, K)
+    assert np.array_equal(x.getData().cpu().numpy(), xv)
+    assert np.array_equal(bits(x.getScales().cpu().numpy()), bits(xs))
+    assert x.getData().any()                                                    # the loop did something
