@@ -77,11 +77,12 @@ constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
 constexpr int kGemmSmem = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 constexpr uint32_t kGroupM = 16;     // tiles are walked in groups of 16 tile-rows so that concurrent CTAs share A and B' panels in L2
 
+template <uint32_t GROUP = kGroupM>
 __device__ __forceinline__ void tile_coords(uint32_t t, uint32_t tiles_m, uint32_t tiles_n, uint32_t &tm, uint32_t &tn) {
-    const uint32_t group_sz = kGroupM * tiles_n;
+    const uint32_t group_sz = GROUP * tiles_n;
     const uint32_t g = t / group_sz, r = t % group_sz;
-    const uint32_t first = g * kGroupM;
-    const uint32_t gm = min(kGroupM, tiles_m - first);
+    const uint32_t first = g * GROUP;
+    const uint32_t gm = min(GROUP, tiles_m - first);
     tm = first + r % gm;
     tn = r / gm;
 }
@@ -123,7 +124,24 @@ __device__ __forceinline__ void epilogue_slab(uint64_t *acc, uint32_t *r, float 
 // SPLIT = true (CLOVER_GEMM_KERNEL=split): every slab is issued as two N=128 halves with their own full/empty barriers
 // (four 128-column TMEM buffers at the same addresses). The warps of the left and of the right half then run about
 // half a slab out of phase, so the FMA bursts of one group overlap the TMEM-load round trips of the other.
-template <bool SPLIT, int PROBE>
+// CL = 2 (CLOVER_GEMM_KERNEL=mc2): clusters of two CTAs on vertically adjacent tiles (same B' panel). Each CTA fetches one
+// half of the B' stage and TMA-multicasts it into both shared memories, so a slab costs 8 + 8 KiB of L2 reads per SM
+// instead of 8 + 16; a stage is refilled only after BOTH CTAs' MMAs have retired it (multicast tcgen05.commit on `empty`).
+// All TMEM hand-off barriers stay CTA-local.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const void *tensor_map, int c0, int c1, uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_dst), "l"(tensor_map), "r"(c0), "r"(c1), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc1(uint32_t bar, uint16_t mask) {       // arrive on `bar` in every CTA of `mask`
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_tc() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool SPLIT, int PROBE, int CL = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
            const float *__restrict__ as, const float *__restrict__ bs, uint32_t M, uint32_t N, uint32_t K,
@@ -136,13 +154,17 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     const uint32_t slot = tempty + 32;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tiles_m = M / kBM, tiles_n = (N + kBN - 1) / kBN, ntiles = tiles_m * tiles_n;
+    const uint32_t tiles_n = (N + kBN - 1) / kBN;
+    const uint32_t ctiles_m = M / (kBM * CL), ntiles = ctiles_m * tiles_n;       // cluster tiles: CL vertically adjacent 128-row tiles
     const uint32_t kblocks = K / kBK, KB = K >> 6, NB = N >> 6;
+    uint32_t crank = 0;
+    if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const uint32_t first_tile = blockIdx.x / CL, tile_step = gridDim.x / CL;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full + 8 * i), "r"(1) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty + 8 * i), "r"(1) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty + 8 * i), "r"(CL) : "memory");
         }
         for (int b = 0; b < 4; ++b) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tfull + 8 * b), "r"(1) : "memory");
@@ -157,7 +179,7 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         tmem_relinquish<1>();
     }
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_tc(); else __syncthreads();     // the peer's barriers exist before anything is multicast at them
     tc_fence_after();
     uint32_t tmem;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
@@ -167,16 +189,19 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         if (warp == 0) {
             // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
             uint32_t stage = 0, phase = 0;
-            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (uint32_t t = first_tile; t < ntiles; t += tile_step) {
                 uint32_t tm, tn;
-                tile_coords(t, tiles_m, tiles_n, tm, tn);
+                tile_coords<kGroupM / CL>(t, ctiles_m, tiles_n, tm, tn);
+                tm = tm * CL + crank;
                 for (uint32_t kb = 0; kb < kblocks; ++kb) {
                     mbar_wait_a(empty + 8 * stage, phase ^ 1);
                     if (elect_one()) {
                         mbar_arrive_expect_tx_a(full + 8 * stage, kStageBytes);
                         const uint32_t sa = smem + stage * kStageBytes;
                         tma_load_2d_a(sa, &map_a, (int)(kb * kBK), (int)(tm * kBM), full + 8 * stage);
-                        tma_load_2d_a(sa + kAStage, &map_b, (int)(kb * kBK), (int)(tn * kBN), full + 8 * stage);
+                        if (CL == 1) tma_load_2d_a(sa + kAStage, &map_b, (int)(kb * kBK), (int)(tn * kBN), full + 8 * stage);
+                        else         tma_load_2d_mc(sa + kAStage + crank * (kBStage / CL), &map_b, (int)(kb * kBK),
+                                                    (int)(tn * kBN + crank * (kBN / CL)), full + 8 * stage, (uint16_t)((1u << CL) - 1));
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -186,7 +211,7 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             // ===== MMA issuer: per stage, K-slab 0 -> TMEM buffer 0, K-slab 1 -> buffer 1 =====
             const uint32_t idesc = umma_idesc(UMMA_E4M3, kBM, kBN), idesc_half = umma_idesc(UMMA_E4M3, kBM, kBN / 2);
             uint32_t stage = 0, phase = 0, pair = 0;
-            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (uint32_t t = first_tile; t < ntiles; t += tile_step) {
                 for (uint32_t kb = 0; kb < kblocks; ++kb, ++pair) {
                     mbar_wait_a(full + 8 * stage, phase);
                     tc_fence_after();
@@ -218,7 +243,10 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                             umma_ss<UMMA_E4M3, 1>(d, da + 4 * h, db + 4 * h, idesc, 0);
                             umma_ss<UMMA_E4M3, 1>(d, da + 4 * h + 2, db + 4 * h + 2, idesc, 1);
                             umma_commit_a<1>(tfull + 8 * h);
-                            if (h == 1) umma_commit_a<1>(empty + 8 * stage);      // smem stage free once its MMAs retire
+                            if (h == 1) {                                         // smem stage free once its MMAs retire
+                                if (CL == 1) umma_commit_a<1>(empty + 8 * stage);
+                                else         umma_commit_mc1(empty + 8 * stage, (uint16_t)((1u << CL) - 1));
+                            }
                         }
                         __syncwarp();
                         }
@@ -235,9 +263,10 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         uint64_t acc[32];
         uint32_t r[32];
         uint32_t pair = 0;
-        for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (uint32_t t = first_tile; t < ntiles; t += tile_step) {
             uint32_t tm, tn;
-            tile_coords(t, tiles_m, tiles_n, tm, tn);
+            tile_coords<kGroupM / CL>(t, ctiles_m, tiles_n, tm, tn);
+            tm = tm * CL + crank;
             const uint32_t jb = tn * 4 + cb;
             const bool live = jb < NB;                      // N is a multiple of 128: a 64-column block is all in or all out
             const float *pa = as + (uint64_t)(tm * 2 + (q >> 1)) * KB;
@@ -273,7 +302,7 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_tc(); else __syncthreads();     // nobody leaves while the peer may still multicast into this CTA
     if (warp == 2) tmem_dealloc<1>(tmem, 512);
 }
 
@@ -316,7 +345,7 @@ int gemm4_tc_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, con
     // CLOVER_GEMM_KERNEL=pipe1|pair selects an experimental 4-slot pipeline (gemm4_tc2.cu); default: this file's kernel
     // read on every call (cheap) so that one measurement process can walk through the variants
     const int variant = [] { const char *e = getenv("CLOVER_GEMM_KERNEL");
-                             return !e ? 0 : !strcmp(e, "pipe1") ? 1 : !strcmp(e, "pair") ? 2 : !strcmp(e, "p192") ? 3 : !strcmp(e, "split") ? 4 : 0; }();
+                             return !e ? 0 : !strcmp(e, "pipe1") ? 1 : !strcmp(e, "pair") ? 2 : !strcmp(e, "p192") ? 3 : !strcmp(e, "split") ? 4 : !strcmp(e, "mc2") ? 5 : 0; }();
     if (variant == 3) return gemm4_tc3_expanded(a8, as, b8, bs, M, N, K, c, ldc, stream);
     if (variant == 1 || variant == 2) return gemm4_tc2_expanded(a8, as, b8, bs, M, N, K, c, ldc, stream, variant);
     CUtensorMap map_a, map_b;
@@ -328,6 +357,30 @@ int gemm4_tc_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, con
     auto kern = variant == 4 ? k_gemm4_tc<true, 0> : probe == 1 ? k_gemm4_tc<false, 1> : probe == 2 ? k_gemm4_tc<false, 2> : k_gemm4_tc<false, 0>;
     CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     const uint64_t ntiles = (M / kBM) * ((N + kBN - 1) / kBN);
+    if (variant == 5 && (M / kBM) % 2 == 0) {
+        // clusters of two CTAs sharing a B' panel through TMA multicast
+        CUtensorMap map_b2;
+        rc = make_tensor_map_u8_2d_sw128(&map_b2, b8, N, K, kBN / 2);
+        if (rc != CLOVER_OK) return rc;
+        auto kern2 = probe == 2 ? k_gemm4_tc<false, 2, 2> : k_gemm4_tc<false, 0, 2>;
+        CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = kGemmSmem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cfg.gridDim = dim3(2);
+        int max_clusters = 0;
+        CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_clusters, kern2, &cfg));
+        const unsigned clusters = (unsigned)std::min<uint64_t>(ntiles / 2, (uint64_t)std::max(1, std::min(max_clusters, sm_count() / 2)));
+        cfg.gridDim = dim3(2 * clusters);
+        CLOVER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern2, map_a, map_b2, as, bs, (uint32_t)M, (uint32_t)N, (uint32_t)K, c, ldc));
+        count_launch();
+        return launch_status("k_gemm4_tc<mc2>");
+    }
     const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sm_count());
     kern<<<grid, kGemmThreads, kGemmSmem, stream>>>(map_a, map_b, as, bs, (uint32_t)M, (uint32_t)N, (uint32_t)K, c, ldc);
     count_launch();

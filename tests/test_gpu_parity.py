@@ -553,7 +553,7 @@ def test_gemm_tensor_core_equals_simt(cb, mnk):
     assert bool((big[:, N:] == 7.0).all())
 
 
-@pytest.mark.parametrize("variant", ["pipe1", "pair", "p192", "split"])
+@pytest.mark.parametrize("variant", ["pipe1", "pair", "p192", "split", "mc2"])
 def test_gemm_experimental_pipelines_equal_simt(variant):
     """The 4-slot TMEM-ring variants (gemm4_tc2.cu, CLOVER_GEMM_KERNEL) stay bit-identical to the DP4A kernel.
     The variant is read once per process, hence the subprocess."""
@@ -566,7 +566,7 @@ def test_gemm_experimental_pipelines_equal_simt(variant):
         "def mk(r, c):\n"
         "    m = cb.CloverMatrix4(r, c); m.values.copy_(random_nibbles(torch, r * c // 2, g, torch.device('cuda')))\n"
         "    m.scales.uniform_(0.05, 4.0, generator=g); return m\n"
-        "for (M, N, K) in [(128, 128, 128), (384, 640, 1152), (2176, 2048, 2048), (4096, 4224, 1024)]:\n"
+        "for (M, N, K) in [(128, 128, 128), (256, 256, 256), (384, 640, 1152), (512, 384, 1152), (2176, 2048, 2048), (4096, 4224, 1024)]:\n"
         "    A, B = mk(M, K), mk(N, K)\n"
         "    assert torch.equal(A.gemm(B, impl='tc').view(torch.int32), A.gemm(B, impl='simt').view(torch.int32)), (M, N, K)\n"
         "print('ok')\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
