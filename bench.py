@@ -49,6 +49,14 @@ def gemv_bytes(rows, cols, bits=4):
     return vec(cols) + int(rows * cols * per) + (rows // 64) * (cols // 64) * 4 + vec(rows)
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch of a kernel/config from the committed `ncu --set full` captures (profiles/ncu_traffic.json); None if not captured"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(key, {}).get("bytes")
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -230,13 +238,21 @@ def extras(torch, cb, peak):
         qs[i[0] % 8].quantize(xs32[i[0] % 2]); i[0] += 1
     t = cuda_time(torch, quant, 20)
     b = n * 4 + qs[0].getBytes()
-    out["C2a_quantize4_n2^26"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b}
+    out["C2a_quantize4_n2^26"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b,
+                                  "traffic": ncu_traffic("k_vquantize4:2^26")}
     res = torch.empty(1, dtype=torch.float32, device=dev)
     def dot():
         k = i[0] % 4; qs[2 * k].dot_device(qs[2 * k + 1], res, DOT_FAST); i[0] += 1
     t = cuda_time(torch, dot, 40)
     b = 2 * qs[0].getBytes()
-    out["C2b_dot4_n2^26_fast_rotating4"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b}
+    out["C2b_dot4_n2^26_fast_rotating4"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b,
+                                            "traffic": ncu_traffic("k_vdot_fast4:2^26")}
+    # threshold at n = 2^26 (radix select, 7 launches); bytes = the reference's own model 2*getBytes (01_measure.h:906)
+    from clover_b200 import THRESHOLD_FAST
+    def thr():
+        qs[i[0] % 8].threshold(n // 64, THRESHOLD_FAST); i[0] += 1
+    t = cuda_time(torch, thr, 8)
+    out["threshold4_n2^26_k=2^20_fast"] = {"ms": t * 1e3, "GBps_ref_model": 2 * qs[0].getBytes() / t / 1e9}
     q8 = [cb.CloverVector8(n) for _ in range(2)]
     def quant8():
         q8[i[0] % 2].quantize(xs32[i[0] % 2]); i[0] += 1
@@ -259,7 +275,8 @@ def extras(torch, cb, peak):
     v = cb.CloverVector32(c8); v.values.uniform_(-1, 1, generator=g); x8.quantize(v)
     t = cuda_time(torch, lambda: m8.mvm(x8, y8), 20)
     b = gemv_bytes(r8, c8, 8)
-    out["C5_gemv8_32768"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b}
+    out["C5_gemv8_32768"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b,
+                             "traffic": ncu_traffic("k_m8_mvm_tma:32768x32768")}
     del m8
     # transpose of a 16384 x 16384 matrix (every byte read once and written once)
     for bits_, M_ in ((4, cb.CloverMatrix4), (8, cb.CloverMatrix8)):
@@ -268,8 +285,28 @@ def extras(torch, cb, peak):
         src.scales.uniform_(0.25, 1.0, generator=g)
         t = cuda_time(torch, lambda: src.transpose(dst), 20)
         b = 2 * src.getBytes()
-        out[f"transpose{bits_}_16384"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b}
+        out[f"transpose{bits_}_16384"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b,
+                                          "traffic": ncu_traffic(f"k_transpose{bits_}:16384x16384")}
         del src, dst
+    # the reference's IHT loop (01_measure.h:924-946) at Phi 8192 x 32768, K = 1024: mvm, scaleAndAdd, mvm,
+    # scaleAndAdd, threshold per iteration, 10 iterations per call, nothing read back
+    from clover_b200 import apps
+    Mi, Ni, Ki = 8192, 32768, 1024
+    Phi, PhiT = cb.CloverMatrix4(Mi, Ni), cb.CloverMatrix4(Ni, Mi)
+    Phi.values.copy_(torch.randint(-128, 128, (Phi.values.numel(),), dtype=torch.int8, device=dev, generator=g))
+    Phi.scales.uniform_(0.01, 0.02, generator=g)
+    Phi.transpose(PhiT)
+    yv = cb.CloverVector4(Mi)
+    v = cb.CloverVector32(Mi); v.values.uniform_(-1, 1, generator=g); yv.quantize(v)
+    xv, t1, t2, t3 = cb.CloverVector4(Ni), cb.CloverVector4(Mi), cb.CloverVector4(Mi), cb.CloverVector4(Ni)
+    t = cuda_time(torch, lambda: apps.Q_IHT(Phi, PhiT, xv, yv, t1, t2, t3, 10, Ki, 0.01, THRESHOLD_FAST), 5) / 10
+    out["iht4_8192x32768_K1024_per_iteration"] = {"us": t * 1e6, "matrix_bytes": 2 * Phi.getBytes(), "GBps": 2 * Phi.getBytes() / t / 1e9,
+                                                   "frac_hbm": 2 * Phi.getBytes() / t / 1e9 / peak}
+    graph = apps.capture(lambda: apps.Q_IHT(Phi, PhiT, xv, yv, t1, t2, t3, 10, Ki, 0.01, THRESHOLD_FAST))
+    t = cuda_time(torch, graph.replay, 5) / 10
+    out["iht4_8192x32768_K1024_per_iteration_cuda_graph"] = {"us": t * 1e6, "GBps": 2 * Phi.getBytes() / t / 1e9,
+                                                              "frac_hbm": 2 * Phi.getBytes() / t / 1e9 / peak}
+    del Phi, PhiT
     # C4: 4-bit GEMM 16384^3
     M = N = K = 16384
     A, Bt = cb.CloverMatrix4(M, K), cb.CloverMatrix4(N, K)
@@ -287,7 +324,8 @@ def extras(torch, cb, peak):
                      "unit": "TOP/s", "frac": ops / tk / 1e12 / INT8_PEAK_TOPS,
                      "peak_source": "measured here: tools/mma_probe peak, tcgen05.mma kind::i8 issue loop on 148 SMs "
                                     "(profiles/r01_mma_probe.txt); kind::f8f6f4, the kind this kernel uses, sustains 3767",
-                     "frac_of_e4m3_sustained_3767": ops / tk / 1e12 / 3767.0, "frac_of_nominal_4500": ops / tk / 1e12 / 4500.0},
+                     "frac_of_e4m3_sustained_3767": ops / tk / 1e12 / 3767.0, "frac_of_nominal_4500": ops / tk / 1e12 / 4500.0,
+                     "traffic": ncu_traffic("k_gemm4_tc:16384^3")},
         "note": "C[i][j] = rowView(A,i).dot(rowView(Bt,j)); bit-identical to the DP4A kernel (tests/test_gpu_parity.py)"}
     return out
 
@@ -442,7 +480,8 @@ def main():
             "gpu_launches": launches,
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "kernel": "k_m4_mvm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "frac": achieved / peak, "peak_source": peak_src,
+                         "traffic": ncu_traffic(f"k_m4_mvm_tma:{rows}x{cols}") if world == 1 else None,
                          "kernel_ms": tk * 1e3, "algorithmic_bytes_per_launch": shard_bytes},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -31,3 +31,22 @@ def Q_GD(Phi, PhiT, x, y, t1, t2, t3, iterations: int, mu: float) -> None:
         y.scaleAndAdd(t1, -1.0, t2)
         PhiT.mvm(t2, t3)
         x.scaleAndAdd(t3, mu)
+
+
+def capture(fn, warmup: int = 2):
+    """Capture ``fn`` (a sequence of container calls with no host read-back, e.g. a Q_IHT call) into a CUDA graph.
+
+    The calls are first run ``warmup`` times on a side stream so that first-use allocations (kernel workspaces, tensor
+    maps' driver entry point) happen outside the capture. Replaying the graph removes the per-call host cost - five
+    launches per IHT iteration otherwise each pay a Python/ctypes round trip."""
+    import torch
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warmup):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fn()
+    return graph

@@ -798,3 +798,28 @@ def test_application_loops(cb, oracle, bits_, algo):
     assert np.array_equal(x.getData().cpu().numpy(), xv)
     assert np.array_equal(bits(x.getScales().cpu().numpy()), bits(xs))
     assert x.getData().any()                                                    # the loop did something
+
+
+def test_application_loop_cuda_graph(cb, oracle):
+    """A whole Q_IHT call captured into a CUDA graph replays to the same bits as the eager call."""
+    from clover_b200 import apps
+    from clover_b200._lib import THRESHOLD_FAST
+    M, N, K = 512, 2048, 100
+    st = oracle.xs_init()
+    phi32 = oracle.fill_floats(M * N, -1.0, 1.0, st).reshape(M, N) * np.float32(0.03)
+    Phi, PhiT = cb.CloverMatrix4(M, N), cb.CloverMatrix4(N, M)
+    Phi.quantize(cb.CloverMatrix32(M, N, phi32))
+    Phi.transpose(PhiT)
+    y = cb.CloverVector4(M)
+    y.quantize(cb.CloverVector32(M, oracle.fill_floats(M, -1.0, 1.0, st)))
+    x, t1, t2, t3 = cb.CloverVector4(N), cb.CloverVector4(M), cb.CloverVector4(M), cb.CloverVector4(N)
+    run = lambda: apps.Q_IHT(Phi, PhiT, x, y, t1, t2, t3, 6, K, 0.05, THRESHOLD_FAST)
+    run()
+    torch.cuda.synchronize()
+    want_v, want_s = x.getData().clone(), x.getScales().clone()
+    assert int((want_v != 0).sum()) > 0
+    graph = apps.capture(run)
+    x.getData().fill_(0x55)                      # poison: the replay must rebuild x from scratch (Q_IHT starts with x.clear())
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(x.getData(), want_v) and torch.equal(x.getScales().view(torch.int32), want_s.view(torch.int32))
