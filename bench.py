@@ -186,6 +186,48 @@ def reference_cpu_gemv(sample_rows, cols, steps, warmup):
             "ms_per_step": total / len(times) * 1e3}
 
 
+def reference_cpu_extras():
+    """The reference's own CPU routines for the other configs, timed beside the GPU numbers on bounded samples
+    (quantize / dot / 8-bit mvm / scaleAndAdd / threshold, `_parallel` on all host threads and the
+    sequential SIMD routine on one). GB/s by the reference's getBytes() model (01_measure.h:644,717,804,906)."""
+    from oracle.pyoracle import Reference, aligned
+    if not Reference.available(False):
+        return {"unavailable": "oracle/_ref not built"}
+    ref = Reference(False)
+    rng = np.random.default_rng(7)
+    out = {"cores": ref.threads(), "kind": "reference"}
+
+    def best(fn, reps=3):
+        ts = []
+        for _ in range(reps + 1):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return min(ts[1:])
+
+    n = 1 << 24
+    x = aligned(n, np.float32); x[:] = rng.uniform(-1, 1, n).astype(np.float32)
+    v4 = lambda: (aligned(n // 2, np.int8), aligned(n // 64, np.float32))
+    qv, qs = ref.v4_quantize(x, n)
+    qv2, qs2 = ref.v4_quantize(x[::-1].copy(), n)
+    vec_bytes = n // 2 + n // 64 * 4
+    for name, var in (("parallel", 2), ("sequential", 0)):
+        out[f"quantize4_n2^24_{name}_GBps"] = (4 * n + vec_bytes) / best(lambda: ref.v4_quantize(x, n, variant=var)) / 1e9
+        out[f"dot4_n2^24_{name}_GBps"] = 2 * vec_bytes / best(lambda: ref.v4_dot(qv, qs, qv2, qs2, n, variant=var)) / 1e9
+        out[f"scaleAndAdd4_n2^24_{name}_GBps"] = 3 * vec_bytes / best(lambda: ref.scale_and_add(4, qv, qs, qv2, qs2, 0.5, n, variant=var)) / 1e9
+    nt, kt = 1 << 20, 1 << 14
+    out["threshold4_n2^20_k2^14_sequential_ms"] = best(lambda: ref.threshold(4, qv[: nt // 2], qs[: nt // 64], nt, kt, variant=0)) * 1e3
+    out["threshold4_n2^20_k2^14_parallel_ms"] = best(lambda: ref.threshold(4, qv[: nt // 2], qs[: nt // 64], nt, kt, variant=2)) * 1e3
+    rows8, cols8 = 4096, 32768
+    mv = rng.integers(-127, 128, rows8 * cols8, dtype=np.int8)
+    ms = rng.uniform(0.25, 1.0, (rows8 // 64) * (cols8 // 64)).astype(np.float32)
+    m8 = ref.m8_from(mv, ms, rows8, cols8)
+    xv = aligned(cols8, np.int8); xv[:] = rng.integers(-127, 128, cols8, dtype=np.int8)
+    xs = aligned(cols8 // 64, np.float32); xs[:] = rng.uniform(0.25, 1.0, cols8 // 64).astype(np.float32)
+    b8 = gemv_bytes(rows8, cols8, 8)
+    out["C5_mvm8_4096of32768rows_parallel_GBps"] = b8 / best(lambda: ref.m8_mvm(m8, xv, xs, variant=2)) / 1e9
+    out["C5_mvm8_4096of32768rows_sequential_GBps"] = b8 / best(lambda: ref.m8_mvm(m8, xv, xs, variant=0), 2) / 1e9
+    return {k: (round(v, 3) if isinstance(v, float) else v) for k, v in out.items()}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -497,6 +539,11 @@ def main():
                 line["extras"] = extras(torch, cb, peak)
             except Exception as exc:
                 line["extras"] = {"error": repr(exc)}
+            if not args.no_cpu_baseline:
+                try:
+                    line["extras"]["cpu_reference"] = reference_cpu_extras()
+                except Exception as exc:
+                    line["extras"]["cpu_reference"] = {"error": repr(exc)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -62,6 +62,16 @@ def main():
     t = cuda_time(torch, lambda: apps.Q_IHT(Phi, PhiT, x, y, t1, t2, t3, 10, K, 0.01, THRESHOLD_FAST), 5)
     out["iht4_8192x32768_per_iteration"] = {"us": round(t * 1e5, 2), "matrix_bytes_per_iteration": 2 * Phi.getBytes(),
                                             "GBps": round(2 * Phi.getBytes() / (t / 10) / 1e9, 1)}
+    graph = apps.capture(lambda: apps.Q_IHT(Phi, PhiT, x, y, t1, t2, t3, 10, K, 0.01, THRESHOLD_FAST))
+    t = cuda_time(torch, graph.replay, 5)
+    out["iht4_8192x32768_per_iteration_cuda_graph"] = {"us": round(t * 1e5, 2), "GBps": round(2 * Phi.getBytes() / (t / 10) / 1e9, 1)}
+    # the five steps of one iteration on their own (each captured in a graph of 20 repeats: device time without host gaps)
+    steps = {"mvm_Phi_8192x32768": lambda: Phi.mvm(x, t1), "scaleAndAdd_M": lambda: y.scaleAndAdd(t1, -1.0, t2),
+             "mvm_PhiT_32768x8192": lambda: PhiT.mvm(t2, t3), "scaleAndAdd_N": lambda: x.scaleAndAdd(t3, 0.01),
+             "threshold_N": lambda: x.threshold(K, THRESHOLD_FAST)}
+    for name, fn in steps.items():
+        gr = apps.capture(lambda: [fn() for _ in range(20)])
+        out["iht_step_" + name] = {"us": round(cuda_time(torch, gr.replay, 5) / 20 * 1e6, 2)}
     print(json.dumps(out))
 
 
