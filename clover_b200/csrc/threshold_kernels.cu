@@ -12,7 +12,8 @@
 //          (include/CloverBase.h:226-249) - executed by one thread over magnitudes a parallel kernel prepared. Which of
 //          several equal magnitudes survives depends on the heap layout; this path leaves exactly the reference's bytes.
 //          Latency-bound, meant for parity runs (n <= clover_threshold_exact_limit()).
-//   FAST   an 8-bit-digit radix select over the magnitude bits (4 histogram passes, all on the device, no host sync)
+//   FAST   an 8-bit-digit radix select over the magnitude bits (4 histogram passes, all on the device, no host sync; one
+//          CTA up to 8192 elements, one 8-CTA cluster merging its histograms through DSMEM up to 262144, 7 launches beyond)
 //          finds the k-th largest magnitude t; everything above t stays, everything below goes, and of the elements equal
 //          to t the ones with the LOWEST indices stay until k survivors are reached (the reference's sequential and
 //          OpenMP variants already disagree with each other on such ties; its acceptance test - 02_vector.cpp:450-500 -
@@ -20,6 +21,7 @@
 #include <stdlib.h>
 #include <algorithm>
 #include <mutex>
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "runtime.cuh"
 
@@ -28,7 +30,9 @@ namespace clover {
 constexpr int kThrThreads = 256;
 constexpr int kThrSmallThreads = 1024;
 constexpr uint64_t kThrExactLimit = 1u << 12;     // AUTO: the sequential heap walk up to 4096 elements
-constexpr uint64_t kThrSmallLimit = 1u << 15;     // FAST: one CTA does the whole selection up to 32768 elements (29 us; the 7-launch path wins beyond)
+constexpr uint64_t kThrSmallLimit = 1u << 13;     // FAST: one CTA does the whole selection up to 8192 elements,
+constexpr uint64_t kThrClusterLimit = 1u << 18;   //       one 8-CTA cluster (histograms merged through DSMEM) up to 262144 (14 us at 32768, 22-27 us at 131072; at 2^20 the seven-launch path wins 40 : 114 us)
+constexpr int kThrClusterSize = 8;
 
 struct ThrState {            // device-resident selection state; hist[] and ticket are zero between calls
     uint32_t prefix;         // magnitude bits decided so far (high digits)
@@ -299,6 +303,85 @@ k_thr_small(uint32_t *__restrict__ values, const float *__restrict__ scales, uin
     apply_range<BITS, kThrSmallThreads>(values, scales, n, 0, nwords, prefix, k_rem, 0, mag);
 }
 
+// ---- FAST (kThrSmallLimit < n <= kThrClusterLimit): the same single launch spread over a thread-block cluster. Every CTA
+// histograms its contiguous slice of the words, the eight partial histograms are summed through distributed shared
+// memory (each CTA reads its peers' bins directly), every CTA picks the digit redundantly - no global state, no host
+// sync, two histogram buffers so that one cluster barrier per pass suffices. Tie ranks: the CTAs publish their tie
+// counts in shared memory and each adds up the counts of the ranks before it.
+template <int BITS>
+__global__ void __launch_bounds__(kThrSmallThreads)
+k_thr_cluster(uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t n, uint32_t nwords, uint64_t k,
+              uint32_t *__restrict__ mag) {
+    namespace cg = cooperative_groups;
+    constexpr int E = ThrWord<BITS>::kElems;
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t rank = cluster.block_rank(), csize = cluster.num_blocks();
+    __shared__ uint32_t h[2][256];
+    __shared__ uint32_t hsum[256];
+    __shared__ uint64_t scratch[256];
+    __shared__ uint32_t my_ties;
+    const uint32_t per = (nwords + csize - 1) / csize, w0 = min(rank * per, nwords), w1 = min(w0 + per, nwords);
+    uint32_t prefix = 0, mask = 0;
+    uint64_t k_rem = k;
+    if (threadIdx.x < 256) { h[0][threadIdx.x] = 0; h[1][threadIdx.x] = 0; }
+    if (threadIdx.x == 0) my_ties = 0;
+    __syncthreads();
+    int buf = 0;
+#pragma unroll 1
+    for (int shift = 24; shift >= 0; shift -= 8, buf ^= 1) {
+        uint32_t *hl = h[buf];
+        if (shift == 24) {
+            for (uint32_t i = w0 + threadIdx.x; i < w1; i += kThrSmallThreads) {
+                uint32_t m[E];
+                ThrWord<BITS>::mags(values[i], scales[((uint64_t)i * E) >> 6], (uint64_t)i * E, n, m);
+#pragma unroll
+                for (int j = 0; j < E / 4; ++j)
+                    reinterpret_cast<uint4 *>(mag)[(uint64_t)i * (E / 4) + j] = make_uint4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
+#pragma unroll
+                for (int e = 0; e < E; ++e) hist_add(hl, m[e] >> 24, (uint64_t)i * E + e < n);
+            }
+        } else {
+#pragma unroll 2
+            for (uint32_t i = w0 + threadIdx.x; i < w1; i += kThrSmallThreads) {
+                uint32_t m[E];
+                load_mags<E>(mag, i, m);
+#pragma unroll
+                for (int e = 0; e < E; ++e) hist_add(hl, (m[e] >> shift) & 0xFFu, (uint64_t)i * E + e < n && (m[e] & mask) == prefix);
+            }
+        }
+        cluster.sync();                                                  // every CTA's partial histogram is complete
+        if (threadIdx.x < 256) {
+            uint32_t sum = 0;
+            for (uint32_t r = 0; r < csize; ++r) sum += cluster.map_shared_rank(&h[buf][0], r)[threadIdx.x];
+            hsum[threadIdx.x] = sum;
+            h[buf ^ 1][threadIdx.x] = 0;                                 // the peers finished reading it before this pass's barrier
+        }
+        __syncthreads();
+        uint64_t above;
+        const uint32_t d = pick_digit(hsum, k_rem, scratch, above);
+        prefix |= d << shift;
+        mask |= 0xFFu << shift;
+        k_rem -= above;
+        __syncthreads();
+    }
+    // ties at the threshold in this CTA's slice
+    uint32_t c = 0;
+    for (uint32_t i = w0 + threadIdx.x; i < w1; i += kThrSmallThreads) {
+        uint32_t m[E];
+        load_mags<E>(mag, i, m);
+#pragma unroll
+        for (int e = 0; e < E; ++e) c += ((uint64_t)i * E + e < n && m[e] == prefix) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&my_ties, c);
+    cluster.sync();
+    uint64_t first_rank = 0;
+    for (uint32_t r = 0; r < rank; ++r) first_rank += *cluster.map_shared_rank(&my_ties, r);
+    apply_range<BITS, kThrSmallThreads>(values, scales, n, w0, w1, prefix, k_rem, first_rank, mag);
+    cluster.sync();                                                      // nobody leaves while a peer may still read its shared memory
+}
+
 // ---- EXACT: magnitudes + sign-extended bits in parallel, the heap walk by one thread, the mask applied in parallel --
 template <int BITS>
 __global__ void k_thr_prepare(const uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t n, uint64_t nwords,
@@ -449,6 +532,24 @@ static int launch_threshold(int8_t *values, const float *scales, uint64_t n, uin
                                                               reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ws) + off_mag));
         count_launch();
         return launch_status("k_thr_small");
+    }
+    if (n <= kThrClusterLimit) {
+        const size_t off_mag = align_up(sizeof(ThrState), 256);
+        void *ws = nullptr;
+        int rc = thr_workspace(off_mag + nwords * E * sizeof(uint32_t), &ws);
+        if (rc != CLOVER_OK) return rc;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kThrClusterSize);
+        cfg.blockDim = dim3(kThrSmallThreads);
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = kThrClusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CLOVER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_thr_cluster<BITS>, v32, scales, n, (uint32_t)nwords, k,
+                                             reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ws) + off_mag)));
+        count_launch();
+        return launch_status("k_thr_cluster");
     }
     const uint64_t words_per_cta = (nwords + grid - 1) / grid;
     const size_t off_cnt = align_up(sizeof(ThrState), 256), off_base = off_cnt + align_up(sizeof(uint32_t) * grid, 256);

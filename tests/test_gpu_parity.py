@@ -662,7 +662,7 @@ def test_vector_threshold_exact(cb, oracle, n, k, kind, bits_):
 
 @pytest.mark.parametrize("bits_", [4, 8])
 @pytest.mark.parametrize("kind", ["floats", "ints"])
-@pytest.mark.parametrize("n,k", THR_CASES + [((1 << 20) + 77, 50000)])
+@pytest.mark.parametrize("n,k", THR_CASES + [((1 << 20) + 77, 50000), ((1 << 22) + 77, 300001)])
 def test_vector_threshold_fast(cb, oracle, n, k, kind, bits_):
     """FAST mode (radix select): exactly min(k, n) survivors with unchanged bits, every magnitude above the k-th largest
     kept, every one below cleared, ties by lowest index; its sorted magnitudes equal the oracle's (the reference's own
@@ -706,10 +706,10 @@ def test_vector_threshold_fast(cb, oracle, n, k, kind, bits_):
 
 
 @pytest.mark.parametrize("bits_", [4, 8])
-@pytest.mark.parametrize("n,k", [(1000, 10), (32768, 777), (100000, 777), (300000, 150001)])
+@pytest.mark.parametrize("n,k", [(1000, 10), (32768, 777), (100000, 777), (300000, 150001), (3000000, 1234567)])
 def test_vector_threshold_fast_all_equal(cb, oracle, n, k, bits_):
     """worst case for the tie rule and for histogram contention: ONE magnitude - the k lowest indices survive
-    (single-CTA path up to 32768 elements, multi-CTA path beyond)"""
+    (single CTA up to 8192 elements, one 8-CTA cluster up to 262144, seven launches beyond)"""
     from clover_b200._lib import THRESHOLD_FAST
     V = cb.CloverVector4 if bits_ == 4 else cb.CloverVector8
     x = np.full(n, -0.75, np.float32)
