@@ -1,6 +1,7 @@
 """Launch ONE hot-path kernel a few times at its BASELINE.json size - the command ncu wraps.
 
-usage: python tools/profile_driver.py {gemv4|gemv8|quantize4|quantize8|dot4|mquantize4|gemm4|quantize4_sr|transpose4|transpose8} [iters]
+usage: python tools/profile_driver.py {gemv4|gemv8|quantize4|quantize8|dot4|mquantize4|gemm4|quantize4_sr|transpose4|transpose8|
+                                        threshold4_cluster|threshold8_cluster|threshold4_large|iht} [iters]
 """
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -62,6 +63,26 @@ elif what == "gemm4":
         m.values.copy_(random_nibbles(torch, n * n // 2, g, dev)); m.scales.uniform_(0.25, 1.0, generator=g)
     out = torch.empty(n, n, device=dev)
     fn = lambda: A.gemm(B, out=out)
+elif what in ("threshold4_cluster", "threshold4_large", "threshold8_cluster"):
+    from clover_b200 import THRESHOLD_FAST
+    n = 32768 if what.endswith("cluster") else 1 << 26
+    V = cb.CloverVector8 if what.startswith("threshold8") else cb.CloverVector4
+    v = cb.CloverVector32(n); v.values.uniform_(-1, 1, generator=g)
+    src, q = V(n), V(n)
+    src.quantize(v)
+    def fn():
+        q.values.copy_(src.values); q.threshold(n // 4 if n <= 32768 else n // 64, THRESHOLD_FAST)
+elif what == "iht":
+    from clover_b200 import THRESHOLD_FAST, apps
+    M, N, K = 8192, 32768, 1024
+    Phi, PhiT = cb.CloverMatrix4(M, N), cb.CloverMatrix4(N, M)
+    Phi.values.copy_(torch.randint(-128, 128, (Phi.values.numel(),), dtype=torch.int8, device=dev, generator=g))
+    Phi.scales.uniform_(0.01, 0.02, generator=g)
+    Phi.transpose(PhiT)
+    y = cb.CloverVector4(M)
+    v = cb.CloverVector32(M); v.values.uniform_(-1, 1, generator=g); y.quantize(v)
+    x, t1, t2, t3 = cb.CloverVector4(N), cb.CloverVector4(M), cb.CloverVector4(M), cb.CloverVector4(N)
+    fn = lambda: apps.Q_IHT(Phi, PhiT, x, y, t1, t2, t3, 2, K, 0.01, THRESHOLD_FAST)
 else:
     raise SystemExit(__doc__)
 
