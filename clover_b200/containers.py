@@ -108,10 +108,15 @@ class _QVector(_Keyed):
         dev = _dev(device)
         nbytes = self.length_pad * self.BITS // 8
         if values is None:
-            # pad values 0, pad scales 1 (include/CloverVector4.h:86-94)
-            self.values = torch.zeros(nbytes, dtype=torch.int8, device=dev)
-            self.scales = torch.ones(self.length_pad // 64, dtype=torch.float32, device=dev)
+            # ONE allocation [values | scales] like the reference (include/CloverVector4.h:68-103): a whole vector moves
+            # between host and device with a single copy of `storage`. Pad values 0, pad scales 1 (:86-94).
+            nscales = self.length_pad // 64
+            self.storage = torch.zeros(nbytes + 4 * nscales, dtype=torch.uint8, device=dev)
+            self.values = self.storage[:nbytes].view(torch.int8)
+            self.scales = self.storage[nbytes:].view(torch.float32)
+            self.scales.fill_(1.0)
         else:  # the reference's borrowing view constructor (include/CloverVector4.h:114-119)
+            self.storage = None
             self.values = torch.as_tensor(values, device=dev).view(torch.int8).reshape(-1)
             self.scales = torch.as_tensor(scales, dtype=torch.float32, device=dev).reshape(-1)
             if self.values.numel() < nbytes or self.scales.numel() < self.length_pad // 64:

@@ -761,7 +761,6 @@ k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
 // =============================================================================================
 constexpr int kG4Rows = 32;
 constexpr int kG4Chunks = 8;                 // 128-byte chunks per stage = 32 blocks of 64 columns
-constexpr int kG4Stages = 5;
 constexpr int kG4Consumers = 256;
 constexpr int kG4Threads = kG4Consumers + 64;
 constexpr int kG4ChunkBytes = kG4Rows * 128;
@@ -770,24 +769,29 @@ struct __align__(1024) Gemv4Stage {
     uint8_t rows[kG4Chunks][kG4ChunkBytes];
     XUnit units[kG4Chunks * 4 * 8];          // unit (block, l)
 };
+// STAGES = 5: one CTA per SM (180 KiB ring). STAGES = 3: 111 KiB, TWO CTAs per SM - the grid is then 2 x SMs and the
+// hardware shares each SM between two work items, which removes the whole-round quantisation of a persistent grid: a
+// shard of 256 or 512 items (8 / 4 GPUs) no longer leaves 14 % of the SM-rounds empty, all items simply stream
+// concurrently at the HBM rate (216 KiB in flight per SM instead of 144).
+template <int STAGES>
 struct Gemv4Smem {
-    Gemv4Stage stage[kG4Stages];
-    uint64_t full[kG4Stages];
-    uint64_t empty[kG4Stages];
+    Gemv4Stage stage[STAGES];
+    uint64_t full[STAGES];
+    uint64_t empty[STAGES];
     float part[kG4Rows][16];
     float red_f[2];
     int red_q[64];
     unsigned int ticket;
 };
 
-template <bool STOCH>
-__global__ void __launch_bounds__(kG4Threads, 1)
+template <bool STOCH, int STAGES>
+__global__ void __launch_bounds__(kG4Threads, STAGES == 5 ? 1 : 2)
 k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows_local,
               uint64_t cols, uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
               float *__restrict__ ybuf, unsigned int *__restrict__ counters, int8_t *__restrict__ yv,
               float *__restrict__ ys, Key4 key, const uint64_t *__restrict__ tables, const __grid_constant__ PeerOut peers) {
     extern __shared__ uint8_t smem_raw4[];
-    Gemv4Smem &sm = *reinterpret_cast<Gemv4Smem *>((reinterpret_cast<uintptr_t>(smem_raw4) + 1023u) & ~(uintptr_t)1023u);
+    Gemv4Smem<STAGES> &sm = *reinterpret_cast<Gemv4Smem<STAGES> *>((reinterpret_cast<uintptr_t>(smem_raw4) + 1023u) & ~(uintptr_t)1023u);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t hb = cols >> 6, nitems = rows_local / kG4Rows;
@@ -796,7 +800,7 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
     const uint32_t steps = (nchunks128 + kG4Chunks - 1) / kG4Chunks;
 
     if (tid == 0) {
-        for (int s = 0; s < kG4Stages; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&sm.full[s], 1 + 32);
             mbar_init(&sm.empty[s], kG4Consumers / 32);
         }
@@ -812,9 +816,9 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
             uint32_t it = 0;
             for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
                 for (uint32_t c = 0; c < steps; ++c, ++it) {
-                    const int s = it % kG4Stages;
+                    const int s = it % STAGES;
                     const uint32_t live = min((uint32_t)kG4Chunks, nchunks128 - c * kG4Chunks);
-                    mbar_wait(&sm.empty[s], ((it / kG4Stages) & 1) ^ 1);
+                    mbar_wait(&sm.empty[s], ((it / STAGES) & 1) ^ 1);
                     mbar_arrive_expect_tx(&sm.full[s], live * kG4ChunkBytes);
                     for (uint32_t j = 0; j < live; ++j)
                         tma_load_2d(sm.stage[s].rows[j], &tmap, (int)((c * kG4Chunks + j) * 128), (int)(item * kG4Rows),
@@ -830,7 +834,7 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
         for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
             const float *su = scales + (item >> 1) * hb;
             for (uint32_t c = 0; c < steps; ++c, ++it) {
-                const int s = it % kG4Stages;
+                const int s = it % STAGES;
                 XUnit u[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -845,7 +849,7 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
                     u[j].cneg = -(786432.0f + 8.0f * (float)(dp4a_ss(xh, 0x01010101, 0) + dp4a_ss(xl, 0x01010101, 0)));
                     u[j].prod = __fmul_rn(__fmul_rn(sa, 1.0f / 49.0f), sb);                       // (:834-837)
                 }
-                mbar_wait(&sm.empty[s], ((it / kG4Stages) & 1) ^ 1);
+                mbar_wait(&sm.empty[s], ((it / STAGES) & 1) ^ 1);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) sm.stage[s].units[lane + 32 * j] = u[j];
                 mbar_arrive(&sm.full[s]);
@@ -864,8 +868,8 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
         for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
             float acc = 0.f, acc2 = 0.f;
             for (uint32_t c = 0; c < steps; ++c, ++it) {
-                const int s = it % kG4Stages;
-                mbar_wait(&sm.full[s], (it / kG4Stages) & 1);
+                const int s = it % STAGES;
+                mbar_wait(&sm.full[s], (it / STAGES) & 1);
                 const Gemv4Stage &st = sm.stage[s];
                 const int live = (int)min((uint32_t)kG4Chunks, nchunks128 - c * kG4Chunks);
                 auto chunk = [&](int j) {
@@ -1040,15 +1044,20 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
     const uint32_t *x32 = reinterpret_cast<const uint32_t *>(xv);
     if (BITS == 4) {
         // CLOVER_GEMV_IMPL (read per call): simple = plain loads, ring64 = 64-row work items (k_m4_mvm_tma),
-        // items32 = 32-row work items (k_m4_mvm_tma2). Default: ring64 (96-99 % of the HBM roofline at 65536 rows) unless
-        // halving the work item fills the last round of the persistent grid markedly better - a 2-GPU shard of C3 has
-        // 512 row blocks = 3.46 rounds on 148 SMs, but 1024 half blocks = 6.92 (measured: 0.179 vs 0.189 ms).
+        // items32 = 32-row work items (k_m4_mvm_tma2), items32x2 = the same at two CTAs per SM.
         const char *impl_env = getenv("CLOVER_GEMV_IMPL");
         const bool force_simple = impl_env && !strcmp(impl_env, "simple");
         const bool force_items32 = impl_env && !strcmp(impl_env, "items32");
+        const bool force_x2 = impl_env && !strcmp(impl_env, "items32x2");
         auto fill = [](uint64_t items, uint64_t sms) { return (double)items / (double)(((items + sms - 1) / sms) * sms); };
-        const bool force_ring64 = (impl_env && !strcmp(impl_env, "ring64")) ||
-                                  (!force_items32 && fill(2 * nrb, (uint64_t)sm_count()) < 1.04 * fill(nrb, (uint64_t)sm_count()));
+        // Default: 32-row items at TWO CTAs per SM (3-stage rings). Measured on B200 (tools/gemv_shapes.py, 65536 columns):
+        // 65536 rows 317 us (ring64 335, items32 356), 32768 rows 169 (186 / 179), 16384 rows 88 (93 / 103), 8192 rows 43
+        // (46 / 55) - the SM is shared by two work items, so a persistent grid no longer runs in whole rounds and 216 KiB
+        // per SM are in flight. Short rows (< 16384 columns: 32768 x 8192 runs 31.4 us under ring64, 33.6 under x2) keep
+        // the 64-row items, whose epilogue is paid half as often.
+        const bool x2 = force_x2 || (!impl_env && cols >= 16384);
+        const bool force_ring64 = !x2 && ((impl_env && !strcmp(impl_env, "ring64")) ||
+                                  (!force_items32 && (cols < 16384 || fill(2 * nrb, (uint64_t)sm_count()) < 1.04 * fill(nrb, (uint64_t)sm_count()))));
         // bulk copies need 16 B aligned rows; anything else takes the plain-load kernel (same arithmetic)
         const bool simple = (force_simple || (reinterpret_cast<uintptr_t>(values) & 15u) != 0) && !peers;
         if (simple) {
@@ -1060,18 +1069,24 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
             unsigned int *counters = nullptr;
             int rc = mvm_scratch(nrb, (row0 >> 6) + nrb, y32 ? nullptr : &ybuf, &counters);
             if (rc != CLOVER_OK) return rc;
-            const int smem = (int)sizeof(Gemv4Smem) + 1024;
-            static bool attr_set2[2] = {false, false};
-            auto kern = stoch ? k_m4_mvm_tma2<true> : k_m4_mvm_tma2<false>;
-            if (!attr_set2[stoch]) {
+            const int smem = (int)(x2 ? sizeof(Gemv4Smem<3>) : sizeof(Gemv4Smem<5>)) + 1024;
+            static bool attr_set2[2][2] = {{false, false}, {false, false}};
+            auto kern = x2 ? (stoch ? k_m4_mvm_tma2<true, 3> : k_m4_mvm_tma2<false, 3>) : (stoch ? k_m4_mvm_tma2<true, 5> : k_m4_mvm_tma2<false, 5>);
+            if (!attr_set2[x2][stoch]) {
                 CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                attr_set2[stoch] = true;
+                attr_set2[x2][stoch] = true;
             }
             CUtensorMap tmap;
             rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows_local, cols >> 1, kG4Rows);
             if (rc != CLOVER_OK) return rc;
             const uint64_t nitems = rows_local / kG4Rows;
-            const unsigned pgrid = (unsigned)(nitems < (uint64_t)sm_count() ? nitems : (uint64_t)sm_count());
+            uint64_t slots = (uint64_t)sm_count();
+            if (x2) {
+                int per_sm = 1;
+                CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kG4Threads, smem));
+                slots *= (uint64_t)std::max(1, std::min(per_sm, 2));
+            }
+            const unsigned pgrid = (unsigned)(nitems < slots ? nitems : slots);
             kern<<<pgrid, kG4Threads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, ybuf, counters, yv, ys,
                                                       key, tables, peers ? *peers : PeerOut());
         } else {

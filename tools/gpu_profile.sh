@@ -8,7 +8,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-fil
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 for k in ${KERNELS:-gemv4 quantize4 dot4 gemv8 gemm4 mquantize4}; do
   case $k in
-    gemv4) re=k_m4_mvm;; gemv8) re=k_m8_mvm;; quantize4|quantize8|quantize4_sr) re=k_vquantize;; dot4) re=k_vdot_fast;;
+    gemv4) re=k_m4_mvm_tma;; gemv8) re=k_m8_mvm;; quantize4|quantize8|quantize4_sr) re=k_vquantize;; dot4) re=k_vdot_fast;;
     mquantize4) re=k_mquantize;; gemm4) re=k_gemm4_tc;; transpose4|transpose8) re=k_mtranspose;;
     threshold4_cluster|threshold8_cluster) re=k_thr_cluster;; threshold4_large) re=k_thr_hist;;
   esac
