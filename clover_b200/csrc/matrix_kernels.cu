@@ -596,7 +596,6 @@ k_m8_mvm(const uint32_t *__restrict__ values, const float *__restrict__ scales, 
 //     block order => fp32 row results and re-quantized bytes identical to k_m8_mvm and to the AVX2 code.
 constexpr int kG8Rows = 32;                 // rows per work item
 constexpr int kG8Chunks = 8;                // 128-byte column chunks per stage = 16 blocks of 64 columns
-constexpr int kG8Stages = 5;
 constexpr int kG8Consumers = 256;
 constexpr int kG8Threads = kG8Consumers + 64;
 constexpr int kG8ChunkBytes = kG8Rows * 128;
@@ -605,10 +604,12 @@ struct __align__(1024) Gemv8Stage {
     uint8_t rows[kG8Chunks][kG8ChunkBytes];   // chunk c: rows 0..31 x 128 B, SWIZZLE_128B (each 4 KiB, 1024-aligned)
     uint4 units[kG8Chunks * 2 * 8];           // unit (block, l): x = xa, y = xb, z = bits of prod
 };
+// STAGES = 5: one CTA per SM; STAGES = 3 (105 KiB): two CTAs per SM, grid = 2 x SMs (see Gemv4Smem)
+template <int STAGES>
 struct Gemv8Smem {
-    Gemv8Stage stage[kG8Stages];
-    uint64_t full[kG8Stages];
-    uint64_t empty[kG8Stages];
+    Gemv8Stage stage[STAGES];
+    uint64_t full[STAGES];
+    uint64_t empty[STAGES];
     float part[kG8Rows][8];
     float ysm[64];
     float red_f[2];
@@ -616,14 +617,14 @@ struct Gemv8Smem {
     unsigned int ticket;
 };
 
-template <bool STOCH>
-__global__ void __launch_bounds__(kG8Threads, 1)
+template <bool STOCH, int STAGES>
+__global__ void __launch_bounds__(kG8Threads, STAGES == 5 ? 1 : 2)
 k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows_local,
              uint64_t cols, uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
              float *__restrict__ ybuf, unsigned int *__restrict__ counters, int8_t *__restrict__ yv,
              float *__restrict__ ys, Key4 key, const uint64_t *__restrict__ tables) {
     extern __shared__ uint8_t smem_raw8[];
-    Gemv8Smem &sm = *reinterpret_cast<Gemv8Smem *>((reinterpret_cast<uintptr_t>(smem_raw8) + 1023u) & ~(uintptr_t)1023u);
+    Gemv8Smem<STAGES> &sm = *reinterpret_cast<Gemv8Smem<STAGES> *>((reinterpret_cast<uintptr_t>(smem_raw8) + 1023u) & ~(uintptr_t)1023u);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t hb = cols >> 6, nitems = rows_local / kG8Rows;
@@ -631,7 +632,7 @@ k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
     const uint32_t steps = (nchunks128 + kG8Chunks - 1) / kG8Chunks;      // stages per work item
 
     if (tid == 0) {
-        for (int s = 0; s < kG8Stages; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&sm.full[s], 1 + 32);              // TMA issuer (posts the tx bytes) + the 32 unit lanes
             mbar_init(&sm.empty[s], kG8Consumers / 32);
         }
@@ -647,9 +648,9 @@ k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
             uint32_t it = 0;
             for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
                 for (uint32_t c = 0; c < steps; ++c, ++it) {
-                    const int s = it % kG8Stages;
+                    const int s = it % STAGES;
                     const uint32_t live = min((uint32_t)kG8Chunks, nchunks128 - c * kG8Chunks);
-                    mbar_wait(&sm.empty[s], ((it / kG8Stages) & 1) ^ 1);
+                    mbar_wait(&sm.empty[s], ((it / STAGES) & 1) ^ 1);
                     mbar_arrive_expect_tx(&sm.full[s], live * kG8ChunkBytes);
                     for (uint32_t j = 0; j < live; ++j)
                         tma_load_2d(sm.stage[s].rows[j], &tmap, (int)((c * kG8Chunks + j) * 128), (int)(item * kG8Rows),
@@ -665,7 +666,7 @@ k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
         for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
             const float *su = scales + (item >> 1) * hb;
             for (uint32_t c = 0; c < steps; ++c, ++it) {
-                const int s = it % kG8Stages;
+                const int s = it % STAGES;
                 uint4 u[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -677,7 +678,7 @@ k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
                     u[j].z = __float_as_uint(__fmul_rn(__fmul_rn(sa, 1.0f / 127.0f), __fmul_rn(sb, 1.0f / 127.0f)));   // (CloverMatrix8.h:1042-1046)
                     u[j].w = 0u;
                 }
-                mbar_wait(&sm.empty[s], ((it / kG8Stages) & 1) ^ 1);
+                mbar_wait(&sm.empty[s], ((it / STAGES) & 1) ^ 1);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sm.stage[s].units[lane + 32 * j] = u[j];
                 mbar_arrive(&sm.full[s]);
@@ -695,8 +696,8 @@ k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
         for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
             float acc = 0.f;
             for (uint32_t c = 0; c < steps; ++c, ++it) {
-                const int s = it % kG8Stages;
-                mbar_wait(&sm.full[s], (it / kG8Stages) & 1);
+                const int s = it % STAGES;
+                mbar_wait(&sm.full[s], (it / STAGES) & 1);
                 const Gemv8Stage &st = sm.stage[s];
                 const int live = (int)min((uint32_t)kG8Chunks, nchunks128 - c * kG8Chunks);
                 auto chunk = [&](int j) {
@@ -1117,18 +1118,30 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
             unsigned int *counters = nullptr;
             int rc = mvm_scratch(nrb, (row0 >> 6) + nrb, y32 ? nullptr : &ybuf, &counters);
             if (rc != CLOVER_OK) return rc;
-            const int smem = (int)sizeof(Gemv8Smem) + 1024;
-            static bool attr_set8[2] = {false, false};
-            auto kern = stoch ? k_m8_mvm_tma<true> : k_m8_mvm_tma<false>;
-            if (!attr_set8[stoch]) {
+            // two CTAs per SM with 3-stage rings, as for the 4-bit kernel, whenever there is more than one round of work items
+            // (tools/gemv_shapes.py 60 8: 32768^2 164 -> 160 us, 16384 x 32768 93 -> 83, 8192 x 32768 48 -> 42, 16384 x 4096
+            // 20.7 -> 16.4; a single round - 4096 x 32768 - prefers the deeper ring: 23.0 vs 24.8). CLOVER_GEMV_IMPL=items32 /
+            // items32x2 force either.
+            const char *impl8 = getenv("CLOVER_GEMV_IMPL");
+            const bool x2 = impl8 ? !strcmp(impl8, "items32x2") : rows_local / kG8Rows > (uint64_t)sm_count();
+            const int smem = (int)(x2 ? sizeof(Gemv8Smem<3>) : sizeof(Gemv8Smem<5>)) + 1024;
+            static bool attr_set8[2][2] = {{false, false}, {false, false}};
+            auto kern = x2 ? (stoch ? k_m8_mvm_tma<true, 3> : k_m8_mvm_tma<false, 3>) : (stoch ? k_m8_mvm_tma<true, 5> : k_m8_mvm_tma<false, 5>);
+            if (!attr_set8[x2][stoch]) {
                 CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                attr_set8[stoch] = true;
+                attr_set8[x2][stoch] = true;
             }
             CUtensorMap tmap;
             rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows_local, cols, kG8Rows);
             if (rc != CLOVER_OK) return rc;
             const uint64_t nitems = rows_local / kG8Rows;
-            const unsigned pgrid = (unsigned)(nitems < (uint64_t)sm_count() ? nitems : (uint64_t)sm_count());
+            uint64_t slots = (uint64_t)sm_count();
+            if (x2) {
+                int per_sm = 1;
+                CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kG8Threads, smem));
+                slots *= (uint64_t)std::max(1, std::min(per_sm, 2));
+            }
+            const unsigned pgrid = (unsigned)(nitems < slots ? nitems : slots);
             kern<<<pgrid, kG8Threads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, ybuf, counters, yv, ys,
                                                       key, tables);
         }
