@@ -1083,9 +1083,9 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
             const uint64_t nitems = rows_local / kG4Rows;
             uint64_t slots = (uint64_t)sm_count();
             if (x2) {
-                int per_sm = 1;
-                CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kG4Threads, smem));
-                slots *= (uint64_t)std::max(1, std::min(per_sm, 2));
+                static int per_sm4[2] = {0, 0};               // asked once per template instance (all devices alike)
+                if (!per_sm4[stoch]) CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4[stoch], kern, kG4Threads, smem));
+                slots *= (uint64_t)std::max(1, std::min(per_sm4[stoch], 2));
             }
             const unsigned pgrid = (unsigned)(nitems < slots ? nitems : slots);
             kern<<<pgrid, kG4Threads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, ybuf, counters, yv, ys,
@@ -1137,9 +1137,9 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
             const uint64_t nitems = rows_local / kG8Rows;
             uint64_t slots = (uint64_t)sm_count();
             if (x2) {
-                int per_sm = 1;
-                CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kG8Threads, smem));
-                slots *= (uint64_t)std::max(1, std::min(per_sm, 2));
+                static int per_sm8[2] = {0, 0};
+                if (!per_sm8[stoch]) CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm8[stoch], kern, kG8Threads, smem));
+                slots *= (uint64_t)std::max(1, std::min(per_sm8[stoch], 2));
             }
             const unsigned pgrid = (unsigned)(nitems < slots ? nitems : slots);
             kern<<<pgrid, kG8Threads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, ybuf, counters, yv, ys,
