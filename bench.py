@@ -295,6 +295,12 @@ def extras(torch, cb, peak):
         qs[i[0] % 8].threshold(n // 64, THRESHOLD_FAST); i[0] += 1
     t = cuda_time(torch, thr, 8)
     out["threshold4_n2^26_k=2^20_fast"] = {"ms": t * 1e3, "GBps_ref_model": 2 * qs[0].getBytes() / t / 1e9}
+    # scaleAndAdd (quantized AXPY) at n = 2^26; bytes = 3 * getBytes (01_measure.h:850)
+    def axpy():
+        k = i[0] % 2; qs[4 * k].scaleAndAdd(qs[4 * k + 1], 0.5, qs[4 * k + 2]); i[0] += 1
+    t = cuda_time(torch, axpy, 20)
+    b = 3 * qs[0].getBytes()
+    out["scaleAndAdd4_n2^26"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b}
     q8 = [cb.CloverVector8(n) for _ in range(2)]
     def quant8():
         q8[i[0] % 2].quantize(xs32[i[0] % 2]); i[0] += 1
@@ -320,6 +326,13 @@ def extras(torch, cb, peak):
     out["C5_gemv8_32768"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b,
                              "traffic": ncu_traffic("k_m8_mvm_tma:32768x32768")}
     del m8
+    # mixed precision, 4-bit matrix x CloverVector8 -> CloverVector8 at 32768^2 (CloverMatrix4.h:1093-1441)
+    m4 = cb.CloverMatrix4(r8, c8)
+    m4.values.copy_(random_nibbles(torch, r8 * c8 // 2, g, dev)); m4.scales.uniform_(0.25, 1.0, generator=g)
+    t = cuda_time(torch, lambda: m4.mvm(x8, y8), 20)
+    b = m4.getBytes() + x8.getBytes() + y8.getBytes()
+    out["mvm4_v8_mixed_32768"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b}
+    del m4
     # transpose of a 16384 x 16384 matrix (every byte read once and written once)
     for bits_, M_ in ((4, cb.CloverMatrix4), (8, cb.CloverMatrix8)):
         src, dst = M_(16384, 16384), M_(16384, 16384)

@@ -11,6 +11,8 @@
 // Stochastic rounding: the SIMD code peels nibbles by POSITION inside each 32-bit word, so element e of a 4-bit
 // block takes noise slot (call p / 4, byte p % 4, lane e / 8) with p = 2 * ((e / 2) % 4) + (e even); an 8-bit element
 // takes (call e / 32, byte e % 4, lane (e % 32) / 4). The thread jumps the object's XORShift stream to 2 * block.
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "runtime.cuh"
 
@@ -128,25 +130,172 @@ k_vscale_add(const uint32_t *u, const float *su, const uint32_t *__restrict__ v,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Second design (default): FOUR threads per block of 64, 16 contiguous elements each - the layout that took the
+// quantizer from 73 % to 93 % of the HBM roofline (vector_kernels.cu, k_vquantize4t). A thread loads its 8 (4-bit) or
+// 16 (8-bit) bytes of u and v with one vector load each, the block absmax is two xor-shuffles away, and its 16
+// roundings pack into exactly the bytes it loaded - so r may still alias u: every byte is read and written by the same
+// thread, and sr[b] is written (by thread 0 of the group) only after the shuffles, which all four threads reach after
+// their read of su[b] has returned. ~45 registers instead of 82-115: full occupancy.
+// Stochastic mode: a group walks R consecutive blocks and all four threads step the same XORShift state.
+// ---------------------------------------------------------------------------------------------
+template <int BITS, bool STOCH>
+__global__ void __launch_bounds__(256)
+k_vscale_add4t(const uint32_t *u, const float *su, const uint32_t *__restrict__ v, const float *__restrict__ sv, float a,
+               uint64_t nblocks, uint64_t R, uint32_t *r, float *sr, Key4 key, const uint64_t *__restrict__ tables) {
+    constexpr float kQmax = BITS == 4 ? 7.0f : 127.0f;
+    constexpr int kW = BITS == 4 ? 2 : 4;                          // 32-bit words per thread
+    const int s = threadIdx.x & 3;
+    const uint64_t group = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 2;
+    const uint64_t ngroups = ((uint64_t)gridDim.x * 256) >> 2;
+    uint64_t blk = STOCH ? group * R : group;
+    const uint64_t step = STOCH ? 1 : ngroups;
+    const uint64_t end = STOCH ? min(nblocks, (group + 1) * R) : nblocks;
+    uint64_t lanes[4] = {0, 0, 0, 0};
+    if (STOCH && blk < end) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lanes[k] = xs_jump(tables, key.x[k], 2 * blk);
+    }
+    for (;; blk += step) {
+        const bool live = blk < end;
+        if (!__any_sync(0xFFFFFFFFu, live)) break;
+        uint32_t wu[kW], wv[kW];
+        float su_ps = 0.f, sv_ps = 0.f;
+#pragma unroll
+        for (int i = 0; i < kW; ++i) wu[i] = wv[i] = BITS == 4 ? 0u : 0u;
+        if (live) {
+            su_ps = __fdiv_rn(su[blk], kQmax);
+            sv_ps = __fdiv_rn(__fmul_rn(sv[blk], a), kQmax);
+            if (BITS == 4) {
+                const uint2 x = *reinterpret_cast<const uint2 *>(u + blk * 8 + 2 * s), y = *reinterpret_cast<const uint2 *>(v + blk * 8 + 2 * s);
+                wu[0] = x.x; wu[1] = x.y; wv[0] = y.x; wv[1] = y.y;
+            } else {
+                const uint4 x = *reinterpret_cast<const uint4 *>(u + blk * 16 + 4 * s), y = *reinterpret_cast<const uint4 *>(v + blk * 16 + 4 * s);
+                wu[0] = x.x; wu[1] = x.y; wu[2] = x.z; wu[3] = x.w; wv[0] = y.x; wv[1] = y.y; wv[2] = y.z; wv[3] = y.w;
+            }
+        }
+        float val[16];
+        if (BITS == 4) {
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const uint32_t bu = wu[w] ^ 0x88888888u, bv = wv[w] ^ 0x88888888u;
+                const uint32_t uh = (bu >> 4) & 0x0F0F0F0Fu, ul = bu & 0x0F0F0F0Fu;
+                const uint32_t vh = (bv >> 4) & 0x0F0F0F0Fu, vl = bv & 0x0F0F0F0Fu;
+#define CLOVER_AXPY4T(J)                                                                                             \
+                val[8 * w + 2 * J]     = __fmaf_rn(byte_to_float<J>(vh, 12582920.0f), sv_ps,                          \
+                                                   __fmul_rn(byte_to_float<J>(uh, 12582920.0f), su_ps));             \
+                val[8 * w + 2 * J + 1] = __fmaf_rn(byte_to_float<J>(vl, 12582920.0f), sv_ps,                          \
+                                                   __fmul_rn(byte_to_float<J>(ul, 12582920.0f), su_ps));
+                CLOVER_AXPY4T(0) CLOVER_AXPY4T(1) CLOVER_AXPY4T(2) CLOVER_AXPY4T(3)
+#undef CLOVER_AXPY4T
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const uint32_t bu = wu[w] ^ 0x80808080u, bv = wv[w] ^ 0x80808080u;
+#define CLOVER_AXPY8T(J)                                                                                             \
+                val[4 * w + J] = __fmaf_rn(byte_to_float<J>(bv, 12583040.0f), sv_ps,                                  \
+                                           __fmul_rn(byte_to_float<J>(bu, 12583040.0f), su_ps));
+                CLOVER_AXPY8T(0) CLOVER_AXPY8T(1) CLOVER_AXPY8T(2) CLOVER_AXPY8T(3)
+#undef CLOVER_AXPY8T
+            }
+        }
+        float m = 0.f;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) m = fmaxf(m, fabsf(val[e]));
+        if (!live) m = 0.f;
+        m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 2));
+        m = guard_zero(m);
+        const float scale = quant_scale(kQmax, m);
+        // noise words: 4-bit - word W of the block takes PRNG word W of call 0 (nibble positions 0..3) and of call 1
+        // (positions 4..7); 8-bit - element e takes (call e / 32, word (e % 32) / 4, byte e % 4)
+        uint32_t nw[2][kW];
+        if (STOCH) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t o = xs_next(lanes[k]);
+                    const uint32_t lo = (uint32_t)o, hi = (uint32_t)(o >> 32);
+                    if (BITS == 4) {                      // this thread's words 2s, 2s+1 = PRNG words of 64-bit lane k = s
+                        if (k == s) { nw[c][0] = lo; nw[c][1] = hi; }
+                    } else if (c == (s >> 1)) {           // elements 16s..16s+15: words (4s + j) % 8, j = 0..3 = lanes 2(s&1), 2(s&1)+1
+                        if (k == 2 * (s & 1)) { nw[0][0] = lo; nw[0][1] = hi; }
+                        if (k == 2 * (s & 1) + 1) { nw[0][2] = lo; nw[0][3] = hi; }
+                    }
+                }
+        }
+        if (!live) continue;
+        if (s == 0) sr[blk] = m;
+        if (BITS == 4) {
+            uint32_t out[2];
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                int q[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int pnib = 2 * ((i >> 1) & 3) + ((i & 1) ? 0 : 1);                 // nibble position of element 8w+i
+                    const float rnd = STOCH ? noise_from_word(nw[pnib >> 2][w], pnib & 3) : 0.f;
+                    q[i] = quant_one(val[8 * w + i], scale, rnd);
+                }
+                out[w] = pack8_nibbles(q);
+            }
+            *reinterpret_cast<uint2 *>(r + blk * 8 + 2 * s) = make_uint2(out[0], out[1]);
+        } else {
+            uint32_t out[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                int q[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float rnd = STOCH ? noise_from_word(nw[0][w], i) : 0.f;
+                    q[i] = quant_one(val[4 * w + i], scale, rnd);
+                }
+                out[w] = pack4_bytes(q);
+            }
+            *reinterpret_cast<uint4 *>(r + blk * 16 + 4 * s) = make_uint4(out[0], out[1], out[2], out[3]);
+        }
+    }
+}
+
 template <int BITS>
 static int launch_scale_add(const int8_t *u, const float *su, const int8_t *v, const float *sv, float a, uint64_t n_pad,
                             int8_t *r, float *sr, uint64_t *key_host, cudaStream_t stream) {
     const uint64_t nblocks = n_pad / kBlock;
     if (nblocks == 0) return CLOVER_OK;
-    const uint64_t want = (nblocks + 255) / 256, cap = (uint64_t)sm_count() * 8;
-    const unsigned grid = (unsigned)(want > cap ? cap : want);
     const uint32_t *u32 = reinterpret_cast<const uint32_t *>(u), *v32 = reinterpret_cast<const uint32_t *>(v);
     uint32_t *r32 = reinterpret_cast<uint32_t *>(r);
+    // CLOVER_AXPY_IMPL=block selects the thread-per-block kernel (kept for A/B measurements)
+    static const bool per_block = getenv("CLOVER_AXPY_IMPL") && !strcmp(getenv("CLOVER_AXPY_IMPL"), "block");
     Key4 key = {};
+    const uint64_t *tables = nullptr;
     if (key_host) {
-        const uint64_t *tables = device_jump_tables();
+        tables = device_jump_tables();
         if (!tables) { set_error("clover: could not upload PRNG jump tables"); return CLOVER_ERR_CUDA; }
         key = key_lanes(key_host);
-        k_vscale_add<BITS, true><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, r32, sr, key, tables);
-        host_key_skip(key_host, 2 * nblocks);
-    } else {
-        k_vscale_add<BITS, false><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, r32, sr, key, nullptr);
     }
+    if (per_block) {
+        const uint64_t want = (nblocks + 255) / 256, cap = (uint64_t)sm_count() * 8;
+        const unsigned grid = (unsigned)(want > cap ? cap : want);
+        if (key_host) k_vscale_add<BITS, true><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, r32, sr, key, tables);
+        else          k_vscale_add<BITS, false><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, r32, sr, key, nullptr);
+    } else {
+        static int ctas_per_sm[2] = {0, 0};
+        int &cps = ctas_per_sm[key_host != nullptr];
+        if (cps == 0) {
+            cudaError_t e = key_host ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vscale_add4t<BITS, true>, 256, 0)
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vscale_add4t<BITS, false>, 256, 0);
+            if (e != cudaSuccess || cps < 1) cps = 1;
+        }
+        const uint64_t max_groups = (uint64_t)sm_count() * cps * 64;                       // one resident wave
+        const uint64_t groups = nblocks < max_groups ? nblocks : max_groups;
+        const uint64_t R = (nblocks + groups - 1) / groups;
+        const unsigned grid = (unsigned)((groups * 4 + 255) / 256);
+        if (key_host) k_vscale_add4t<BITS, true><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, R, r32, sr, key, tables);
+        else          k_vscale_add4t<BITS, false><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, R, r32, sr, key, nullptr);
+    }
+    if (key_host) host_key_skip(key_host, 2 * nblocks);
     count_launch();
     return launch_status("k_vscale_add");
 }
