@@ -600,14 +600,18 @@ constexpr int kG8Consumers = 256;
 constexpr int kG8Threads = kG8Consumers + 64;
 constexpr int kG8ChunkBytes = kG8Rows * 128;
 
+// MBITS = 8: CloverMatrix8 (a 128-byte chunk holds 2 blocks of 64 columns); MBITS = 4: the mixed-precision
+// CloverMatrix4::mvm(V8,V8) (CloverMatrix4.h:1093-1441) - the same chains on a nibble matrix, 4 blocks per chunk
+template <int MBITS>
 struct __align__(1024) Gemv8Stage {
+    static constexpr int kBlocksPerChunk = MBITS == 8 ? 2 : 4;
     uint8_t rows[kG8Chunks][kG8ChunkBytes];   // chunk c: rows 0..31 x 128 B, SWIZZLE_128B (each 4 KiB, 1024-aligned)
-    uint4 units[kG8Chunks * 2 * 8];           // unit (block, l): x = xa, y = xb, z = bits of prod
+    uint4 units[kG8Chunks * kBlocksPerChunk * 8];   // unit (block, l): x = xa, y = xb, z = bits of prod
 };
 // STAGES = 5: one CTA per SM; STAGES = 3 (105 KiB): two CTAs per SM, grid = 2 x SMs (see Gemv4Smem)
-template <int STAGES>
+template <int STAGES, int MBITS>
 struct Gemv8Smem {
-    Gemv8Stage stage[STAGES];
+    Gemv8Stage<MBITS> stage[STAGES];
     uint64_t full[STAGES];
     uint64_t empty[STAGES];
     float part[kG8Rows][8];
@@ -617,18 +621,21 @@ struct Gemv8Smem {
     unsigned int ticket;
 };
 
-template <bool STOCH, int STAGES>
+template <bool STOCH, int STAGES, int MBITS>
 __global__ void __launch_bounds__(kG8Threads, STAGES == 5 ? 1 : 2)
 k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows_local,
              uint64_t cols, uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
              float *__restrict__ ybuf, unsigned int *__restrict__ counters, int8_t *__restrict__ yv,
              float *__restrict__ ys, Key4 key, const uint64_t *__restrict__ tables) {
     extern __shared__ uint8_t smem_raw8[];
-    Gemv8Smem<STAGES> &sm = *reinterpret_cast<Gemv8Smem<STAGES> *>((reinterpret_cast<uintptr_t>(smem_raw8) + 1023u) & ~(uintptr_t)1023u);
+    Gemv8Smem<STAGES, MBITS> &sm = *reinterpret_cast<Gemv8Smem<STAGES, MBITS> *>((reinterpret_cast<uintptr_t>(smem_raw8) + 1023u) & ~(uintptr_t)1023u);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t hb = cols >> 6, nitems = rows_local / kG8Rows;
-    const uint32_t nchunks128 = (uint32_t)(cols >> 7);                    // 128-byte chunks per row
+    constexpr int kBPC = Gemv8Stage<MBITS>::kBlocksPerChunk;
+    // 128-byte chunks per row; a nibble row of cols = 128 mod 256 ends half-way through its last chunk: TMA zero-fills the
+    // rest and the x-units of the blocks beyond hb are zero
+    const uint32_t nchunks128 = MBITS == 8 ? (uint32_t)(cols >> 7) : (uint32_t)((cols + 255) >> 8);
     const uint32_t steps = (nchunks128 + kG8Chunks - 1) / kG8Chunks;      // stages per work item
 
     if (tid == 0) {
@@ -660,27 +667,29 @@ k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
         }
     } else if (warp == kG8Consumers / 32 + 1) {
         // ------------------------------- x-unit warp -------------------------------
-        // lane owns units lane + 32j (j = 0..3) of a stage = (block 4j + lane/8, AVX lane lane%8)
+        // lane owns units lane + 32j (j = 0..4*kBPC/2-1) of a stage = (block 4j + lane/8, AVX lane lane%8)
+        constexpr int kUnitsPerLane = kG8Chunks * kBPC / 4;
         uint32_t it = 0;
         const int l = lane & 7;
         for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
             const float *su = scales + (item >> 1) * hb;
             for (uint32_t c = 0; c < steps; ++c, ++it) {
                 const int s = it % STAGES;
-                uint4 u[4];
+                uint4 u[kUnitsPerLane];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint64_t b = (uint64_t)c * (2 * kG8Chunks) + 4 * j + (lane >> 3);
+                for (int j = 0; j < kUnitsPerLane; ++j) {
+                    const uint64_t b = (uint64_t)c * (kBPC * kG8Chunks) + 4 * j + (lane >> 3);
                     const bool ok = b < hb;
                     u[j].x = ok ? __ldg(xv + b * 16 + l) : 0u;
                     u[j].y = ok ? __ldg(xv + b * 16 + 8 + l) : 0u;
                     const float sa = ok ? __ldg(su + b) : 0.f, sb = ok ? __ldg(xs + b) : 0.f;
-                    u[j].z = __float_as_uint(__fmul_rn(__fmul_rn(sa, 1.0f / 127.0f), __fmul_rn(sb, 1.0f / 127.0f)));   // (CloverMatrix8.h:1042-1046)
+                    u[j].z = MBITS == 8 ? __float_as_uint(__fmul_rn(__fmul_rn(sa, 1.0f / 127.0f), __fmul_rn(sb, 1.0f / 127.0f)))    // (CloverMatrix8.h:1042-1046)
+                                        : __float_as_uint(__fmul_rn(__fmul_rn(sa, 1.0f / 7.0f), __fmul_rn(sb, 1.0f / 127.0f)));     // (CloverMatrix4.h:1093-1441)
                     u[j].w = 0u;
                 }
                 mbar_wait(&sm.empty[s], ((it / STAGES) & 1) ^ 1);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) sm.stage[s].units[lane + 32 * j] = u[j];
+                for (int j = 0; j < kUnitsPerLane; ++j) sm.stage[s].units[lane + 32 * j] = u[j];
                 mbar_arrive(&sm.full[s]);
             }
         }
@@ -692,25 +701,41 @@ k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
         const uint32_t base = (uint32_t)r * 128u + 4u * (uint32_t)(lane & 3);
         const uint32_t oa0 = base + ((uint32_t)((0 + ty) ^ rin) << 4), ob0 = base + ((uint32_t)((2 + ty) ^ rin) << 4);
         const uint32_t oa1 = base + ((uint32_t)((4 + ty) ^ rin) << 4), ob1 = base + ((uint32_t)((6 + ty) ^ rin) << 4);
+        // nibble matrix: block b of a chunk = 16-byte chunks 2b (elements 0..31) and 2b+1 (32..63); lane l owns halfword l of each
+        const uint32_t hbase = (uint32_t)r * 128u + 2u * (uint32_t)l;
         uint32_t it = 0;
         for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
             float acc = 0.f;
             for (uint32_t c = 0; c < steps; ++c, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&sm.full[s], (it / STAGES) & 1);
-                const Gemv8Stage &st = sm.stage[s];
+                const Gemv8Stage<MBITS> &st = sm.stage[s];
                 const int live = (int)min((uint32_t)kG8Chunks, nchunks128 - c * kG8Chunks);
                 auto chunk = [&](int j) {
                     const uint8_t *p = st.rows[j];
-                    const uint32_t wa0 = *reinterpret_cast<const uint32_t *>(p + oa0), wb0 = *reinterpret_cast<const uint32_t *>(p + ob0);
-                    const uint32_t wa1 = *reinterpret_cast<const uint32_t *>(p + oa1), wb1 = *reinterpret_cast<const uint32_t *>(p + ob1);
-                    const uint4 u0 = st.units[(2 * j) * 8 + l], u1 = st.units[(2 * j + 1) * 8 + l];
-                    int d0 = dp4a_ss((int)wa0, (int)u0.x, (int)kMagicBits);
-                    d0 = dp4a_ss((int)wb0, (int)u0.y, d0);
-                    int d1 = dp4a_ss((int)wa1, (int)u1.x, (int)kMagicBits);
-                    d1 = dp4a_ss((int)wb1, (int)u1.y, d1);
-                    acc = __fmaf_rn(__uint_as_float(u0.z), __fsub_rn(__int_as_float(d0), 12582912.0f), acc);   // (:1093-1094)
-                    acc = __fmaf_rn(__uint_as_float(u1.z), __fsub_rn(__int_as_float(d1), 12582912.0f), acc);
+                    if (MBITS == 8) {
+                        const uint32_t wa0 = *reinterpret_cast<const uint32_t *>(p + oa0), wb0 = *reinterpret_cast<const uint32_t *>(p + ob0);
+                        const uint32_t wa1 = *reinterpret_cast<const uint32_t *>(p + oa1), wb1 = *reinterpret_cast<const uint32_t *>(p + ob1);
+                        const uint4 u0 = st.units[(2 * j) * 8 + l], u1 = st.units[(2 * j + 1) * 8 + l];
+                        int d0 = dp4a_ss((int)wa0, (int)u0.x, (int)kMagicBits);
+                        d0 = dp4a_ss((int)wb0, (int)u0.y, d0);
+                        int d1 = dp4a_ss((int)wa1, (int)u1.x, (int)kMagicBits);
+                        d1 = dp4a_ss((int)wb1, (int)u1.y, d1);
+                        acc = __fmaf_rn(__uint_as_float(u0.z), __fsub_rn(__int_as_float(d0), 12582912.0f), acc);   // (:1093-1094)
+                        acc = __fmaf_rn(__uint_as_float(u1.z), __fsub_rn(__int_as_float(d1), 12582912.0f), acc);
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const uint32_t h0 = *reinterpret_cast<const uint16_t *>(p + hbase + ((uint32_t)((2 * b) ^ rin) << 4));
+                            const uint32_t h1 = *reinterpret_cast<const uint16_t *>(p + hbase + ((uint32_t)((2 * b + 1) ^ rin) << 4));
+                            const uint4 ux = st.units[(4 * j + b) * 8 + l];
+                            // nibbles -> 16*q bytes like the reference (:1150-1166); the sum is a multiple of 16, so
+                            // (as_float(magic + d) - magic) * 2^-4 IS float(d >> 4), the reference's srai 4 (:1196)
+                            int d = dp4a_ss((int)nibbles4_to_bytes16(h0), (int)ux.x, (int)kMagicBits);
+                            d = dp4a_ss((int)nibbles4_to_bytes16(h1), (int)ux.y, d);
+                            acc = __fmaf_rn(__uint_as_float(ux.z), __fmul_rn(__fsub_rn(__int_as_float(d), 12582912.0f), 0.0625f), acc);
+                        }
+                    }
                 };
                 if (live == kG8Chunks) {
 #pragma unroll
@@ -1026,6 +1051,47 @@ static int mvm_scratch(uint64_t nrb_local, uint64_t nrb_global_end, float **ybuf
     return CLOVER_OK;
 }
 
+// the TMA-ring kernel for an 8-bit product vector; MBITS = 8: CloverMatrix8::mvm, MBITS = 4: CloverMatrix4::mvm(V8,V8)
+template <int MBITS>
+static int launch_mvm8_tma(const int8_t *values, const float *scales, uint64_t rows_local, uint64_t cols, uint64_t row0,
+                           const uint32_t *x32, const float *xs, float *y32, int8_t *yv, float *ys, bool stoch, Key4 key,
+                           const uint64_t *tables, cudaStream_t stream) {
+    const uint64_t nrb = rows_local >> 6;
+    // fp32 row results pass through global memory (the caller's y32, else a grow-only per-device scratch) and a
+    // zero-initialised counter per row block, re-armed by the kernel itself (one GEMV stream per device).
+    float *ybuf = y32;
+    unsigned int *counters = nullptr;
+    int rc = mvm_scratch(nrb, (row0 >> 6) + nrb, y32 ? nullptr : &ybuf, &counters);
+    if (rc != CLOVER_OK) return rc;
+    // two CTAs per SM with 3-stage rings, as for the 4-bit kernel, whenever there is more than one round of work items
+    // (tools/gemv_shapes.py 60 8: 32768^2 164 -> 160 us, 16384 x 32768 93 -> 83, 8192 x 32768 48 -> 42, 16384 x 4096
+    // 20.7 -> 16.4; a single round - 4096 x 32768 - prefers the deeper ring: 23.0 vs 24.8). CLOVER_GEMV_IMPL=items32 /
+    // items32x2 force either.
+    const char *impl8 = getenv("CLOVER_GEMV_IMPL");
+    const bool x2 = impl8 ? !strcmp(impl8, "items32x2") : rows_local / kG8Rows > (uint64_t)sm_count();
+    const int smem = (int)(x2 ? sizeof(Gemv8Smem<3, MBITS>) : sizeof(Gemv8Smem<5, MBITS>)) + 1024;
+    static bool attr_set8[2][2] = {{false, false}, {false, false}};
+    auto kern = x2 ? (stoch ? k_m8_mvm_tma<true, 3, MBITS> : k_m8_mvm_tma<false, 3, MBITS>) : (stoch ? k_m8_mvm_tma<true, 5, MBITS> : k_m8_mvm_tma<false, 5, MBITS>);
+    if (!attr_set8[x2][stoch]) {
+        CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set8[x2][stoch] = true;
+    }
+    CUtensorMap tmap;
+    rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows_local, MBITS == 8 ? cols : cols >> 1, kG8Rows);
+    if (rc != CLOVER_OK) return rc;
+    const uint64_t nitems = rows_local / kG8Rows;
+    uint64_t slots = (uint64_t)sm_count();
+    if (x2) {
+        static int per_sm8[2] = {0, 0};
+        if (!per_sm8[stoch]) CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm8[stoch], kern, kG8Threads, smem));
+        slots *= (uint64_t)std::max(1, std::min(per_sm8[stoch], 2));
+    }
+    const unsigned pgrid = (unsigned)(nitems < slots ? nitems : slots);
+    kern<<<pgrid, kG8Threads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, ybuf, counters, yv, ys,
+                                              key, tables);
+    return CLOVER_OK;
+}
+
 template <int BITS>
 static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_local, uint64_t cols, uint64_t row0,
                       const int8_t *xv, const float *xs, float *y32, int8_t *yv, float *ys, const uint64_t *key_host,
@@ -1112,38 +1178,8 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
             if (stoch) k_m8_mvm<8, true><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
             else       k_m8_mvm<8, false><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
         } else {
-            // fp32 row results pass through global memory (the caller's y32, else a grow-only per-device scratch) and a
-            // zero-initialised counter per row block, re-armed by the kernel itself (one GEMV stream per device).
-            float *ybuf = y32;
-            unsigned int *counters = nullptr;
-            int rc = mvm_scratch(nrb, (row0 >> 6) + nrb, y32 ? nullptr : &ybuf, &counters);
+            int rc = launch_mvm8_tma<8>(values, scales, rows_local, cols, row0, x32, xs, y32, yv, ys, stoch, key, tables, stream);
             if (rc != CLOVER_OK) return rc;
-            // two CTAs per SM with 3-stage rings, as for the 4-bit kernel, whenever there is more than one round of work items
-            // (tools/gemv_shapes.py 60 8: 32768^2 164 -> 160 us, 16384 x 32768 93 -> 83, 8192 x 32768 48 -> 42, 16384 x 4096
-            // 20.7 -> 16.4; a single round - 4096 x 32768 - prefers the deeper ring: 23.0 vs 24.8). CLOVER_GEMV_IMPL=items32 /
-            // items32x2 force either.
-            const char *impl8 = getenv("CLOVER_GEMV_IMPL");
-            const bool x2 = impl8 ? !strcmp(impl8, "items32x2") : rows_local / kG8Rows > (uint64_t)sm_count();
-            const int smem = (int)(x2 ? sizeof(Gemv8Smem<3>) : sizeof(Gemv8Smem<5>)) + 1024;
-            static bool attr_set8[2][2] = {{false, false}, {false, false}};
-            auto kern = x2 ? (stoch ? k_m8_mvm_tma<true, 3> : k_m8_mvm_tma<false, 3>) : (stoch ? k_m8_mvm_tma<true, 5> : k_m8_mvm_tma<false, 5>);
-            if (!attr_set8[x2][stoch]) {
-                CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                attr_set8[x2][stoch] = true;
-            }
-            CUtensorMap tmap;
-            rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows_local, cols, kG8Rows);
-            if (rc != CLOVER_OK) return rc;
-            const uint64_t nitems = rows_local / kG8Rows;
-            uint64_t slots = (uint64_t)sm_count();
-            if (x2) {
-                static int per_sm8[2] = {0, 0};
-                if (!per_sm8[stoch]) CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm8[stoch], kern, kG8Threads, smem));
-                slots *= (uint64_t)std::max(1, std::min(per_sm8[stoch], 2));
-            }
-            const unsigned pgrid = (unsigned)(nitems < slots ? nitems : slots);
-            kern<<<pgrid, kG8Threads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, ybuf, counters, yv, ys,
-                                                      key, tables);
         }
     }
     count_launch();
@@ -1208,10 +1244,17 @@ int clover_m4_mvm_v8(const int8_t *values, const float *scales, uint64_t rows, u
     }
     const uint32_t *v32 = reinterpret_cast<const uint32_t *>(values), *x32 = reinterpret_cast<const uint32_t *>(xv);
     cudaStream_t st = (cudaStream_t)stream;
-    if (key_host) k_m8_mvm<4, true><<<(unsigned)nrb, 512, 0, st>>>(v32, scales, rows, cols, 0, x32, xs, y32, yv, ys, key, tables);
-    else          k_m8_mvm<4, false><<<(unsigned)nrb, 512, 0, st>>>(v32, scales, rows, cols, 0, x32, xs, y32, yv, ys, key, tables);
+    // CLOVER_GEMV_IMPL=simple (or an unaligned matrix): plain-load kernel; default: the TMA ring of the 8-bit GEMV on nibble rows
+    const char *impl = getenv("CLOVER_GEMV_IMPL");
+    if ((impl && !strcmp(impl, "simple")) || (reinterpret_cast<uintptr_t>(values) & 15u) != 0) {
+        if (key_host) k_m8_mvm<4, true><<<(unsigned)nrb, 512, 0, st>>>(v32, scales, rows, cols, 0, x32, xs, y32, yv, ys, key, tables);
+        else          k_m8_mvm<4, false><<<(unsigned)nrb, 512, 0, st>>>(v32, scales, rows, cols, 0, x32, xs, y32, yv, ys, key, tables);
+    } else {
+        const int rc2 = launch_mvm8_tma<4>(values, scales, rows, cols, 0, x32, xs, y32, yv, ys, key_host != nullptr, key, tables, st);
+        if (rc2 != CLOVER_OK) return rc2;
+    }
     count_launch();
-    const int rc = launch_status("k_m8_mvm<4>");
+    const int rc = launch_status("k_m4_mvm_v8");
     if (rc == CLOVER_OK && key_host) host_key_skip(key_host, 2 * nrb);
     return rc;
 }
