@@ -483,9 +483,12 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
 constexpr int kMvm8ChunkBlocks = 64;
 
 // two bytes (four nibbles: elements e, e+1 in byte 0, e+2, e+3 in byte 1) -> [16*q_e, 16*q_e+1, 16*q_e+2, 16*q_e+3]
+// (three instructions: h << 4 puts every LOW nibble into the high half of a byte, one PRMT interleaves the bytes of h
+// and of h << 4, one AND drops the neighbours' bits)
 __device__ __forceinline__ uint32_t nibbles4_to_bytes16(uint32_t h) {
-    const uint32_t y = (h & 0x00FFu) | ((h & 0xFF00u) << 8);
-    return (y & 0x00F000F0u) | ((y & 0x000F000Fu) << 12);
+    uint32_t p;
+    asm("prmt.b32 %0, %1, %2, 0x5140;" : "=r"(p) : "r"(h), "r"(h << 4));
+    return p & 0xF0F0F0F0u;
 }
 
 template <int MBITS, bool STOCH>
