@@ -57,10 +57,46 @@ static void validate_mvm(uint64_t m, uint64_t n) {
     if (worst > 1.001) exit(1);
 }
 
+// The shape of the reference's application loop (test/performance/01_measure.h:924-946): gradient step on
+// ||y - Phi x||^2 followed by hard thresholding, all operands quantized - exercises transpose, scaleAndAdd (both
+// forms), threshold and (QVector = CloverVector8 with a 4-bit matrix) the mixed-precision mvm.
+template <class QMatrix, class QVector>
+static void iterate(uint64_t m, uint64_t n, uint64_t K) {
+    CloverMatrix32 phi32(m, n);
+    CloverVector32 y32(m);
+    uint32_t lcg = 777;
+    auto next = [&]() { lcg = lcg * 1664525u + 1013904223u; return (float)((int)(lcg >> 24) % 21 - 10) * 0.01f; };
+    for (uint64_t i = 0; i < m * n; ++i) phi32.getData()[i] = next();
+    for (uint64_t i = 0; i < m; ++i) y32.getData()[i] = next();
+    QMatrix Phi(m, n), PhiT(n, m);
+    Phi.quantize(phi32);
+    Phi.transpose(PhiT);
+    for (uint64_t i = 0; i < m; i += 37)
+        for (uint64_t j = 0; j < n; j += 41)
+            if (Phi.get(i, j) != PhiT.get(j, i)) { std::cout << "transpose mismatch" << std::endl; exit(1); }
+    QVector x(n), y(m), t1(m), t2(m), t3(n);
+    y.quantize(y32);
+    x.clear();
+    for (int it = 0; it < 3; ++it) {
+        Phi.mvm(x, t1);
+        y.scaleAndAdd(t1, -1.0f, t2);
+        PhiT.mvm(t2, t3);
+        x.scaleAndAdd(t3, 0.5f);
+        x.threshold(K);
+    }
+    uint64_t nonzero = 0;
+    for (uint64_t i = 0; i < n; ++i) nonzero += x.getBits(i) != 0;
+    std::cout << "loop " << m << "x" << n << " K=" << K << " bits=" << x.getBitsLength() << ": " << nonzero << " survivors" << std::endl;
+    if (nonzero == 0 || nonzero > K) exit(1);
+}
+
 int main() {
     example();
     validate_mvm<CloverMatrix4, CloverVector4>(256, 384);
     validate_mvm<CloverMatrix8, CloverVector8>(256, 384);
+    iterate<CloverMatrix4, CloverVector4>(256, 512, 40);
+    iterate<CloverMatrix8, CloverVector8>(256, 512, 40);
+    iterate<CloverMatrix4, CloverVector8>(256, 512, 40);      // mixed precision (include/CloverMatrix4.h:1093)
     std::cout << "OK" << std::endl;
     return 0;
 }

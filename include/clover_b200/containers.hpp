@@ -150,6 +150,14 @@ public:
     void quantize_scalar(const CloverVector32 &o) { quantize(o); }
     void quantize_parallel(const CloverVector32 &o) { quantize(o); }
 
+    // all values 0, all scales 1 (include/CloverVector4.h:306-318) - the start vector of the IHT / GD loops
+    void clear() {
+        unsigned char *h = buf.host_rw();
+        std::memset(h, 0, value_bytes());
+        float *s = reinterpret_cast<float *>(h + value_bytes());
+        for (uint64_t i = 0; i < scale_count(); ++i) s[i] = 1.0f;
+    }
+
     void restore(CloverVector32 &other) const {
         if (other.size_pad() != length_pad) { std::cout << "Vectors do not have the same size. Exiting ..." << std::endl; exit(1); }
         const int rc = BITS == 4 ? clover_v4_restore(device_values(), device_scales(), length_pad, other.device_out(), nullptr)
