@@ -277,3 +277,37 @@ def test_vector_threshold(oracle, reference, n, k, bits_):
     mags = np.sort(oracle.v_abs(bits_, qv, qs, n))[::-1]
     kept = np.sort(oracle.v_abs(bits_, got, qs, n))[::-1]
     assert np.array_equal(kept[:k], mags[:k]) and not kept[k:].any()
+
+
+@pytest.mark.parametrize("bits_", [4, 8])
+def test_application_loop_iht(oracle, reference, bits_):
+    """The reference's IHT iteration (test/performance/01_measure.h:924-946) composed from its own sequential methods
+    - mvm, scaleAndAdd (3-argument), mvm on the transpose, scaleAndAdd (in place), threshold - stays byte-identical
+    between the restatement and the compiled reference over several iterations (ties in threshold included)."""
+    from oracle.pyoracle import pad_matrix
+    M, N, K, mu = 256, 512, 40, 0.05
+    phi = pad_matrix((_inputs(oracle, M * N, "floats")[: M * N] * np.float32(0.0625)).reshape(M, N))
+    y32 = _inputs(oracle, M, "floats", seed_skip=11)
+    mq_o, mq_r = getattr(oracle, f"m{bits_}_quantize"), getattr(reference, f"m{bits_}_quantize")
+    pv, ps = mq_o(phi)
+    rpv, rps, rphi = mq_r(phi)
+    assert np.array_equal(pv, rpv)
+    tv, ts = getattr(oracle, f"m{bits_}_transpose")(pv, ps, M, N)
+    rphit = getattr(reference, f"m{bits_}_from")(tv, ts, N, M)
+    yv, ys = getattr(oracle, f"v{bits_}_quantize")(y32, M)
+    mvm_o, mvm_r = getattr(oracle, f"m{bits_}_mvm"), getattr(reference, f"m{bits_}_mvm")
+    xo = (np.zeros(N * bits_ // 8, np.int8), np.ones(N // 64, np.float32))
+    xr = (xo[0].copy(), xo[1].copy())
+    for _ in range(4):
+        t1 = mvm_o(pv, ps, M, N, *xo)
+        t2 = oracle.scale_and_add(bits_, yv, ys, t1[0], t1[1], -1.0, M)
+        t3 = mvm_o(tv, ts, N, M, *t2)
+        xo = oracle.scale_and_add(bits_, xo[0], xo[1], t3[0], t3[1], mu, N)
+        xo = (oracle.threshold(bits_, xo[0], xo[1], N, K), xo[1])
+        r1 = mvm_r(rphi, *xr)
+        r2 = reference.scale_and_add(bits_, yv, ys, r1[0], r1[1], -1.0, M)
+        r3 = mvm_r(rphit, *r2)
+        xr = reference.scale_and_add(bits_, xr[0], xr[1], r3[0], r3[1], mu, N)
+        xr = (reference.threshold(bits_, xr[0], xr[1], N, K), xr[1])
+        assert np.array_equal(xo[0], xr[0]) and np.array_equal(xo[1].view(np.uint32), xr[1].view(np.uint32))
+    assert xo[0].any()
