@@ -732,11 +732,11 @@ k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
                             const uint32_t h0 = *reinterpret_cast<const uint16_t *>(p + hbase + ((uint32_t)((2 * b) ^ rin) << 4));
                             const uint32_t h1 = *reinterpret_cast<const uint16_t *>(p + hbase + ((uint32_t)((2 * b + 1) ^ rin) << 4));
                             const uint4 ux = st.units[(4 * j + b) * 8 + l];
-                            // nibbles -> 16*q bytes like the reference (:1150-1166); the sum is a multiple of 16, so
-                            // (as_float(magic + d) - magic) * 2^-4 IS float(d >> 4), the reference's srai 4 (:1196)
+                            // nibbles -> 16*q bytes like the reference (:1150-1166); the sum d = 16 S is a multiple of 16, so
+                            // as_float(magic + d) * 2^-4 - magic * 2^-4 IS float(d >> 4), the reference's srai 4 (:1196)
                             int d = dp4a_ss((int)nibbles4_to_bytes16(h0), (int)ux.x, (int)kMagicBits);
                             d = dp4a_ss((int)nibbles4_to_bytes16(h1), (int)ux.y, d);
-                            acc = __fmaf_rn(__uint_as_float(ux.z), __fmul_rn(__fsub_rn(__int_as_float(d), 12582912.0f), 0.0625f), acc);
+                            acc = __fmaf_rn(__uint_as_float(ux.z), __fmaf_rn(__int_as_float(d), 0.0625f, -786432.0f), acc);     // exact: (magic + 16 S) / 16 - magic / 16 = S
                         }
                     }
                 };

@@ -72,6 +72,13 @@ elif what in ("threshold4_cluster", "threshold4_large", "threshold8_cluster"):
     src.quantize(v)
     def fn():
         q.values.copy_(src.values); q.threshold(n // 4 if n <= 32768 else n // 64, THRESHOLD_FAST)
+elif what == "mvm4v8":
+    n = 32768
+    M = cb.CloverMatrix4(n, n)
+    M.values.copy_(random_nibbles(torch, n * n // 2, g, dev)); M.scales.uniform_(0.25, 1.0, generator=g)
+    x, y = cb.CloverVector8(n), cb.CloverVector8(n)
+    v = cb.CloverVector32(n); v.values.uniform_(-1, 1, generator=g); x.quantize(v)
+    fn = lambda: M.mvm(x, y)
 elif what == "iht":
     from clover_b200 import THRESHOLD_FAST, apps
     M, N, K = 8192, 32768, 1024
