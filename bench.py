@@ -331,7 +331,8 @@ def extras(torch, cb, peak):
     m4.values.copy_(random_nibbles(torch, r8 * c8 // 2, g, dev)); m4.scales.uniform_(0.25, 1.0, generator=g)
     t = cuda_time(torch, lambda: m4.mvm(x8, y8), 20)
     b = m4.getBytes() + x8.getBytes() + y8.getBytes()
-    out["mvm4_v8_mixed_32768"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b}
+    out["mvm4_v8_mixed_32768"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b,
+                                  "traffic": ncu_traffic("mvm4_v8_mixed:32768x32768")}
     del m4
     # transpose of a 16384 x 16384 matrix (every byte read once and written once)
     for bits_, M_ in ((4, cb.CloverMatrix4), (8, cb.CloverMatrix8)):
