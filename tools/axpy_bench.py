@@ -1,5 +1,6 @@
+"""Time scaleAndAdd at n = 2^26 for both widths (CLOVER_AXPY_IMPL=block selects the thread-per-block kernel)."""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from clover_b200 import containers as cb
 from bench import cuda_time

@@ -1,5 +1,6 @@
+"""Time the mixed-precision mvm (4-bit matrix x CloverVector8) under every kernel selection; checks the bits agree."""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from clover_b200 import containers as cb
 from bench import cuda_time, random_nibbles, measured_peaks
