@@ -542,7 +542,9 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_m4_mvm_tma2 (32-row items, 2 CTAs/SM)" if cols >= 16384 else "k_m4_mvm_tma", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
                          "traffic": ncu_traffic(f"C3_mvm4:{rows}x{cols}") if world == 1 else None,
-                         "kernel_ms": tk * 1e3, "algorithmic_bytes_per_launch": shard_bytes},
+                         "kernel_ms": tk * 1e3, "algorithmic_bytes_per_launch": shard_bytes,
+                         "note": "peak is the measured COPY bandwidth (a kernel that reads and writes); this kernel only reads, "
+                                 "so frac may exceed 1 (ncu: 6.86 TB/s of DRAM traffic, profiles/r01d_gemv4_ncu_summary.txt)"},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
