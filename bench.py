@@ -333,6 +333,14 @@ def extras(torch, cb, peak):
     b = m4.getBytes() + x8.getBytes() + y8.getBytes()
     out["mvm4_v8_mixed_32768"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b,
                                   "traffic": ncu_traffic("mvm4_v8_mixed:32768x32768")}
+    # CloverMatrix4::mvm(V32,V32) - fp32 vectors, 32 chains per row (CloverMatrix4.h:1451-1547); bytes = matrix + x + y
+    x32v, y32v = cb.CloverVector32(c8), cb.CloverVector32(r8)
+    x32v.values.uniform_(-1, 1, generator=g)
+    t = cuda_time(torch, lambda: m4.mvm(x32v, y32v), 20)
+    b = m4.getBytes() + 4 * (c8 + r8)
+    out["mvm4_f32_32768"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b,
+                             "fp32_ops_per_s": 2.0 * r8 * c8 / t,
+                             "note": "one int->float, one multiply and one fma per matrix element (the reference's order): CUDA-core bound, not HBM bound"}
     del m4
     # transpose of a 16384 x 16384 matrix (every byte read once and written once)
     for bits_, M_ in ((4, cb.CloverMatrix4), (8, cb.CloverMatrix8)):

@@ -203,7 +203,7 @@ def test_matrix_quantize_and_mvm(cb, oracle, shape, kind, bits_):
         assert np.float32(qa.get(i, j)) == val
 
 
-@pytest.mark.parametrize("shape", [(128, 128), (256, 384), (640, 1152)])
+@pytest.mark.parametrize("shape", [(128, 128), (256, 384), (640, 1152), (128, 4224), (384, 2048)])
 def test_matrix_mvm_f32(cb, oracle, shape):
     """mvm(V32,V32) (CloverMatrix4.h:1451-1547): bit-exact, far inside the reference's own 0.01 bound."""
     from oracle.pyoracle import pad_matrix
