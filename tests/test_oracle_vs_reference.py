@@ -311,3 +311,32 @@ def test_application_loop_iht(oracle, reference, bits_):
         xr = (reference.threshold(bits_, xr[0], xr[1], N, K), xr[1])
         assert np.array_equal(xo[0], xr[0]) and np.array_equal(xo[1].view(np.uint32), xr[1].view(np.uint32))
     assert xo[0].any()
+
+
+def test_application_loop_iht_mixed(oracle, reference):
+    """The reference's most accurate IHT configuration (test/accuracy/00_accuracy.cpp:84,112): 4-bit matrix, 8-bit vectors,
+    mixed mvm (CloverMatrix4.h:1093-1441) - the composed iteration stays byte-identical between oracle and reference."""
+    from oracle.pyoracle import pad_matrix
+    M, N, K, mu = 256, 384, 30, 0.05
+    phi = pad_matrix((_inputs(oracle, M * N, "floats")[: M * N] * np.float32(0.0625)).reshape(M, N))
+    y32 = _inputs(oracle, M, "floats", seed_skip=11)
+    pv, ps = oracle.m4_quantize(phi)
+    _, _, rphi = reference.m4_quantize(phi)
+    tv, ts = oracle.m4_transpose(pv, ps, M, N)
+    rphit = reference.m4_from(tv, ts, N, M)
+    yv, ys = oracle.v8_quantize(y32, M)
+    xo = (np.zeros(N, np.int8), np.ones(N // 64, np.float32))
+    xr = (xo[0].copy(), xo[1].copy())
+    for _ in range(3):
+        t1 = oracle.m4_mvm_v8(pv, ps, M, N, *xo)
+        t2 = oracle.scale_and_add(8, yv, ys, t1[0], t1[1], -1.0, M)
+        t3 = oracle.m4_mvm_v8(tv, ts, N, M, *t2)
+        xo = oracle.scale_and_add(8, xo[0], xo[1], t3[0], t3[1], mu, N)
+        xo = (oracle.threshold(8, xo[0], xo[1], N, K), xo[1])
+        r1 = reference.m4_mvm_v8(rphi, *xr)
+        r2 = reference.scale_and_add(8, yv, ys, r1[0], r1[1], -1.0, M)
+        r3 = reference.m4_mvm_v8(rphit, *r2)
+        xr = reference.scale_and_add(8, xr[0], xr[1], r3[0], r3[1], mu, N)
+        xr = (reference.threshold(8, xr[0], xr[1], N, K), xr[1])
+        assert np.array_equal(xo[0], xr[0]) and np.array_equal(xo[1].view(np.uint32), xr[1].view(np.uint32))
+    assert xo[0].any()
