@@ -77,6 +77,37 @@ def main():
     out = os.path.join(ROOT, "tests", "golden", "clover_golden.npz")
     np.savez_compressed(out, **{k: np.ascontiguousarray(val) for k, val in g.items()})
     print("wrote", out, os.path.getsize(out), "bytes,", len(g), "arrays")
+    golden_f(ref, ref_sr, g)
+
+
+def golden_f(ref, ref_sr, g):
+    """SURVEY.md 8f rows - scaleAndAdd, mixed mvm(V8), transpose, threshold - on the same inputs -> clover_golden_f.npz"""
+    f = {}
+    for bits in (4, 8):
+        for (p, q_, n) in (("a", "b", 4096), ("c", "d", 1000)):
+            u, su, v, sv = (g[f"v{bits}_{p}_values"], g[f"v{bits}_{p}_scales"], g[f"v{bits}_{q_}_values"], g[f"v{bits}_{q_}_scales"])
+            for tag, alpha in (("p5", 0.5), ("m1", -1.0)):
+                r, sr = ref.scale_and_add(bits, u, su, v, sv, alpha, n)
+                f[f"axpy{bits}_{p}{q_}_{tag}_values"], f[f"axpy{bits}_{p}{q_}_{tag}_scales"] = r, sr
+        key = ref_sr.xs_init(11, 13)
+        r, sr = ref_sr.scale_and_add(bits, g[f"v{bits}_c_values"], g[f"v{bits}_c_scales"], g[f"v{bits}_d_values"],
+                                     g[f"v{bits}_d_scales"], 0.5, 1000, state=key)
+        f[f"sr_axpy{bits}_cd_values"], f[f"sr_axpy{bits}_cd_scales"], f[f"sr_axpy{bits}_key_after"] = r, sr, key.copy()
+        h = getattr(ref, f"m{bits}_from")(g[f"m{bits}_values"], g[f"m{bits}_scales"], 256, 384)
+        tv, ts = getattr(ref, f"m{bits}_transpose")(h)
+        f[f"m{bits}_transpose_values"], f[f"m{bits}_transpose_scales"] = tv, ts
+        for name, n, k in (("ints", 1000, 64), ("a", 4096, 300), ("c", 1000, 999)):
+            f[f"thr{bits}_{name}_k{k}"] = ref.threshold(bits, g[f"v{bits}_{name}_values"], g[f"v{bits}_{name}_scales"], n, k)
+    h4 = ref.m4_from(g["m4_values"], g["m4_scales"], 256, 384)
+    yv, ys = ref.m4_mvm_v8(h4, g["v8_v_values"], g["v8_v_scales"])
+    f["m4_mvm_v8_values"], f["m4_mvm_v8_scales"] = yv, ys
+    key = ref_sr.xs_init(21, 22)
+    h4s = ref_sr.m4_from(g["m4_values"], g["m4_scales"], 256, 384)
+    yv, ys = ref_sr.m4_mvm_v8(h4s, g["v8_v_values"], g["v8_v_scales"], state=key)
+    f["sr_m4_mvm_v8_values"], f["sr_m4_mvm_v8_scales"], f["sr_m4_mvm_v8_key_after"] = yv, ys, key.copy()
+    out = os.path.join(ROOT, "tests", "golden", "clover_golden_f.npz")
+    np.savez_compressed(out, **{k: np.ascontiguousarray(val) for k, val in f.items()})
+    print("wrote", out, os.path.getsize(out), "bytes,", len(f), "arrays")
 
 
 if __name__ == "__main__":

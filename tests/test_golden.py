@@ -89,3 +89,44 @@ def test_stochastic_with_key(oracle, g, bits):
     yv, ys = getattr(oracle, f"m{bits}_mvm")(mv, ms, 256, 384, g[f"v{bits}_v_values"], g[f"v{bits}_v_scales"], state=key)
     assert same_bits(yv, g[f"sr_m{bits}_mvm_values"]) and same_bits(ys, g[f"sr_m{bits}_mvm_scales"])
     assert np.array_equal(key, g[f"sr_m{bits}_key_after_mvm"])
+
+
+# ---- scaleAndAdd, mixed mvm(V8), transpose, threshold (tests/golden/clover_golden_f.npz) ----------
+GOLDEN_F = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clover_golden_f.npz")
+
+
+@pytest.fixture(scope="module")
+def gf():
+    return np.load(GOLDEN_F)
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_f_rows_vectors(oracle, g, gf, bits):
+    for p, q, n in (("a", "b", 4096), ("c", "d", 1000)):
+        u, su, v, sv = (g[f"v{bits}_{p}_values"], g[f"v{bits}_{p}_scales"], g[f"v{bits}_{q}_values"], g[f"v{bits}_{q}_scales"])
+        for tag, alpha in (("p5", 0.5), ("m1", -1.0)):
+            r, sr = oracle.scale_and_add(bits, u, su, v, sv, alpha, n)
+            assert same_bits(r, gf[f"axpy{bits}_{p}{q}_{tag}_values"]) and same_bits(sr, gf[f"axpy{bits}_{p}{q}_{tag}_scales"])
+    key = oracle.xs_init(11, 13)
+    r, sr = oracle.scale_and_add(bits, g[f"v{bits}_c_values"], g[f"v{bits}_c_scales"], g[f"v{bits}_d_values"],
+                                 g[f"v{bits}_d_scales"], 0.5, 1000, key)
+    assert same_bits(r, gf[f"sr_axpy{bits}_cd_values"]) and same_bits(sr, gf[f"sr_axpy{bits}_cd_scales"])
+    assert np.array_equal(key, gf[f"sr_axpy{bits}_key_after"])
+    for name, n, k in (("ints", 1000, 64), ("a", 4096, 300), ("c", 1000, 999)):
+        got = oracle.threshold(bits, g[f"v{bits}_{name}_values"], g[f"v{bits}_{name}_scales"], n, k)
+        assert same_bits(got, gf[f"thr{bits}_{name}_k{k}"]), (name, k)
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_f_rows_transpose(oracle, g, gf, bits):
+    tv, ts = getattr(oracle, f"m{bits}_transpose")(g[f"m{bits}_values"], g[f"m{bits}_scales"], 256, 384)
+    assert same_bits(tv, gf[f"m{bits}_transpose_values"]) and same_bits(ts, gf[f"m{bits}_transpose_scales"])
+
+
+def test_f_rows_mixed_mvm(oracle, g, gf):
+    yv, ys = oracle.m4_mvm_v8(g["m4_values"], g["m4_scales"], 256, 384, g["v8_v_values"], g["v8_v_scales"])
+    assert same_bits(yv, gf["m4_mvm_v8_values"]) and same_bits(ys, gf["m4_mvm_v8_scales"])
+    key = oracle.xs_init(21, 22)
+    yv, ys = oracle.m4_mvm_v8(g["m4_values"], g["m4_scales"], 256, 384, g["v8_v_values"], g["v8_v_scales"], state=key)
+    assert same_bits(yv, gf["sr_m4_mvm_v8_values"]) and same_bits(ys, gf["sr_m4_mvm_v8_scales"])
+    assert np.array_equal(key, gf["sr_m4_mvm_v8_key_after"])
