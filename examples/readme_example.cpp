@@ -4,6 +4,8 @@
 #include <clover_b200/containers.hpp>
 
 #include <cmath>
+#include <cstring>
+#include <vector>
 
 static void example() {
     const int n = 128;
@@ -90,10 +92,38 @@ static void iterate(uint64_t m, uint64_t n, uint64_t K) {
     if (nonzero == 0 || nonzero > K) exit(1);
 }
 
+// The borrowing view constructor (include/CloverVector4.h:114-119): the container works on the caller's own host
+// buffers - quantize INTO a view, read the bytes through the caller's pointers, use views as operands.
+template <class QVector>
+static void views(uint64_t n) {
+    CloverVector32 a32(n), b32(n);
+    for (uint64_t i = 0; i < n; ++i) { a32.getData()[i] = (float)((int)(i % 13) - 6); b32.getData()[i] = (float)((int)(i % 7) - 3); }
+    QVector qa(n), qb(n);
+    qa.quantize(a32);
+    qb.quantize(b32);
+    const uint64_t n_pad = qa.size_pad(), vbytes = n_pad * qa.getBitsLength() / 8;
+    std::vector<int8_t> va(vbytes), vb(vbytes);
+    std::vector<float> sa(n_pad / 64), sb(n_pad / 64);
+    QVector wa(n, va.data(), sa.data()), wb(n, vb.data(), sb.data());
+    wa.quantize(a32);                                           // lands in va / sa
+    if (std::memcmp(va.data(), qa.getData(), vbytes) != 0 || std::memcmp(sa.data(), qa.getScales(), sa.size() * sizeof(float)) != 0) {
+        std::cout << "view quantize mismatch" << std::endl; exit(1);
+    }
+    std::memcpy(vb.data(), qb.getData(), vbytes);               // the caller fills the view's memory itself
+    std::memcpy(sb.data(), qb.getScales(), sb.size() * sizeof(float));
+    if (wa.dot(wb) != qa.dot(qb) || wb.get(5) != qb.get(5)) { std::cout << "view dot mismatch" << std::endl; exit(1); }
+    QVector copy(wa);                                           // deep copy of a view owns its bytes
+    va[0] = 0;                                                  // ... so changing the caller's buffer does not reach it
+    if (copy.dot(qb) != qa.dot(qb)) { std::cout << "view copy mismatch" << std::endl; exit(1); }
+    std::cout << "views n=" << n << " bits=" << qa.getBitsLength() << " ok" << std::endl;
+}
+
 int main() {
     example();
     validate_mvm<CloverMatrix4, CloverVector4>(256, 384);
     validate_mvm<CloverMatrix8, CloverVector8>(256, 384);
+    views<CloverVector4>(1000);
+    views<CloverVector8>(1000);
     iterate<CloverMatrix4, CloverVector4>(256, 512, 40);
     iterate<CloverMatrix8, CloverVector8>(256, 512, 40);
     iterate<CloverMatrix4, CloverVector8>(256, 512, 40);      // mixed precision (include/CloverMatrix4.h:1093)

@@ -18,6 +18,9 @@
 // Stochastic rounding is a run-time switch: containers start WITHOUT a key (= the reference built with
 // CLOVER_STOCHASTIC_ROUNDING_DISABLED); setRandomKeys()/seed() enables the reference's XORShift128+ stream.
 //
+// The borrowing view constructor CloverVector4/8(n, values, scales) (include/CloverVector4.h:114-119) works on the caller's
+// host buffers: they are re-read before every kernel that reads the view and written back after every kernel that writes
+// it (one PCIe copy per call - keep hot operands in owning containers).
 // Not provided (outside the hot path): 16-bit containers, fp32 BLAS on CloverVector32/CloverMatrix32.
 #ifndef CLOVER_B200_CONTAINERS_HPP
 #define CLOVER_B200_CONTAINERS_HPP
@@ -42,34 +45,80 @@ inline void check(int status, const char *what) {
     }
 }
 
-// One device buffer + host mirror with lazy synchronisation.
+// One device buffer + host mirror with lazy synchronisation. A VIEW (the reference's borrowing constructor,
+// include/CloverVector4.h:114-119) has its bytes in two host regions owned by the caller (values, scales): those
+// regions are authoritative whenever the host side is, so they are re-read before every kernel that reads the
+// container (the caller may have written through its own pointers) and written back right after every kernel that
+// writes it (the caller reads its own memory without asking) - a compatibility path that pays a PCIe copy per call.
 class Mirror {
     void *dev_ = nullptr;
     std::vector<unsigned char> host_;
     mutable bool host_fresh_ = true, dev_fresh_ = true;
+    unsigned char *ext_a_ = nullptr, *ext_b_ = nullptr;     // view: the caller's values / scales
+    size_t ext_a_bytes_ = 0;
+    void pull_view() const {
+        std::memcpy(const_cast<unsigned char *>(host_.data()), ext_a_, ext_a_bytes_);
+        std::memcpy(const_cast<unsigned char *>(host_.data()) + ext_a_bytes_, ext_b_, host_.size() - ext_a_bytes_);
+    }
+    void push_view() const {
+        std::memcpy(ext_a_, host_.data(), ext_a_bytes_);
+        std::memcpy(ext_b_, host_.data() + ext_a_bytes_, host_.size() - ext_a_bytes_);
+    }
 public:
     explicit Mirror(size_t bytes) : host_(bytes, 0) { check(clover_malloc(&dev_, bytes), "clover_malloc"); dev_fresh_ = false; }
-    Mirror(const Mirror &o) : host_(o.host_.size()) {
+    Mirror(unsigned char *a, size_t a_bytes, unsigned char *b, size_t b_bytes)
+        : host_(a_bytes + b_bytes, 0), ext_a_(a), ext_b_(b), ext_a_bytes_(a_bytes) {
         check(clover_malloc(&dev_, host_.size()), "clover_malloc");
-        o.to_host();
-        host_ = o.host_;
+        dev_fresh_ = false;
+    }
+    Mirror(const Mirror &o) : host_(o.host_.size()) {        // deep copy (of a view too: the copy owns its bytes)
+        check(clover_malloc(&dev_, host_.size()), "clover_malloc");
+        host_.assign(o.host_ro(), o.host_ro() + o.host_.size());
         dev_fresh_ = false;
     }
     Mirror &operator=(const Mirror &) = delete;
-    ~Mirror() { if (dev_) clover_free(dev_); }
+    ~Mirror() {
+        if (is_view() && !host_fresh_) to_host();
+        if (dev_) clover_free(dev_);
+    }
+    bool is_view() const { return ext_a_ != nullptr; }
     size_t bytes() const { return host_.size(); }
     void to_host() const {
         if (!host_fresh_) {
             check(clover_copy_d2h(const_cast<unsigned char *>(host_.data()), dev_, host_.size(), nullptr), "clover_copy_d2h");
             check(clover_stream_sync(nullptr), "clover_stream_sync");
             host_fresh_ = true;
+            if (is_view()) push_view();
         }
     }
+    // view: write a kernel's result back into the caller's memory now
+    void flush_view() const { if (is_view()) to_host(); }
     // host pointer the caller may write through: the device copy becomes stale
     unsigned char *host_rw() { to_host(); dev_fresh_ = false; return host_.data(); }
-    const unsigned char *host_ro() const { to_host(); return host_.data(); }
+    // the same for the part that starts at `offset` (0 = values, value bytes = scales): a view hands out the caller's own regions
+    unsigned char *host_rw_part(size_t offset) {
+        if (!is_view()) return host_rw() + offset;
+        to_host();
+        dev_fresh_ = false;
+        return offset < ext_a_bytes_ ? ext_a_ + offset : ext_b_ + (offset - ext_a_bytes_);
+    }
+    // contiguous read-only image [values | scales]
+    const unsigned char *host_ro() const {
+        const bool host_was_authoritative = host_fresh_;
+        to_host();
+        if (is_view() && host_was_authoritative) pull_view();
+        return host_.data();
+    }
     // device pointer for a kernel that READS the buffer
     const void *dev_in() {
+        if (is_view()) {
+            if (host_fresh_) {                                 // the caller's memory is authoritative: always re-read it
+                pull_view();
+                check(clover_copy_h2d(dev_, host_.data(), host_.size(), nullptr), "clover_copy_h2d");
+            }
+            dev_fresh_ = true;
+            return dev_;
+        }
         if (!dev_fresh_) { check(clover_copy_h2d(dev_, host_.data(), host_.size(), nullptr), "clover_copy_h2d"); dev_fresh_ = true; }
         return dev_;
     }
@@ -128,12 +177,18 @@ public:
     explicit CloverQuantizedVector(uint64_t s)
         : length(s), length_pad(clover_b200_detail::pad128(s)), buf(length_pad * BITS / 8 + (length_pad / 64) * sizeof(float)) { init_padding(); }
     CloverQuantizedVector(const CloverVector32 &other) : CloverQuantizedVector(other.size()) { quantize(other); }
+    // borrowing view over the caller's host buffers, not freed here (include/CloverVector4.h:114-119, CloverVector8.h:104-109)
+    CloverQuantizedVector(uint64_t s, int8_t *values, float *scales)
+        : length(s), length_pad(clover_b200_detail::pad128(s)),
+          buf(reinterpret_cast<unsigned char *>(values), length_pad * BITS / 8, reinterpret_cast<unsigned char *>(scales),
+              (length_pad / 64) * sizeof(float)) {}
+    void sync_view() const { buf.flush_view(); }            // a kernel wrote this container: hand the bytes to a view's owner
     uint64_t size() const { return length; }
     uint64_t size_pad() const { return length_pad; }
     uint64_t getBitsLength() const { return BITS; }
     uint64_t getBytes() const { return value_bytes() + scale_count() * sizeof(float); }
-    int8_t *getData() const { return reinterpret_cast<int8_t *>(buf.host_rw()); }
-    float *getScales() const { return reinterpret_cast<float *>(buf.host_rw() + value_bytes()); }
+    int8_t *getData() const { return reinterpret_cast<int8_t *>(buf.host_rw_part(0)); }
+    float *getScales() const { return reinterpret_cast<float *>(buf.host_rw_part(value_bytes())); }
     const int8_t *device_values() const { return static_cast<const int8_t *>(buf.dev_in()); }
     const float *device_scales() const { return reinterpret_cast<const float *>(static_cast<const char *>(buf.dev_in()) + value_bytes()); }
     int8_t *device_values_out() { return static_cast<int8_t *>(buf.dev_out()); }
@@ -146,15 +201,15 @@ public:
         const int rc = BITS == 4 ? clover_v4_quantize(other.device_in(), length_pad, v, s, key_ptr(), nullptr)
                                  : clover_v8_quantize(other.device_in(), length_pad, v, s, key_ptr(), nullptr);
         clover_b200_detail::check(rc, "quantize");
+        sync_view();
     }
     void quantize_scalar(const CloverVector32 &o) { quantize(o); }
     void quantize_parallel(const CloverVector32 &o) { quantize(o); }
 
     // all values 0, all scales 1 (include/CloverVector4.h:306-318) - the start vector of the IHT / GD loops
     void clear() {
-        unsigned char *h = buf.host_rw();
-        std::memset(h, 0, value_bytes());
-        float *s = reinterpret_cast<float *>(h + value_bytes());
+        std::memset(getData(), 0, value_bytes());
+        float *s = getScales();
         for (uint64_t i = 0; i < scale_count(); ++i) s[i] = 1.0f;
     }
 
@@ -193,6 +248,7 @@ public:
         const int rc = BITS == 4 ? clover_v4_scale_and_add(u, su, v, sv, a, length_pad, r, sr, key_ptr(), nullptr)
                                  : clover_v8_scale_and_add(u, su, v, sv, a, length_pad, r, sr, key_ptr(), nullptr);
         clover_b200_detail::check(rc, "scaleAndAdd");
+        result.sync_view();
     }
     // hard thresholding in place: only the k largest magnitudes survive (include/CloverVector4.h:1913-1973, CloverVector8.h:1680-1740)
     void threshold(uint64_t k, int mode = CLOVER_THRESHOLD_AUTO) {
@@ -200,6 +256,7 @@ public:
         const int rc = BITS == 4 ? clover_v4_threshold(v, device_scales(), length, k, mode, nullptr)
                                  : clover_v8_threshold(v, device_scales(), length, k, mode, nullptr);
         clover_b200_detail::check(rc, "threshold");
+        sync_view();
     }
     void threshold_parallel(uint64_t k) { threshold(k); }
     void scaleAndAdd_scalar(const CloverQuantizedVector &o, float a) { scaleAndAdd(o, a); }
@@ -286,6 +343,7 @@ public:
         const int rc = BITS == 4 ? clover_m4_mvm(device_values(), device_scales(), rows, cols, productVector.device_values(), productVector.device_scales(), yv, ys, nullptr, key_ptr(), nullptr)
                                  : clover_m8_mvm(device_values(), device_scales(), rows, cols, productVector.device_values(), productVector.device_scales(), yv, ys, nullptr, key_ptr(), nullptr);
         clover_b200_detail::check(rc, "mvm");
+        resultVector.sync_view();
     }
     void mvm_scalar(const QVector &x, QVector &y) { mvm(x, y); }
     void mvm_parallel(const QVector &x, QVector &y) { mvm(x, y); }
@@ -334,6 +392,7 @@ public:
         float *ys = resultVector.device_scales_out();
         clover_b200_detail::check(clover_m4_mvm_v8(device_values(), device_scales(), rows, cols, productVector.device_values(),
                                                    productVector.device_scales(), yv, ys, nullptr, key_ptr(), nullptr), "mvm");
+        resultVector.sync_view();
     }
     void mvm_parallel(const CloverVector8 &x, CloverVector8 &y) { mvm(x, y); }
     using CloverQuantizedMatrix<4, CloverVector4>::mvm_parallel;
