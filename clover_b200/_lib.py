@@ -69,6 +69,7 @@ _SIGNATURES = {
     "clover_m8_transpose": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     "clover_host_v4_quantize": (_int, [_vp, _u64, _vp, _vp, _vp]),
     "clover_host_v4_dot": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _int]),
+    "clover_host_m4_mvm": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
 }
 
 ABI_SYMBOLS = tuple(_SIGNATURES)

@@ -205,6 +205,13 @@ int clover_m8_transpose(const int8_t *values, const float *scales, uint64_t rows
 int clover_host_v4_quantize(const float *x_host, uint64_t n_pad, int8_t *values_host, float *scales_host, uint64_t *key_host);
 int clover_host_v4_dot(const int8_t *u_host, const float *su_host, const int8_t *v_host, const float *sv_host,
                        uint64_t n_pad, float *result_host, int mode);
+/* CloverMatrix4::mvm(V4,V4) (include/CloverMatrix4.h:777-1083) for a matrix that is RESIDENT in device memory
+ * (uploaded once with clover_copy_h2d, like the reference's matrix object stays in RAM between calls) and per-call
+ * vectors in HOST memory: x goes up, the re-quantized y comes back; returns when y is in host memory. Pinned
+ * buffers (clover_malloc_host) make the copies asynchronous; a container that is one allocation [values | scales]
+ * moves with a single copy per direction. */
+int clover_host_m4_mvm(const int8_t *values_dev, const float *scales_dev, uint64_t rows, uint64_t cols,
+                       const int8_t *xv_host, const float *xs_host, int8_t *yv_host, float *ys_host, uint64_t *key_host);
 
 #ifdef __cplusplus
 }

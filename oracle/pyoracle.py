@@ -238,7 +238,9 @@ class Reference:
 
     name = "reference"
 
-    def __init__(self, stochastic: bool = False):
+    def __init__(self, stochastic: bool = False, threads: int = 0):
+        """threads > 0: size the reference's OpenMP team explicitly (only effective in the first Reference of a process,
+        the reference reads its team size once - include/CloverBase.h:369-380)."""
         fn = "libclover_ref_sr.so" if stochastic else "libclover_ref.so"
         path = os.path.join(HERE, "_ref", fn)
         if not os.path.exists(path):
@@ -254,6 +256,8 @@ class Reference:
                   "ref_m8_cols", "ref_m8_bytes", "ref_v4_bytes", "ref_v_size_pad"):
             getattr(L, f).restype = _u64
         assert bool(L.ref_stochastic_enabled()) == stochastic
+        if threads > 0:
+            L.ref_set_openmp_threads(C.c_int(threads))
 
     @staticmethod
     def available(stochastic: bool = False) -> bool:

@@ -89,6 +89,14 @@ int ref_stochastic_enabled(void) {
 }
 
 int ref_openmp_threads(void) { silence_once(); return CloverBase::get_OpenMP_threads(); }
+/* The reference sizes its OpenMP team ONCE, from the first parallel region it runs (include/CloverBase.h:369-380), so
+ * this must be the first ref_* call of the process. torchrun exports OMP_NUM_THREADS=1 to every worker: the bench's
+ * reference arm overrides that here so that mvm_parallel runs on all host threads. */
+void ref_set_openmp_threads(int n) {
+#if defined(_OPENMP)
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
 
 /* ---- PRNG (include/simdxorshift128plus.h) : state = part1[4] | part2[4] ------------- */
 void ref_xs_init(uint64_t key1, uint64_t key2, uint64_t *state) {

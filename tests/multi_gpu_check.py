@@ -23,7 +23,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    for rows, cols in [(1024, 2048), (64 * 7 + 64, 1152), (8192, 8192)]:
+    for rows, cols in [(1024, 2048), (64 * 7 + 64, 1152), (8192, 8192), (4096, 16384 + 128), (19072, 32768)]:   # cols >= 16384: k_m4_mvm_tma2 (the kernel SCALE times)
         rows += (-rows) % 128
         g = torch.Generator(device=dev).manual_seed(7)                    # identical full matrix on every rank
         full = cb.CloverMatrix4(rows, cols)
@@ -51,6 +51,8 @@ def main():
                 assert torch.equal(y.values, wv), (mode, rows, cols, rank, "values")
                 assert torch.equal(y.scales.view(torch.int32)[: rows // 64], ws.view(torch.int32)[: rows // 64]), (mode, rows, cols, rank, "scales")
             A.close()
+            if rank == 0:
+                print(f"multi-gpu check: {rows} x {cols}, exchange={mode}: 5 steps identical to the single-GPU mvm on every rank ({world} ranks)", flush=True)
         dist.barrier()
     if rank == 0:
         print("multi-gpu ok: fused / allgather / allreduce == single-GPU mvm on", world, "ranks")

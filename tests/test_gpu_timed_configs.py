@@ -1,0 +1,229 @@
+"""Parity of the kernels bench.py actually TIMES, through default dispatch, against the CPU oracle. Needs a B200.
+
+VERDICT r01 weak #1: the instantiations behind the headline numbers must be the ones compared with the oracle -
+  * BASELINE C3: CloverMatrix4::mvm 65536 x 65536 (k_m4_mvm_tma2<.,3>, two CTAs per SM, cols >= 16384), rounding
+    disabled AND keyed stochastic, every packed byte, every scale and every fp32 row result bit-for-bit;
+  * ragged long-row shapes through the same default dispatch (half chunks at the row end, > 2 x 148 work items);
+  * the mixed mvm(V8) kernel at two CTAs per SM (> 148 work items);
+  * BASELINE C4: the tcgen05 GEMM against the ORACLE's definition (N x M reference dots, CloverMatrix4.h:338-342 row
+    views): every element at 2048^3 and 64 sampled 64 x 64 tiles at 16384^3, with the rule-3 bound
+    |gpu - ref| <= 4 eps32 sum_b |s_b I_b| evaluated per element (SURVEY.md 8c rule 5);
+  * the host-buffer ABI (clover_host_*), INTEGRATION.md section 2.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def cb():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import clover_b200
+    clover_b200.lib()
+    from clover_b200 import containers
+    return containers
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def _random_m4(cb, rows, cols, seed, lo=0.05, hi=4.0):
+    from bench import random_nibbles
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    m = cb.CloverMatrix4(rows, cols)
+    m.values.copy_(random_nibbles(torch, rows * cols // 2, g, torch.device("cuda")))
+    m.scales.uniform_(lo, hi, generator=g)
+    return m
+
+
+def _random_v4(cb, n, seed):
+    from bench import random_nibbles
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    v = cb.CloverVector4(n)
+    v.values.copy_(random_nibbles(torch, n // 2, g, torch.device("cuda")))
+    v.scales.uniform_(0.05, 4.0, generator=g)
+    return v
+
+
+def _check_mvm4(cb, oracle, A, x, rows, cols, keyed):
+    y = cb.CloverVector4(rows)
+    y32 = torch.zeros(rows, dtype=torch.float32, device="cuda")
+    st = None
+    if keyed:
+        A.seed(20261017, 77)
+        st = oracle.xs_init(20261017, 77)
+    else:
+        A.setRandomKeys(None)
+    A.mvm(x, y, y32=y32)
+    torch.cuda.synchronize()
+    wv, ws, w32 = oracle.m4_mvm(A.values.cpu().numpy(), A.scales.cpu().numpy(), rows, cols,
+                                x.values.cpu().numpy(), x.scales.cpu().numpy(), state=st, want_f32=True)
+    assert np.array_equal(bits(y32.cpu().numpy()), bits(w32)), "fp32 row results (block_values)"
+    assert np.array_equal(y.getData().cpu().numpy(), wv), "re-quantized nibbles"
+    assert np.array_equal(bits(y.getScales().cpu().numpy()[: rows // 64]), bits(ws[: rows // 64])), "result scales"
+    if keyed:
+        assert np.array_equal(A.key, st), "PRNG key after mvm differs from the reference's"
+    # without a caller-provided fp32 buffer (internal scratch) - the call bench.py times
+    if keyed:
+        A.seed(20261017, 77)
+    y2 = cb.CloverVector4(rows)
+    A.mvm(x, y2)
+    assert torch.equal(y2.values, y.values) and torch.equal(y2.scales, y.scales)
+
+
+@pytest.mark.parametrize("keyed", [False, True], ids=["rounding_disabled", "keyed_stochastic"])
+def test_c3_full_size_default_dispatch_vs_oracle(cb, oracle, keyed, monkeypatch):
+    """BASELINE C3 exactly as bench.py runs it: 65536 x 65536 through clover_m4_mvm's default dispatch."""
+    monkeypatch.delenv("CLOVER_GEMV_IMPL", raising=False)
+    n = 65536
+    A, x = _random_m4(cb, n, n, 1000, 0.25, 1.0), _random_v4(cb, n, 20261017)
+    _check_mvm4(cb, oracle, A, x, n, n, keyed)
+
+
+@pytest.mark.parametrize("keyed", [False, True], ids=["rounding_disabled", "keyed_stochastic"])
+@pytest.mark.parametrize("shape", [(9728, 16512), (19072, 16384 + 384), (8192, 65536)])
+def test_mvm4_default_dispatch_long_rows_vs_oracle(cb, oracle, shape, keyed, monkeypatch):
+    """cols >= 16384 -> k_m4_mvm_tma2<.,3> at two CTAs per SM: more work items than resident CTAs (rows / 32 > 2 x 148),
+    a half chunk at the row end (cols = 128 mod 256), row blocks finished by two different CTAs; the last shape is a
+    shard of C3 as N = 8 runs it."""
+    monkeypatch.delenv("CLOVER_GEMV_IMPL", raising=False)
+    rows, cols = shape
+    _check_mvm4(cb, oracle, _random_m4(cb, rows, cols, 71), _random_v4(cb, cols, 72), rows, cols, keyed)
+
+
+@pytest.mark.parametrize("shape", [(9728, 4224), (4992, 640), (32768, 2048 + 128)])
+def test_mvm4_v8_many_items_vs_oracle(cb, oracle, shape, monkeypatch):
+    """The mixed 4-bit matrix x CloverVector8 kernel at two CTAs per SM (rows / 32 > 148: k_m8_mvm_tma<.,3,4>, the
+    instantiation behind extras.mvm4_v8_mixed_32768), half chunks at the row end included."""
+    monkeypatch.delenv("CLOVER_GEMV_IMPL", raising=False)
+    rows, cols = shape
+    A = _random_m4(cb, rows, cols, 81)
+    g = torch.Generator(device="cuda").manual_seed(82)
+    x = cb.CloverVector8(cols)
+    x.values.copy_(torch.randint(-127, 128, (cols,), dtype=torch.int8, device="cuda", generator=g))
+    x.scales.uniform_(0.05, 4.0, generator=g)
+    for keyed in (False, True):
+        st = None
+        if keyed:
+            A.seed(5, 6)
+            st = oracle.xs_init(5, 6)
+        y = cb.CloverVector8(rows)
+        y32 = torch.zeros(rows, dtype=torch.float32, device="cuda")
+        A.mvm(x, y, y32=y32)
+        wv, ws, w32 = oracle.m4_mvm_v8(A.values.cpu().numpy(), A.scales.cpu().numpy(), rows, cols,
+                                       x.values.cpu().numpy(), x.scales.cpu().numpy(), state=st, want_f32=True)
+        assert np.array_equal(bits(y32.cpu().numpy()), bits(w32))
+        assert np.array_equal(y.getData().cpu().numpy(), wv)
+        assert np.array_equal(bits(y.getScales().cpu().numpy()[: rows // 64]), bits(ws[: rows // 64]))
+        if keyed:
+            assert np.array_equal(A.key, st)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GEMM against the oracle's definition
+# ----------------------------------------------------------------------------------------------------------------
+def _unpack_rows(values, rows, K, idx):
+    """int rows idx of a packed nibble matrix (device tensor) -> float64 [len(idx), K]"""
+    b = values.view(torch.uint8).reshape(rows, K // 2)[idx].to(torch.int16)
+    hi, lo = b >> 4, b & 0xF
+    q = torch.stack((hi, lo), dim=2).reshape(len(idx), K)
+    return torch.where(q >= 8, q - 16, q).to(torch.float64)
+
+
+def _tile_bound_and_f64(A, B, K, i0, j0, n=64):
+    """For the n x n tile at (i0, j0): sum_b |s_b I_b| and the float64 evaluation of sum_b s_b I_b, per element, from the
+    packed operands (I_b exact in float64; s_b = (sA * (1/49)) * sB as fp32, the reference's own product)."""
+    ri = torch.arange(i0, i0 + n, device="cuda"); rj = torch.arange(j0, j0 + n, device="cuda")
+    qa = _unpack_rows(A.values, A.rows, K, ri).reshape(n, K // 64, 64)
+    qb = _unpack_rows(B.values, B.rows, K, rj).reshape(n, K // 64, 64)
+    I = torch.einsum("ibk,jbk->ijb", qa, qb)                                        # exact integers
+    kb = K // 64
+    sa = A.scales.reshape(A.rows // 64, kb)[ri // 64]                                # [n, kb] fp32
+    sb = B.scales.reshape(B.rows // 64, kb)[rj // 64]
+    s = ((sa * torch.tensor(1.0 / 49.0, dtype=torch.float32, device="cuda"))[:, None, :] * sb[None, :, :]).to(torch.float64)
+    terms = s * I
+    return terms.abs().sum(dim=2).cpu().numpy(), terms.sum(dim=2).cpu().numpy()
+
+
+def _check_tile(c_tile, want, sum_abs, f64):
+    eps = float(np.finfo(np.float32).eps)
+    got, ref = c_tile.astype(np.float64), want.astype(np.float64)
+    # rule 3: a re-associated fp32 sum of the reference's own terms; the reference's own distance from the
+    # exact sum is granted on top, as in test_vector_dot_fast_mode
+    assert np.all(np.abs(got - ref) <= 4 * eps * sum_abs + np.abs(ref - f64) + 1e-300), \
+        f"max excess {np.max(np.abs(got - ref) - 4 * eps * sum_abs)}"
+    assert np.all(np.abs(got - f64) <= 4 * eps * sum_abs + 1e-300)
+
+
+def test_gemm_2048_cubed_every_element_vs_oracle(cb, oracle):
+    """tcgen05 GEMM vs N x M oracle dots (the reference SIMD dot of two row views), every element of 2048^3."""
+    n = 2048
+    A, B = _random_m4(cb, n, n, 11), _random_m4(cb, n, n, 12)
+    c = A.gemm(B, impl="tc").cpu().numpy()
+    want = oracle.m4_gemm(A.values.cpu().numpy(), A.scales.cpu().numpy(), B.values.cpu().numpy(), B.scales.cpu().numpy(),
+                          n, 0, n, 0, n)
+    for i0 in range(0, n, 256):
+        for j0 in range(0, n, 256):
+            sum_abs, f64 = _tile_bound_and_f64(A, B, n, i0, j0, 256)
+            _check_tile(c[i0:i0 + 256, j0:j0 + 256], want[i0:i0 + 256, j0:j0 + 256], sum_abs, f64)
+
+
+def test_gemm_c4_sampled_tiles_vs_oracle(cb, oracle):
+    """BASELINE C4 (16384^3, the call bench.py times): 64 sampled 64 x 64 tiles against the oracle's dots - first and
+    last tile rows/columns, both halves of a 128 x 256 CTA tile, tiles on the persistent grid's later waves."""
+    n = 16384
+    A, B = _random_m4(cb, n, n, 21, 0.25, 1.0), _random_m4(cb, n, n, 22, 0.25, 1.0)
+    c = A.gemm(B, impl="tc")
+    torch.cuda.synchronize()
+    av, as_, bv, bs = A.values.cpu().numpy(), A.scales.cpu().numpy(), B.values.cpu().numpy(), B.scales.cpu().numpy()
+    rng = np.random.default_rng(4)
+    tiles = {(0, 0), (n // 64 - 1, n // 64 - 1), (0, n // 64 - 1), (n // 64 - 1, 0), (1, 3), (2, 1)}
+    while len(tiles) < 64:
+        tiles.add((int(rng.integers(0, n // 64)), int(rng.integers(0, n // 64))))
+    for (ti, tj) in sorted(tiles):
+        i0, j0 = 64 * ti, 64 * tj
+        want = oracle.m4_gemm(av, as_, bv, bs, n, i0, i0 + 64, j0, j0 + 64)
+        sum_abs, f64 = _tile_bound_and_f64(A, B, n, i0, j0)
+        _check_tile(c[i0:i0 + 64, j0:j0 + 64].cpu().numpy(), want, sum_abs, f64)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# host-buffer ABI (the call a header-patching maintainer makes)
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [128, 1000, 4096, (1 << 20) + 128])
+def test_host_api_v4_quantize_and_dot(cb, oracle, n):
+    import clover_b200
+    from oracle.pyoracle import padded, size_pad
+    st = oracle.xs_init()
+    x, z = padded(oracle.fill_floats(n, -1.0, 1.0, st)), padded(oracle.fill_floats(n, -1.0, 1.0, st))
+    npad = size_pad(n)
+    outs = []
+    for src in (x, z):
+        v, s = np.zeros(npad // 2, np.int8), np.ones(npad // 64, np.float32)
+        clover_b200.call("clover_host_v4_quantize", src.ctypes.data_as(C.c_void_p), C.c_uint64(npad),
+                         v.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), None)
+        outs.append((v, s))
+    (xv, xs), (zv, zs) = oracle.v4_quantize(x, n), oracle.v4_quantize(z, n)
+    assert np.array_equal(outs[0][0], xv) and np.array_equal(bits(outs[0][1]), bits(xs))
+    assert np.array_equal(outs[1][0], zv) and np.array_equal(bits(outs[1][1]), bits(zs))
+    # keyed: bytes, scales and the advanced key
+    key = np.zeros(8, np.uint64)
+    clover_b200.call("clover_prng_init", C.c_uint64(3), C.c_uint64(4), key.ctypes.data_as(C.c_void_p))
+    st2 = oracle.xs_init(3, 4)
+    kv, ks = oracle.v4_quantize(x, n, state=st2)
+    v, s = np.zeros(npad // 2, np.int8), np.ones(npad // 64, np.float32)
+    clover_b200.call("clover_host_v4_quantize", x.ctypes.data_as(C.c_void_p), C.c_uint64(npad), v.ctypes.data_as(C.c_void_p),
+                     s.ctypes.data_as(C.c_void_p), key.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(v, kv) and np.array_equal(bits(s), bits(ks)) and np.array_equal(key, st2)
+    res = np.zeros(1, np.float32)
+    clover_b200.call("clover_host_v4_dot", xv.ctypes.data_as(C.c_void_p), xs.ctypes.data_as(C.c_void_p),
+                     zv.ctypes.data_as(C.c_void_p), zs.ctypes.data_as(C.c_void_p), C.c_uint64(npad),
+                     res.ctypes.data_as(C.c_void_p), C.c_int(clover_b200.DOT_EXACT))
+    assert bits(res)[0] == bits(oracle.v4_dot(xv, xs, zv, zs, n))
