@@ -42,6 +42,8 @@ _SIGNATURES = {
     "clover_prng_init": (_int, [_u64, _u64, _vp]),
     "clover_prng_next": (_int, [_vp, _vp]),
     "clover_prng_skip": (_int, [_vp, _u64]),
+    "clover_v32_set_random_floats": (_int, [_vp, _u64, C.c_float, C.c_float, _vp, _vp]),
+    "clover_v32_set_random_integers": (_int, [_vp, _u64, C.c_float, C.c_float, _vp, _vp]),
     "clover_v4_quantize": (_int, [_vp, _u64, _vp, _vp, _vp, _vp]),
     "clover_v4_restore": (_int, [_vp, _vp, _u64, _vp, _vp]),
     "clover_v4_dot": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _int, _vp]),
@@ -56,6 +58,9 @@ _SIGNATURES = {
     "clover_m4_mvm": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "clover_m4_mvm_v8": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "clover_m4_mvm_f32": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp]),
+    "clover_m4_restore": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
+    "clover_m8_restore": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
+    "clover_m8_mvm_f32": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     "clover_m4_mvm_shard": (_int, [_vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "clover_m4_mvm_shard_fused": (_int, [_vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, C.c_uint32, _vp, _vp]),
     "clover_v4_requantize_mvm": (_int, [_vp, _u64, _vp, _vp, _vp, _vp]),

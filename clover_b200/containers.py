@@ -76,9 +76,42 @@ class _Keyed:
     def _key_ptr(self):
         return None if self.key is None else self.key.ctypes.data_as(C.c_void_p)
 
+    def _generator_key(self, key):
+        """The key pair a generator call consumes: an explicit uint64[8] (advanced in place, like the reference's
+        `__m256i &key1, &key2` arguments) or the object's own key - seeded from the OS on first use, as the reference
+        seeds every object from RDRAND (include/CloverRandom.h:96-114)."""
+        if key is not None:
+            if not (isinstance(key, np.ndarray) and key.dtype == np.uint64 and key.size == 8 and key.flags.c_contiguous):
+                raise ValueError("a key is a contiguous uint64[8] array = random_key1[4] | random_key2[4]")
+            return key
+        if self.key is None:
+            import os
+            k = np.frombuffer(os.urandom(16), dtype=np.uint64)
+            self.seed(int(k[0]) | 1, int(k[1]) | 1)
+        return self.key
 
-class CloverVector32(_Keyed):
+
+class _Generators(_Keyed):
+    """setRandomFloats / setRandomInteger of CloverVector32 (include/CloverVector32.h:751-783, :712-744) and
+    CloverMatrix32 (include/CloverMatrix32.h:252-323), run on the device, bit-identical to the reference's stream."""
+
+    def _fill(self, fn, lo, hi, key):
+        k = self._generator_key(key)
+        call(fn, _ptr(self.values), C.c_uint64(self._generator_length()), C.c_float(lo), C.c_float(hi),
+             k.ctypes.data_as(C.c_void_p), _stream())
+
+    def setRandomFloats(self, min_value: float, max_value: float, key=None) -> None:
+        self._fill("clover_v32_set_random_floats", min_value, max_value, key)
+
+    def setRandomInteger(self, min_value: float, max_value: float, key=None) -> None:
+        self._fill("clover_v32_set_random_integers", min_value, max_value, key)
+
+
+class CloverVector32(_Generators):
     """fp32 input/output container (include/CloverVector32.h:53-70): length padded to x128, pad zeroed."""
+
+    def _generator_length(self):
+        return self.length               # the generators fill `length` elements, the pad stays 0 (:757)
 
     def __init__(self, n: int, data=None, device=None):
         self.length = int(n)
@@ -208,8 +241,11 @@ class CloverVector8(_QVector):
         return float(np.float32(self.getBits(pos)) * np.float32(self.scales[pos >> 6].item()) / np.float32(127.0))
 
 
-class CloverMatrix32:
+class CloverMatrix32(_Generators):
     """fp32 matrix, rows and cols padded to x128 (include/CloverMatrix.h:48-50, CloverMatrix32.h:43-50)."""
+
+    def _generator_length(self):
+        return self.rows * self.cols     # size() of the PADDED matrix: the pad is filled too (CloverMatrix32.h:254, :294)
 
     def __init__(self, rows: int, cols: int, data=None, device=None):
         self.rows, self.cols = size_pad(int(rows)), size_pad(int(cols))
@@ -261,11 +297,10 @@ class _QMatrix(_Keyed):
     def mvm(self, productVector, resultVector, y32=None) -> None:
         """y = A x. (V4,V4)/(V8,V8): include/CloverMatrix4.h:777, CloverMatrix8.h:1002; (V32,V32): :1451."""
         if isinstance(productVector, CloverVector32):
-            if self.BITS != 4:
-                raise NotImplementedError("mvm(V32,V32) is on the hot path for CloverMatrix4 only")
+            # fp32 vectors: include/CloverMatrix4.h:1451-1547, include/CloverMatrix8.h:558-661
             if productVector.size() != self.cols or resultVector.size_pad() < self.rows:
                 raise CloverSizeError("MVM can not be performed.")
-            call("clover_m4_mvm_f32", _ptr(self.values), _ptr(self.scales), C.c_uint64(self.rows), C.c_uint64(self.cols),
+            call(f"clover_m{self.BITS}_mvm_f32", _ptr(self.values), _ptr(self.scales), C.c_uint64(self.rows), C.c_uint64(self.cols),
                  _ptr(productVector.values), _ptr(resultVector.values), _stream())
             return
         if self.BITS == 4 and isinstance(productVector, CloverVector8) and isinstance(resultVector, CloverVector8):
@@ -284,6 +319,16 @@ class _QMatrix(_Keyed):
         call(f"clover_m{self.BITS}_mvm", _ptr(self.values), _ptr(self.scales), C.c_uint64(self.rows), C.c_uint64(self.cols),
              _ptr(productVector.values), _ptr(productVector.scales), _ptr(resultVector.values), _ptr(resultVector.scales),
              _ptr(y32), self._key_ptr(), _stream())
+
+    def restore(self, other: CloverMatrix32) -> None:
+        """other = the fp32 values this matrix represents (include/CloverMatrix4.h:266-301; 8-bit: get(i, j),
+        include/CloverMatrix8.h:117-129)."""
+        if other.getRows() != self.rows or other.getCols() != self.cols:
+            raise CloverSizeError("Matrices do not have the same size.")
+        call(f"clover_m{self.BITS}_restore", _ptr(self.values), _ptr(self.scales), C.c_uint64(self.rows), C.c_uint64(self.cols),
+             _ptr(other.values), _stream())
+
+    restore_scalar = restore
 
     def transpose(self, other) -> None:
         """other(j, i) = self(i, j), scales included (include/CloverMatrix4.h:1549-1663, CloverMatrix8.h:1359-1385)."""

@@ -2,7 +2,7 @@
 //
 //   quantize   include/CloverMatrix4.h:512-766, include/CloverMatrix8.h:203-479
 //   mvm(V4,V4) include/CloverMatrix4.h:777-1083      mvm(V8,V8) include/CloverMatrix8.h:1002-1298
-//   mvm(V32)   include/CloverMatrix4.h:1451-1547
+//   (mvm with fp32 vectors: mvm_f32_kernels.cu)
 //
 // The GEMVs are HBM-bound (the matrix is read exactly once: 0.5 B/elem + scales) and reproduce the
 // reference's fp32 accumulation ORDER, so the fp32 row results and therefore the re-quantized
@@ -982,78 +982,6 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
     }
 }
 
-// =============================================================================================
-// mvm(V32,V32): 4-bit matrix, fp32 vectors (CloverMatrix4.h:1451-1547). One warp per row; lane 8k+l
-// is the reference's chain (accumulator k, AVX lane l): per block element 8k+l, then 32+8k+l.
-// =============================================================================================
-__global__ void __launch_bounds__(256)
-k_m4_mvm_f32(const uint32_t *__restrict__ values, const float *__restrict__ scales, uint64_t rows, uint64_t cols,
-             const float *__restrict__ x, float *__restrict__ y) {
-    const int lane = threadIdx.x & 31, k = lane >> 3, l = lane & 7;
-    const uint64_t hb = cols >> 6, wpr = cols >> 3;
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    // nibble l of a word: byte l/2, high nibble when l is even; float(q) without I2F: (nibble ^ 8) spliced under the
-    // bits of 1.5 * 2^23 is 12582912 + q + 8
-    const int sh = 8 * (l >> 1) + ((l & 1) ? 0 : 4);
-    auto nib_float = [&](uint32_t w) { return __fadd_rn(__uint_as_float(((w >> sh) & 0xFu) ^ 0x4B400008u), -12582920.0f); };
-    // A warp owns TWO consecutive rows (rows is a multiple of 128, so both lie in the same 64-row tile): the x loads and
-    // the scale broadcasts are shared, the two fp32 chains are independent.
-    for (uint64_t r = 2 * warp; r < rows; r += 2 * nwarps) {
-        const uint32_t *row0 = values + r * wpr, *row1 = row0 + wpr;
-        const float *su = scales + (r >> 6) * hb;
-        float acc0 = 0.f, acc1 = 0.f;
-        // The rows are streamed in chunks of 8 blocks = 64 words: lane i holds words i and 32 + i (two coalesced 128-byte
-        // loads per row), the chunk after next is already in flight (the kernel was bound by DRAM latency when every lane
-        // fetched its own words block by block: 128 B in flight per warp), and a lane gets its words (block j, word k and
-        // 4 + k) by shuffle from lane (8 j + k) % 32.
-        const uint64_t nchunks = (hb + 7) >> 3;
-        auto load_chunk = [&](const uint32_t *row, uint64_t c, uint32_t &lo, uint32_t &hi) {
-            const uint64_t w = c * 64 + lane;
-            lo = (c < nchunks && w < wpr) ? ldg_stream(row + w) : 0u;
-            hi = (c < nchunks && w + 32 < wpr) ? ldg_stream(row + w + 32) : 0u;
-        };
-        uint32_t a_lo0, a_hi0, a_lo1, a_hi1, b_lo0, b_hi0, b_lo1, b_hi1;
-        load_chunk(row0, 0, a_lo0, a_hi0); load_chunk(row1, 0, b_lo0, b_hi0);
-        load_chunk(row0, 1, a_lo1, a_hi1); load_chunk(row1, 1, b_lo1, b_hi1);
-        float sv = 0.f;
-        for (uint64_t c = 0; c < nchunks; ++c) {
-            uint32_t a_lo2, a_hi2, b_lo2, b_hi2;
-            load_chunk(row0, c + 2, a_lo2, a_hi2); load_chunk(row1, c + 2, b_lo2, b_hi2);
-            if ((c & 3) == 0) {
-                // lane j owns s = scale / 7.0f (IEEE divide, :1488) of block 8c + j: one divide per 32 blocks and lane
-                const uint64_t bl = 8 * c + lane < hb ? 8 * c + lane : hb - 1;
-                sv = __fdiv_rn(__ldg(su + bl), 7.0f);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint64_t blk = 8 * c + j;
-                // shuffles are executed by the whole warp even for the blocks beyond the row (zero words, x not read)
-                const float s = __shfl_sync(0xFFFFFFFFu, sv, 8 * (int)(c & 3) + j);
-                const uint32_t sa = j < 4 ? a_lo0 : a_hi0, sb = j < 4 ? b_lo0 : b_hi0;
-                const uint32_t wa0 = __shfl_sync(0xFFFFFFFFu, sa, (8 * j + k) & 31), wb0 = __shfl_sync(0xFFFFFFFFu, sa, (8 * j + 4 + k) & 31);
-                const uint32_t wa1 = __shfl_sync(0xFFFFFFFFu, sb, (8 * j + k) & 31), wb1 = __shfl_sync(0xFFFFFFFFu, sb, (8 * j + 4 + k) & 31);
-                if (blk < hb) {
-                    const float xa = __ldg(x + blk * 64 + lane), xb = __ldg(x + blk * 64 + 32 + lane);
-                    acc0 = __fmaf_rn(xa, __fmul_rn(nib_float(wa0), s), acc0);             // element 8k+l      (:1529-1532)
-                    acc0 = __fmaf_rn(xb, __fmul_rn(nib_float(wb0), s), acc0);             // element 32+8k+l   (:1534-1537)
-                    acc1 = __fmaf_rn(xa, __fmul_rn(nib_float(wa1), s), acc1);
-                    acc1 = __fmaf_rn(xb, __fmul_rn(nib_float(wb1), s), acc1);
-                }
-            }
-            a_lo0 = a_lo1; a_hi0 = a_hi1; a_lo1 = a_lo2; a_hi1 = a_hi2;
-            b_lo0 = b_lo1; b_hi0 = b_hi1; b_lo1 = b_lo2; b_hi1 = b_hi2;
-        }
-        acc0 = __fadd_rn(acc0, __shfl_xor_sync(0xFFFFFFFFu, acc0, 8));            // acc_1+acc_2 | acc_3+acc_4
-        acc0 = __fadd_rn(acc0, __shfl_xor_sync(0xFFFFFFFFu, acc0, 16));           // sum_1 + sum_2
-        acc0 = hadd8_butterfly(acc0);
-        acc1 = __fadd_rn(acc1, __shfl_xor_sync(0xFFFFFFFFu, acc1, 8));
-        acc1 = __fadd_rn(acc1, __shfl_xor_sync(0xFFFFFFFFu, acc1, 16));
-        acc1 = hadd8_butterfly(acc1);
-        if (lane == 0) { y[r] = acc0; y[r + 1] = acc1; }
-    }
-}
-
 // re-quantize a full fp32 vector like the mvm tail (used after the multi-GPU exchange)
 template <int BITS, bool STOCH>
 __global__ void __launch_bounds__(64)
@@ -1353,18 +1281,6 @@ int clover_v4_requantize_mvm(const float *y32, uint64_t rows, int8_t *yv, float 
     }
     count_launch();
     return launch_status("k_requantize_mvm");
-}
-
-int clover_m4_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
-                      const float *x32, float *y32, void *stream) {
-    CLOVER_REQUIRE(values && scales && x32 && y32, CLOVER_ERR_INVALID, "null pointer");
-    CLOVER_CHECK_MAT(rows, cols);
-    if (rows == 0 || cols == 0) return CLOVER_OK;
-    const uint64_t want = (rows / 2 + 7) / 8, cap = (uint64_t)sm_count() * 8;       // a warp per pair of rows
-    k_m4_mvm_f32<<<(unsigned)(want > cap ? cap : want), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const uint32_t *>(values), scales, rows, cols, x32, y32);
-    count_launch();
-    return launch_status("k_m4_mvm_f32");
 }
 
 }  // extern "C"

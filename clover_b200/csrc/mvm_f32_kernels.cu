@@ -1,0 +1,302 @@
+// mvm_f32_kernels.cu - mvm with fp32 vectors: CloverMatrix4::mvm(V32,V32) and CloverMatrix8::mvm(V32,V32).
+//
+//   4-bit  include/CloverMatrix4.h:1451-1547:  s = su[b] / 7.0f;   f = float(q) * s;   acc = fma(x, f, acc)
+//   8-bit  include/CloverMatrix8.h:558-661:    s = su[b] / 127.0f; t = x * s;          acc = fma(t, float(q), acc)
+//
+// Both run 32 fp32 chains per row: accumulator k = 0..3, AVX lane l = 0..7; per block chain (k, l) takes element
+// 8k+l and then element 32+8k+l; the row result is ((acc0+acc1)+(acc2+acc3)) folded by the hadd tree of
+// include/CloverBase.h:149-157. Every element costs an int->float, a rounded multiply and an fma in that order, so
+// these kernels are bound by the CUDA cores' issue rate, not by HBM; the design minimises instructions per element:
+//
+//   * thread = one matrix row, warp = 32 consecutive rows (one work item), all 32 chains of the row in registers
+//     (16 packed f32x2 accumulators): the final reduction is thread-local, no shuffles anywhere in the loop;
+//   * the matrix streams through per-warp TMA rings: cp.async.bulk.tensor boxes of 32 rows x 128 bytes with the
+//     128-byte swizzle (a quarter warp's 16-byte loads fall into 8 different 16-byte bank groups), the matching slice
+//     of x by a 1D bulk copy into the same stage; the warp's own lane 0 refills a stage as soon as the warp has
+//     consumed it (no producer warp, no empty-barriers);
+//   * int -> float without I2F: the biased nibble / byte is spliced under the bits of 1.5 * 2^23 by one PRMT and the
+//     bias removed by a packed add; multiply and fma are packed too (add/mul/fma.rn.f32x2 round each half like the
+//     scalar instruction) - 2.9 (4-bit) / 3.1 (8-bit) instructions per element;
+//   * x is read from shared memory as warp-wide broadcasts (every row needs the same 64 floats per block).
+//
+// k_mvm_f32_simple (one warp per row, plain loads) is the same arithmetic for unaligned operands and the cross-check.
+#include <stdlib.h>
+#include <string.h>
+#include "async_copy.cuh"
+#include "common.cuh"
+#include "runtime.cuh"
+
+namespace clover {
+
+constexpr int kF32Warps = 8;            // warps (= concurrent work items) per CTA
+constexpr int kF32Stages = 4;           // ring depth per warp
+constexpr int kF32StageBytes = 5120;    // 32 rows x 128 B + up to 256 floats of x, a multiple of 1024 (swizzle atom)
+
+struct __align__(1024) F32Stage {
+    uint8_t rows[32 * 128];
+    float x[256];
+};
+static_assert(sizeof(F32Stage) == kF32StageBytes, "stage size");
+
+constexpr int kF32SmemBytes = kF32Warps * kF32Stages * kF32StageBytes + kF32Warps * kF32Stages * 8 + 1024 /* alignment slack */;
+
+__device__ __forceinline__ uint64_t pack2(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) { return pack2(__float_as_uint(lo), __float_as_uint(hi)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ void fma2(uint64_t &acc, uint64_t a, uint64_t b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+__device__ __forceinline__ uint32_t prmt_f32(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ float lo_f(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi_f(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+
+constexpr uint32_t kMagic = 0x4B400000u;                 // 1.5 * 2^23: as_float(kMagic | u) = 12582912 + u for u < 2^22
+
+// Constants that must live in REGISTERS: SASS PRMT / LOP3 take one immediate only. With the magic bits as an immediate
+// ptxas keeps the PRMT selectors in uniform registers and re-materialises each one with an extra IMAD.U32 per PRMT;
+// with two immediates a mask-and-bias costs two LOP3. `zero` is a kernel argument the compiler cannot fold (always 0 at run time).
+struct RegConsts { uint32_t magic, m0f, c08, c80; };
+__device__ __forceinline__ RegConsts reg_consts(uint32_t zero) {        // zero: a kernel ARGUMENT that is always 0
+    return {kMagic | zero, 0x0F0F0F0Fu | zero, 0x08080808u | zero, 0x80808080u | zero};
+}
+__device__ __forceinline__ uint32_t and_xor(uint32_t a, uint32_t m, uint32_t c) {      // (a & m) ^ c in one LOP3
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(d) : "r"(a), "r"(m), "r"(c));
+    return d;
+}
+template <int P> __device__ __forceinline__ uint32_t splice(uint32_t bytes, uint32_t magic) {   // [byte P of bytes, magic bytes 1..3]
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(bytes), "r"(magic), "n"(0x7650 + P));
+    return d;
+}
+
+// one 32-bit word of the 4-bit matrix (elements e..e+7 of a row: byte i = element 2i in the HIGH nibble, 2i+1 in the
+// low one) against x[e..e+7]: acc[p] += x2[p] * ((float(q2[p])) * s), p = element pair (2p, 2p+1)
+__device__ __forceinline__ void word4(uint32_t w, const float4 xa, const float4 xb, uint64_t ss, uint64_t neg, const RegConsts &rc,
+                                      uint64_t *acc) {
+    const uint32_t lo = and_xor(w, rc.m0f, rc.c08);                  // byte p: q + 8 of element 2p+1
+    const uint32_t hi = and_xor(w >> 4, rc.m0f, rc.c08);             // byte p: q + 8 of element 2p
+    // f = float(q) * s (:1520-1527), acc = fma(x, f, acc) (:1529-1537)
+    fma2(acc[0], pack2f(xa.x, xa.y), mul2(add2(pack2(splice<0>(hi, rc.magic), splice<0>(lo, rc.magic)), neg), ss));
+    fma2(acc[1], pack2f(xa.z, xa.w), mul2(add2(pack2(splice<1>(hi, rc.magic), splice<1>(lo, rc.magic)), neg), ss));
+    fma2(acc[2], pack2f(xb.x, xb.y), mul2(add2(pack2(splice<2>(hi, rc.magic), splice<2>(lo, rc.magic)), neg), ss));
+    fma2(acc[3], pack2f(xb.z, xb.w), mul2(add2(pack2(splice<3>(hi, rc.magic), splice<3>(lo, rc.magic)), neg), ss));
+}
+// one 32-bit word of the 8-bit matrix (elements e..e+3) against x[e..e+3]: acc[p] += (x2[p] * s) * float(q2[p])
+__device__ __forceinline__ void word8(uint32_t w, const float4 xv, uint64_t ss, uint64_t neg, const RegConsts &rc, uint64_t *acc) {
+    const uint32_t u = w ^ rc.c80;                                    // byte i: q + 128
+    // t = x * s (:632-639), acc = fma(t, float(q), acc) (:641-649)
+    fma2(acc[0], mul2(pack2f(xv.x, xv.y), ss), add2(pack2(splice<0>(u, rc.magic), splice<1>(u, rc.magic)), neg));
+    fma2(acc[1], mul2(pack2f(xv.z, xv.w), ss), add2(pack2(splice<2>(u, rc.magic), splice<3>(u, rc.magic)), neg));
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+template <int MBITS>
+__global__ void __launch_bounds__(kF32Warps * 32, 1)
+k_mvm_f32_ring(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows, uint64_t cols,
+               const float *__restrict__ x, float *__restrict__ y, uint32_t zero) {
+    extern __shared__ uint8_t smem_raw_f32[];
+    constexpr int kBPC = MBITS == 4 ? 4 : 2;                          // blocks of 64 columns per 128-byte chunk
+    constexpr float kQ = MBITS == 4 ? 7.0f : 127.0f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t hb = (uint32_t)(cols >> 6), nitems = (uint32_t)(rows >> 5);
+    const uint32_t nchunks = (hb + kBPC - 1) / kBPC;
+    const uint32_t wstride = gridDim.x * kF32Warps;
+    const uint32_t first = (uint32_t)warp * gridDim.x + blockIdx.x;      // warp-major: every SM gets the same number of busy warps
+    if (first >= nitems) return;
+
+    // this warp's ring: stages at base + s * kF32StageBytes (1024-aligned), barriers behind all rings
+    const uint32_t smem0 = (smem_u32(smem_raw_f32) + 1023u) & ~1023u;
+    const uint32_t ring = smem0 + (uint32_t)warp * (kF32Stages * kF32StageBytes);
+    const uint32_t bars = smem0 + kF32Warps * kF32Stages * kF32StageBytes + (uint32_t)warp * (8 * kF32Stages);
+    if (lane == 0) {
+        for (int s = 0; s < kF32Stages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8 * s), "r"(1) : "memory");
+        mbar_fence_init();
+        tma_prefetch_descriptor(&tmap);
+    }
+    __syncwarp();
+
+    // producer state (lane 0): the next (item, chunk) to request and its stage
+    uint32_t p_item = first, p_c = 0, p_s = 0;
+    auto issue = [&]() {                                               // lane 0 only; no-op when the warp's work is exhausted
+        if (p_item >= nitems) return;
+        const uint32_t nb = min((uint32_t)kBPC, hb - p_c * kBPC);
+        const uint32_t dst = ring + p_s * kF32StageBytes, bar = bars + 8 * p_s;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the warp's reads of this stage precede the refill
+        mbar_arrive_expect_tx_a(bar, 32 * 128 + nb * 256);
+        tma_load_2d_a(dst, &tmap, (int)(p_c * 128), (int)(p_item * 32), bar);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst + 4096u), "l"(x + (uint64_t)p_c * kBPC * 64), "r"(nb * 256u), "r"(bar) : "memory");
+        if (++p_s == kF32Stages) p_s = 0;
+        if (++p_c == nchunks) { p_c = 0; p_item += wstride; }
+    };
+    if (lane == 0)
+        for (int i = 0; i < kF32Stages; ++i) issue();
+
+    // lane j (< kBPC) of every group of kBPC lanes holds the raw scale of block c * kBPC + j, one chunk ahead
+    auto load_scale = [&](uint32_t item, uint32_t c) -> float {
+        if (item >= nitems) return 1.0f;
+        const uint32_t b = min(c * kBPC + (uint32_t)(lane & (kBPC - 1)), hb - 1);
+        return __ldg(scales + (uint64_t)(item >> 1) * hb + b);
+    };
+
+    const uint64_t neg = MBITS == 4 ? pack2f(-12582920.0f, -12582920.0f) : pack2f(-12583040.0f, -12583040.0f);   // -(magic + bias)
+    const RegConsts rc = reg_consts(zero);
+    const uint32_t rsw = (uint32_t)(lane & 7), rowoff = (uint32_t)lane * 128u;
+    uint32_t s = 0, phase = 0;
+    float sraw = load_scale(first, 0);
+    for (uint32_t item = first; item < nitems; item += wstride) {
+        uint64_t acc[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[k][p] = 0ull;
+        for (uint32_t c = 0; c < nchunks; ++c) {
+            const float sdiv = __fdiv_rn(sraw, kQ);                    // s = su[b] / 7.0f (:1488) resp. / 127.0f (:587)
+            sraw = c + 1 < nchunks ? load_scale(item, c + 1) : load_scale(item + wstride, 0);
+            mbar_wait_a(bars + 8 * s, phase);
+            const uint32_t st = ring + s * kF32StageBytes, rowp = st + rowoff, xs = st + 4096u;
+            const int nb = (int)min((uint32_t)kBPC, hb - c * kBPC);
+            for (int j = 0; j < nb; ++j) {
+                const float sj = __shfl_sync(0xFFFFFFFFu, sdiv, j);
+                const uint64_t ss = pack2f(sj, sj);
+                const uint32_t xb = xs + (uint32_t)j * 256u;
+                if (MBITS == 4) {
+                    const uint4 w0 = lds128(rowp + ((((uint32_t)(2 * j)) ^ rsw) << 4));        // elements  0..31
+                    const uint4 w1 = lds128(rowp + ((((uint32_t)(2 * j + 1)) ^ rsw) << 4));    // elements 32..63
+                    const uint32_t a0[4] = {w0.x, w0.y, w0.z, w0.w}, a1[4] = {w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        word4(a0[k], lds128f(xb + 32 * k), lds128f(xb + 32 * k + 16), ss, neg, rc, acc[k]);                // element 8k+l
+                        word4(a1[k], lds128f(xb + 128 + 32 * k), lds128f(xb + 128 + 32 * k + 16), ss, neg, rc, acc[k]);    // element 32+8k+l
+                    }
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {                      // half h: elements 32h .. 32h+31 = 16-byte chunks 4j+2h, 4j+2h+1
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc) {
+                            const uint4 w = lds128(rowp + ((((uint32_t)(4 * j + 2 * h + cc)) ^ rsw) << 4));
+                            const uint32_t xq = xb + 128 * h + 64 * cc;    // x[32h + 16cc ...]
+                            // 16 elements = accumulators k = 2cc, 2cc+1; word i covers lanes 4(i&1)..4(i&1)+3 of accumulator 2cc + (i>>1)
+                            word8(w.x, lds128f(xq), ss, neg, rc, &acc[2 * cc][0]);
+                            word8(w.y, lds128f(xq + 16), ss, neg, rc, &acc[2 * cc][2]);
+                            word8(w.z, lds128f(xq + 32), ss, neg, rc, &acc[2 * cc + 1][0]);
+                            word8(w.w, lds128f(xq + 48), ss, neg, rc, &acc[2 * cc + 1][2]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) issue();
+            if (++s == kF32Stages) { s = 0; phase ^= 1; }
+        }
+        // (acc_1 + acc_2) + (acc_3 + acc_4), then the hadd tree ((a4+a0)+(a6+a2))+((a5+a1)+(a7+a3)) (CloverBase.h:149-157)
+        float t[8];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            t[2 * p] = __fadd_rn(__fadd_rn(lo_f(acc[0][p]), lo_f(acc[1][p])), __fadd_rn(lo_f(acc[2][p]), lo_f(acc[3][p])));
+            t[2 * p + 1] = __fadd_rn(__fadd_rn(hi_f(acc[0][p]), hi_f(acc[1][p])), __fadd_rn(hi_f(acc[2][p]), hi_f(acc[3][p])));
+        }
+        y[(uint64_t)item * 32 + lane] = __fadd_rn(__fadd_rn(__fadd_rn(t[4], t[0]), __fadd_rn(t[6], t[2])),
+                                                  __fadd_rn(__fadd_rn(t[5], t[1]), __fadd_rn(t[7], t[3])));
+    }
+}
+
+// One warp per row, lane 8k+l = the reference's chain (accumulator k, AVX lane l); plain loads. Same bits as the ring kernel.
+template <int MBITS>
+__global__ void __launch_bounds__(256)
+k_mvm_f32_simple(const uint8_t *__restrict__ values, const float *__restrict__ scales, uint64_t rows, uint64_t cols,
+                 const float *__restrict__ x, float *__restrict__ y) {
+    constexpr float kQ = MBITS == 4 ? 7.0f : 127.0f;
+    const int lane = threadIdx.x & 31, k = lane >> 3, l = lane & 7;
+    const uint64_t hb = cols >> 6;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < rows; r += nwarps) {
+        const uint8_t *row = values + (MBITS == 4 ? (r * cols) >> 1 : r * cols);
+        const float *su = scales + (r >> 6) * hb;
+        float acc = 0.f;
+        for (uint64_t b = 0; b < hb; ++b) {
+            const float s = __fdiv_rn(__ldg(su + b), kQ);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int e = 32 * h + 8 * k + l;
+                int q;
+                if (MBITS == 4) {
+                    const int byte = (int)(int8_t)row[b * 32 + (e >> 1)];
+                    q = (e & 1) ? ((byte << 28) >> 28) : (byte >> 4);
+                } else {
+                    q = (int)(int8_t)row[b * 64 + e];
+                }
+                const float xv = __ldg(x + b * 64 + e), qf = __int2float_rn(q);
+                if (MBITS == 4) acc = __fmaf_rn(xv, __fmul_rn(qf, s), acc);
+                else            acc = __fmaf_rn(__fmul_rn(xv, s), qf, acc);
+            }
+        }
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, 8));             // acc_1+acc_2 | acc_3+acc_4
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, 16));            // sum_1 + sum_2
+        acc = hadd8_butterfly(acc);
+        if (lane == 0) y[r] = acc;
+    }
+}
+
+template <int MBITS>
+static int launch_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols, const float *x32,
+                          float *y32, cudaStream_t stream) {
+    if (rows == 0 || cols == 0) return CLOVER_OK;
+    const char *impl = getenv("CLOVER_GEMV_IMPL");
+    const bool simple = (impl && !strcmp(impl, "simple")) || (reinterpret_cast<uintptr_t>(values) & 15u) != 0 ||
+                        (reinterpret_cast<uintptr_t>(x32) & 15u) != 0;
+    if (simple) {
+        const uint64_t want = (rows + 7) / 8, cap = (uint64_t)sm_count() * 8;
+        k_mvm_f32_simple<MBITS><<<(unsigned)(want > cap ? cap : want), 256, 0, stream>>>(
+            reinterpret_cast<const uint8_t *>(values), scales, rows, cols, x32, y32);
+    } else {
+        CUtensorMap tmap;
+        int rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows, MBITS == 4 ? cols >> 1 : cols, 32);
+        if (rc != CLOVER_OK) return rc;
+        const int smem = kF32SmemBytes;
+        auto kern = k_mvm_f32_ring<MBITS>;
+        CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   // per device and call: cheap
+        const uint64_t nitems = rows >> 5, want = (nitems + kF32Warps - 1) / kF32Warps;
+        const unsigned grid = (unsigned)(want < (uint64_t)sm_count() ? want : (uint64_t)sm_count());
+        kern<<<grid, kF32Warps * 32, smem, stream>>>(tmap, scales, rows, cols, x32, y32, 0u);
+    }
+    count_launch();
+    return launch_status("k_mvm_f32");
+}
+
+}  // namespace clover
+
+using namespace clover;
+
+extern "C" {
+
+int clover_m4_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                      const float *x32, float *y32, void *stream) {
+    CLOVER_REQUIRE(values && scales && x32 && y32, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_REQUIRE(rows % 128u == 0 && cols % 128u == 0, CLOVER_ERR_INVALID, "rows and cols must be multiples of 128 (include/CloverMatrix.h:48-50)");
+    return launch_mvm_f32<4>(values, scales, rows, cols, x32, y32, (cudaStream_t)stream);
+}
+
+int clover_m8_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                      const float *x32, float *y32, void *stream) {
+    CLOVER_REQUIRE(values && scales && x32 && y32, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_REQUIRE(rows % 128u == 0 && cols % 128u == 0, CLOVER_ERR_INVALID, "rows and cols must be multiples of 128 (include/CloverMatrix.h:48-50)");
+    return launch_mvm_f32<8>(values, scales, rows, cols, x32, y32, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -118,8 +118,52 @@ static void views(uint64_t n) {
     std::cout << "views n=" << n << " bits=" << qa.getBitsLength() << " ok" << std::endl;
 }
 
+// The reference's own generators and the retained-pointer idiom of its harnesses (test/performance/01_measure.h:699-720):
+// keys from avx_xorshift128plus_init(445560390295639063, 2935984234003016713) (test/random/00_random.cpp:42), inputs
+// drawn with setRandomFloats(-1, 1, key1, key2) - the first draws must be the known answers of SURVEY.md 8c - then
+// quantize -> restore / mvm(V32) consistency for both matrix widths.
+template <class QMatrix>
+static void reference_harness(uint64_t m, uint64_t n) {
+    uint64_t key[8];
+    if (clover_prng_init(445560390295639063ULL, 2935984234003016713ULL, key) != CLOVER_OK) exit(1);
+    CloverVector32 a(4096);
+    a.setRandomFloats(-1.0f, 1.0f, key, key + 4);
+    if (a.get(0) != 0x1.ff90ap-4f || a.get(1) != -0x1.604778p-3f || a.get(2) != 0x1.8b518p-2f || a.get(3) != 0x1.31567p-2f) {
+        std::cout << "generator mismatch: " << a.get(0) << " " << a.get(1) << std::endl; exit(1);
+    }
+    CloverMatrix32 M(m, n), R(m, n);
+    CloverVector32 x(n), y(m);
+    M.setRandomFloats(-1.0f, 1.0f, key, key + 4);
+    x.setRandomInteger(-10.0f, 10.0f, key, key + 4);
+    for (uint64_t i = 0; i < n; ++i) if (x.get(i) != (float)(int)x.get(i) || x.get(i) < -10.f || x.get(i) > 10.f) { std::cout << "setRandomInteger" << std::endl; exit(1); }
+    QMatrix Q(m, n);
+    Q.quantize(M);
+    Q.restore(R);
+    for (uint64_t i = 0; i < m; i += 7)
+        for (uint64_t j = 0; j < n; j += 5)
+            if (R.get(i, j) != Q.get(i, j)) { std::cout << "matrix restore mismatch" << std::endl; exit(1); }
+    Q.mvm(x, y);                                                // fp32 vectors (CloverMatrix4.h:1451, CloverMatrix8.h:558)
+    for (uint64_t i = 0; i < m; i += 11) {
+        double want = 0;
+        for (uint64_t j = 0; j < n; ++j) want += (double)R.get(i, j) * (double)x.get(j);
+        if (std::fabs(want - (double)y.get(i)) > 0.01) { std::cout << "mvm(V32) mismatch " << want << " " << y.get(i) << std::endl; exit(1); }   // 03_matrix.cpp:419-491
+    }
+    // fetch the raw pointer ONCE, refill it before each quantize (the reference's idiom): the device copy must follow
+    CloverVector32 v(256);
+    float *raw = v.getData();
+    CloverVector4 q(256);
+    for (int round = 1; round <= 3; ++round) {
+        for (uint64_t i = 0; i < 256; ++i) raw[i] = (float)round * (float)((int)(i % 15) - 7);
+        q.quantize(v);
+        if (q.get(14) != (float)round * 7.0f || q.get(0) != (float)round * -7.0f) { std::cout << "retained pointer not re-read" << std::endl; exit(1); }
+    }
+    std::cout << "reference harness " << m << "x" << n << " bits=" << Q.getBitsLength() << " ok" << std::endl;
+}
+
 int main() {
     example();
+    reference_harness<CloverMatrix4>(256, 384);
+    reference_harness<CloverMatrix8>(256, 384);
     validate_mvm<CloverMatrix4, CloverVector4>(256, 384);
     validate_mvm<CloverMatrix8, CloverVector8>(256, 384);
     views<CloverVector4>(1000);

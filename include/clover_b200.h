@@ -92,6 +92,15 @@ int clover_prng_init(uint64_t key1, uint64_t key2, uint64_t *key_host);   /* avx
 int clover_prng_next(uint64_t *key_host, uint32_t *out8);                 /* avx_xorshift128plus      :97-109 */
 int clover_prng_skip(uint64_t *key_host, uint64_t ncalls);                /* O(log n) GF(2) jump-ahead */
 
+/* ---- CloverVector32 / CloverMatrix32: the reference's input generators on the device ------------
+ * CloverVector32::setRandomFloats include/CloverVector32.h:751-783, ::setRandomInteger :712-744; the CloverMatrix32 twins
+ * (include/CloverMatrix32.h:252-323) run the same loop over size() = rows * cols (PADDED dimensions, the pad is filled
+ * too). x: n fp32 in device memory; one XORShift128+ call per 8 elements plus one per left-over element; key_host
+ * (required) is consumed exactly like the reference consumes its key pair and advanced in place. These are the
+ * synthetic inputs of the reference's harnesses (test/random/00_random.cpp:42, test/performance/01_measure.h:641,711). */
+int clover_v32_set_random_floats(float *x, uint64_t n, float min_value, float max_value, uint64_t *key_host, void *stream);
+int clover_v32_set_random_integers(float *x, uint64_t n, float min_value, float max_value, uint64_t *key_host, void *stream);
+
 /* ---- CloverVector4 ------------------------------------------------------------------------------ */
 /* CloverVector4::quantize      include/CloverVector4.h:605-807   (x: n_pad fp32) */
 int clover_v4_quantize(const float *x, uint64_t n_pad, int8_t *values, float *scales, uint64_t *key_host, void *stream);
@@ -144,6 +153,8 @@ int clover_m4_mvm_v8(const int8_t *values, const float *scales, uint64_t rows, u
 /* CloverMatrix4::mvm(V32,V32)  include/CloverMatrix4.h:1451-1547 */
 int clover_m4_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
                       const float *x32, float *y32, void *stream);
+/* CloverMatrix4::restore_scalar include/CloverMatrix4.h:266-301: out (rows * cols fp32) = (scale / 7.0f) * q */
+int clover_m4_restore(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols, float *out, void *stream);
 /* Row-sharded mvm for multi-GPU (no counterpart in the reference): this rank holds rows
  * [row0, row0 + rows_local) of the matrix. Writes the fp32 results into y32_full[row0 ...] of a
  * full-length vector (the NCCL collective runs on that buffer) and the requantized slice into
@@ -189,6 +200,13 @@ int clover_m8_quantize(const float *a, uint64_t rows, uint64_t cols, int8_t *val
 int clover_m8_mvm(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
                   const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32,
                   uint64_t *key_host, void *stream);
+
+/* CloverMatrix8::mvm(V32,V32)  include/CloverMatrix8.h:558-661: t = x * (scale / 127.0f), acc = fma(t, q, acc) */
+int clover_m8_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                      const float *x32, float *y32, void *stream);
+/* CloverMatrix8 restore: out[i][j] = get(i, j) = (scale / 127.0f) * q (include/CloverMatrix8.h:117-129; the reference's
+ * restore_scalar, :1300-1309, is that assignment inside a loop that does not terminate as written) */
+int clover_m8_restore(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols, float *out, void *stream);
 
 /* ---- transpose -------------------------------------------------------------------
  * CloverMatrix4::transpose     include/CloverMatrix4.h:1549-1663 (_scalar :435-502, _parallel :2508-2640)

@@ -12,7 +12,10 @@
 // Where the data lives: every container owns ONE device allocation in the reference's exact byte layout
 // ([values | scales], include/CloverVector4.h:68-103) plus a host mirror of the same bytes. getData()/getScales()
 // return HOST pointers like the reference does; the mirror is synchronised lazily (device -> host before a host
-// read, host -> device before the next kernel when the host copy was handed out writable).
+// read, host -> device before the next kernel). Once a WRITABLE pointer has been handed out, the caller may keep it
+// (the reference's idiom): the host image is then re-uploaded before every kernel that reads the container and
+// refreshed after every kernel that writes it, until commit() declares the pointer dead - always correct, one PCIe
+// copy per call only for containers whose raw pointers escaped.
 //
 // Errors keep the reference's behaviour: a message on std::cout and exit(1) (include/CloverMatrix4.h:779-782).
 // Stochastic rounding is a run-time switch: containers start WITHOUT a key (= the reference built with
@@ -29,7 +32,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <random>
 #include <vector>
+#if defined(__AVX2__)
+#include <immintrin.h>      // the reference's __m256i key arguments (include/CloverRandom.h:90-94) are accepted as well
+#endif
 
 #include "../clover_b200.h"
 
@@ -56,6 +63,11 @@ class Mirror {
     mutable bool host_fresh_ = true, dev_fresh_ = true;
     unsigned char *ext_a_ = nullptr, *ext_b_ = nullptr;     // view: the caller's values / scales
     size_t ext_a_bytes_ = 0;
+    // An owning container whose WRITABLE host pointer was handed out (getData() / getScales()): the reference's idiom is
+    // to fetch that pointer once and keep writing / reading through it, so from then on the host image is treated like a
+    // view's memory - re-uploaded before every kernel that reads the container, refreshed after every kernel that writes
+    // it. Correct but one PCIe copy per call; commit() ends that mode once the caller is done with the raw pointer.
+    bool escaped_ = false;
     void pull_view() const {
         std::memcpy(const_cast<unsigned char *>(host_.data()), ext_a_, ext_a_bytes_);
         std::memcpy(const_cast<unsigned char *>(host_.data()) + ext_a_bytes_, ext_b_, host_.size() - ext_a_bytes_);
@@ -91,10 +103,13 @@ public:
             if (is_view()) push_view();
         }
     }
-    // view: write a kernel's result back into the caller's memory now
-    void flush_view() const { if (is_view()) to_host(); }
+    // view / escaped host pointer: write a kernel's result back into the caller-visible memory now
+    void flush_view() const { if (is_view() || escaped_) to_host(); }
+    void commit() { if (!is_view()) { (void)dev_in(); escaped_ = false; } }
     // host pointer the caller may write through: the device copy becomes stale
-    unsigned char *host_rw() { to_host(); dev_fresh_ = false; return host_.data(); }
+    unsigned char *host_rw() { to_host(); dev_fresh_ = false; if (!is_view()) escaped_ = true; return host_.data(); }
+    // the same for the container's own code: the pointer does not outlive the call
+    unsigned char *host_rw_internal() { to_host(); dev_fresh_ = false; return host_.data(); }
     // the same for the part that starts at `offset` (0 = values, value bytes = scales): a view hands out the caller's own regions
     unsigned char *host_rw_part(size_t offset) {
         if (!is_view()) return host_rw() + offset;
@@ -119,7 +134,8 @@ public:
             dev_fresh_ = true;
             return dev_;
         }
-        if (!dev_fresh_) { check(clover_copy_h2d(dev_, host_.data(), host_.size(), nullptr), "clover_copy_h2d"); dev_fresh_ = true; }
+        // escaped: the caller may have written through a retained pointer at any time while the host image is current
+        if (!dev_fresh_ || (escaped_ && host_fresh_)) { check(clover_copy_h2d(dev_, host_.data(), host_.size(), nullptr), "clover_copy_h2d"); dev_fresh_ = true; }
         return dev_;
     }
     // device pointer for a kernel that OVERWRITES (part of) the buffer
@@ -140,15 +156,54 @@ public:
     void seed(uint64_t k1, uint64_t k2) { check(clover_prng_init(k1, k2, key_), "clover_prng_init"); has_key_ = true; }
     void disableStochasticRounding() { has_key_ = false; }
     const uint64_t *getRandomKeys() const { return has_key_ ? key_ : nullptr; }
+#if defined(__AVX2__)
+    void setRandomKeys(const __m256i &key1, const __m256i &key2) {         // the reference's exact signature
+        std::memcpy(key_, &key1, 32); std::memcpy(key_ + 4, &key2, 32); has_key_ = true;
+    }
+#endif
+protected:
+    // the object's own key, seeded from the OS on first use like the reference seeds from RDRAND (include/CloverRandom.h:96-114)
+    uint64_t *own_key() {
+        if (!has_key_) { std::random_device rd; seed(((uint64_t)rd() << 32) | rd() | 1u, ((uint64_t)rd() << 32) | rd() | 1u); }
+        return key_;
+    }
+};
+
+// setRandomFloats / setRandomInteger of CloverVector32 and CloverMatrix32 (include/CloverVector32.h:712-783,
+// include/CloverMatrix32.h:252-323) on the device: `Derived` provides device_out() and generator_length().
+template <class Derived>
+class Generators : public Keyed {
+    void fill(bool integer, float lo, float hi, uint64_t *key) {
+        Derived &d = static_cast<Derived &>(*this);
+        check((integer ? clover_v32_set_random_integers : clover_v32_set_random_floats)(d.device_out(), d.generator_length(), lo, hi, key, nullptr),
+              "setRandom");
+        d.sync_view();
+    }
+    void fill_pair(bool integer, float lo, float hi, void *key1, void *key2) {          // two separate 32-byte halves, advanced in place
+        uint64_t k[8];
+        std::memcpy(k, key1, 32); std::memcpy(k + 4, key2, 32);
+        fill(integer, lo, hi, k);
+        std::memcpy(key1, k, 32); std::memcpy(key2, k + 4, 32);
+    }
+public:
+    void setRandomFloats(float min_value, float max_value) { fill(false, min_value, max_value, own_key()); }
+    void setRandomInteger(float min_value, float max_value) { fill(true, min_value, max_value, own_key()); }
+    void setRandomFloats(float min_value, float max_value, uint64_t key1[4], uint64_t key2[4]) { fill_pair(false, min_value, max_value, key1, key2); }
+    void setRandomInteger(float min_value, float max_value, uint64_t key1[4], uint64_t key2[4]) { fill_pair(true, min_value, max_value, key1, key2); }
+#if defined(__AVX2__)
+    void setRandomFloats(float min_value, float max_value, __m256i &key1, __m256i &key2) { fill_pair(false, min_value, max_value, &key1, &key2); }
+    void setRandomInteger(float min_value, float max_value, __m256i &key1, __m256i &key2) { fill_pair(true, min_value, max_value, &key1, &key2); }
+#endif
 };
 
 }  // namespace clover_b200_detail
 
 // ---------------------------------------------------------------------------------------------------------------
-class CloverVector32 {   // include/CloverVector32.h:53-70 - fp32, length padded to x128, pad zeroed
+class CloverVector32 : public clover_b200_detail::Generators<CloverVector32> {   // include/CloverVector32.h:53-70 - fp32, length padded to x128, pad zeroed
     uint64_t length, length_pad;
     mutable clover_b200_detail::Mirror buf;
 public:
+    uint64_t generator_length() const { return length; }        // the generators fill `length` elements, the pad stays 0
     explicit CloverVector32(uint64_t s) : length(s), length_pad(clover_b200_detail::pad128(s)), buf(length_pad * sizeof(float)) {}
     uint64_t size() const { return length; }
     uint64_t size_pad() const { return length_pad; }
@@ -159,6 +214,8 @@ public:
     void set(uint64_t i, float v) { getData()[i] = v; }
     const float *device_in() const { return static_cast<const float *>(buf.dev_in()); }
     float *device_out() { return static_cast<float *>(buf.dev_out()); }
+    void sync_view() const { buf.flush_view(); }
+    void commit() { buf.commit(); }                          // the caller is done with pointers obtained from getData()
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -170,7 +227,7 @@ protected:
     uint64_t value_bytes() const { return length_pad * BITS / 8; }
     uint64_t scale_count() const { return length_pad / 64; }
     void init_padding() {                                   // pad values 0 (already), pad scales 1 (:86-94)
-        float *s = reinterpret_cast<float *>(buf.host_rw() + value_bytes());
+        float *s = reinterpret_cast<float *>(buf.host_rw_internal() + value_bytes());
         for (uint64_t i = length / 64; i < scale_count(); ++i) s[i] = 1.0f;
     }
 public:
@@ -183,6 +240,7 @@ public:
           buf(reinterpret_cast<unsigned char *>(values), length_pad * BITS / 8, reinterpret_cast<unsigned char *>(scales),
               (length_pad / 64) * sizeof(float)) {}
     void sync_view() const { buf.flush_view(); }            // a kernel wrote this container: hand the bytes to a view's owner
+    void commit() { buf.commit(); }                         // the caller is done with pointers obtained from getData() / getScales()
     uint64_t size() const { return length; }
     uint64_t size_pad() const { return length_pad; }
     uint64_t getBitsLength() const { return BITS; }
@@ -208,8 +266,15 @@ public:
 
     // all values 0, all scales 1 (include/CloverVector4.h:306-318) - the start vector of the IHT / GD loops
     void clear() {
-        std::memset(getData(), 0, value_bytes());
-        float *s = getScales();
+        if (buf.is_view()) {
+            std::memset(getData(), 0, value_bytes());
+            float *s = getScales();
+            for (uint64_t i = 0; i < scale_count(); ++i) s[i] = 1.0f;
+            return;
+        }
+        unsigned char *h = buf.host_rw_internal();
+        std::memset(h, 0, value_bytes());
+        float *s = reinterpret_cast<float *>(h + value_bytes());
         for (uint64_t i = 0; i < scale_count(); ++i) s[i] = 1.0f;
     }
 
@@ -218,6 +283,7 @@ public:
         const int rc = BITS == 4 ? clover_v4_restore(device_values(), device_scales(), length_pad, other.device_out(), nullptr)
                                  : clover_v8_restore(device_values(), device_scales(), length_pad, other.device_out(), nullptr);
         clover_b200_detail::check(rc, "restore");
+        other.sync_view();
     }
     void restore_scalar(CloverVector32 &o) const { restore(o); }
 
@@ -289,10 +355,15 @@ public:
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-class CloverMatrix32 {   // include/CloverMatrix32.h:43-66
+class CloverMatrix32 : public clover_b200_detail::Generators<CloverMatrix32> {   // include/CloverMatrix32.h:43-66
     uint64_t rows, cols;
     mutable clover_b200_detail::Mirror buf;
 public:
+    uint64_t generator_length() const { return rows * cols; }   // size() of the padded matrix (CloverMatrix32.h:254)
+    float *device_out() { return static_cast<float *>(buf.dev_out()); }
+    void sync_view() const { buf.flush_view(); }
+    void commit() { buf.commit(); }
+    float get(uint64_t i, uint64_t j) const { return reinterpret_cast<const float *>(buf.host_ro())[i * cols + j]; }
     CloverMatrix32(uint64_t h, uint64_t w) : rows(clover_b200_detail::pad128(h)), cols(clover_b200_detail::pad128(w)), buf(rows * cols * sizeof(float)) {}
     uint64_t getRows() const { return rows; }
     uint64_t getCols() const { return cols; }
@@ -329,8 +400,32 @@ public:
         const int rc = BITS == 4 ? clover_m4_quantize(m.device_in(), rows, cols, reinterpret_cast<int8_t *>(d), reinterpret_cast<float *>(d + value_bytes()), key_ptr(), nullptr)
                                  : clover_m8_quantize(m.device_in(), rows, cols, reinterpret_cast<int8_t *>(d), reinterpret_cast<float *>(d + value_bytes()), key_ptr(), nullptr);
         clover_b200_detail::check(rc, "quantize");
+        buf.flush_view();
     }
     void quantize_scalar(const CloverMatrix32 &m) { quantize(m); }
+    void commit() { buf.commit(); }                         // the caller is done with pointers obtained from getData() / getScales()
+
+    // include/CloverMatrix4.h:266-301 (restore_scalar); 8-bit: other(i, j) = get(i, j) (include/CloverMatrix8.h:117-129, :1300)
+    void restore(CloverMatrix32 &other) const {
+        if (other.getRows() != rows || other.getCols() != cols) { std::cout << "Matrices do not have the same size. Exiting ..." << std::endl; exit(1); }
+        const int rc = BITS == 4 ? clover_m4_restore(device_values(), device_scales(), rows, cols, other.device_out(), nullptr)
+                                 : clover_m8_restore(device_values(), device_scales(), rows, cols, other.device_out(), nullptr);
+        clover_b200_detail::check(rc, "restore");
+        other.sync_view();
+    }
+    void restore_scalar(CloverMatrix32 &other) const { restore(other); }
+
+    // fp32 vectors: include/CloverMatrix4.h:1451-1547, include/CloverMatrix8.h:558-661
+    void mvm(const CloverVector32 &productVector, CloverVector32 &resultVector) {
+        if (productVector.size() != getCols() || resultVector.size_pad() < getRows()) {
+            std::cout << "MVM can not be performed. Exiting ..." << std::endl;
+            exit(1);
+        }
+        const int rc = BITS == 4 ? clover_m4_mvm_f32(device_values(), device_scales(), rows, cols, productVector.device_in(), resultVector.device_out(), nullptr)
+                                 : clover_m8_mvm_f32(device_values(), device_scales(), rows, cols, productVector.device_in(), resultVector.device_out(), nullptr);
+        clover_b200_detail::check(rc, "mvm");
+        resultVector.sync_view();
+    }
 
     // include/CloverMatrix4.h:777-1083 / include/CloverMatrix8.h:1002-1298
     void mvm(const QVector &productVector, QVector &resultVector) {
@@ -357,6 +452,7 @@ public:
         const int rc = BITS == 4 ? clover_m4_transpose(device_values(), device_scales(), rows, cols, ov, os, nullptr)
                                  : clover_m8_transpose(device_values(), device_scales(), rows, cols, ov, os, nullptr);
         clover_b200_detail::check(rc, "transpose");
+        other.buf.flush_view();
     }
     void transpose_scalar(CloverQuantizedMatrix &other) { transpose(other); }
     void transpose_parallel(CloverQuantizedMatrix &other) { transpose(other); }
@@ -372,15 +468,6 @@ public:
         const int8_t q = (pos & 1) ? (int8_t)((int8_t)(b << 4) >> 4) : (int8_t)(b >> 4);
         const float *s = reinterpret_cast<const float *>(buf.host_ro() + value_bytes());
         return (s[(i >> 6) * (cols >> 6) + (j >> 6)] / 7.0f) * (float)q;
-    }
-    // include/CloverMatrix4.h:1451-1547
-    void mvm(const CloverVector32 &productVector, CloverVector32 &resultVector) {
-        if (productVector.size() != getCols() || resultVector.size_pad() < getRows()) {
-            std::cout << "MVM can not be performed. Exiting ..." << std::endl;
-            exit(1);
-        }
-        clover_b200_detail::check(clover_m4_mvm_f32(device_values(), device_scales(), rows, cols, productVector.device_in(),
-                                                    resultVector.device_out(), nullptr), "mvm");
     }
     // mixed precision, include/CloverMatrix4.h:1093-1441 (mvm_parallel :2017): 4-bit matrix x 8-bit vector -> 8-bit vector
     void mvm(const CloverVector8 &productVector, CloverVector8 &resultVector) {
@@ -407,6 +494,7 @@ public:
 class CloverMatrix8 : public CloverQuantizedMatrix<8, CloverVector8> {
 public:
     using CloverQuantizedMatrix<8, CloverVector8>::CloverQuantizedMatrix;
+    using CloverQuantizedMatrix<8, CloverVector8>::mvm;
     float get(uint64_t i, uint64_t j) const {               // include/CloverMatrix8.h:117-129
         const int8_t q = reinterpret_cast<const int8_t *>(buf.host_ro())[i * cols + j];
         const float *s = reinterpret_cast<const float *>(buf.host_ro() + value_bytes());

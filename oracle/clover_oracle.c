@@ -501,6 +501,59 @@ void orc_m4_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, ui
     }
 }
 
+/* CloverMatrix8::mvm(V32,V32): include/CloverMatrix8.h:558-661. The same 32 chains as the 4-bit variant (accumulator
+ * k = 0..3, AVX lane l; per block element 8k+l, then element 32+8k+l), but the scale is folded into the VECTOR side:
+ * s = su[b] / 127.0f, t = x[e] * s (rounded, :632-639), acc = fma(t, float(q[e]), acc) (:641-649). */
+void orc_m8_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                    const float *x32, float *y32) {
+    const uint64_t hb = cols >> 6;
+    #pragma omp parallel for schedule(static)
+    for (uint64_t r = 0; r < rows; ++r) {
+        const int8_t *u = values + r * cols;
+        const float *su = scales + (r >> 6) * hb;
+        float acc[4][8];
+        memset(acc, 0, sizeof acc);
+        for (uint64_t b = 0; b < hb; ++b) {
+            const float s = su[b] / 127.0f;
+            const float *x = x32 + b * 64;
+            for (int half = 0; half < 2; ++half)
+                for (int k = 0; k < 4; ++k)
+                    for (int l = 0; l < 8; ++l) {
+                        const int e = 32 * half + 8 * k + l;
+                        const float t = x[e] * s;
+                        acc[k][l] = fmaf(t, (float)u[b * 64 + e], acc[k][l]);
+                    }
+        }
+        float t[8];
+        for (int l = 0; l < 8; ++l) t[l] = (acc[0][l] + acc[1][l]) + (acc[2][l] + acc[3][l]);
+        y32[r] = hadd8(t);
+    }
+}
+
+/* Matrix restore. 4-bit: include/CloverMatrix4.h:266-301 (restore_scalar, the only variant): (s / 7.0f) * float(q).
+ * 8-bit: include/CloverMatrix8.h:1300-1309 (restore_scalar) is r[pos] = get(i, j) with get = (s / 127.0f) * float(q)
+ * (:117-129); its inner loop increments `i` instead of `j` and never terminates as written, so the restatement is
+ * pinned to get(i, j) element by element instead. */
+void orc_m4_restore(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols, float *out) {
+    const uint64_t hb = cols >> 6;
+    #pragma omp parallel for schedule(static)
+    for (uint64_t i = 0; i < rows; ++i)
+        for (uint64_t j = 0; j < cols; ++j) {
+            const float s = scales[(i >> 6) * hb + (j >> 6)] / 7.0f;
+            const int8_t byte = values[(i * cols + j) >> 1];
+            out[i * cols + j] = s * (float)((j & 1) ? nib_lo(byte) : nib_hi(byte));
+        }
+}
+void orc_m8_restore(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols, float *out) {
+    const uint64_t hb = cols >> 6;
+    #pragma omp parallel for schedule(static)
+    for (uint64_t i = 0; i < rows; ++i)
+        for (uint64_t j = 0; j < cols; ++j) {
+            const float s = scales[(i >> 6) * hb + (j >> 6)] / 127.0f;
+            out[i * cols + j] = s * (float)values[i * cols + j];
+        }
+}
+
 /* GEMM (extension): every C[i][j] is the reference SIMD dot of two row views. */
 void orc_m4_gemm(const int8_t *av, const float *as, const int8_t *btv, const float *bts,
                  uint64_t K, uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1, float *c, uint64_t ldc) {

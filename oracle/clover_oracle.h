@@ -61,6 +61,12 @@ void orc_m4_mvm_v8(const int8_t *values, const float *scales, uint64_t rows, uin
                    const int8_t *xv, const float *xs, int8_t *yv, float *ys, float *y32_or_null, uint64_t *state);
 void orc_m4_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
                     const float *x32, float *y32);
+/* CloverMatrix8::mvm(V32,V32): include/CloverMatrix8.h:558-661 */
+void orc_m8_mvm_f32(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols,
+                    const float *x32, float *y32);
+/* matrix restore: include/CloverMatrix4.h:266-301; 8-bit = get(i, j) element by element (include/CloverMatrix8.h:117-129) */
+void orc_m4_restore(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols, float *out);
+void orc_m8_restore(const int8_t *values, const float *scales, uint64_t rows, uint64_t cols, float *out);
 /* GEMM definition of this project: C[i][j] = rowView(A,i).dot(rowView(Bt,j)). */
 void orc_m4_gemm(const int8_t *av, const float *as, const int8_t *btv, const float *bts,
                  uint64_t K, uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1, float *c, uint64_t ldc);

@@ -105,6 +105,14 @@ def golden_f(ref, ref_sr, g):
     h4s = ref_sr.m4_from(g["m4_values"], g["m4_scales"], 256, 384)
     yv, ys = ref_sr.m4_mvm_v8(h4s, g["v8_v_values"], g["v8_v_scales"], state=key)
     f["sr_m4_mvm_v8_values"], f["sr_m4_mvm_v8_scales"], f["sr_m4_mvm_v8_key_after"] = yv, ys, key.copy()
+    # round 2: CloverMatrix8::mvm(V32,V32) (CloverMatrix8.h:558-661) and the matrix restores (CloverMatrix4.h:266-301;
+    # 8-bit through get(i, j), CloverMatrix8.h:117-129) on the same M, w
+    h8 = ref.m8_from(g["m8_values"], g["m8_scales"], 256, 384)
+    f["m8_mvm_f32"] = ref.m8_mvm_f32(h8, g["w"]).copy()
+    for bits, h in ((4, h4), (8, h8)):
+        r = ref.m_restore(bits, h)
+        f[f"m{bits}_restore_rows8"] = r[:8].copy()
+        f[f"m{bits}_restore_fnv"] = np.array([int(fnv1a64(r.tobytes()), 16)], np.uint64)
     out = os.path.join(ROOT, "tests", "golden", "clover_golden_f.npz")
     np.savez_compressed(out, **{k: np.ascontiguousarray(val) for k, val in f.items()})
     print("wrote", out, os.path.getsize(out), "bytes,", len(f), "arrays")

@@ -210,6 +210,18 @@ class Oracle:
         self.lib.orc_m4_mvm_f32(_p(mv), _p(ms), _u64(rows), _u64(cols), _p(x32), _p(y))
         return y
 
+    def m8_mvm_f32(self, mv, ms, rows, cols, x32):
+        """CloverMatrix8::mvm(V32,V32) (CloverMatrix8.h:558-661)"""
+        y = np.zeros(rows, np.float32)
+        self.lib.orc_m8_mvm_f32(_p(mv), _p(ms), _u64(rows), _u64(cols), _p(x32), _p(y))
+        return y
+
+    def m_restore(self, bits, mv, ms, rows, cols):
+        """matrix restore (CloverMatrix4.h:266-301; 8-bit: get(i, j), CloverMatrix8.h:117-129) -> fp32 [rows, cols]"""
+        out = np.zeros((rows, cols), np.float32)
+        getattr(self.lib, f"orc_m{bits}_restore")(_p(mv), _p(ms), _u64(rows), _u64(cols), _p(out))
+        return out
+
     def m4_gemm(self, av, as_, btv, bts, K, i0, i1, j0, j1):
         c = np.zeros((i1 - i0, j1 - j0), np.float32)
         self.lib.orc_m4_gemm(_p(av), _p(as_), _p(btv), _p(bts), _u64(K), _u64(i0), _u64(i1), _u64(j0), _u64(j1),
@@ -423,6 +435,19 @@ class Reference:
         y = aligned(size_pad(m.rows), np.float32)
         self.lib.ref_m4_mvm_f32(m.h, _p(x32), _p(y), C.c_int(variant))
         return y[: m.rows]
+
+    def m8_mvm_f32(self, m, x32, variant=0):
+        y = aligned(size_pad(m.rows), np.float32)
+        self.lib.ref_m8_mvm_f32(m.h, _p(x32), _p(y), C.c_int(variant))
+        return y[: m.rows]
+
+    def m_restore(self, bits, m):
+        out = np.zeros((m.rows, m.cols), np.float32)
+        if bits == 4:
+            self.lib.ref_m4_restore(m.h, _p(out))
+        else:
+            self.lib.ref_m8_restore_by_get(m.h, _p(out))
+        return out
 
     def m4_gemm(self, ma, mbt, i0, i1, j0, j1):
         c = np.zeros((i1 - i0, j1 - j0), np.float32)

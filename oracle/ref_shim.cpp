@@ -321,6 +321,30 @@ void ref_m8_mvm(void *h, const int8_t *xv, const float *xs, int8_t *yv, float *y
     m->get_state(state);
 }
 
+/* fp32 x / fp32 y on the 8-bit matrix (include/CloverMatrix8.h:558 SIMD, :546 scalar with a double accumulator). */
+void ref_m8_mvm_f32(void *h, const float *x32, float *y32, int variant) {
+    M8 *m = (M8 *)h;
+    CloverVector32 x(m->getCols(), (float *)x32);
+    CloverVector32 y(m->getRows(), y32);
+    if (variant == 1) m->mvm_scalar(x, y); else m->mvm(x, y);
+}
+/* matrix restore: the 4-bit class has restore_scalar only (include/CloverMatrix4.h:266); the 8-bit restore_scalar
+ * (include/CloverMatrix8.h:1300) does not terminate as written, so the 8-bit matrix is read through get(i, j) (:117). */
+void ref_m4_restore(void *h, float *out) {
+    M4 *m = (M4 *)h;
+    CloverMatrix32 *o = new CloverMatrix32(m->getRows(), m->getCols());
+    m->restore_scalar(*o);
+    memcpy(out, o->getData(), (size_t)m->getRows() * m->getCols() * sizeof(float));
+    delete o;
+}
+float ref_m8_get(void *h, uint64_t i, uint64_t j) { return ((M8 *)h)->get(i, j); }
+void ref_m8_restore_by_get(void *h, float *out) {
+    M8 *m = (M8 *)h;
+    const uint64_t R = m->getRows(), Cc = m->getCols();
+    for (uint64_t i = 0; i < R; ++i)
+        for (uint64_t j = 0; j < Cc; ++j) out[i * Cc + j] = m->get(i, j);
+}
+
 /* include/CloverMatrix8.h:1359 (IPP), :1312 scalar, :1338 parallel */
 void ref_m8_transpose(void *h, void *hout, int variant) {
     M8 *m = (M8 *)h, *o = (M8 *)hout;

@@ -130,3 +130,32 @@ def test_f_rows_mixed_mvm(oracle, g, gf):
     yv, ys = oracle.m4_mvm_v8(g["m4_values"], g["m4_scales"], 256, 384, g["v8_v_values"], g["v8_v_scales"], state=key)
     assert same_bits(yv, gf["sr_m4_mvm_v8_values"]) and same_bits(ys, gf["sr_m4_mvm_v8_scales"])
     assert np.array_equal(key, gf["sr_m4_mvm_v8_key_after"])
+
+
+def test_round2_rows_m8_mvm_f32_and_matrix_restore(oracle, g, gf):
+    """CloverMatrix8::mvm(V32,V32) (CloverMatrix8.h:558-661) and the matrix restores (CloverMatrix4.h:266-301; 8-bit through
+    get(i, j), CloverMatrix8.h:117-129): the oracle reproduces the bytes the compiled reference produced."""
+    from oracle.pyoracle import fnv1a64
+    assert same_bits(oracle.m8_mvm_f32(g["m8_values"], g["m8_scales"], 256, 384, g["w"]), gf["m8_mvm_f32"][:256])
+    for bits in (4, 8):
+        r = oracle.m_restore(bits, g[f"m{bits}_values"], g[f"m{bits}_scales"], 256, 384)
+        assert same_bits(r[:8], gf[f"m{bits}_restore_rows8"])
+        assert int(fnv1a64(r.tobytes()), 16) == int(gf[f"m{bits}_restore_fnv"][0])
+
+
+def test_generators_known_answers(oracle, g):
+    """SURVEY.md 8c known-answer table: the first draws of setRandomFloats(-1, 1) from the reference seeds, the matrix
+    generator (the whole PADDED matrix is one run of the vector loop) and the integer variant."""
+    st = oracle.xs_init()
+    a = oracle.fill_floats(4096, -1.0, 1.0, st)
+    assert [float(v).hex() for v in a[:4]] == ["0x1.ff90a00000000p-4", "-0x1.6047780000000p-3", "0x1.8b51800000000p-2", "0x1.3156700000000p-2"]
+    assert same_bits(a[:4096], g["a"][:4096])
+    st = g["seed_state"].copy()
+    for name, n in (("a", 4096), ("b", 4096), ("c", 1000), ("d", 1000)):
+        assert same_bits(oracle.fill_floats(n, -1.0, 1.0, st)[:n], g[name][:n])
+    M = oracle.fill_floats(256 * 384, -1.0, 1.0, st)[: 256 * 384].reshape(256, 384)
+    assert same_bits(M, g["M"])
+    for name in ("v", "w"):
+        assert same_bits(oracle.fill_floats(384, -1.0, 1.0, st)[:384], g[name][:384])
+    assert same_bits(oracle.fill_integers(1000, -10.0, 10.0, st)[:1000], g["ints"][:1000])
+    assert np.array_equal(st, g["state_after_inputs"])

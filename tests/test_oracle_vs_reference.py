@@ -125,6 +125,15 @@ def test_matrix_quantize_mvm(oracle, reference, shape, kind):
     y = oracle.m4_mvm_f32(mv, ms, R, Cc, xvec)
     y_r = reference.m4_mvm_f32(h, xvec)
     assert np.array_equal(y.view(np.uint32), y_r.view(np.uint32)), "mvm(V32,V32)"
+    assert np.array_equal(oracle.m_restore(4, mv, ms, R, Cc).view(np.uint32), reference.m_restore(4, h).view(np.uint32)), "M4 restore"
+    # round 2: CloverMatrix8::mvm(V32,V32) (CloverMatrix8.h:558-661) and the 8-bit restore (= get(i, j), :117-129)
+    mv8, ms8 = oracle.m8_quantize(a)
+    _, _, h8 = reference.m8_quantize(a)
+    y8, y8_r = oracle.m8_mvm_f32(mv8, ms8, R, Cc, xvec), reference.m8_mvm_f32(h8, xvec)
+    assert np.array_equal(y8.view(np.uint32), y8_r.view(np.uint32)), "M8 mvm(V32,V32)"
+    # the reference's own acceptance bound against its double-accumulating scalar twin (03_matrix.cpp:419-491)
+    assert np.max(np.abs(y8 - reference.m8_mvm_f32(h8, xvec, variant=1))) <= 0.01 * max(1.0, float(np.abs(y8).max()))
+    assert np.array_equal(oracle.m_restore(8, mv8, ms8, R, Cc).view(np.uint32), reference.m_restore(8, h8).view(np.uint32)), "M8 restore"
 
 
 @pytest.mark.parametrize("shape", [(128, 128), (256, 384)])
