@@ -393,6 +393,14 @@ def extras(torch, cb, peak):
                              "fp32_ops_per_s": 2.0 * r8 * c8 / t,
                              "note": "one int->float, one multiply and one fma per matrix element (the reference's order): CUDA-core bound, not HBM bound"}
     del m4
+    # CloverMatrix8::mvm(V32,V32) (CloverMatrix8.h:558-661)
+    m8 = cb.CloverMatrix8(r8, c8)
+    m8.values.copy_(torch.randint(-127, 128, (r8 * c8,), dtype=torch.int8, device=dev, generator=g))
+    m8.scales.uniform_(0.25, 1.0, generator=g)
+    t = cuda_time(torch, lambda: m8.mvm(x32v, y32v), 20)
+    b = m8.getBytes() + 4 * (c8 + r8)
+    out["mvm8_f32_32768"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b, "fp32_ops_per_s": 2.0 * r8 * c8 / t}
+    del m8
     # transpose of a 16384 x 16384 matrix (every byte read once and written once)
     for bits_, M_ in ((4, cb.CloverMatrix4), (8, cb.CloverMatrix8)):
         src, dst = M_(16384, 16384), M_(16384, 16384)

@@ -36,9 +36,15 @@ def Q_GD(Phi, PhiT, x, y, t1, t2, t3, iterations: int, mu: float) -> None:
 def capture(fn, warmup: int = 2):
     """Capture ``fn`` (a sequence of container calls with no host read-back, e.g. a Q_IHT call) into a CUDA graph.
 
-    The calls are first run ``warmup`` times on a side stream so that first-use allocations (kernel workspaces, tensor
-    maps' driver entry point) happen outside the capture. Replaying the graph removes the per-call host cost - five
-    launches per IHT iteration otherwise each pay a Python/ctypes round trip."""
+    Kernel scratch (tickets, fp32 intermediates) is keyed by (device, stream) and allocated on first use, which is not
+    allowed inside a capture: ``fn`` is therefore first run ``warmup`` times on the SAME side stream the capture then
+    uses, so that every allocation has happened and the graph references that stream's blocks (which are never freed).
+    Replaying the graph removes the per-call host cost - five launches per IHT iteration otherwise each pay a
+    Python/ctypes round trip.
+
+    Containers with a PRNG key cannot be captured: the kernels receive the key lanes BY VALUE, so every replay would
+    reuse the same rounding noise and the host key would no longer track the stream the reference consumes
+    (``_Keyed._key_ptr`` raises while a capture is in progress)."""
     import torch
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -47,6 +53,6 @@ def capture(fn, warmup: int = 2):
             fn()
     torch.cuda.current_stream().wait_stream(side)
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
+    with torch.cuda.graph(graph, stream=side):
         fn()
     return graph

@@ -74,7 +74,12 @@ class _Keyed:
         call("clover_prng_init", C.c_uint64(key1), C.c_uint64(key2), self.key.ctypes.data_as(C.c_void_p))
 
     def _key_ptr(self):
-        return None if self.key is None else self.key.ctypes.data_as(C.c_void_p)
+        if self.key is None:
+            return None
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("a container with a PRNG key cannot be captured into a CUDA graph: the key lanes are passed by value, "
+                               "every replay would reuse the same rounding noise (setRandomKeys(None) disables stochastic rounding)")
+        return self.key.ctypes.data_as(C.c_void_p)
 
     def _generator_key(self, key):
         """The key pair a generator call consumes: an explicit uint64[8] (advanced in place, like the reference's

@@ -309,21 +309,9 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
-static void *g_ws[64] = {nullptr};
-static size_t g_ws_bytes[64] = {0};
-
-// grow-only per-device workspace for the expanded operands (not thread-safe; one GEMM stream per device)
-static int gemm_workspace(size_t bytes, void **out) {
-    int dev = 0;
-    CLOVER_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
-    if (g_ws_bytes[dev] < bytes) {
-        if (g_ws[dev]) { CLOVER_CUDA_CHECK(cudaDeviceSynchronize()); CLOVER_CUDA_CHECK(cudaFree(g_ws[dev])); g_ws[dev] = nullptr; g_ws_bytes[dev] = 0; }
-        CLOVER_CUDA_CHECK(cudaMalloc(&g_ws[dev], bytes));
-        g_ws_bytes[dev] = bytes;
-    }
-    *out = g_ws[dev];
-    return CLOVER_OK;
+// workspace for the expanded operands, keyed by (device, stream)
+static int gemm_workspace(cudaStream_t stream, size_t bytes, void **out) {
+    return stream_scratch(kScratchGemm, stream, bytes, 0, out);
 }
 
 int gemm4_expand(const int8_t *values, uint64_t rows, uint64_t cols, uint8_t *out, cudaStream_t stream) {
@@ -390,7 +378,7 @@ int gemm4_tc_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, con
 int gemm4_tc(const int8_t *av, const float *as, const int8_t *btv, const float *bts, uint64_t M, uint64_t N, uint64_t K,
              float *c, uint64_t ldc, cudaStream_t stream) {
     void *ws = nullptr;
-    int rc = gemm_workspace((M + N) * K, &ws);
+    int rc = gemm_workspace(stream, (M + N) * K, &ws);
     if (rc != CLOVER_OK) return rc;
     uint8_t *a8 = static_cast<uint8_t *>(ws), *b8 = a8 + M * K;
     rc = gemm4_expand(av, M, K, a8, stream);

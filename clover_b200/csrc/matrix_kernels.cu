@@ -995,29 +995,19 @@ k_requantize_mvm(const float *__restrict__ y32, uint64_t nblocks, int8_t *__rest
     }
 }
 
-// grow-only per-device scratch of the pipelined 8-bit GEMV: fp32 row results (when the caller passes no y32) and one
-// zero-initialised counter per row block. Not thread-safe: one GEMV stream per device, like the GEMM workspace.
-static int mvm_scratch(uint64_t nrb_local, uint64_t nrb_global_end, float **ybuf, unsigned int **counters) {
-    static float *g_y[64] = {nullptr};
-    static uint64_t g_y_blocks[64] = {0};
-    static unsigned int *g_c[64] = {nullptr};
-    static uint64_t g_c_blocks[64] = {0};
-    int dev = 0;
-    CLOVER_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
-    if (ybuf && g_y_blocks[dev] < nrb_global_end) {
-        if (g_y[dev]) { CLOVER_CUDA_CHECK(cudaDeviceSynchronize()); CLOVER_CUDA_CHECK(cudaFree(g_y[dev])); g_y[dev] = nullptr; g_y_blocks[dev] = 0; }
-        CLOVER_CUDA_CHECK(cudaMalloc(&g_y[dev], nrb_global_end * 64 * sizeof(float)));
-        g_y_blocks[dev] = nrb_global_end;
+// scratch of the pipelined GEMVs: fp32 row results (when the caller passes no y32) and one zero-initialised counter per
+// row block, re-armed by the kernel itself. Keyed by (device, stream): calls on different streams never share counters.
+static int mvm_scratch(cudaStream_t stream, uint64_t nrb_local, uint64_t nrb_global_end, float **ybuf, unsigned int **counters) {
+    void *p = nullptr;
+    if (ybuf) {
+        int rc = stream_scratch(kScratchMvmY, stream, nrb_global_end * 64 * sizeof(float), 0, &p);
+        if (rc != CLOVER_OK) return rc;
+        *ybuf = static_cast<float *>(p);
     }
-    if (g_c_blocks[dev] < nrb_local) {
-        if (g_c[dev]) { CLOVER_CUDA_CHECK(cudaDeviceSynchronize()); CLOVER_CUDA_CHECK(cudaFree(g_c[dev])); g_c[dev] = nullptr; g_c_blocks[dev] = 0; }
-        CLOVER_CUDA_CHECK(cudaMalloc(&g_c[dev], nrb_local * sizeof(unsigned int)));
-        CLOVER_CUDA_CHECK(cudaMemset(g_c[dev], 0, nrb_local * sizeof(unsigned int)));
-        g_c_blocks[dev] = nrb_local;
-    }
-    if (ybuf) *ybuf = g_y[dev];
-    *counters = g_c[dev];
+    // counters: every counter of a block is zero between launches, so the whole (possibly larger) new block is zeroed
+    int rc = stream_scratch(kScratchMvmCounters, stream, nrb_local * sizeof(unsigned int), ~(size_t)0, &p);
+    if (rc != CLOVER_OK) return rc;
+    *counters = static_cast<unsigned int *>(p);
     return CLOVER_OK;
 }
 
@@ -1027,11 +1017,11 @@ static int launch_mvm8_tma(const int8_t *values, const float *scales, uint64_t r
                            const uint32_t *x32, const float *xs, float *y32, int8_t *yv, float *ys, bool stoch, Key4 key,
                            const uint64_t *tables, cudaStream_t stream) {
     const uint64_t nrb = rows_local >> 6;
-    // fp32 row results pass through global memory (the caller's y32, else a grow-only per-device scratch) and a
-    // zero-initialised counter per row block, re-armed by the kernel itself (one GEMV stream per device).
+    // fp32 row results pass through global memory (the caller's y32, else a grow-only per-stream scratch) and a
+    // zero-initialised counter per row block, re-armed by the kernel itself.
     float *ybuf = y32;
     unsigned int *counters = nullptr;
-    int rc = mvm_scratch(nrb, (row0 >> 6) + nrb, y32 ? nullptr : &ybuf, &counters);
+    int rc = mvm_scratch(stream, nrb, (row0 >> 6) + nrb, y32 ? nullptr : &ybuf, &counters);
     if (rc != CLOVER_OK) return rc;
     // two CTAs per SM with 3-stage rings, as for the 4-bit kernel, whenever there is more than one round of work items
     // (tools/gemv_shapes.py 60 8: 32768^2 164 -> 160 us, 16384 x 32768 93 -> 83, 8192 x 32768 48 -> 42, 16384 x 4096
@@ -1040,11 +1030,14 @@ static int launch_mvm8_tma(const int8_t *values, const float *scales, uint64_t r
     const char *impl8 = getenv("CLOVER_GEMV_IMPL");
     const bool x2 = impl8 ? !strcmp(impl8, "items32x2") : rows_local / kG8Rows > (uint64_t)sm_count();
     const int smem = (int)(x2 ? sizeof(Gemv8Smem<3, MBITS>) : sizeof(Gemv8Smem<5, MBITS>)) + 1024;
-    static bool attr_set8[2][2] = {{false, false}, {false, false}};
+    // function attributes and occupancy belong to a device's context: remembered per device (clover_set_device may switch)
+    static bool attr_set8[kMaxDevices][2][2] = {};
+    const int dev = current_device();
+    if (dev < 0) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
     auto kern = x2 ? (stoch ? k_m8_mvm_tma<true, 3, MBITS> : k_m8_mvm_tma<false, 3, MBITS>) : (stoch ? k_m8_mvm_tma<true, 5, MBITS> : k_m8_mvm_tma<false, 5, MBITS>);
-    if (!attr_set8[x2][stoch]) {
+    if (!attr_set8[dev][x2][stoch]) {
         CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set8[x2][stoch] = true;
+        attr_set8[dev][x2][stoch] = true;
     }
     CUtensorMap tmap;
     rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows_local, MBITS == 8 ? cols : cols >> 1, kG8Rows);
@@ -1052,9 +1045,9 @@ static int launch_mvm8_tma(const int8_t *values, const float *scales, uint64_t r
     const uint64_t nitems = rows_local / kG8Rows;
     uint64_t slots = (uint64_t)sm_count();
     if (x2) {
-        static int per_sm8[2] = {0, 0};
-        if (!per_sm8[stoch]) CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm8[stoch], kern, kG8Threads, smem));
-        slots *= (uint64_t)std::max(1, std::min(per_sm8[stoch], 2));
+        static int per_sm8[kMaxDevices][2] = {};
+        if (!per_sm8[dev][stoch]) CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm8[dev][stoch], kern, kG8Threads, smem));
+        slots *= (uint64_t)std::max(1, std::min(per_sm8[dev][stoch], 2));
     }
     const unsigned pgrid = (unsigned)(nitems < slots ? nitems : slots);
     kern<<<pgrid, kG8Threads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, ybuf, counters, yv, ys,
@@ -1104,14 +1097,16 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
             // default: 32-row work items, swizzled boxes (k_m4_mvm_tma2)
             float *ybuf = y32;
             unsigned int *counters = nullptr;
-            int rc = mvm_scratch(nrb, (row0 >> 6) + nrb, y32 ? nullptr : &ybuf, &counters);
+            int rc = mvm_scratch(stream, nrb, (row0 >> 6) + nrb, y32 ? nullptr : &ybuf, &counters);
             if (rc != CLOVER_OK) return rc;
             const int smem = (int)(x2 ? sizeof(Gemv4Smem<3>) : sizeof(Gemv4Smem<5>)) + 1024;
-            static bool attr_set2[2][2] = {{false, false}, {false, false}};
+            static bool attr_set2[kMaxDevices][2][2] = {};      // per device: function attributes belong to a device's context
+            const int dev = current_device();
+            if (dev < 0) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
             auto kern = x2 ? (stoch ? k_m4_mvm_tma2<true, 3> : k_m4_mvm_tma2<false, 3>) : (stoch ? k_m4_mvm_tma2<true, 5> : k_m4_mvm_tma2<false, 5>);
-            if (!attr_set2[x2][stoch]) {
+            if (!attr_set2[dev][x2][stoch]) {
                 CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                attr_set2[x2][stoch] = true;
+                attr_set2[dev][x2][stoch] = true;
             }
             CUtensorMap tmap;
             rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows_local, cols >> 1, kG4Rows);
@@ -1119,20 +1114,22 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
             const uint64_t nitems = rows_local / kG4Rows;
             uint64_t slots = (uint64_t)sm_count();
             if (x2) {
-                static int per_sm4[2] = {0, 0};               // asked once per template instance (all devices alike)
-                if (!per_sm4[stoch]) CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4[stoch], kern, kG4Threads, smem));
-                slots *= (uint64_t)std::max(1, std::min(per_sm4[stoch], 2));
+                static int per_sm4[kMaxDevices][2] = {};      // asked once per template instance and device
+                if (!per_sm4[dev][stoch]) CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4[dev][stoch], kern, kG4Threads, smem));
+                slots *= (uint64_t)std::max(1, std::min(per_sm4[dev][stoch], 2));
             }
             const unsigned pgrid = (unsigned)(nitems < slots ? nitems : slots);
             kern<<<pgrid, kG4Threads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, ybuf, counters, yv, ys,
                                                       key, tables, peers ? *peers : PeerOut());
         } else {
             const int smem = (int)sizeof(GemvSmem);
-            static bool attr_set[2] = {false, false};      // per template instance (process-wide; all devices alike)
+            static bool attr_set[kMaxDevices][2] = {};      // per template instance and device
+            const int dev = current_device();
+            if (dev < 0) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
             auto kern = stoch ? k_m4_mvm_tma<true> : k_m4_mvm_tma<false>;
-            if (!attr_set[stoch]) {
+            if (!attr_set[dev][stoch]) {
                 CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                attr_set[stoch] = true;
+                attr_set[dev][stoch] = true;
             }
             CUtensorMap tmap;
             int rc = make_tensor_map_u32_2d(&tmap, values, rows_local, cols >> 3, cols >> 1, 32, kKC * 8);

@@ -1,6 +1,8 @@
 // runtime.cu - library state: error string, launch counter, PRNG jump tables, memory helpers.
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <stdarg.h>
 #include <string.h>
 #include <vector>
@@ -25,6 +27,12 @@ int cuda_fail(cudaError_t e, const char *what) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+    return dev;
+}
+
 int sm_count() {
     static int cached[64] = {0};
     int dev = 0;
@@ -35,6 +43,34 @@ int sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+// ---- per-(device, stream, slot) scratch -------------------------------------------------------------
+struct ScratchBlock { void *ptr = nullptr; size_t bytes = 0; };
+static std::mutex g_scratch_mutex;
+static std::map<std::tuple<int, cudaStream_t, int>, ScratchBlock> g_scratch;
+static std::vector<void *> g_scratch_retired;         // kept alive until the library is unloaded (captured graphs)
+
+int stream_scratch(ScratchSlot slot, cudaStream_t stream, size_t bytes, size_t zero_bytes, void **out) {
+    int dev = 0;
+    CLOVER_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    ScratchBlock &b = g_scratch[std::make_tuple(dev, stream, (int)slot)];
+    if (b.bytes < bytes) {
+        const size_t want = b.bytes ? std::max(bytes, 2 * b.bytes) : bytes;
+        void *p = nullptr;
+        CLOVER_CUDA_CHECK(cudaMalloc(&p, want));
+        if (zero_bytes) {
+            // ordered before the caller's first kernel on `stream`; the legacy default stream orders itself
+            cudaError_t e = cudaMemsetAsync(p, 0, std::min(zero_bytes, want), stream);
+            if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaMemsetAsync(scratch)"); }
+        }
+        if (b.ptr) g_scratch_retired.push_back(b.ptr);
+        b.ptr = p;
+        b.bytes = want;
+    }
+    *out = b.ptr;
+    return CLOVER_OK;
 }
 
 // ---- jump tables: level i holds L^(2^i) as 8 byte-indexed tables --------------------------------

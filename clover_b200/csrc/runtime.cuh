@@ -15,6 +15,17 @@ void set_error(const char *fmt, ...);
 int  cuda_fail(cudaError_t e, const char *what);     // records the message, returns CLOVER_ERR_CUDA
 void count_launch(int n = 1);
 int  sm_count();                                      // SMs of the current device (148 on B200)
+constexpr int kMaxDevices = 64;
+int  current_device();                                // cudaGetDevice, or -1 when outside [0, kMaxDevices)
+
+// Kernel scratch (tickets, partial results, expanded operands): grow-only blocks keyed by (current device, stream, slot),
+// so that calls on different streams of one device never share tickets or intermediates (the ABI takes a stream per
+// call). A block that has to grow is RETIRED, not freed - a CUDA graph captured earlier may still reference it - and
+// the replacement is at least twice as large, which bounds the retired memory by the live block. The first
+// `zero_bytes` of a NEW block are zeroed (counters that every kernel leaves clean). Allocation is a synchronous
+// cudaMalloc: call once outside a stream capture with the sizes the capture will use (clover_b200.h, "Streams").
+enum ScratchSlot { kScratchMvmY = 0, kScratchMvmCounters, kScratchGemm, kScratchThreshold, kScratchDotPartials, kScratchDotTicket, kScratchSlots };
+int stream_scratch(ScratchSlot slot, cudaStream_t stream, size_t bytes, size_t zero_bytes, void **out);
 
 // device copy of the jump tables for the CURRENT device (uploaded on first use); nullptr on failure
 const uint64_t *device_jump_tables();

@@ -471,25 +471,9 @@ __global__ void k_thr_apply_mask(uint32_t *__restrict__ values, uint64_t n, uint
 
 // ---- host side -----------------------------------------------------------------------------------------------------
 struct ThrWorkspace { void *p; size_t bytes; };
-static std::mutex g_thr_mutex;
-static ThrWorkspace g_thr_ws[64] = {};
-
-// grow-only per-device scratch (selection state, per-CTA tie counts, EXACT-mode magnitudes / heap / mask);
-// one threshold stream per device at a time, like the GEMM workspace
-static int thr_workspace(size_t bytes, void **out) {
-    int dev = 0;
-    CLOVER_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
-    std::lock_guard<std::mutex> lock(g_thr_mutex);
-    ThrWorkspace &ws = g_thr_ws[dev];
-    if (ws.bytes < bytes) {
-        if (ws.p) { CLOVER_CUDA_CHECK(cudaDeviceSynchronize()); CLOVER_CUDA_CHECK(cudaFree(ws.p)); ws.p = nullptr; ws.bytes = 0; }
-        CLOVER_CUDA_CHECK(cudaMalloc(&ws.p, bytes));
-        CLOVER_CUDA_CHECK(cudaMemset(ws.p, 0, sizeof(ThrState)));      // hist[] / ticket start clean; every pass leaves them clean
-        ws.bytes = bytes;
-    }
-    *out = ws.p;
-    return CLOVER_OK;
+// workspace keyed by (device, stream): hist[] / ticket (the ThrState at its head) start clean and every pass leaves them clean
+static int thr_workspace(cudaStream_t stream, size_t bytes, void **out) {
+    return stream_scratch(kScratchThreshold, stream, bytes, sizeof(ThrState), out);
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -512,7 +496,7 @@ static int launch_threshold(int8_t *values, const float *scales, uint64_t n, uin
         const size_t off_mag = align_up(sizeof(ThrState), 256);          // the FAST path's state keeps the head of the workspace
         const size_t off_heap = off_mag + align_up(n * sizeof(float), 256), off_keep = off_heap + align_up(k * sizeof(HeapItem), 256);
         void *ws = nullptr;
-        int rc = thr_workspace(off_keep + align_up(n, 256), &ws);
+        int rc = thr_workspace(stream, off_keep + align_up(n, 256), &ws);
         if (rc != CLOVER_OK) return rc;
         float *mag = reinterpret_cast<float *>(static_cast<uint8_t *>(ws) + off_mag);
         HeapItem *heap = reinterpret_cast<HeapItem *>(static_cast<uint8_t *>(ws) + off_heap);
@@ -526,7 +510,7 @@ static int launch_threshold(int8_t *values, const float *scales, uint64_t n, uin
     if (n <= kThrSmallLimit) {
         const size_t off_mag = align_up(sizeof(ThrState), 256);
         void *ws = nullptr;
-        int rc = thr_workspace(off_mag + nwords * E * sizeof(uint32_t), &ws);
+        int rc = thr_workspace(stream, off_mag + nwords * E * sizeof(uint32_t), &ws);
         if (rc != CLOVER_OK) return rc;
         k_thr_small<BITS><<<1, kThrSmallThreads, 0, stream>>>(v32, scales, n, (uint32_t)nwords, k,
                                                               reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ws) + off_mag));
@@ -536,7 +520,7 @@ static int launch_threshold(int8_t *values, const float *scales, uint64_t n, uin
     if (n <= kThrClusterLimit) {
         const size_t off_mag = align_up(sizeof(ThrState), 256);
         void *ws = nullptr;
-        int rc = thr_workspace(off_mag + nwords * E * sizeof(uint32_t), &ws);
+        int rc = thr_workspace(stream, off_mag + nwords * E * sizeof(uint32_t), &ws);
         if (rc != CLOVER_OK) return rc;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(kThrClusterSize);
@@ -554,7 +538,7 @@ static int launch_threshold(int8_t *values, const float *scales, uint64_t n, uin
     const uint64_t words_per_cta = (nwords + grid - 1) / grid;
     const size_t off_cnt = align_up(sizeof(ThrState), 256), off_base = off_cnt + align_up(sizeof(uint32_t) * grid, 256);
     void *ws = nullptr;
-    int rc = thr_workspace(off_base + sizeof(uint64_t) * grid, &ws);
+    int rc = thr_workspace(stream, off_base + sizeof(uint64_t) * grid, &ws);
     if (rc != CLOVER_OK) return rc;
     ThrState *st = static_cast<ThrState *>(ws);
     uint32_t *tie_count = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ws) + off_cnt);

@@ -417,24 +417,15 @@ k_vdot_fast(const uint4 *__restrict__ u, const float *__restrict__ su, const uin
 }
 
 // per-(device, stream) workspace for the cross-CTA reduction
-static std::mutex g_ws_mutex;
-static std::map<std::pair<int, cudaStream_t>, DotWorkspace> g_ws;
-
 static int dot_workspace(cudaStream_t stream, int grid, DotWorkspace *out) {
-    int dev = 0;
-    CLOVER_CUDA_CHECK(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
-    DotWorkspace &ws = g_ws[std::make_pair(dev, stream)];
-    if (ws.capacity < grid) {
-        if (ws.partials) cudaFree(ws.partials);
-        if (ws.ticket) cudaFree(ws.ticket);
-        ws = DotWorkspace{nullptr, nullptr, 0};
-        CLOVER_CUDA_CHECK(cudaMalloc(&ws.partials, sizeof(double) * (size_t)grid));
-        CLOVER_CUDA_CHECK(cudaMalloc(&ws.ticket, sizeof(unsigned int)));
-        CLOVER_CUDA_CHECK(cudaMemset(ws.ticket, 0, sizeof(unsigned int)));
-        ws.capacity = grid;
-    }
-    *out = ws;
+    void *p = nullptr, *t = nullptr;
+    int rc = stream_scratch(kScratchDotPartials, stream, sizeof(double) * (size_t)grid, 0, &p);
+    if (rc != CLOVER_OK) return rc;
+    rc = stream_scratch(kScratchDotTicket, stream, sizeof(unsigned int), sizeof(unsigned int), &t);
+    if (rc != CLOVER_OK) return rc;
+    out->partials = static_cast<double *>(p);
+    out->ticket = static_cast<unsigned int *>(t);
+    out->capacity = grid;
     return CLOVER_OK;
 }
 

@@ -25,6 +25,12 @@
  *     the reference's CLOVER_STOCHASTIC_ROUNDING_DISABLED behaviour (CMakeLists.txt:78-80). A non-NULL
  *     key is consumed exactly like the reference's sequential code consumes it (same XORShift128+
  *     stream, include/simdxorshift128plus.h:97-109) and is advanced in place before the call returns.
+ *   - Streams: calls on DIFFERENT streams of one device are independent - kernel scratch (tickets, fp32 intermediates,
+ *     the GEMM's expanded operands) is keyed by (device, stream), allocated on the first call that needs it and grown
+ *     with a synchronous cudaMalloc; a replaced block is kept alive, so CUDA graphs captured earlier stay valid. Because
+ *     of that first-use allocation, run a call sequence once on the capturing stream BEFORE capturing it. A call with a
+ *     non-NULL key cannot be captured usefully (the key is read on the host at launch time).
+ *     Calls on the SAME stream are ordered like any other stream work.
  *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with
  *     CLOVER_ERR_CUDA.
  */

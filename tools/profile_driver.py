@@ -79,10 +79,15 @@ elif what == "mvm4v8":
     x, y = cb.CloverVector8(n), cb.CloverVector8(n)
     v = cb.CloverVector32(n); v.values.uniform_(-1, 1, generator=g); x.quantize(v)
     fn = lambda: M.mvm(x, y)
-elif what == "mvmf32":
+elif what in ("mvmf32", "mvm8f32"):
     n = 32768
-    M = cb.CloverMatrix4(n, n)
-    M.values.copy_(random_nibbles(torch, n * n // 2, g, dev)); M.scales.uniform_(0.25, 1.0, generator=g)
+    if what == "mvmf32":
+        M = cb.CloverMatrix4(n, n)
+        M.values.copy_(random_nibbles(torch, n * n // 2, g, dev))
+    else:
+        M = cb.CloverMatrix8(n, n)
+        M.values.copy_(torch.randint(-127, 128, (n * n,), dtype=torch.int8, device=dev, generator=g))
+    M.scales.uniform_(0.25, 1.0, generator=g)
     x, y = cb.CloverVector32(n), cb.CloverVector32(n)
     x.values.uniform_(-1, 1, generator=g)
     fn = lambda: M.mvm(x, y)
