@@ -75,6 +75,12 @@ _SIGNATURES = {
     "clover_host_v4_quantize": (_int, [_vp, _u64, _vp, _vp, _vp]),
     "clover_host_v4_dot": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _int]),
     "clover_host_m4_mvm": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "clover_m4_sharded_create": (_int, [C.POINTER(_vp), _u64, _u64, _int, _vp]),
+    "clover_m4_sharded_destroy": (_int, [_vp]),
+    "clover_m4_sharded_world": (_int, [_vp]),
+    "clover_m4_sharded_shard": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp]),
+    "clover_m4_sharded_load_host": (_int, [_vp, _vp, _vp]),
+    "clover_m4_sharded_mvm_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 ABI_SYMBOLS = tuple(_SIGNATURES)

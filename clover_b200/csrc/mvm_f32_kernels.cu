@@ -8,9 +8,11 @@
 // include/CloverBase.h:149-157. Every element costs an int->float, a rounded multiply and an fma in that order, so
 // these kernels are bound by the CUDA cores' issue rate, not by HBM; the design minimises instructions per element:
 //
-//   * thread = one matrix row, warp = 32 consecutive rows (one work item), all 32 chains of the row in registers
-//     (16 packed f32x2 accumulators): the final reduction is thread-local, no shuffles anywhere in the loop;
-//   * the matrix streams through per-warp TMA rings: cp.async.bulk.tensor boxes of 32 rows x 128 bytes with the
+//   * thread = half of one matrix row's chains (accumulators 2kh, 2kh+1 = 16 of the 32 chains, 8 packed f32x2
+//     accumulators), warp = 16 consecutive rows (one work item): no shuffles anywhere in the loop, one exchange
+//     between the two threads of a row at its end; 16-row items give 2048 items at 32768 rows = 14 warps per SM
+//     (32-row items: 7 warps per SM issued in 61 % of the cycles, ncu r02b);
+//   * the matrix streams through per-warp TMA rings: cp.async.bulk.tensor boxes of 16 rows x 128 bytes with the
 //     128-byte swizzle (a quarter warp's 16-byte loads fall into 8 different 16-byte bank groups), the matching slice
 //     of x by a 1D bulk copy into the same stage; the warp's own lane 0 refills a stage as soon as the warp has
 //     consumed it (no producer warp, no empty-barriers);
@@ -28,15 +30,10 @@
 
 namespace clover {
 
-constexpr int kF32Warps = 8;            // warps (= concurrent work items) per CTA
+constexpr int kF32Rows = 16;            // rows per work item (= per warp)
+constexpr int kF32Warps = 16;           // warps (= concurrent work items) per CTA
 constexpr int kF32Stages = 4;           // ring depth per warp
-constexpr int kF32StageBytes = 5120;    // 32 rows x 128 B + up to 256 floats of x, a multiple of 1024 (swizzle atom)
-
-struct __align__(1024) F32Stage {
-    uint8_t rows[32 * 128];
-    float x[256];
-};
-static_assert(sizeof(F32Stage) == kF32StageBytes, "stage size");
+constexpr int kF32StageBytes = 3072;    // 16 rows x 128 B + up to 256 floats of x, a multiple of 1024 (swizzle atom)
 
 constexpr int kF32SmemBytes = kF32Warps * kF32Stages * kF32StageBytes + kF32Warps * kF32Stages * 8 + 1024 /* alignment slack */;
 
@@ -104,6 +101,12 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
     return v;
 }
 
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
 template <int MBITS>
 __global__ void __launch_bounds__(kF32Warps * 32, 1)
 k_mvm_f32_ring(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows, uint64_t cols,
@@ -112,7 +115,11 @@ k_mvm_f32_ring(const __grid_constant__ CUtensorMap tmap, const float *__restrict
     constexpr int kBPC = MBITS == 4 ? 4 : 2;                          // blocks of 64 columns per 128-byte chunk
     constexpr float kQ = MBITS == 4 ? 7.0f : 127.0f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t hb = (uint32_t)(cols >> 6), nitems = (uint32_t)(rows >> 5);
+    // thread = (row r of the 16-row work item, accumulator pair kh: accumulators 2kh, 2kh+1 = elements 16kh .. 16kh+15 of
+    // each half block). The mapping keeps every shared-memory load conflict-free under the 128-byte swizzle: the 4-bit
+    // kernel loads 8 bytes per half block (a half warp = 8 rows x 2 kh), the 8-bit kernel 16 bytes (a quarter warp = 8 rows).
+    const int r = MBITS == 4 ? lane >> 1 : lane & 15, kh = MBITS == 4 ? lane & 1 : lane >> 4;
+    const uint32_t hb = (uint32_t)(cols >> 6), nitems = (uint32_t)(rows / kF32Rows);
     const uint32_t nchunks = (hb + kBPC - 1) / kBPC;
     const uint32_t wstride = gridDim.x * kF32Warps;
     const uint32_t first = (uint32_t)warp * gridDim.x + blockIdx.x;      // warp-major: every SM gets the same number of busy warps
@@ -137,10 +144,10 @@ k_mvm_f32_ring(const __grid_constant__ CUtensorMap tmap, const float *__restrict
         const uint32_t nb = min((uint32_t)kBPC, hb - p_c * kBPC);
         const uint32_t dst = ring + p_s * kF32StageBytes, bar = bars + 8 * p_s;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the warp's reads of this stage precede the refill
-        mbar_arrive_expect_tx_a(bar, 32 * 128 + nb * 256);
-        tma_load_2d_a(dst, &tmap, (int)(p_c * 128), (int)(p_item * 32), bar);
+        mbar_arrive_expect_tx_a(bar, kF32Rows * 128 + nb * 256);
+        tma_load_2d_a(dst, &tmap, (int)(p_c * 128), (int)(p_item * kF32Rows), bar);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(dst + 4096u), "l"(x + (uint64_t)p_c * kBPC * 64), "r"(nb * 256u), "r"(bar) : "memory");
+                     ::"r"(dst + kF32Rows * 128u), "l"(x + (uint64_t)p_c * kBPC * 64), "r"(nb * 256u), "r"(bar) : "memory");
         if (++p_s == kF32Stages) p_s = 0;
         if (++p_c == nchunks) { p_c = 0; p_item += wstride; }
     };
@@ -151,52 +158,46 @@ k_mvm_f32_ring(const __grid_constant__ CUtensorMap tmap, const float *__restrict
     auto load_scale = [&](uint32_t item, uint32_t c) -> float {
         if (item >= nitems) return 1.0f;
         const uint32_t b = min(c * kBPC + (uint32_t)(lane & (kBPC - 1)), hb - 1);
-        return __ldg(scales + (uint64_t)(item >> 1) * hb + b);
+        return __ldg(scales + (uint64_t)(item / (64 / kF32Rows)) * hb + b);
     };
 
     const uint64_t neg = MBITS == 4 ? pack2f(-12582920.0f, -12582920.0f) : pack2f(-12583040.0f, -12583040.0f);   // -(magic + bias)
     const RegConsts rc = reg_consts(zero);
-    const uint32_t rsw = (uint32_t)(lane & 7), rowoff = (uint32_t)lane * 128u;
+    const uint32_t rsw = (uint32_t)(r & 7), rowoff = (uint32_t)r * 128u;
     uint32_t s = 0, phase = 0;
     float sraw = load_scale(first, 0);
     for (uint32_t item = first; item < nitems; item += wstride) {
-        uint64_t acc[4][4];
+        uint64_t acc[2][4];                                            // accumulators 2kh, 2kh+1; pair p = AVX lanes 2p, 2p+1
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 2; ++k)
 #pragma unroll
             for (int p = 0; p < 4; ++p) acc[k][p] = 0ull;
         for (uint32_t c = 0; c < nchunks; ++c) {
             const float sdiv = __fdiv_rn(sraw, kQ);                    // s = su[b] / 7.0f (:1488) resp. / 127.0f (:587)
             sraw = c + 1 < nchunks ? load_scale(item, c + 1) : load_scale(item + wstride, 0);
             mbar_wait_a(bars + 8 * s, phase);
-            const uint32_t st = ring + s * kF32StageBytes, rowp = st + rowoff, xs = st + 4096u;
+            const uint32_t st = ring + s * kF32StageBytes, rowp = st + rowoff, xs = st + kF32Rows * 128u + 64u * (uint32_t)kh;
             const int nb = (int)min((uint32_t)kBPC, hb - c * kBPC);
             for (int j = 0; j < nb; ++j) {
                 const float sj = __shfl_sync(0xFFFFFFFFu, sdiv, j);
                 const uint64_t ss = pack2f(sj, sj);
-                const uint32_t xb = xs + (uint32_t)j * 256u;
+                const uint32_t xb = xs + (uint32_t)j * 256u;           // x[64j + 16kh ...]; the second half block is 128 bytes further
                 if (MBITS == 4) {
-                    const uint4 w0 = lds128(rowp + ((((uint32_t)(2 * j)) ^ rsw) << 4));        // elements  0..31
-                    const uint4 w1 = lds128(rowp + ((((uint32_t)(2 * j + 1)) ^ rsw) << 4));    // elements 32..63
-                    const uint32_t a0[4] = {w0.x, w0.y, w0.z, w0.w}, a1[4] = {w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        word4(a0[k], lds128f(xb + 32 * k), lds128f(xb + 32 * k + 16), ss, neg, rc, acc[k]);                // element 8k+l
-                        word4(a1[k], lds128f(xb + 128 + 32 * k), lds128f(xb + 128 + 32 * k + 16), ss, neg, rc, acc[k]);    // element 32+8k+l
-                    }
+                    const uint2 w0 = lds64(rowp + ((((uint32_t)(2 * j)) ^ rsw) << 4) + 8u * (uint32_t)kh);        // elements 16kh .. 16kh+15
+                    const uint2 w1 = lds64(rowp + ((((uint32_t)(2 * j + 1)) ^ rsw) << 4) + 8u * (uint32_t)kh);    // elements 32+16kh ..
+                    word4(w0.x, lds128f(xb), lds128f(xb + 16), ss, neg, rc, acc[0]);                // element 8k+l, k = 2kh
+                    word4(w0.y, lds128f(xb + 32), lds128f(xb + 48), ss, neg, rc, acc[1]);           //               k = 2kh+1
+                    word4(w1.x, lds128f(xb + 128), lds128f(xb + 144), ss, neg, rc, acc[0]);         // element 32+8k+l
+                    word4(w1.y, lds128f(xb + 160), lds128f(xb + 176), ss, neg, rc, acc[1]);
                 } else {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {                      // half h: elements 32h .. 32h+31 = 16-byte chunks 4j+2h, 4j+2h+1
-#pragma unroll
-                        for (int cc = 0; cc < 2; ++cc) {
-                            const uint4 w = lds128(rowp + ((((uint32_t)(4 * j + 2 * h + cc)) ^ rsw) << 4));
-                            const uint32_t xq = xb + 128 * h + 64 * cc;    // x[32h + 16cc ...]
-                            // 16 elements = accumulators k = 2cc, 2cc+1; word i covers lanes 4(i&1)..4(i&1)+3 of accumulator 2cc + (i>>1)
-                            word8(w.x, lds128f(xq), ss, neg, rc, &acc[2 * cc][0]);
-                            word8(w.y, lds128f(xq + 16), ss, neg, rc, &acc[2 * cc][2]);
-                            word8(w.z, lds128f(xq + 32), ss, neg, rc, &acc[2 * cc + 1][0]);
-                            word8(w.w, lds128f(xq + 48), ss, neg, rc, &acc[2 * cc + 1][2]);
-                        }
+                    for (int h = 0; h < 2; ++h) {                      // half h: this thread's 16 bytes = 16-byte chunk 4j + 2h + kh
+                        const uint4 w = lds128(rowp + ((((uint32_t)(4 * j + 2 * h) + (uint32_t)kh) ^ rsw) << 4));
+                        const uint32_t xq = xb + 128u * h;
+                        word8(w.x, lds128f(xq), ss, neg, rc, &acc[0][0]);          // accumulator 2kh, lanes 0..3
+                        word8(w.y, lds128f(xq + 16), ss, neg, rc, &acc[0][2]);     //                   lanes 4..7
+                        word8(w.z, lds128f(xq + 32), ss, neg, rc, &acc[1][0]);     // accumulator 2kh+1
+                        word8(w.w, lds128f(xq + 48), ss, neg, rc, &acc[1][2]);
                     }
                 }
             }
@@ -204,15 +205,19 @@ k_mvm_f32_ring(const __grid_constant__ CUtensorMap tmap, const float *__restrict
             if (lane == 0) issue();
             if (++s == kF32Stages) { s = 0; phase ^= 1; }
         }
-        // (acc_1 + acc_2) + (acc_3 + acc_4), then the hadd tree ((a4+a0)+(a6+a2))+((a5+a1)+(a7+a3)) (CloverBase.h:149-157)
+        // (acc_1 + acc_2) resp. (acc_3 + acc_4) in this thread, their sum across the thread pair, then the hadd tree
+        // ((a4+a0)+(a6+a2))+((a5+a1)+(a7+a3)) (CloverBase.h:149-157)
         float t[8];
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            t[2 * p] = __fadd_rn(__fadd_rn(lo_f(acc[0][p]), lo_f(acc[1][p])), __fadd_rn(lo_f(acc[2][p]), lo_f(acc[3][p])));
-            t[2 * p + 1] = __fadd_rn(__fadd_rn(hi_f(acc[0][p]), hi_f(acc[1][p])), __fadd_rn(hi_f(acc[2][p]), hi_f(acc[3][p])));
+            t[2 * p] = __fadd_rn(lo_f(acc[0][p]), lo_f(acc[1][p]));
+            t[2 * p + 1] = __fadd_rn(hi_f(acc[0][p]), hi_f(acc[1][p]));
         }
-        y[(uint64_t)item * 32 + lane] = __fadd_rn(__fadd_rn(__fadd_rn(t[4], t[0]), __fadd_rn(t[6], t[2])),
-                                                  __fadd_rn(__fadd_rn(t[5], t[1]), __fadd_rn(t[7], t[3])));
+#pragma unroll
+        for (int l = 0; l < 8; ++l) t[l] = __fadd_rn(t[l], __shfl_xor_sync(0xFFFFFFFFu, t[l], MBITS == 4 ? 1 : 16));   // fp32 add commutes bit for bit
+        if (kh == 0)
+            y[(uint64_t)item * kF32Rows + r] = __fadd_rn(__fadd_rn(__fadd_rn(t[4], t[0]), __fadd_rn(t[6], t[2])),
+                                                         __fadd_rn(__fadd_rn(t[5], t[1]), __fadd_rn(t[7], t[3])));
     }
 }
 
@@ -266,13 +271,15 @@ static int launch_mvm_f32(const int8_t *values, const float *scales, uint64_t ro
             reinterpret_cast<const uint8_t *>(values), scales, rows, cols, x32, y32);
     } else {
         CUtensorMap tmap;
-        int rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows, MBITS == 4 ? cols >> 1 : cols, 32);
+        int rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows, MBITS == 4 ? cols >> 1 : cols, kF32Rows);
         if (rc != CLOVER_OK) return rc;
         const int smem = kF32SmemBytes;
         auto kern = k_mvm_f32_ring<MBITS>;
         CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   // per device and call: cheap
-        const uint64_t nitems = rows >> 5, want = (nitems + kF32Warps - 1) / kF32Warps;
-        const unsigned grid = (unsigned)(want < (uint64_t)sm_count() ? want : (uint64_t)sm_count());
+        // one CTA per SM as soon as there are that many work items: the warp-major item order then spreads the busy warps
+        // evenly over all SMs (round 2a launched ceil(items / warps) CTAs and left 20 SMs idle at 32768 rows)
+        const uint64_t nitems = rows / kF32Rows;
+        const unsigned grid = (unsigned)(nitems < (uint64_t)sm_count() ? nitems : (uint64_t)sm_count());
         kern<<<grid, kF32Warps * 32, smem, stream>>>(tmap, scales, rows, cols, x32, y32, 0u);
     }
     count_launch();

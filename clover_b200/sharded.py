@@ -162,8 +162,9 @@ class ShardedCloverMatrix4:
         self._peer = None
 
     def _mvm_fused(self, x: CloverVector4, y, key_ptr):
-        """y = None: returns a CloverVector4 VIEW of the shared result buffer of this step (valid until the step
-        after next) - no copy at all; otherwise the result is copied into the caller's vector."""
+        """y = None: returns a CloverVector4 VIEW of the shared result buffer of this step - no copy at all. The view is
+        valid until this rank issues its NEXT mvm (a faster peer may then already be storing the step after that into the
+        same buffer); otherwise the result is copied into the caller's vector."""
         pr = self._peer
         pr["epoch"] += 1
         k = pr["epoch"] & 1

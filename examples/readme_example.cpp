@@ -3,6 +3,7 @@
 //   g++ -std=c++17 -Iinclude examples/readme_example.cpp -Lclover_b200 -lclover_b200 -Wl,-rpath,$PWD/clover_b200 -o /tmp/readme_example
 #include <clover_b200/containers.hpp>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -160,8 +161,38 @@ static void reference_harness(uint64_t m, uint64_t n) {
     std::cout << "reference harness " << m << "x" << n << " bits=" << Q.getBitsLength() << " ok" << std::endl;
 }
 
+// The sharded matrix over every GPU this process can see gives the bytes of the single-GPU mvm.
+static void sharded(uint64_t m, uint64_t n) {
+    const int gpus = std::min(clover_device_count(), 8);
+    CloverMatrix32 a32(m, n);
+    CloverVector32 x32(n);
+    uint64_t key[8];
+    clover_prng_init(7, 9, key);
+    a32.setRandomFloats(-1.0f, 1.0f, key, key + 4);
+    x32.setRandomFloats(-1.0f, 1.0f, key, key + 4);
+    CloverMatrix4 A(m, n);
+    A.quantize(a32);
+    CloverVector4 x(n), y(m), ys(m);
+    x.quantize(x32);
+    A.mvm(x, y);
+    for (int g = 1; g <= gpus; g *= 2) {
+        ShardedCloverMatrix4 S(m, n, g);
+        S.load(A);
+        for (int round = 0; round < 3; ++round) {          // epochs / alternating result buffers
+            S.mvm(x, ys);
+            if (std::memcmp(y.host_values(), ys.host_values(), y.size_pad() / 2) != 0 ||
+                std::memcmp(y.host_scales(), ys.host_scales(), y.size_pad() / 64 * sizeof(float)) != 0) {
+                std::cout << "sharded mvm mismatch on " << g << " GPUs" << std::endl; exit(1);
+            }
+        }
+        std::cout << "sharded mvm " << m << "x" << n << " on " << g << " GPU(s) ok" << std::endl;
+    }
+}
+
 int main() {
     example();
+    sharded(1024, 2048);
+    sharded(4096, 16384 + 128);
     reference_harness<CloverMatrix4>(256, 384);
     reference_harness<CloverMatrix8>(256, 384);
     validate_mvm<CloverMatrix4, CloverVector4>(256, 384);

@@ -237,6 +237,25 @@ int clover_host_v4_dot(const int8_t *u_host, const float *su_host, const int8_t 
 int clover_host_m4_mvm(const int8_t *values_dev, const float *scales_dev, uint64_t rows, uint64_t cols,
                        const int8_t *xv_host, const float *xs_host, int8_t *yv_host, float *ys_host, uint64_t *key_host);
 
+
+/* ---- row-sharded multi-GPU mvm behind one handle (no counterpart in the reference) --------------------
+ * ONE host process drives `ngpus` GPUs of the node (devices[] or 0..ngpus-1; peer access must be possible between all of
+ * them): rows are sharded in whole 64-row blocks, x is replicated, every GPU runs clover_m4_mvm_shard_fused - the GEMV
+ * whose epilogue stores each re-quantized block into every GPU's result vector over NVLink and synchronises with flags,
+ * no collective library. The result is the CloverVector4 the single-GPU clover_m4_mvm returns, bit for bit.
+ *   _shard      : where rank's rows live (fill them on the device, e.g. with clover_m4_quantize on that device)
+ *   _load_host  : scatter a whole matrix (reference layout, host memory) to the shards
+ *   _mvm_host   : x from host memory to every GPU, one kernel per GPU, y back to host memory; returns when y is there */
+typedef struct clover_m4_sharded clover_m4_sharded;
+int clover_m4_sharded_create(clover_m4_sharded **out, uint64_t rows, uint64_t cols, int ngpus, const int *devices);
+int clover_m4_sharded_destroy(clover_m4_sharded *h);
+int clover_m4_sharded_world(const clover_m4_sharded *h);
+int clover_m4_sharded_shard(clover_m4_sharded *h, int rank, int *device, uint64_t *row0, uint64_t *rows_local,
+                            int8_t **values_dev, float **scales_dev);
+int clover_m4_sharded_load_host(clover_m4_sharded *h, const int8_t *values_host, const float *scales_host);
+int clover_m4_sharded_mvm_host(clover_m4_sharded *h, const int8_t *xv_host, const float *xs_host, int8_t *yv_host, float *ys_host,
+                               uint64_t *key_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -249,6 +249,8 @@ public:
     float *getScales() const { return reinterpret_cast<float *>(buf.host_rw_part(value_bytes())); }
     const int8_t *device_values() const { return static_cast<const int8_t *>(buf.dev_in()); }
     const float *device_scales() const { return reinterpret_cast<const float *>(static_cast<const char *>(buf.dev_in()) + value_bytes()); }
+    const int8_t *host_values() const { return reinterpret_cast<const int8_t *>(buf.host_ro()); }      // read-only host image
+    const float *host_scales() const { return reinterpret_cast<const float *>(buf.host_ro() + value_bytes()); }
     int8_t *device_values_out() { return static_cast<int8_t *>(buf.dev_out()); }
     float *device_scales_out() { return reinterpret_cast<float *>(static_cast<char *>(buf.dev_out()) + value_bytes()); }
 
@@ -393,6 +395,8 @@ public:
     float *getScales() const { return reinterpret_cast<float *>(buf.host_rw() + value_bytes()); }
     const int8_t *device_values() const { return static_cast<const int8_t *>(buf.dev_in()); }
     const float *device_scales() const { return reinterpret_cast<const float *>(static_cast<const char *>(buf.dev_in()) + value_bytes()); }
+    const int8_t *host_values() const { return reinterpret_cast<const int8_t *>(buf.host_ro()); }      // read-only host image
+    const float *host_scales() const { return reinterpret_cast<const float *>(buf.host_ro() + value_bytes()); }
 
     void quantize(const CloverMatrix32 &m) {
         if (m.getRows() != rows || m.getCols() != cols) { std::cout << "Matrices do not have the same size. Exiting ..." << std::endl; exit(1); }
@@ -500,6 +504,40 @@ public:
         const float *s = reinterpret_cast<const float *>(buf.host_ro() + value_bytes());
         return (s[(i >> 6) * (cols >> 6) + (j >> 6)] / 127.0f) * (float)q;
     }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row-sharded CloverMatrix4 over several GPUs of the node, driven by this one process: mvm() returns the
+// same CloverVector4 bytes as CloverMatrix4::mvm on one GPU. No counterpart in the reference.
+class ShardedCloverMatrix4 : public clover_b200_detail::Keyed {
+    clover_m4_sharded *h = nullptr;
+    uint64_t rows, cols;
+public:
+    ShardedCloverMatrix4(uint64_t r, uint64_t c, int ngpus, const int *devices = nullptr)
+        : rows(clover_b200_detail::pad128(r)), cols(clover_b200_detail::pad128(c)) {
+        clover_b200_detail::check(clover_m4_sharded_create(&h, rows, cols, ngpus, devices), "clover_m4_sharded_create");
+    }
+    ShardedCloverMatrix4(const ShardedCloverMatrix4 &) = delete;
+    ShardedCloverMatrix4 &operator=(const ShardedCloverMatrix4 &) = delete;
+    ~ShardedCloverMatrix4() { clover_m4_sharded_destroy(h); }
+    uint64_t getRows() const { return rows; }
+    uint64_t getCols() const { return cols; }
+    int getGpus() const { return clover_m4_sharded_world(h); }
+    // scatter a quantized matrix (host image in the reference layout) to the shards
+    void load(const CloverMatrix4 &m) {
+        if (m.getRows() != rows || m.getCols() != cols) { std::cout << "Matrices do not have the same size. Exiting ..." << std::endl; exit(1); }
+        clover_b200_detail::check(clover_m4_sharded_load_host(h, m.host_values(), m.host_scales()), "clover_m4_sharded_load_host");
+    }
+    void mvm(const CloverVector4 &productVector, CloverVector4 &resultVector) {
+        if (productVector.size() != getCols() || resultVector.size_pad() != getRows()) {
+            std::cout << "MVM can not be performed. Exiting ..." << std::endl;
+            exit(1);
+        }
+        // host images: x is read, y is overwritten entirely (values and scales of every block)
+        clover_b200_detail::check(clover_m4_sharded_mvm_host(h, productVector.host_values(), productVector.host_scales(),
+                                                             resultVector.getData(), resultVector.getScales(), key_ptr()), "mvm");
+    }
+    void mvm_parallel(const CloverVector4 &x, CloverVector4 &y) { mvm(x, y); }
 };
 
 #endif  // CLOVER_B200_CONTAINERS_HPP

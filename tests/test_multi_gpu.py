@@ -46,3 +46,54 @@ def test_exchange_modes_two_gpus():
            "--master-port", "29511", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0 and "multi-gpu ok" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("shape", [(1024, 2048), (64 * 7 + 64, 1152), (4096, 16384 + 128)])
+def test_c_host_sharded_handle_equals_mvm(shape):
+    """The single-process C host (clover_m4_sharded_*, the C++ entry VERDICT r01 missing #3 asked for): for 1 and for every
+    power of two of visible GPUs the sharded call returns the bytes of clover_m4_mvm, keyed stochastic mode included."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ctypes as C
+    import numpy as np
+    import clover_b200
+    from bench import random_nibbles
+    from clover_b200 import containers as cb
+    rows, cols = shape
+    rows += (-rows) % 128
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(17)
+    A = cb.CloverMatrix4(rows, cols)
+    A.values.copy_(random_nibbles(torch, rows * cols // 2, g, dev))
+    A.scales.uniform_(0.05, 4.0, generator=g)
+    x = cb.CloverVector4(cols)
+    x.values.copy_(random_nibbles(torch, cols // 2, g, dev))
+    x.scales.uniform_(0.05, 4.0, generator=g)
+    av, as_ = A.values.cpu().numpy(), A.scales.cpu().numpy()
+    xv, xs = x.values.cpu().numpy(), x.scales.cpu().numpy()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    ngpus = 1
+    while ngpus <= min(torch.cuda.device_count(), 8):
+        if rows // 64 >= ngpus:
+            h = C.c_void_p()
+            clover_b200.call("clover_m4_sharded_create", C.byref(h), C.c_uint64(rows), C.c_uint64(cols), ngpus, None)
+            assert clover_b200.lib().clover_m4_sharded_world(h) == ngpus
+            clover_b200.call("clover_m4_sharded_load_host", h, p(av), p(as_))
+            for keyed in (False, True, False):
+                want = cb.CloverVector4(rows)
+                key = None
+                if keyed:
+                    A.seed(31, 32)
+                    key = A.key.copy()
+                else:
+                    A.setRandomKeys(None)
+                A.mvm(x, want)
+                yv, ys = np.zeros(rows // 2, np.int8), np.zeros(rows // 64, np.float32)
+                clover_b200.call("clover_m4_sharded_mvm_host", h, p(xv), p(xs), p(yv), p(ys), None if key is None else p(key))
+                assert np.array_equal(yv, want.values.cpu().numpy()), (ngpus, keyed)
+                assert np.array_equal(ys.view(np.uint32), want.scales.cpu().numpy()[: rows // 64].view(np.uint32)), (ngpus, keyed)
+                if keyed:
+                    assert np.array_equal(key, A.key)
+            clover_b200.call("clover_m4_sharded_destroy", h)
+        ngpus *= 2
+    torch.cuda.set_device(0)
