@@ -88,87 +88,53 @@ __device__ __forceinline__ void tile_coords(uint32_t t, uint32_t tiles_m, uint32
 }
 
 // one K-slab of one 32-lane x 64-column block: acc += s * D, D read from TMEM in two 32-column chunks
-// PROBE (measurement only, wrong results): 1 = TMEM loads but no FMAs, 2 = neither (pure MMA / TMA / barrier hand-off)
-template <int PROBE>
 __device__ __forceinline__ void epilogue_slab(uint64_t *acc, uint32_t *r, float s, uint32_t taddr, uint32_t tfull, uint32_t tempty,
                                               uint32_t parity, int lane) {
     mbar_wait_a(tfull, parity);
     tc_fence_after();
-    if (PROBE == 2) {
-        tc_fence_before();
-        if (lane == 0) mbar_arrive_a(tempty);
-        return;
-    }
     tmem_ld32(taddr, r);
     tmem_ld_wait(r);
-    if (PROBE == 1) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) acc[0] ^= r[j];
-    } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) ffma2(acc[j], s, r[2 * j], r[2 * j + 1]);
-    }
+    for (int j = 0; j < 16; ++j) ffma2(acc[j], s, r[2 * j], r[2 * j + 1]);
     tmem_ld32(taddr + 32, r);
     tmem_ld_wait(r);
     tc_fence_before();                                   // this warp's share of the buffer is drained
     if (lane == 0) mbar_arrive_a(tempty);
-    if (PROBE == 1) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) acc[1] ^= r[j];
-    } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) ffma2(acc[16 + j], s, r[2 * j], r[2 * j + 1]);
-    }
+    for (int j = 0; j < 16; ++j) ffma2(acc[16 + j], s, r[2 * j], r[2 * j + 1]);
 }
 
-// SPLIT = true (CLOVER_GEMM_KERNEL=split): every slab is issued as two N=128 halves with their own full/empty barriers
-// (four 128-column TMEM buffers at the same addresses). The warps of the left and of the right half then run about
-// half a slab out of phase, so the FMA bursts of one group overlap the TMEM-load round trips of the other.
-// CL = 2 (CLOVER_GEMM_KERNEL=mc2): clusters of two CTAs on vertically adjacent tiles (same B' panel). Each CTA fetches one
-// half of the B' stage and TMA-multicasts it into both shared memories, so a slab costs 8 + 8 KiB of L2 reads per SM
-// instead of 8 + 16; a stage is refilled only after BOTH CTAs' MMAs have retired it (multicast tcgen05.commit on `empty`).
-// All TMEM hand-off barriers stay CTA-local.
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const void *tensor_map, int c0, int c1, uint32_t bar, uint16_t mask) {
+// TMA load with an L2 eviction-priority hint
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t smem_dst, const void *tensor_map, int c0, int c1, uint32_t bar, uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
-        ::"r"(smem_dst), "l"(tensor_map), "r"(c0), "r"(c1), "r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc1(uint32_t bar, uint16_t mask) {       // arrive on `bar` in every CTA of `mask`
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_tc() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_dst), "l"(tensor_map), "r"(c0), "r"(c1), "r"(bar), "l"(policy) : "memory");
 }
 
-template <bool SPLIT, int PROBE, int CL = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
            const float *__restrict__ as, const float *__restrict__ bs, uint32_t M, uint32_t N, uint32_t K,
            float *__restrict__ c, uint64_t ldc) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;             // 1024-aligned: SWIZZLE_128B atoms
-    // barrier block behind the stages: full[4] empty[4] tfull[4] tempty[4] tmem_slot (tfull/tempty: 2 used unless SPLIT)
+    // barrier block behind the stages: full[4] empty[4] tfull[2] tempty[2] tmem_slot
     const uint32_t bars = smem + kStages * kStageBytes;
     const uint32_t full = bars, empty = bars + 8 * kStages, tfull = bars + 16 * kStages, tempty = tfull + 32;
     const uint32_t slot = tempty + 32;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_n = (N + kBN - 1) / kBN;
-    const uint32_t ctiles_m = M / (kBM * CL), ntiles = ctiles_m * tiles_n;       // cluster tiles: CL vertically adjacent 128-row tiles
+    const uint32_t tiles_m = M / kBM, ntiles = tiles_m * tiles_n;
     const uint32_t kblocks = K / kBK, KB = K >> 6, NB = N >> 6;
-    uint32_t crank = 0;
-    if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-    const uint32_t first_tile = blockIdx.x / CL, tile_step = gridDim.x / CL;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full + 8 * i), "r"(1) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty + 8 * i), "r"(CL) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty + 8 * i), "r"(1) : "memory");
         }
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < 2; ++b) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tfull + 8 * b), "r"(1) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tempty + 8 * b), "r"(SPLIT ? kEpiWarps / 2 : kEpiWarps) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tempty + 8 * b), "r"(kEpiWarps) : "memory");
         }
         mbar_fence_init();
         tma_prefetch_descriptor(&map_a);
@@ -179,7 +145,7 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         tmem_relinquish<1>();
     }
     tc_fence_before();
-    if (CL > 1) cluster_sync_tc(); else __syncthreads();     // the peer's barriers exist before anything is multicast at them
+    __syncthreads();
     tc_fence_after();
     uint32_t tmem;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
@@ -188,20 +154,24 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         reg_dealloc<32>();   // 128*32 + 512*112 = 640*96: exactly the registers this CTA was launched with
         if (warp == 0) {
             // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
+            // The persistent grid walks the tiles in groups of kGroupM tile-rows: within a group the 16 A' panels (2 MiB each
+            // at K = 16384) are re-read by every wave while the B' panels stream through once. A' is therefore loaded with an
+            // evict-last hint and B' with evict-first, so that the streaming operand does not push the re-used one out of L2
+            // (round 1: 4.16 GB of DRAM reads per 16384^3 launch against 0.54 GB of operands).
+            uint64_t keep, stream;
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream));
             uint32_t stage = 0, phase = 0;
-            for (uint32_t t = first_tile; t < ntiles; t += tile_step) {
+            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 uint32_t tm, tn;
-                tile_coords<kGroupM / CL>(t, ctiles_m, tiles_n, tm, tn);
-                tm = tm * CL + crank;
+                tile_coords<kGroupM>(t, tiles_m, tiles_n, tm, tn);
                 for (uint32_t kb = 0; kb < kblocks; ++kb) {
                     mbar_wait_a(empty + 8 * stage, phase ^ 1);
                     if (elect_one()) {
                         mbar_arrive_expect_tx_a(full + 8 * stage, kStageBytes);
                         const uint32_t sa = smem + stage * kStageBytes;
-                        tma_load_2d_a(sa, &map_a, (int)(kb * kBK), (int)(tm * kBM), full + 8 * stage);
-                        if (CL == 1) tma_load_2d_a(sa + kAStage, &map_b, (int)(kb * kBK), (int)(tn * kBN), full + 8 * stage);
-                        else         tma_load_2d_mc(sa + kAStage + crank * (kBStage / CL), &map_b, (int)(kb * kBK),
-                                                    (int)(tn * kBN + crank * (kBN / CL)), full + 8 * stage, (uint16_t)((1u << CL) - 1));
+                        tma_load_2d_hint(sa, &map_a, (int)(kb * kBK), (int)(tm * kBM), full + 8 * stage, keep);
+                        tma_load_2d_hint(sa + kAStage, &map_b, (int)(kb * kBK), (int)(tn * kBN), full + 8 * stage, stream);
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -209,9 +179,9 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             }
         } else if (warp == 1) {
             // ===== MMA issuer: per stage, K-slab 0 -> TMEM buffer 0, K-slab 1 -> buffer 1 =====
-            const uint32_t idesc = umma_idesc(UMMA_E4M3, kBM, kBN), idesc_half = umma_idesc(UMMA_E4M3, kBM, kBN / 2);
+            const uint32_t idesc = umma_idesc(UMMA_E4M3, kBM, kBN);
             uint32_t stage = 0, phase = 0, pair = 0;
-            for (uint32_t t = first_tile; t < ntiles; t += tile_step) {
+            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 for (uint32_t kb = 0; kb < kblocks; ++kb, ++pair) {
                     mbar_wait_a(full + 8 * stage, phase);
                     tc_fence_after();
@@ -219,23 +189,6 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                     const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + kAStage);
 #pragma unroll
                     for (uint32_t h = 0; h < 2; ++h) {
-                        if (SPLIT) {
-#pragma unroll
-                            for (uint32_t half = 0; half < 2; ++half) {
-                                const uint32_t hb = 2 * h + half;
-                                mbar_wait_a(tempty + 8 * hb, (pair & 1) ^ 1);
-                                tc_fence_after();
-                                const uint32_t d = tmem + h * 256 + half * 128;
-                                const uint64_t dbh = db + half * ((128 * kBK) >> 4);       // rows 128..255 of the B' stage
-                                if (elect_one()) {
-                                    umma_ss<UMMA_E4M3, 1>(d, da + 4 * h, dbh + 4 * h, idesc_half, 0);
-                                    umma_ss<UMMA_E4M3, 1>(d, da + 4 * h + 2, dbh + 4 * h + 2, idesc_half, 1);
-                                    umma_commit_a<1>(tfull + 8 * hb);
-                                    if (hb == 3) umma_commit_a<1>(empty + 8 * stage);
-                                }
-                                __syncwarp();
-                            }
-                        } else {
                         mbar_wait_a(tempty + 8 * h, (pair & 1) ^ 1);
                         tc_fence_after();
                         const uint32_t d = tmem + h * 256;
@@ -243,13 +196,9 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                             umma_ss<UMMA_E4M3, 1>(d, da + 4 * h, db + 4 * h, idesc, 0);
                             umma_ss<UMMA_E4M3, 1>(d, da + 4 * h + 2, db + 4 * h + 2, idesc, 1);
                             umma_commit_a<1>(tfull + 8 * h);
-                            if (h == 1) {                                         // smem stage free once its MMAs retire
-                                if (CL == 1) umma_commit_a<1>(empty + 8 * stage);
-                                else         umma_commit_mc1(empty + 8 * stage, (uint16_t)((1u << CL) - 1));
-                            }
+                            if (h == 1) umma_commit_a<1>(empty + 8 * stage);      // smem stage free once its MMAs retire
                         }
                         __syncwarp();
-                        }
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -263,10 +212,9 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         uint64_t acc[32];
         uint32_t r[32];
         uint32_t pair = 0;
-        for (uint32_t t = first_tile; t < ntiles; t += tile_step) {
+        for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
             uint32_t tm, tn;
-            tile_coords<kGroupM / CL>(t, ctiles_m, tiles_n, tm, tn);
-            tm = tm * CL + crank;
+            tile_coords<kGroupM>(t, tiles_m, tiles_n, tm, tn);
             const uint32_t jb = tn * 4 + cb;
             const bool live = jb < NB;                      // N is a multiple of 128: a 64-column block is all in or all out
             const float *pa = as + (uint64_t)(tm * 2 + (q >> 1)) * KB;
@@ -280,13 +228,8 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                 const uint32_t n = min(32u, KB - kb0);
                 for (uint32_t k = 0; k < n; k += 2, ++pair) {
                     const float s_even = __shfl_sync(0xFFFFFFFFu, sv, k), s_odd = __shfl_sync(0xFFFFFFFFu, sv, k + 1);
-                    if (SPLIT) {     // barriers of (slab parity, half): index 2 * parity + (cb >> 1)
-                        epilogue_slab<PROBE>(acc, r, s_even, taddr, tfull + 8 * (cb >> 1), tempty + 8 * (cb >> 1), pair & 1, lane);
-                        epilogue_slab<PROBE>(acc, r, s_odd, taddr + 256, tfull + 16 + 8 * (cb >> 1), tempty + 16 + 8 * (cb >> 1), pair & 1, lane);
-                    } else {
-                        epilogue_slab<PROBE>(acc, r, s_even, taddr, tfull, tempty, pair & 1, lane);
-                        epilogue_slab<PROBE>(acc, r, s_odd, taddr + 256, tfull + 8, tempty + 8, pair & 1, lane);
-                    }
+                    epilogue_slab(acc, r, s_even, taddr, tfull, tempty, pair & 1, lane);
+                    epilogue_slab(acc, r, s_odd, taddr + 256, tfull + 8, tempty + 8, pair & 1, lane);
                 }
             }
             if (live) {
@@ -296,13 +239,13 @@ k_gemm4_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                     float4 o;
                     o.x = __uint_as_float((uint32_t)acc[2 * j]);     o.y = __uint_as_float((uint32_t)(acc[2 * j] >> 32));
                     o.z = __uint_as_float((uint32_t)acc[2 * j + 1]); o.w = __uint_as_float((uint32_t)(acc[2 * j + 1] >> 32));
-                    *reinterpret_cast<float4 *>(crow + 4 * j) = o;
+                    __stcs(reinterpret_cast<float4 *>(crow + 4 * j), o);          // C is written once and not re-read: streaming store
                 }
             }
         }
     }
     tc_fence_before();
-    if (CL > 1) cluster_sync_tc(); else __syncthreads();     // nobody leaves while the peer may still multicast into this CTA
+    __syncthreads();
     if (warp == 2) tmem_dealloc<1>(tmem, 512);
 }
 
@@ -323,54 +266,17 @@ int gemm4_expand(const int8_t *values, uint64_t rows, uint64_t cols, uint8_t *ou
     return launch_status("k_expand_e4m3");
 }
 
-int gemm4_tc2_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, const float *bs, uint64_t M, uint64_t N,
-                       uint64_t K, float *c, uint64_t ldc, cudaStream_t stream, int cta_group);      // gemm4_tc2.cu
-int gemm4_tc3_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, const float *bs, uint64_t M, uint64_t N,
-                       uint64_t K, float *c, uint64_t ldc, cudaStream_t stream);                     // gemm4_tc3.cu
-
 int gemm4_tc_expanded(const uint8_t *a8, const float *as, const uint8_t *b8, const float *bs, uint64_t M, uint64_t N,
                       uint64_t K, float *c, uint64_t ldc, cudaStream_t stream) {
-    // CLOVER_GEMM_KERNEL=pipe1|pair selects an experimental 4-slot pipeline (gemm4_tc2.cu); default: this file's kernel
-    // read on every call (cheap) so that one measurement process can walk through the variants
-    const int variant = [] { const char *e = getenv("CLOVER_GEMM_KERNEL");
-                             return !e ? 0 : !strcmp(e, "pipe1") ? 1 : !strcmp(e, "pair") ? 2 : !strcmp(e, "p192") ? 3 : !strcmp(e, "split") ? 4 : !strcmp(e, "mc2") ? 5 : 0; }();
-    if (variant == 3) return gemm4_tc3_expanded(a8, as, b8, bs, M, N, K, c, ldc, stream);
-    if (variant == 1 || variant == 2) return gemm4_tc2_expanded(a8, as, b8, bs, M, N, K, c, ldc, stream, variant);
     CUtensorMap map_a, map_b;
     int rc = make_tensor_map_u8_2d_sw128(&map_a, a8, M, K, kBM);
     if (rc != CLOVER_OK) return rc;
     rc = make_tensor_map_u8_2d_sw128(&map_b, b8, N, K, kBN);
     if (rc != CLOVER_OK) return rc;
-    const int probe = [] { const char *e = getenv("CLOVER_GEMM_PROBE"); return e ? atoi(e) : 0; }();   // measurement only
-    auto kern = variant == 4 ? k_gemm4_tc<true, 0> : probe == 1 ? k_gemm4_tc<false, 1> : probe == 2 ? k_gemm4_tc<false, 2> : k_gemm4_tc<false, 0>;
-    CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    CLOVER_CUDA_CHECK(cudaFuncSetAttribute(k_gemm4_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     const uint64_t ntiles = (M / kBM) * ((N + kBN - 1) / kBN);
-    if (variant == 5 && (M / kBM) % 2 == 0) {
-        // clusters of two CTAs sharing a B' panel through TMA multicast
-        CUtensorMap map_b2;
-        rc = make_tensor_map_u8_2d_sw128(&map_b2, b8, N, K, kBN / 2);
-        if (rc != CLOVER_OK) return rc;
-        auto kern2 = probe == 2 ? k_gemm4_tc<false, 2, 2> : k_gemm4_tc<false, 0, 2>;
-        CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-        cudaLaunchConfig_t cfg = {};
-        cfg.blockDim = dim3(kGemmThreads);
-        cfg.dynamicSmemBytes = kGemmSmem;
-        cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        cfg.gridDim = dim3(2);
-        int max_clusters = 0;
-        CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_clusters, kern2, &cfg));
-        const unsigned clusters = (unsigned)std::min<uint64_t>(ntiles / 2, (uint64_t)std::max(1, std::min(max_clusters, sm_count() / 2)));
-        cfg.gridDim = dim3(2 * clusters);
-        CLOVER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern2, map_a, map_b2, as, bs, (uint32_t)M, (uint32_t)N, (uint32_t)K, c, ldc));
-        count_launch();
-        return launch_status("k_gemm4_tc<mc2>");
-    }
     const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sm_count());
-    kern<<<grid, kGemmThreads, kGemmSmem, stream>>>(map_a, map_b, as, bs, (uint32_t)M, (uint32_t)N, (uint32_t)K, c, ldc);
+    k_gemm4_tc<<<grid, kGemmThreads, kGemmSmem, stream>>>(map_a, map_b, as, bs, (uint32_t)M, (uint32_t)N, (uint32_t)K, c, ldc);
     count_launch();
     return launch_status("k_gemm4_tc");
 }

@@ -553,28 +553,6 @@ def test_gemm_tensor_core_equals_simt(cb, mnk):
     assert bool((big[:, N:] == 7.0).all())
 
 
-@pytest.mark.parametrize("variant", ["pipe1", "pair", "p192", "split", "mc2"])
-def test_gemm_experimental_pipelines_equal_simt(variant):
-    """The 4-slot TMEM-ring variants (gemm4_tc2.cu, CLOVER_GEMM_KERNEL) stay bit-identical to the DP4A kernel.
-    The variant is read once per process, hence the subprocess."""
-    import os, subprocess, sys
-    code = (
-        "import torch, sys; sys.path.insert(0, %r)\n"
-        "from clover_b200 import containers as cb\n"
-        "from bench import random_nibbles\n"
-        "g = torch.Generator(device='cuda').manual_seed(3)\n"
-        "def mk(r, c):\n"
-        "    m = cb.CloverMatrix4(r, c); m.values.copy_(random_nibbles(torch, r * c // 2, g, torch.device('cuda')))\n"
-        "    m.scales.uniform_(0.05, 4.0, generator=g); return m\n"
-        "for (M, N, K) in [(128, 128, 128), (256, 256, 256), (384, 640, 1152), (512, 384, 1152), (2176, 2048, 2048), (4096, 4224, 1024)]:\n"
-        "    A, B = mk(M, K), mk(N, K)\n"
-        "    assert torch.equal(A.gemm(B, impl='tc').view(torch.int32), A.gemm(B, impl='simt').view(torch.int32)), (M, N, K)\n"
-        "print('ok')\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    env = dict(os.environ, CLOVER_GEMM_KERNEL=variant)
-    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, env=env)
-    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
-
-
 def test_gemm_c4_full_size_properties(cb):
     """BASELINE config C4 (16384^3): tensor-core result == DP4A result on every element (both exact-integer slabs),
     and linearity in the scales: doubling sA doubles C bit-for-bit (power-of-two scaling is exact)."""
