@@ -24,6 +24,7 @@
 // k_mvm_f32_simple (one warp per row, plain loads) is the same arithmetic for unaligned operands and the cross-check.
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 #include "async_copy.cuh"
 #include "common.cuh"
 #include "runtime.cuh"
@@ -64,30 +65,60 @@ __device__ __forceinline__ uint32_t and_xor(uint32_t a, uint32_t m, uint32_t c) 
     asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(d) : "r"(a), "r"(m), "r"(c));
     return d;
 }
-template <int P> __device__ __forceinline__ uint32_t splice(uint32_t bytes, uint32_t magic) {   // [byte P of bytes, magic bytes 1..3]
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(bytes), "r"(magic), "n"(0x7650 + P));
-    return d;
+// The per-pair arithmetic as ONE asm block each, so that ptxas allocates the two PRMT results as an aligned register pair
+// (built from separate C++ values the pair cost an extra IMAD.MOV per element, 11 % of all instructions - ncu r02e).
+//   pair4: acc += x2 * ((splice(hi, P) | splice(lo, P)) - bias) * s      f = float(q) * s (:1520-1527), acc = fma(x, f, acc) (:1529-1537)
+//   pair8: acc += (x2 * s) * ((splice(u, P) | splice(u, P + 1)) - bias)  t = x * s (CloverMatrix8.h:632-639), acc = fma(t, float(q), acc) (:641-649)
+template <int P>
+__device__ __forceinline__ void pair4(uint64_t &acc, uint64_t x2, uint32_t hi, uint32_t lo, uint32_t magic, uint64_t neg, uint64_t ss) {
+    asm("{\n\t.reg .b32 a, b;\n\t.reg .b64 m;\n\t"
+        "prmt.b32 a, %2, %4, %7;\n\t"
+        "prmt.b32 b, %3, %4, %7;\n\t"
+        "mov.b64 m, {a, b};\n\t"
+        "add.rn.f32x2 m, m, %5;\n\t"
+        "mul.rn.f32x2 m, m, %6;\n\t"
+        "fma.rn.f32x2 %0, %1, m, %0;\n\t}"
+        : "+l"(acc) : "l"(x2), "r"(hi), "r"(lo), "r"(magic), "l"(neg), "l"(ss), "n"(0x7650 + P));
+}
+template <int P>
+__device__ __forceinline__ void pair8(uint64_t &acc, uint64_t x2, uint32_t u, uint32_t magic, uint64_t neg, uint64_t ss) {
+    asm("{\n\t.reg .b32 a, b;\n\t.reg .b64 m, t;\n\t"
+        "prmt.b32 a, %2, %3, %6;\n\t"
+        "prmt.b32 b, %2, %3, %7;\n\t"
+        "mov.b64 m, {a, b};\n\t"
+        "add.rn.f32x2 m, m, %4;\n\t"
+        "mul.rn.f32x2 t, %1, %5;\n\t"
+        "fma.rn.f32x2 %0, t, m, %0;\n\t}"
+        : "+l"(acc) : "l"(x2), "r"(u), "r"(magic), "l"(neg), "l"(ss), "n"(0x7650 + P), "n"(0x7651 + P));
+}
+
+// x as packed f32x2 operands straight from shared memory (immediate offsets: no address arithmetic per load)
+template <int OFF> __device__ __forceinline__ void lds_x4(uint32_t base, uint64_t &a, uint64_t &b) {
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2+%3];" : "=l"(a), "=l"(b) : "r"(base), "n"(OFF));
 }
 
 // one 32-bit word of the 4-bit matrix (elements e..e+7 of a row: byte i = element 2i in the HIGH nibble, 2i+1 in the
-// low one) against x[e..e+7]: acc[p] += x2[p] * ((float(q2[p])) * s), p = element pair (2p, 2p+1)
-__device__ __forceinline__ void word4(uint32_t w, const float4 xa, const float4 xb, uint64_t ss, uint64_t neg, const RegConsts &rc,
-                                      uint64_t *acc) {
+// low one) against x[e..e+7] at shared address xaddr + XOFF
+template <int XOFF>
+__device__ __forceinline__ void word4(uint32_t w, uint32_t xaddr, uint64_t ss, uint64_t neg, const RegConsts &rc, uint64_t *acc) {
     const uint32_t lo = and_xor(w, rc.m0f, rc.c08);                  // byte p: q + 8 of element 2p+1
     const uint32_t hi = and_xor(w >> 4, rc.m0f, rc.c08);             // byte p: q + 8 of element 2p
-    // f = float(q) * s (:1520-1527), acc = fma(x, f, acc) (:1529-1537)
-    fma2(acc[0], pack2f(xa.x, xa.y), mul2(add2(pack2(splice<0>(hi, rc.magic), splice<0>(lo, rc.magic)), neg), ss));
-    fma2(acc[1], pack2f(xa.z, xa.w), mul2(add2(pack2(splice<1>(hi, rc.magic), splice<1>(lo, rc.magic)), neg), ss));
-    fma2(acc[2], pack2f(xb.x, xb.y), mul2(add2(pack2(splice<2>(hi, rc.magic), splice<2>(lo, rc.magic)), neg), ss));
-    fma2(acc[3], pack2f(xb.z, xb.w), mul2(add2(pack2(splice<3>(hi, rc.magic), splice<3>(lo, rc.magic)), neg), ss));
+    uint64_t x0, x1, x2, x3;
+    lds_x4<XOFF>(xaddr, x0, x1);
+    lds_x4<XOFF + 16>(xaddr, x2, x3);
+    pair4<0>(acc[0], x0, hi, lo, rc.magic, neg, ss);
+    pair4<1>(acc[1], x1, hi, lo, rc.magic, neg, ss);
+    pair4<2>(acc[2], x2, hi, lo, rc.magic, neg, ss);
+    pair4<3>(acc[3], x3, hi, lo, rc.magic, neg, ss);
 }
-// one 32-bit word of the 8-bit matrix (elements e..e+3) against x[e..e+3]: acc[p] += (x2[p] * s) * float(q2[p])
-__device__ __forceinline__ void word8(uint32_t w, const float4 xv, uint64_t ss, uint64_t neg, const RegConsts &rc, uint64_t *acc) {
+// one 32-bit word of the 8-bit matrix (elements e..e+3) against x[e..e+3] at shared address xaddr + XOFF
+template <int XOFF>
+__device__ __forceinline__ void word8(uint32_t w, uint32_t xaddr, uint64_t ss, uint64_t neg, const RegConsts &rc, uint64_t *acc) {
     const uint32_t u = w ^ rc.c80;                                    // byte i: q + 128
-    // t = x * s (:632-639), acc = fma(t, float(q), acc) (:641-649)
-    fma2(acc[0], mul2(pack2f(xv.x, xv.y), ss), add2(pack2(splice<0>(u, rc.magic), splice<1>(u, rc.magic)), neg));
-    fma2(acc[1], mul2(pack2f(xv.z, xv.w), ss), add2(pack2(splice<2>(u, rc.magic), splice<3>(u, rc.magic)), neg));
+    uint64_t x0, x1;
+    lds_x4<XOFF>(xaddr, x0, x1);
+    pair8<0>(acc[0], x0, u, rc.magic, neg, ss);
+    pair8<2>(acc[1], x1, u, rc.magic, neg, ss);
 }
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -95,12 +126,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ float4 lds128f(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
@@ -178,29 +203,43 @@ k_mvm_f32_ring(const __grid_constant__ CUtensorMap tmap, const float *__restrict
             mbar_wait_a(bars + 8 * s, phase);
             const uint32_t st = ring + s * kF32StageBytes, rowp = st + rowoff, xs = st + kF32Rows * 128u + 64u * (uint32_t)kh;
             const int nb = (int)min((uint32_t)kBPC, hb - c * kBPC);
-            for (int j = 0; j < nb; ++j) {
-                const float sj = __shfl_sync(0xFFFFFFFFu, sdiv, j);
-                const uint64_t ss = pack2f(sj, sj);
-                const uint32_t xb = xs + (uint32_t)j * 256u;           // x[64j + 16kh ...]; the second half block is 128 bytes further
-                if (MBITS == 4) {
-                    const uint2 w0 = lds64(rowp + ((((uint32_t)(2 * j)) ^ rsw) << 4) + 8u * (uint32_t)kh);        // elements 16kh .. 16kh+15
-                    const uint2 w1 = lds64(rowp + ((((uint32_t)(2 * j + 1)) ^ rsw) << 4) + 8u * (uint32_t)kh);    // elements 32+16kh ..
-                    word4(w0.x, lds128f(xb), lds128f(xb + 16), ss, neg, rc, acc[0]);                // element 8k+l, k = 2kh
-                    word4(w0.y, lds128f(xb + 32), lds128f(xb + 48), ss, neg, rc, acc[1]);           //               k = 2kh+1
-                    word4(w1.x, lds128f(xb + 128), lds128f(xb + 144), ss, neg, rc, acc[0]);         // element 32+8k+l
-                    word4(w1.y, lds128f(xb + 160), lds128f(xb + 176), ss, neg, rc, acc[1]);
-                } else {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {                      // half h: this thread's 16 bytes = 16-byte chunk 4j + 2h + kh
-                        const uint4 w = lds128(rowp + ((((uint32_t)(4 * j + 2 * h) + (uint32_t)kh) ^ rsw) << 4));
-                        const uint32_t xq = xb + 128u * h;
-                        word8(w.x, lds128f(xq), ss, neg, rc, &acc[0][0]);          // accumulator 2kh, lanes 0..3
-                        word8(w.y, lds128f(xq + 16), ss, neg, rc, &acc[0][2]);     //                   lanes 4..7
-                        word8(w.z, lds128f(xq + 32), ss, neg, rc, &acc[1][0]);     // accumulator 2kh+1
-                        word8(w.w, lds128f(xq + 48), ss, neg, rc, &acc[1][2]);
+            // nb is warp-uniform; the full chunk is the common case and fully unrolled (shuffle lanes and shared-memory
+            // offsets become immediates)
+            auto block_step = [&](auto J) {
+                constexpr int j = decltype(J)::value;
+                if (j < kBPC && j < nb) {
+                    const float sj = __shfl_sync(0xFFFFFFFFu, sdiv, j);
+                    const uint64_t ss = pack2f(sj, sj);
+                    // x[64j + 16kh ...] of this stage; the second half block is 128 bytes further
+                    if (MBITS == 4) {
+                        const uint2 w0 = lds64(rowp + ((((uint32_t)(2 * j)) ^ rsw) << 4) + 8u * (uint32_t)kh);        // elements 16kh .. 16kh+15
+                        const uint2 w1 = lds64(rowp + ((((uint32_t)(2 * j + 1)) ^ rsw) << 4) + 8u * (uint32_t)kh);    // elements 32+16kh ..
+                        word4<256 * j>(w0.x, xs, ss, neg, rc, acc[0]);               // element 8k+l, k = 2kh
+                        word4<256 * j + 32>(w0.y, xs, ss, neg, rc, acc[1]);          //               k = 2kh+1
+                        word4<256 * j + 128>(w1.x, xs, ss, neg, rc, acc[0]);         // element 32+8k+l
+                        word4<256 * j + 160>(w1.y, xs, ss, neg, rc, acc[1]);
+                    } else {
+                        {   // half 0: this thread's 16 bytes = 16-byte chunk 4j + kh
+                            const uint4 w = lds128(rowp + ((((uint32_t)(4 * j) + (uint32_t)kh) ^ rsw) << 4));
+                            word8<256 * j>(w.x, xs, ss, neg, rc, &acc[0][0]);          // accumulator 2kh, lanes 0..3
+                            word8<256 * j + 16>(w.y, xs, ss, neg, rc, &acc[0][2]);     //                   lanes 4..7
+                            word8<256 * j + 32>(w.z, xs, ss, neg, rc, &acc[1][0]);     // accumulator 2kh+1
+                            word8<256 * j + 48>(w.w, xs, ss, neg, rc, &acc[1][2]);
+                        }
+                        {   // half 1: chunk 4j + 2 + kh, x 128 bytes further
+                            const uint4 w = lds128(rowp + ((((uint32_t)(4 * j + 2) + (uint32_t)kh) ^ rsw) << 4));
+                            word8<256 * j + 128>(w.x, xs, ss, neg, rc, &acc[0][0]);
+                            word8<256 * j + 144>(w.y, xs, ss, neg, rc, &acc[0][2]);
+                            word8<256 * j + 160>(w.z, xs, ss, neg, rc, &acc[1][0]);
+                            word8<256 * j + 176>(w.w, xs, ss, neg, rc, &acc[1][2]);
+                        }
                     }
                 }
-            }
+            };
+            block_step(std::integral_constant<int, 0>{});
+            block_step(std::integral_constant<int, 1>{});
+            block_step(std::integral_constant<int, 2>{});
+            block_step(std::integral_constant<int, 3>{});
             __syncwarp();
             if (lane == 0) issue();
             if (++s == kF32Stages) { s = 0; phase ^= 1; }
