@@ -31,6 +31,56 @@ __device__ __forceinline__ float byte_to_float(uint32_t biased, float magic_plus
     return __fadd_rn(__uint_as_float(bits), -magic_plus_bias);
 }
 
+// ---- packed (f32x2) arithmetic of the rounding-disabled path -----------------------------------------------------
+// SASS PRMT / LOP3 take one immediate: the magic bits and the masks live in registers (built from a kernel argument
+// that is always 0, so that ptxas cannot fold them back into immediates - see mvm_f32_kernels.cu).
+struct AxpyConsts { uint32_t magic, m0f, c08, c80; };
+__device__ __forceinline__ uint32_t and_xor_r(uint32_t a, uint32_t m, uint32_t c) {      // (a & m) ^ c in one LOP3
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(d) : "r"(a), "r"(m), "r"(c));
+    return d;
+}
+// val2 = fma(float(qv2), sv, float(qu2) * su) for the two elements whose biased codes sit in byte P of (ua, ub) / (va, vb):
+// value = fma(qv, sv_ps, qu * su_ps) (include/CloverVector4.h:1300-1340), both halves rounded like the scalar instructions
+template <int PA, int PB>
+__device__ __forceinline__ uint64_t axpy_pair(uint32_t ua, uint32_t ub, uint32_t va, uint32_t vb, uint32_t magic, uint64_t neg,
+                                              uint64_t su2, uint64_t sv2) {
+    uint64_t r;
+    asm("{\n\t.reg .b32 a, b, c, d;\n\t.reg .b64 mu, mv;\n\t"
+        "prmt.b32 a, %1, %5, %9;\n\t"
+        "prmt.b32 b, %2, %5, %10;\n\t"
+        "prmt.b32 c, %3, %5, %9;\n\t"
+        "prmt.b32 d, %4, %5, %10;\n\t"
+        "mov.b64 mu, {a, b};\n\t"
+        "mov.b64 mv, {c, d};\n\t"
+        "add.rn.f32x2 mu, mu, %6;\n\t"
+        "add.rn.f32x2 mv, mv, %6;\n\t"
+        "mul.rn.f32x2 mu, mu, %7;\n\t"
+        "fma.rn.f32x2 %0, mv, %8, mu;\n\t}"
+        : "=l"(r) : "r"(ua), "r"(ub), "r"(va), "r"(vb), "r"(magic), "l"(neg), "l"(su2), "l"(sv2), "n"(0x7650 + PA), "n"(0x7650 + PB));
+    return r;
+}
+__device__ __forceinline__ float f2_lo(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float f2_hi(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) { return ((uint64_t)__float_as_uint(hi) << 32) | __float_as_uint(lo); }
+__device__ __forceinline__ float max3_abs(float m, float a, float b) {                    // one FMNMX3 on sm_100
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(m), "f"(fabsf(a)), "f"(fabsf(b)));
+    return d;
+}
+// d = (c << 8) | (nibble(a) << 4) | nibble(b): one instruction per byte of the reference's nibble layout
+__device__ __forceinline__ uint32_t pack_s4(int a, int b, uint32_t c) {
+    uint32_t d;
+    asm("cvt.pack.sat.s4.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// d = (c << 16) | (byte(a) << 8) | byte(b)
+__device__ __forceinline__ uint32_t pack_s8(int a, int b, uint32_t c) {
+    uint32_t d;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 template <int BITS, bool STOCH>
 __global__ void __launch_bounds__(256)
 k_vscale_add(const uint32_t *u, const float *su, const uint32_t *__restrict__ v,       // u / su may alias r / sr (in place)
@@ -142,8 +192,9 @@ k_vscale_add(const uint32_t *u, const float *su, const uint32_t *__restrict__ v,
 template <int BITS, bool STOCH>
 __global__ void __launch_bounds__(256)
 k_vscale_add4t(const uint32_t *u, const float *su, const uint32_t *__restrict__ v, const float *__restrict__ sv, float a,
-               uint64_t nblocks, uint64_t R, uint32_t *r, float *sr, Key4 key, const uint64_t *__restrict__ tables) {
+               uint64_t nblocks, uint64_t R, uint32_t *r, float *sr, Key4 key, const uint64_t *__restrict__ tables, uint32_t zero) {
     constexpr float kQmax = BITS == 4 ? 7.0f : 127.0f;
+    const AxpyConsts kc = {0x4B400000u | zero, 0x0F0F0F0Fu | zero, 0x08080808u | zero, 0x80808080u | zero};
     constexpr int kW = BITS == 4 ? 2 : 4;                          // 32-bit words per thread
     const int s = threadIdx.x & 3;
     const uint64_t group = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 2;
@@ -173,6 +224,64 @@ k_vscale_add4t(const uint32_t *u, const float *su, const uint32_t *__restrict__ 
                 const uint4 x = *reinterpret_cast<const uint4 *>(u + blk * 16 + 4 * s), y = *reinterpret_cast<const uint4 *>(v + blk * 16 + 4 * s);
                 wu[0] = x.x; wu[1] = x.y; wu[2] = x.z; wu[3] = x.w; wv[0] = y.x; wv[1] = y.y; wv[2] = y.z; wv[3] = y.w;
             }
+        }
+        if (!STOCH) {
+            // ---- rounding disabled: packed arithmetic, ~7 instructions per element (the scalar path below needs ~14) ----
+            // q = sign(val) * trunc(fma(|val|, scale, 0)) = trunc(val * scale): rounding to nearest is sign-symmetric and
+            // truncation is odd, so neither the abs nor the sign transfer of the general formula is needed
+            const uint64_t su2 = f2_pack(su_ps, su_ps), sv2 = f2_pack(sv_ps, sv_ps);
+            uint64_t val2[8];
+            if (BITS == 4) {
+                const uint64_t neg = f2_pack(-12582920.0f, -12582920.0f);
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {                         // byte p of a word: element 2p in the HIGH nibble, 2p+1 in the low one
+                    const uint32_t ul = and_xor_r(wu[w], kc.m0f, kc.c08), uh = and_xor_r(wu[w] >> 4, kc.m0f, kc.c08);
+                    const uint32_t vl = and_xor_r(wv[w], kc.m0f, kc.c08), vh = and_xor_r(wv[w] >> 4, kc.m0f, kc.c08);
+                    val2[4 * w + 0] = axpy_pair<0, 0>(uh, ul, vh, vl, kc.magic, neg, su2, sv2);
+                    val2[4 * w + 1] = axpy_pair<1, 1>(uh, ul, vh, vl, kc.magic, neg, su2, sv2);
+                    val2[4 * w + 2] = axpy_pair<2, 2>(uh, ul, vh, vl, kc.magic, neg, su2, sv2);
+                    val2[4 * w + 3] = axpy_pair<3, 3>(uh, ul, vh, vl, kc.magic, neg, su2, sv2);
+                }
+            } else {
+                const uint64_t neg = f2_pack(-12583040.0f, -12583040.0f);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t bu = wu[w] ^ kc.c80, bv = wv[w] ^ kc.c80;          // q + 128 per byte
+                    val2[2 * w + 0] = axpy_pair<0, 1>(bu, bu, bv, bv, kc.magic, neg, su2, sv2);
+                    val2[2 * w + 1] = axpy_pair<2, 3>(bu, bu, bv, bv, kc.magic, neg, su2, sv2);
+                }
+            }
+            float m = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) m = max3_abs(m, f2_lo(val2[e]), f2_hi(val2[e]));
+            if (!live) m = 0.f;
+            m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 2));
+            m = guard_zero(m);
+            if (!live) continue;
+            const float scale = quant_scale(kQmax, m);
+            const uint64_t sc2 = f2_pack(scale, scale);
+            if (s == 0) sr[blk] = m;
+            int q[16];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                uint64_t p;
+                asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p) : "l"(val2[e]), "l"(sc2));
+                q[2 * e] = __float2int_rz(f2_lo(p));
+                q[2 * e + 1] = __float2int_rz(f2_hi(p));
+            }
+            if (BITS == 4) {
+                uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+                for (int b = 3; b >= 0; --b) { o0 = pack_s4(q[2 * b], q[2 * b + 1], o0); o1 = pack_s4(q[8 + 2 * b], q[8 + 2 * b + 1], o1); }
+                *reinterpret_cast<uint2 *>(r + blk * 8 + 2 * s) = make_uint2(o0, o1);
+            } else {
+                uint32_t o[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) o[w] = pack_s8(q[4 * w + 1], q[4 * w], pack_s8(q[4 * w + 3], q[4 * w + 2], 0u));
+                *reinterpret_cast<uint4 *>(r + blk * 16 + 4 * s) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            continue;
         }
         float val[16];
         if (BITS == 4) {
@@ -292,8 +401,8 @@ static int launch_scale_add(const int8_t *u, const float *su, const int8_t *v, c
         const uint64_t groups = nblocks < max_groups ? nblocks : max_groups;
         const uint64_t R = (nblocks + groups - 1) / groups;
         const unsigned grid = (unsigned)((groups * 4 + 255) / 256);
-        if (key_host) k_vscale_add4t<BITS, true><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, R, r32, sr, key, tables);
-        else          k_vscale_add4t<BITS, false><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, R, r32, sr, key, nullptr);
+        if (key_host) k_vscale_add4t<BITS, true><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, R, r32, sr, key, tables, 0u);
+        else          k_vscale_add4t<BITS, false><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, R, r32, sr, key, nullptr, 0u);
     }
     if (key_host) host_key_skip(key_host, 2 * nblocks);
     count_launch();
