@@ -599,6 +599,28 @@ def main():
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = total_bytes * args.steps / (float(ms2.item()) * 1e-3) / 1e9
 
+    # ---- north_star's wording, measured beside the fused exchange in the same run: the shard kernel,
+    # ONE ncclAllReduce of the fp32 output, the re-quantize pass - same shards, same x, same timing protocol
+    nccl = None
+    if world > 1 and args.exchange == "fused":
+        B = ShardedCloverMatrix4.__new__(ShardedCloverMatrix4)
+        B.__dict__.update(A.__dict__)
+        B.exchange, B._peer = "allreduce", None
+        y_ar = cb.CloverVector4(rows)
+        for _ in range(args.warmup):
+            B.mvm(x, y_ar)
+        barrier()
+        same = bool(torch.equal(y_ar.values, out["y"].values)) and bool(torch.equal(y_ar.scales.view(torch.int32)[: rows // 64], out["y"].scales.view(torch.int32)[: rows // 64]))
+        e0.record()
+        for _ in range(args.steps):
+            B.mvm(x, y_ar)
+        e1.record()
+        barrier()
+        ms3 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+        nccl = {"exchange": "shard kernel + one ncclAllReduce(fp32 y) + re-quantize", "value": total_bytes * args.steps / (float(ms3.item()) * 1e-3) / 1e9,
+                "unit": "GB/s", "ms_per_step": float(ms3.item()) / args.steps, "same_bytes_as_fused": same}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
@@ -621,6 +643,9 @@ def main():
                     "ms_per_step": float(ms2.item()) / args.steps, "wall_ms_per_step": wall / args.steps * 1e3},
             "gpu_launches": launches,
             "clocks": clk.summary(),
+            "exchange": {"mode": args.exchange if world > 1 else "none (1 GPU)",
+                         "step_minus_kernel_us": (secs / args.steps - tk) * 1e6,      # what the exchange + launch gaps cost per step
+                         "nccl_allreduce": nccl},
             "roofline": {"bound": "hbm", "kernel": "k_m4_mvm_tma2 (32-row items, 2 CTAs/SM)" if cols >= 16384 else "k_m4_mvm_tma", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
                          "traffic": ncu_traffic(f"C3_mvm4:{rows}x{cols}") if world == 1 else None,

@@ -433,25 +433,45 @@ k_thr4_apply(uint4 *__restrict__ values, const uint64_t *__restrict__ levels, co
 #pragma unroll
         for (int x = 0; x < kThrThreads / 32; ++x) { const uint32_t v = ws[x]; if (x < warp) before += v; total += v; }
         uint64_t rank = running + before + (incl - ties);
-        // a block is rewritten only if something in it goes: all its levels survive <=> nothing to do
-        const bool all_stay = (keep_mask | (rank + ties <= keep_ties ? tie_mask : 0u)) == 0x1FFu;
-        if (live && !all_stay) {
+        // Levels are monotone in j for an ordinary scale, so the survivors of a block are "every nibble with level >= jc" as
+        // long as its ties are kept or dropped as a whole: eight nibbles per word are then filtered at once (byte-wise add
+        // of 16 - jc to the levels spread over bytes: bit 4 of a byte = level >= jc). Blocks where a tie level is cut in
+        // the middle, or whose levels do not order (zero / non-finite scale, subnormal products), walk their nibbles.
+        uint32_t eff = keep_mask;
+        bool fast = true;
+        if (ties) {
+            if (rank + ties <= keep_ties) eff |= tie_mask;
+            else if (rank < keep_ties) fast = false;
+        }
+        const uint32_t jc = eff ? (uint32_t)__ffs(eff) - 1u : 9u;
+        fast = fast && eff == ((0x1FFu >> jc) << jc);
+        if (live && !(fast && jc == 0)) {                                   // jc == 0: everything stays, the block is not rewritten
             uint4 v[2] = {values[2 * b], values[2 * b + 1]};
             uint32_t *w = reinterpret_cast<uint32_t *>(v);
+            if (fast) {
+                const uint32_t add = (16u - jc) * 0x01010101u;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint32_t a = nibble_abs8(w[i]);
-                uint32_t out = w[i];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    if ((uint32_t)(8 * i + e) >= valid) continue;
-                    const int sh = 4 * (e ^ 1);
-                    const uint32_t lv = (a >> sh) & 0xFu;
-                    bool keep = (keep_mask >> lv) & 1u;
-                    if ((tie_mask >> lv) & 1u) { keep = rank < keep_ties; ++rank; }
-                    if (!keep) out &= ~(0xFu << sh);
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t a = nibble_abs8(w[i]);
+                    const uint32_t ke = (((a & 0x0F0F0F0Fu) + add) >> 4) & 0x01010101u;          // low nibbles with level >= jc
+                    const uint32_t ko = ((((a >> 4) & 0x0F0F0F0Fu) + add) >> 4) & 0x01010101u;   // high nibbles
+                    w[i] &= ke * 0x0Fu + ko * 0xF0u;
                 }
-                w[i] = out;
+            } else {
+#pragma unroll 1
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t a = nibble_abs8(w[i]);
+                    uint32_t out = w[i];
+                    for (int e = 0; e < 8; ++e) {
+                        if ((uint32_t)(8 * i + e) >= valid) continue;
+                        const int sh = 4 * (e ^ 1);
+                        const uint32_t lv = (a >> sh) & 0xFu;
+                        bool keep = (keep_mask >> lv) & 1u;
+                        if ((tie_mask >> lv) & 1u) { keep = rank < keep_ties; ++rank; }
+                        if (!keep) out &= ~(0xFu << sh);
+                    }
+                    w[i] = out;
+                }
             }
             values[2 * b] = v[0];
             values[2 * b + 1] = v[1];
