@@ -321,8 +321,13 @@ def extras(torch, cb, peak):
     # C2: quantize + dot at n = 2^26. dot operands (75.5 MB) fit in L2, so rotate over 4 operand sets.
     n = 1 << 26
     xs32 = []
-    for _ in range(2):
-        v = cb.CloverVector32(n); v.values.uniform_(-1.0, 1.0, generator=g); xs32.append(v)
+    gen_key = np.zeros(8, np.uint64)
+    import clover_b200 as _cbm
+    _cbm.call("clover_prng_init", C.c_uint64(445560390295639063), C.c_uint64(2935984234003016713), gen_key.ctypes.data_as(C.c_void_p))
+    for _ in range(2):                                   # the reference's generator and seeds
+        v = cb.CloverVector32(n); v.setRandomFloats(-1.0, 1.0, gen_key); xs32.append(v)
+    t = cuda_time(torch, lambda: xs32[0].setRandomFloats(-1.0, 1.0, gen_key), 10)
+    out["setRandomFloats_n2^26"] = {"ms": t * 1e3, "GBps": n * 4 / t / 1e9, "note": "CloverVector32::setRandomFloats on the device, bit-identical to the reference's stream"}
     qs = [cb.CloverVector4(n) for _ in range(8)]
     for i, q in enumerate(qs):
         q.quantize(xs32[i % 2])
@@ -490,9 +495,13 @@ def main():
     rows, cols = args.rows, args.cols
 
     # ---- operands: this rank's rows of the matrix, replicated x -------------------------------------------------
-    g = torch.Generator(device=dev).manual_seed(20261017)           # same x on every rank
+    # x: the reference's own generator and seeds (setRandomFloats(-1, 1), test/random/00_random.cpp:42), run on the
+    # device by clover_v32_set_random_floats - the same x on every rank; the 2 GiB matrix is generated directly in its
+    # quantized form (SURVEY.md 8d allows that for the perf-only runs, the quantizer is measured separately in C2)
+    ref_key = np.zeros(8, np.uint64)
+    clover_b200.call("clover_prng_init", C.c_uint64(445560390295639063), C.c_uint64(2935984234003016713), ref_key.ctypes.data_as(C.c_void_p))
     xf = cb.CloverVector32(cols)
-    xf.values.uniform_(-1.0, 1.0, generator=g)
+    xf.setRandomFloats(-1.0, 1.0, ref_key)
     x = cb.CloverVector4(cols)
     x.quantize(xf)
     y = cb.CloverVector4(rows)
@@ -630,6 +639,8 @@ def main():
             "config": {"workload": f"CloverMatrix4::mvm {rows}x{cols} x CloverVector4 -> CloverVector4 (BASELINE C3)",
                        "rows": rows, "cols": cols, "algorithmic_bytes_per_step": total_bytes,
                        "rounding": "stochastic rounding disabled (parity configuration)",
+                       "inputs": "x: the reference's setRandomFloats(-1, 1) stream from its fixed seeds (device generator), quantized; "
+                                 "matrix: uniform nibbles in [-7, 7] and scales in [0.25, 1) generated on the device",
                        "l2_policy": "inputs larger than L2 (2 GiB matrix streamed per step vs 126 MB L2)",
                        "parallelism": "1 GPU" if world == 1 else
                                       (f"rows sharded over {world} GPUs in 64-row blocks; fused exchange: the GEMV epilogue stores each "

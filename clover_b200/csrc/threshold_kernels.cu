@@ -33,6 +33,7 @@ constexpr uint64_t kThrExactLimit = 1u << 12;     // AUTO: the sequential heap w
 constexpr uint64_t kThrSmallLimit = 1u << 13;     // FAST: one CTA does the whole selection up to 8192 elements,
 constexpr uint64_t kThrClusterLimit = 1u << 18;   //       one 8-CTA cluster (histograms merged through DSMEM) up to 262144 (14 us at 32768, 22-27 us at 131072; at 2^20 the seven-launch path wins 40 : 114 us)
 constexpr int kThrClusterSize = 8;
+constexpr uint64_t kThr4OneCtaLimit = 1u << 18;  // FAST, 4-bit: level-based selection in one CTA up to 262144 elements (4096 blocks)
 
 struct ThrState {            // device-resident selection state; hist[] and ticket are zero between calls
     uint32_t prefix;         // magnitude bits decided so far (high digits)
@@ -270,26 +271,30 @@ __device__ __forceinline__ uint32_t nibble_abs8(uint32_t w) {          // |q| of
 }
 __device__ __forceinline__ uint32_t level_bits(float s7, int j) { return __float_as_uint(fabsf(__fmul_rn(s7, (float)j))); }   // = abs_bits4 for |q| = j
 
-// thread = block: counts of levels 1..8 in byte lanes 0..7; elements at index >= n do not exist
+// counts of levels 1..8 of block b in byte lanes 0..7; elements at index >= n do not exist
+__device__ __forceinline__ uint64_t block_levels(const uint4 *__restrict__ values, uint64_t n, uint64_t b) {
+    const uint4 v0 = values[2 * b], v1 = values[2 * b + 1];
+    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const uint64_t valid = n - b * 64 < 64 ? n - b * 64 : 64;            // elements of this block below n
+    uint64_t cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t a = nibble_abs8(w[i]);
+        // element 8i + e sits in nibble (e ^ 1) of the word (even elements in the HIGH nibble of each byte)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t lv = (a >> (4 * (e ^ 1))) & 0xFu;
+            if (lv != 0 && (uint64_t)(8 * i + e) < valid) cnt += 1ull << (8 * (lv - 1));
+        }
+    }
+    return cnt;
+}
+
+// thread = block
 __global__ void __launch_bounds__(kThrThreads)
 k_thr4_levels(const uint4 *__restrict__ values, uint64_t n, uint64_t nblocks, uint64_t *__restrict__ levels) {
-    for (uint64_t b = (uint64_t)blockIdx.x * kThrThreads + threadIdx.x; b < nblocks; b += (uint64_t)gridDim.x * kThrThreads) {
-        const uint4 v0 = values[2 * b], v1 = values[2 * b + 1];
-        const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        const uint64_t valid = n - b * 64 < 64 ? n - b * 64 : 64;            // elements of this block below n
-        uint64_t cnt = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            uint32_t a = nibble_abs8(w[i]);
-            // element 8i + e sits in nibble (e ^ 1) of the word (even elements in the HIGH nibble of each byte)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const uint32_t lv = (a >> (4 * (e ^ 1))) & 0xFu;
-                if (lv != 0 && (uint64_t)(8 * i + e) < valid) cnt += 1ull << (8 * (lv - 1));
-            }
-        }
-        levels[b] = cnt;
-    }
+    for (uint64_t b = (uint64_t)blockIdx.x * kThrThreads + threadIdx.x; b < nblocks; b += (uint64_t)gridDim.x * kThrThreads)
+        levels[b] = block_levels(values, n, b);
 }
 
 // element count of level j (0..8) of a block
@@ -301,28 +306,22 @@ __device__ __forceinline__ uint32_t level_count(uint64_t cnt, uint32_t valid, in
     return valid - (uint32_t)((t + (t >> 32)) & 0xFFFFu);
 }
 
-template <bool TOP>
-__global__ void __launch_bounds__(kThrThreads)
-k_thr4_hist(const uint64_t *__restrict__ levels, const float *__restrict__ scales, uint64_t n, uint64_t nblocks, int shift,
-            uint64_t k, ThrState *__restrict__ st) {
-    __shared__ uint32_t h[256];
-    __shared__ uint64_t scratch[256];
-    __shared__ bool is_last;
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t prefix = TOP ? 0u : st->prefix, mask = TOP ? 0u : st->mask;
-    // The magnitudes of neighbouring blocks share their high digits, so plain shared-memory atomics would serialise on a
-    // handful of bins (9 same-address atomics per thread: 130 us of the first version's 184 us at n = 2^26). A thread
-    // therefore merges the consecutive levels that fall into one bin (levels are monotone in j) and the warp merges equal
-    // bins across its lanes (match.any + redux) before ONE atomic per distinct bin. Warp-uniform trip count.
+// Histogram of digit `shift` of the level magnitudes that match the decided prefix, blocks first, first + stride, ... < nblocks
+// (`first` is the position of the calling WARP's lane 0; all 32 lanes call with the same trip count).
+// The magnitudes of neighbouring blocks share their high digits, so plain shared-memory atomics would serialise on a
+// handful of bins (9 same-address atomics per thread: 130 us of the first version's 184 us at n = 2^26). A thread
+// therefore merges the consecutive levels that fall into one bin (levels are monotone in j) and the warp merges equal
+// bins across its lanes (match.any + redux) before ONE atomic per distinct bin.
+__device__ __forceinline__ void thr4_hist_range(const uint64_t *__restrict__ levels, const float *__restrict__ scales, uint64_t n,
+                                                uint64_t nblocks, uint64_t warp_first, uint64_t stride, int shift, uint32_t prefix,
+                                                uint32_t mask, uint32_t *h) {
     auto flush = [&](uint32_t digit, uint32_t c) {
         const uint32_t key = c ? digit : 0x100u;                             // 0x100: this lane has nothing to add
         const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
         const uint32_t total = __reduce_add_sync(peers, c);
         if (c && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[digit], total);
     };
-    const uint64_t stride = (uint64_t)gridDim.x * kThrThreads;
-    for (uint64_t base = (uint64_t)blockIdx.x * kThrThreads + (threadIdx.x & ~31u); base < nblocks; base += stride) {
+    for (uint64_t base = warp_first; base < nblocks; base += stride) {
         const uint64_t b = base + (threadIdx.x & 31);
         const bool live = b < nblocks;
         const uint64_t cnt = live ? levels[b] : 0ull;
@@ -344,6 +343,20 @@ k_thr4_hist(const uint64_t *__restrict__ levels, const float *__restrict__ scale
         }
         flush(run_digit, run_count);
     }
+}
+
+template <bool TOP>
+__global__ void __launch_bounds__(kThrThreads)
+k_thr4_hist(const uint64_t *__restrict__ levels, const float *__restrict__ scales, uint64_t n, uint64_t nblocks, int shift,
+            uint64_t k, ThrState *__restrict__ st) {
+    __shared__ uint32_t h[256];
+    __shared__ uint64_t scratch[256];
+    __shared__ bool is_last;
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t prefix = TOP ? 0u : st->prefix, mask = TOP ? 0u : st->mask;
+    thr4_hist_range(levels, scales, n, nblocks, (uint64_t)blockIdx.x * kThrThreads + (threadIdx.x & ~31u), (uint64_t)gridDim.x * kThrThreads,
+                    shift, prefix, mask, h);
     __syncthreads();
     if (h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], h[threadIdx.x]);
     __threadfence();
@@ -397,18 +410,15 @@ k_thr4_count_ties(const uint64_t *__restrict__ levels, const float *__restrict__
 
 // thread = block, the CTA walks its range in index order: levels above t stay, below t go, a nibble whose level equals t
 // stays while fewer than keep_ties such elements precede it
-__global__ void __launch_bounds__(kThrThreads)
-k_thr4_apply(uint4 *__restrict__ values, const uint64_t *__restrict__ levels, const float *__restrict__ scales, uint64_t n,
-             uint64_t nblocks, uint64_t blocks_per_cta, const ThrState *__restrict__ st, const uint64_t *__restrict__ tie_base) {
-    __shared__ uint32_t ws[kThrThreads / 32];
+template <int NT>
+__device__ __forceinline__ void thr4_apply_range(uint4 *__restrict__ values, const uint64_t *__restrict__ levels, const float *__restrict__ scales,
+                                                 uint64_t n, uint64_t b0, uint64_t b1, uint32_t t, uint64_t keep_ties, uint64_t first_rank) {
+    __shared__ uint32_t ws[NT / 32];
     __shared__ uint64_t running;
-    const uint32_t t = st->prefix;
-    const uint64_t keep_ties = st->k_rem;
-    const uint64_t b0 = (uint64_t)blockIdx.x * blocks_per_cta, b1 = min(b0 + blocks_per_cta, nblocks);
-    if (threadIdx.x == 0) running = tie_base[blockIdx.x];
+    if (threadIdx.x == 0) running = first_rank;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint64_t base = b0; base < b1; base += kThrThreads) {
+    for (uint64_t base = b0; base < b1; base += NT) {
         const uint64_t b = base + threadIdx.x;
         const bool live = b < b1;
         uint32_t valid = 0, ties = 0, keep_mask = 0, tie_mask = 0;           // bit j: level j survives / ties
@@ -431,7 +441,7 @@ k_thr4_apply(uint4 *__restrict__ values, const uint64_t *__restrict__ levels, co
         __syncthreads();
         uint32_t before = 0, total = 0;
 #pragma unroll
-        for (int x = 0; x < kThrThreads / 32; ++x) { const uint32_t v = ws[x]; if (x < warp) before += v; total += v; }
+        for (int x = 0; x < NT / 32; ++x) { const uint32_t v = ws[x]; if (x < warp) before += v; total += v; }
         uint64_t rank = running + before + (incl - ties);
         // Levels are monotone in j for an ordinary scale, so the survivors of a block are "every nibble with level >= jc" as
         // long as its ties are kept or dropped as a whole: eight nibbles per word are then filtered at once (byte-wise add
@@ -480,6 +490,40 @@ k_thr4_apply(uint4 *__restrict__ values, const uint64_t *__restrict__ levels, co
         if (threadIdx.x == 0) running += total;
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(kThrThreads)
+k_thr4_apply(uint4 *__restrict__ values, const uint64_t *__restrict__ levels, const float *__restrict__ scales, uint64_t n,
+             uint64_t nblocks, uint64_t blocks_per_cta, const ThrState *__restrict__ st, const uint64_t *__restrict__ tie_base) {
+    const uint64_t b0 = (uint64_t)blockIdx.x * blocks_per_cta, b1 = min(b0 + blocks_per_cta, nblocks);
+    thr4_apply_range<kThrThreads>(values, levels, scales, n, b0, b1, st->prefix, st->k_rem, tie_base[blockIdx.x]);
+}
+
+// ---- FAST, 4-bit, n <= kThr4OneCtaLimit (the IHT sizes): the whole level-based selection in ONE CTA and one launch -
+// level counts (kept in a small global scratch), four radix passes with a shared-memory histogram, ordered apply.
+// 512 blocks at n = 32768: a fraction of the work of the element-wise single-CTA / cluster kernels.
+__global__ void __launch_bounds__(kThrSmallThreads)
+k_thr4_one_cta(uint4 *__restrict__ values, const float *__restrict__ scales, uint64_t n, uint64_t nblocks, uint64_t k,
+               uint64_t *__restrict__ levels) {
+    __shared__ uint32_t h[256];
+    __shared__ uint64_t scratch[256];
+    for (uint64_t b = threadIdx.x; b < nblocks; b += kThrSmallThreads) levels[b] = block_levels(values, n, b);
+    uint32_t prefix = 0, mask = 0;
+    uint64_t k_rem = k;
+#pragma unroll 1
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        if (threadIdx.x < 256) h[threadIdx.x] = 0;
+        __syncthreads();                                                     // also orders the levels[] writes before their reads
+        thr4_hist_range(levels, scales, n, nblocks, threadIdx.x & ~31u, kThrSmallThreads, shift, prefix, mask, h);
+        __syncthreads();
+        uint64_t above;
+        const uint32_t d = pick_digit(h, k_rem, scratch, above);
+        prefix |= d << shift;
+        mask |= 0xFFu << shift;
+        k_rem -= above;
+        __syncthreads();
+    }
+    thr4_apply_range<kThrSmallThreads>(values, levels, scales, n, 0, nblocks, prefix, k_rem, 0);
 }
 
 // ---- FAST (n <= kThrSmallLimit, the IHT sizes): ONE CTA does the four digit passes and the ordered apply - one launch.
@@ -732,6 +776,17 @@ static int launch_threshold(int8_t *values, const float *scales, uint64_t n, uin
         k_thr_apply_mask<BITS><<<grid, kThrThreads, 0, stream>>>(v32, n, nwords, keep);
         count_launch(3);
         return launch_status("k_thr_heap");
+    }
+    if (BITS == 4 && n <= kThr4OneCtaLimit && (reinterpret_cast<uintptr_t>(values) & 15u) == 0) {
+        const uint64_t nblocks = (n + 63) / 64;
+        const size_t off_lev = align_up(sizeof(ThrState), 256);
+        void *ws = nullptr;
+        int rc = thr_workspace(stream, off_lev + nblocks * sizeof(uint64_t), &ws);
+        if (rc != CLOVER_OK) return rc;
+        k_thr4_one_cta<<<1, kThrSmallThreads, 0, stream>>>(reinterpret_cast<uint4 *>(values), scales, n, nblocks, k,
+                                                            reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(ws) + off_lev));
+        count_launch();
+        return launch_status("k_thr4_one_cta");
     }
     if (n <= kThrSmallLimit) {
         const size_t off_mag = align_up(sizeof(ThrState), 256);
