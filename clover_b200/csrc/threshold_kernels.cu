@@ -33,7 +33,6 @@ constexpr uint64_t kThrExactLimit = 1u << 12;     // AUTO: the sequential heap w
 constexpr uint64_t kThrSmallLimit = 1u << 13;     // FAST: one CTA does the whole selection up to 8192 elements,
 constexpr uint64_t kThrClusterLimit = 1u << 18;   //       one 8-CTA cluster (histograms merged through DSMEM) up to 262144 (14 us at 32768, 22-27 us at 131072; at 2^20 the seven-launch path wins 40 : 114 us)
 constexpr int kThrClusterSize = 8;
-constexpr uint64_t kThr4OneCtaLimit = 1u << 18;  // FAST, 4-bit: level-based selection in one CTA up to 262144 elements (4096 blocks)
 
 struct ThrState {            // device-resident selection state; hist[] and ticket are zero between calls
     uint32_t prefix;         // magnitude bits decided so far (high digits)
@@ -263,8 +262,9 @@ k_thr_apply(uint32_t *__restrict__ values, const float *__restrict__ scales, uin
 // uint64; level 0 = the valid elements that are left); the four radix passes and the tie count then walk 12 bytes per
 // BLOCK (counts + scale: 1/3 of the vector, no per-element magnitude rebuild) and add a level's count to the histogram
 // with one atomic; the apply pass compares each nibble's level with the threshold. Same selection rule as the
-// element-wise path (everything above the k-th largest magnitude stays, ties are kept in index order), 6 x fewer bytes
-// and ~20 x fewer instructions: 476 -> ~70 us at n = 2^26.
+// element-wise path (everything above the k-th largest magnitude stays, ties are kept in index order): 476 -> 143 us at
+// n = 2^26 (levels 36, four radix passes 64, ties 14, apply ~25 us). Used beyond 2^18 elements only: a single-CTA version
+// of the same scheme measured 14 / 35 us at n = 32768 / 131072 against 13.6 / 24 us of the cluster kernel (r02n).
 __device__ __forceinline__ uint32_t nibble_abs8(uint32_t w) {          // |q| of the 8 two's-complement nibbles, SIMD within the word (0..8, no carries)
     const uint32_t sign = (w >> 3) & 0x11111111u;
     return ((w ^ (sign * 0xFu)) + sign);
@@ -497,33 +497,6 @@ k_thr4_apply(uint4 *__restrict__ values, const uint64_t *__restrict__ levels, co
              uint64_t nblocks, uint64_t blocks_per_cta, const ThrState *__restrict__ st, const uint64_t *__restrict__ tie_base) {
     const uint64_t b0 = (uint64_t)blockIdx.x * blocks_per_cta, b1 = min(b0 + blocks_per_cta, nblocks);
     thr4_apply_range<kThrThreads>(values, levels, scales, n, b0, b1, st->prefix, st->k_rem, tie_base[blockIdx.x]);
-}
-
-// ---- FAST, 4-bit, n <= kThr4OneCtaLimit (the IHT sizes): the whole level-based selection in ONE CTA and one launch -
-// level counts (kept in a small global scratch), four radix passes with a shared-memory histogram, ordered apply.
-// 512 blocks at n = 32768: a fraction of the work of the element-wise single-CTA / cluster kernels.
-__global__ void __launch_bounds__(kThrSmallThreads)
-k_thr4_one_cta(uint4 *__restrict__ values, const float *__restrict__ scales, uint64_t n, uint64_t nblocks, uint64_t k,
-               uint64_t *__restrict__ levels) {
-    __shared__ uint32_t h[256];
-    __shared__ uint64_t scratch[256];
-    for (uint64_t b = threadIdx.x; b < nblocks; b += kThrSmallThreads) levels[b] = block_levels(values, n, b);
-    uint32_t prefix = 0, mask = 0;
-    uint64_t k_rem = k;
-#pragma unroll 1
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        if (threadIdx.x < 256) h[threadIdx.x] = 0;
-        __syncthreads();                                                     // also orders the levels[] writes before their reads
-        thr4_hist_range(levels, scales, n, nblocks, threadIdx.x & ~31u, kThrSmallThreads, shift, prefix, mask, h);
-        __syncthreads();
-        uint64_t above;
-        const uint32_t d = pick_digit(h, k_rem, scratch, above);
-        prefix |= d << shift;
-        mask |= 0xFFu << shift;
-        k_rem -= above;
-        __syncthreads();
-    }
-    thr4_apply_range<kThrSmallThreads>(values, levels, scales, n, 0, nblocks, prefix, k_rem, 0);
 }
 
 // ---- FAST (n <= kThrSmallLimit, the IHT sizes): ONE CTA does the four digit passes and the ordered apply - one launch.
@@ -776,17 +749,6 @@ static int launch_threshold(int8_t *values, const float *scales, uint64_t n, uin
         k_thr_apply_mask<BITS><<<grid, kThrThreads, 0, stream>>>(v32, n, nwords, keep);
         count_launch(3);
         return launch_status("k_thr_heap");
-    }
-    if (BITS == 4 && n <= kThr4OneCtaLimit && (reinterpret_cast<uintptr_t>(values) & 15u) == 0) {
-        const uint64_t nblocks = (n + 63) / 64;
-        const size_t off_lev = align_up(sizeof(ThrState), 256);
-        void *ws = nullptr;
-        int rc = thr_workspace(stream, off_lev + nblocks * sizeof(uint64_t), &ws);
-        if (rc != CLOVER_OK) return rc;
-        k_thr4_one_cta<<<1, kThrSmallThreads, 0, stream>>>(reinterpret_cast<uint4 *>(values), scales, n, nblocks, k,
-                                                            reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(ws) + off_lev));
-        count_launch();
-        return launch_status("k_thr4_one_cta");
     }
     if (n <= kThrSmallLimit) {
         const size_t off_mag = align_up(sizeof(ThrState), 256);

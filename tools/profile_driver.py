@@ -91,6 +91,16 @@ elif what in ("mvmf32", "mvm8f32"):
     x, y = cb.CloverVector32(n), cb.CloverVector32(n)
     x.values.uniform_(-1, 1, generator=g)
     fn = lambda: M.mvm(x, y)
+elif what in ("axpy4", "axpy8"):
+    n = 1 << 26
+    V = cb.CloverVector4 if what == "axpy4" else cb.CloverVector8
+    v = cb.CloverVector32(n)
+    qs = []
+    for _ in range(6):
+        v.values.uniform_(-1, 1, generator=g); q = V(n); q.quantize(v); qs.append(q)
+    k = [0]
+    def fn():
+        i = k[0] % 2; qs[3 * i].scaleAndAdd(qs[3 * i + 1], 0.5, qs[3 * i + 2]); k[0] += 1
 elif what == "iht":
     from clover_b200 import THRESHOLD_FAST, apps
     M, N, K = 8192, 32768, 1024
