@@ -168,7 +168,8 @@ k_mvm_f32_ring(const __grid_constant__ CUtensorMap tmap, const float *__restrict
         if (p_item >= nitems) return;
         const uint32_t nb = min((uint32_t)kBPC, hb - p_c * kBPC);
         const uint32_t dst = ring + p_s * kF32StageBytes, bar = bars + 8 * p_s;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the warp's reads of this stage precede the refill
+        // (the warp's own reads of this stage are ordered before the refill by the __syncwarp() in front of this call - the
+        //  generic-proxy hand-over every TMA consumer/producer ring uses; no cross-proxy fence is needed for a write AFTER reads)
         mbar_arrive_expect_tx_a(bar, kF32Rows * 128 + nb * 256);
         tma_load_2d_a(dst, &tmap, (int)(p_c * 128), (int)(p_item * kF32Rows), bar);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -179,10 +180,13 @@ k_mvm_f32_ring(const __grid_constant__ CUtensorMap tmap, const float *__restrict
     if (lane == 0)
         for (int i = 0; i < kF32Stages; ++i) issue();
 
-    // lane j (< kBPC) of every group of kBPC lanes holds the raw scale of block c * kBPC + j, one chunk ahead
-    auto load_scale = [&](uint32_t item, uint32_t c) -> float {
+    // Block scales: lane L holds s = su[b] / 7.0f (:1488) resp. / 127.0f (CloverMatrix8.h:587) of block 32g + L of the current
+    // row - ONE load and ONE IEEE divide per lane and 32 blocks (kCPG chunks); the raw value of the next group is requested
+    // a group ahead. Per chunk the warp only shuffles.
+    constexpr uint32_t kCPG = 32 / kBPC;                               // chunks per group of 32 blocks
+    auto load_scale = [&](uint32_t item, uint32_t g) -> float {
         if (item >= nitems) return 1.0f;
-        const uint32_t b = min(c * kBPC + (uint32_t)(lane & (kBPC - 1)), hb - 1);
+        const uint32_t b = min(g * 32u + (uint32_t)lane, hb - 1);
         return __ldg(scales + (uint64_t)(item / (64 / kF32Rows)) * hb + b);
     };
 
@@ -197,19 +201,23 @@ k_mvm_f32_ring(const __grid_constant__ CUtensorMap tmap, const float *__restrict
         for (int k = 0; k < 2; ++k)
 #pragma unroll
             for (int p = 0; p < 4; ++p) acc[k][p] = 0ull;
+        float sdiv = 0.f;
         for (uint32_t c = 0; c < nchunks; ++c) {
-            const float sdiv = __fdiv_rn(sraw, kQ);                    // s = su[b] / 7.0f (:1488) resp. / 127.0f (:587)
-            sraw = c + 1 < nchunks ? load_scale(item, c + 1) : load_scale(item + wstride, 0);
+            if (c % kCPG == 0) {
+                sdiv = __fdiv_rn(sraw, kQ);
+                sraw = (c + kCPG) * kBPC < hb ? load_scale(item, c / kCPG + 1) : load_scale(item + wstride, 0);
+            }
             mbar_wait_a(bars + 8 * s, phase);
             const uint32_t st = ring + s * kF32StageBytes, rowp = st + rowoff, xs = st + kF32Rows * 128u + 64u * (uint32_t)kh;
             const int nb = (int)min((uint32_t)kBPC, hb - c * kBPC);
-            // nb is warp-uniform; the full chunk is the common case and fully unrolled (shuffle lanes and shared-memory
-            // offsets become immediates)
+            // the block scales of the chunk, broadcast once (lane j of every group of kBPC lanes holds block j's)
+            float sjs[4];
+#pragma unroll
+            for (int j = 0; j < kBPC; ++j) sjs[j] = __shfl_sync(0xFFFFFFFFu, sdiv, (int)(c % kCPG) * kBPC + j);
             auto block_step = [&](auto J) {
                 constexpr int j = decltype(J)::value;
-                if (j < kBPC && j < nb) {
-                    const float sj = __shfl_sync(0xFFFFFFFFu, sdiv, j);
-                    const uint64_t ss = pack2f(sj, sj);
+                if (j < kBPC) {
+                    const uint64_t ss = pack2f(sjs[j], sjs[j]);
                     // x[64j + 16kh ...] of this stage; the second half block is 128 bytes further
                     if (MBITS == 4) {
                         const uint2 w0 = lds64(rowp + ((((uint32_t)(2 * j)) ^ rsw) << 4) + 8u * (uint32_t)kh);        // elements 16kh .. 16kh+15
@@ -236,10 +244,18 @@ k_mvm_f32_ring(const __grid_constant__ CUtensorMap tmap, const float *__restrict
                     }
                 }
             };
-            block_step(std::integral_constant<int, 0>{});
-            block_step(std::integral_constant<int, 1>{});
-            block_step(std::integral_constant<int, 2>{});
-            block_step(std::integral_constant<int, 3>{});
+            // nb is warp-uniform. A full chunk (every chunk but possibly the last of a row) runs without any guard, so that
+            // the accumulators stay in place; the partial chunk at a row end takes the guarded path.
+            if (nb == kBPC) {
+                block_step(std::integral_constant<int, 0>{});
+                block_step(std::integral_constant<int, 1>{});
+                block_step(std::integral_constant<int, 2>{});
+                block_step(std::integral_constant<int, 3>{});
+            } else {
+                if (nb > 0) block_step(std::integral_constant<int, 0>{});
+                if (nb > 1) block_step(std::integral_constant<int, 1>{});
+                if (nb > 2) block_step(std::integral_constant<int, 2>{});
+            }
             __syncwarp();
             if (lane == 0) issue();
             if (++s == kF32Stages) { s = 0; phase ^= 1; }
