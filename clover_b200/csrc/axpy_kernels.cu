@@ -81,107 +81,8 @@ __device__ __forceinline__ uint32_t pack_s8(int a, int b, uint32_t c) {
     return d;
 }
 
-template <int BITS, bool STOCH>
-__global__ void __launch_bounds__(256)
-k_vscale_add(const uint32_t *u, const float *su, const uint32_t *__restrict__ v,       // u / su may alias r / sr (in place)
-             const float *__restrict__ sv, float a, uint64_t nblocks, uint32_t *r, float *sr, Key4 key,
-             const uint64_t *__restrict__ tables) {
-    constexpr float kQmax = BITS == 4 ? 7.0f : 127.0f;
-    constexpr int kWords = BITS == 4 ? 8 : 16;                    // 32-bit words per block
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t blk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; blk < nblocks; blk += stride) {
-        const float su_ps = __fdiv_rn(su[blk], kQmax);
-        const float sv_ps = __fdiv_rn(__fmul_rn(sv[blk], a), kQmax);
-        uint32_t wu[kWords], wv[kWords];
-#pragma unroll
-        for (int i = 0; i < kWords / 4; ++i) {
-            const uint4 x = reinterpret_cast<const uint4 *>(u + blk * kWords)[i];
-            const uint4 y = reinterpret_cast<const uint4 *>(v + blk * kWords)[i];
-            wu[4 * i] = x.x; wu[4 * i + 1] = x.y; wu[4 * i + 2] = x.z; wu[4 * i + 3] = x.w;
-            wv[4 * i] = y.x; wv[4 * i + 1] = y.y; wv[4 * i + 2] = y.z; wv[4 * i + 3] = y.w;
-        }
-        float val[64];
-        if (BITS == 4) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                // q + 8 per nibble; even elements sit in the HIGH nibbles (byte j: elements 8w+2j, 8w+2j+1)
-                const uint32_t bu = wu[w] ^ 0x88888888u, bv = wv[w] ^ 0x88888888u;
-                const uint32_t uh = (bu >> 4) & 0x0F0F0F0Fu, ul = bu & 0x0F0F0F0Fu;
-                const uint32_t vh = (bv >> 4) & 0x0F0F0F0Fu, vl = bv & 0x0F0F0F0Fu;
-#define CLOVER_AXPY4(J)                                                                                              \
-                val[8 * w + 2 * J]     = __fmaf_rn(byte_to_float<J>(vh, 12582920.0f), sv_ps,                          \
-                                                   __fmul_rn(byte_to_float<J>(uh, 12582920.0f), su_ps));             \
-                val[8 * w + 2 * J + 1] = __fmaf_rn(byte_to_float<J>(vl, 12582920.0f), sv_ps,                          \
-                                                   __fmul_rn(byte_to_float<J>(ul, 12582920.0f), su_ps));
-                CLOVER_AXPY4(0) CLOVER_AXPY4(1) CLOVER_AXPY4(2) CLOVER_AXPY4(3)
-#undef CLOVER_AXPY4
-            }
-        } else {
-#pragma unroll
-            for (int w = 0; w < 16; ++w) {
-                const uint32_t bu = wu[w] ^ 0x80808080u, bv = wv[w] ^ 0x80808080u;       // q + 128 per byte
-#define CLOVER_AXPY8(J)                                                                                              \
-                val[4 * w + J] = __fmaf_rn(byte_to_float<J>(bv, 12583040.0f), sv_ps,                                  \
-                                           __fmul_rn(byte_to_float<J>(bu, 12583040.0f), su_ps));
-                CLOVER_AXPY8(0) CLOVER_AXPY8(1) CLOVER_AXPY8(2) CLOVER_AXPY8(3)
-#undef CLOVER_AXPY8
-            }
-        }
-        float m = 0.f;
-#pragma unroll
-        for (int e = 0; e < 64; ++e) m = fmaxf(m, fabsf(val[e]));
-        m = guard_zero(m);
-        sr[blk] = m;
-        const float scale = quant_scale(kQmax, m);
-
-        uint32_t nw[2][8];
-        if (STOCH) {
-            uint64_t lanes[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) lanes[k] = xs_jump(tables, key.x[k], 2 * blk);
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t o = xs_next(lanes[k]);
-                    nw[c][2 * k] = (uint32_t)o;
-                    nw[c][2 * k + 1] = (uint32_t)(o >> 32);
-                }
-        }
-        uint32_t out[kWords];
-        if (BITS == 4) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                int q[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int p = 2 * ((i >> 1) & 3) + ((i & 1) ? 0 : 1);              // nibble position of element 8w+i
-                    const float rnd = STOCH ? noise_from_word(nw[p >> 2][w], p & 3) : 0.f;
-                    q[i] = quant_one(val[8 * w + i], scale, rnd);
-                }
-                out[w] = pack8_nibbles(q);
-            }
-        } else {
-#pragma unroll
-            for (int w = 0; w < 16; ++w) {
-                int q[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int e = 4 * w + i;
-                    const float rnd = STOCH ? noise_from_word(nw[e >> 5][(e & 31) >> 2], e & 3) : 0.f;
-                    q[i] = quant_one(val[e], scale, rnd);
-                }
-                out[w] = pack4_bytes(q);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < kWords / 4; ++i)
-            reinterpret_cast<uint4 *>(r + blk * kWords)[i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// Second design (default): FOUR threads per block of 64, 16 contiguous elements each - the layout that took the
+// Keyed (stochastic-rounding) kernel: FOUR threads per block of 64, 16 contiguous elements each - the layout that took the
 // quantizer from 73 % to 93 % of the HBM roofline (vector_kernels.cu, k_vquantize4t). A thread loads its 8 (4-bit) or
 // 16 (8-bit) bytes of u and v with one vector load each, the block absmax is two xor-shuffles away, and its 16
 // roundings pack into exactly the bytes it loaded - so r may still alias u: every byte is read and written by the same
@@ -242,64 +143,6 @@ k_vscale_add4t(const uint32_t *u, const float *su, const uint32_t *__restrict__ 
         if (live) {
             su_ps = __fdiv_rn(su_raw, kQmax);
             sv_ps = __fdiv_rn(__fmul_rn(sv_raw, a), kQmax);
-        }
-        if (!STOCH) {
-            // ---- rounding disabled: packed arithmetic, ~7 instructions per element (the scalar path below needs ~14) ----
-            // q = sign(val) * trunc(fma(|val|, scale, 0)) = trunc(val * scale): rounding to nearest is sign-symmetric and
-            // truncation is odd, so neither the abs nor the sign transfer of the general formula is needed
-            const uint64_t su2 = f2_pack(su_ps, su_ps), sv2 = f2_pack(sv_ps, sv_ps);
-            uint64_t val2[8];
-            if (BITS == 4) {
-                const uint64_t neg = f2_pack(-12582920.0f, -12582920.0f);
-#pragma unroll
-                for (int w = 0; w < 2; ++w) {                         // byte p of a word: element 2p in the HIGH nibble, 2p+1 in the low one
-                    const uint32_t ul = and_xor_r(wu[w], kc.m0f, kc.c08), uh = and_xor_r(wu[w] >> 4, kc.m0f, kc.c08);
-                    const uint32_t vl = and_xor_r(wv[w], kc.m0f, kc.c08), vh = and_xor_r(wv[w] >> 4, kc.m0f, kc.c08);
-                    val2[4 * w + 0] = axpy_pair<0, 0>(uh, ul, vh, vl, kc.magic, neg, su2, sv2);
-                    val2[4 * w + 1] = axpy_pair<1, 1>(uh, ul, vh, vl, kc.magic, neg, su2, sv2);
-                    val2[4 * w + 2] = axpy_pair<2, 2>(uh, ul, vh, vl, kc.magic, neg, su2, sv2);
-                    val2[4 * w + 3] = axpy_pair<3, 3>(uh, ul, vh, vl, kc.magic, neg, su2, sv2);
-                }
-            } else {
-                const uint64_t neg = f2_pack(-12583040.0f, -12583040.0f);
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const uint32_t bu = wu[w] ^ kc.c80, bv = wv[w] ^ kc.c80;          // q + 128 per byte
-                    val2[2 * w + 0] = axpy_pair<0, 1>(bu, bu, bv, bv, kc.magic, neg, su2, sv2);
-                    val2[2 * w + 1] = axpy_pair<2, 3>(bu, bu, bv, bv, kc.magic, neg, su2, sv2);
-                }
-            }
-            float m = 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) m = max3_abs(m, f2_lo(val2[e]), f2_hi(val2[e]));
-            if (!live) m = 0.f;
-            m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 1));
-            m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 2));
-            m = guard_zero(m);
-            if (!live) continue;
-            const float scale = quant_scale(kQmax, m);
-            const uint64_t sc2 = f2_pack(scale, scale);
-            if (s == 0) sr[blk] = m;
-            int q[16];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                uint64_t p;
-                asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p) : "l"(val2[e]), "l"(sc2));
-                q[2 * e] = __float2int_rz(f2_lo(p));
-                q[2 * e + 1] = __float2int_rz(f2_hi(p));
-            }
-            if (BITS == 4) {
-                uint32_t o0 = 0, o1 = 0;
-#pragma unroll
-                for (int b = 3; b >= 0; --b) { o0 = pack_s4(q[2 * b], q[2 * b + 1], o0); o1 = pack_s4(q[8 + 2 * b], q[8 + 2 * b + 1], o1); }
-                *reinterpret_cast<uint2 *>(r + blk * 8 + 2 * s) = make_uint2(o0, o1);
-            } else {
-                uint32_t o[4];
-#pragma unroll
-                for (int w = 0; w < 4; ++w) o[w] = pack_s8(q[4 * w + 1], q[4 * w], pack_s8(q[4 * w + 3], q[4 * w + 2], 0u));
-                *reinterpret_cast<uint4 *>(r + blk * 16 + 4 * s) = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-            continue;
         }
         float val[16];
         if (BITS == 4) {
@@ -386,6 +229,137 @@ k_vscale_add4t(const uint32_t *u, const float *su, const uint32_t *__restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Rounding-disabled kernel, TPB threads per block of 64 (EPT = 64 / TPB elements each), packed arithmetic throughout.
+// Everything a block costs ONCE - two operand-scale divides, the 7 / max divide, address arithmetic, the loop - is paid
+// per thread, so fewer threads per block means fewer instructions per element: ncu counted 15.3 instructions per
+// element with four threads per block against 7.3 in the arithmetic itself (profiles/r02p). r may alias u (every byte
+// is read and written by the same thread; the next block's operands are prefetched before the current block is stored).
+// ---------------------------------------------------------------------------------------------
+template <int BITS, int TPB>
+__global__ void __launch_bounds__(256)
+k_vscale_add_pk(const uint32_t *u, const float *su, const uint32_t *__restrict__ v, const float *__restrict__ sv, float a,
+                uint64_t nblocks, uint32_t *r, float *sr, uint32_t zero) {
+    constexpr float kQmax = BITS == 4 ? 7.0f : 127.0f;
+    constexpr int EPT = 64 / TPB;                                  // elements per thread
+    constexpr int kW = BITS == 4 ? EPT / 8 : EPT / 4;              // 32-bit words per thread
+    constexpr int kBW = BITS == 4 ? 8 : 16;                        // words per block
+    const AxpyConsts kc = {0x4B400000u | zero, 0x0F0F0F0Fu | zero, 0x08080808u | zero, 0x80808080u | zero};
+    const int s = threadIdx.x & (TPB - 1);
+    const uint64_t group = ((uint64_t)blockIdx.x * 256 + threadIdx.x) / TPB, ngroups = ((uint64_t)gridDim.x * 256) / TPB;
+    uint32_t wu[kW], wv[kW], nwu[kW], nwv[kW];
+    float su_raw, sv_raw, nsu_raw, nsv_raw;
+    auto fetch = [&](uint64_t b, uint32_t *pu, uint32_t *pv, float &psu, float &psv) {
+#pragma unroll
+        for (int i = 0; i < kW; ++i) pu[i] = pv[i] = 0u;
+        psu = psv = 0.f;
+        if (b < nblocks) {
+            psu = su[b];
+            psv = sv[b];
+            const uint32_t *gu = u + b * kBW + s * kW, *gv = v + b * kBW + s * kW;
+            if (kW == 2) {
+                const uint2 x = *reinterpret_cast<const uint2 *>(gu), y = *reinterpret_cast<const uint2 *>(gv);
+                pu[0] = x.x; pu[1] = x.y; pv[0] = y.x; pv[1] = y.y;
+            } else {
+#pragma unroll
+                for (int i = 0; i < kW / 4; ++i) {
+                    const uint4 x = reinterpret_cast<const uint4 *>(gu)[i], y = reinterpret_cast<const uint4 *>(gv)[i];
+                    pu[4 * i] = x.x; pu[4 * i + 1] = x.y; pu[4 * i + 2] = x.z; pu[4 * i + 3] = x.w;
+                    pv[4 * i] = y.x; pv[4 * i + 1] = y.y; pv[4 * i + 2] = y.z; pv[4 * i + 3] = y.w;
+                }
+            }
+        }
+    };
+    uint64_t blk = group;
+    fetch(blk, wu, wv, su_raw, sv_raw);
+    for (;; blk += ngroups) {
+        const bool live = blk < nblocks;
+        if (!__any_sync(0xFFFFFFFFu, live)) break;
+        fetch(blk + ngroups, nwu, nwv, nsu_raw, nsv_raw);
+        const float su_ps = __fdiv_rn(su_raw, kQmax), sv_ps = __fdiv_rn(__fmul_rn(sv_raw, a), kQmax);
+        const uint64_t su2 = f2_pack(su_ps, su_ps), sv2 = f2_pack(sv_ps, sv_ps);
+        uint64_t val2[EPT / 2];
+        if (BITS == 4) {
+            const uint64_t neg = f2_pack(-12582920.0f, -12582920.0f);
+#pragma unroll
+            for (int w = 0; w < kW; ++w) {                            // byte p of a word: element 2p in the HIGH nibble, 2p+1 in the low one
+                const uint32_t ul = and_xor_r(wu[w], kc.m0f, kc.c08), uh = and_xor_r(wu[w] >> 4, kc.m0f, kc.c08);
+                const uint32_t vl = and_xor_r(wv[w], kc.m0f, kc.c08), vh = and_xor_r(wv[w] >> 4, kc.m0f, kc.c08);
+                val2[4 * w + 0] = axpy_pair<0, 0>(uh, ul, vh, vl, kc.magic, neg, su2, sv2);
+                val2[4 * w + 1] = axpy_pair<1, 1>(uh, ul, vh, vl, kc.magic, neg, su2, sv2);
+                val2[4 * w + 2] = axpy_pair<2, 2>(uh, ul, vh, vl, kc.magic, neg, su2, sv2);
+                val2[4 * w + 3] = axpy_pair<3, 3>(uh, ul, vh, vl, kc.magic, neg, su2, sv2);
+            }
+        } else {
+            const uint64_t neg = f2_pack(-12583040.0f, -12583040.0f);
+#pragma unroll
+            for (int w = 0; w < kW; ++w) {
+                const uint32_t bu = wu[w] ^ kc.c80, bv = wv[w] ^ kc.c80;              // q + 128 per byte
+                val2[2 * w + 0] = axpy_pair<0, 1>(bu, bu, bv, bv, kc.magic, neg, su2, sv2);
+                val2[2 * w + 1] = axpy_pair<2, 3>(bu, bu, bv, bv, kc.magic, neg, su2, sv2);
+            }
+        }
+        float m = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPT / 2; ++e) m = max3_abs(m, f2_lo(val2[e]), f2_hi(val2[e]));
+        if (!live) m = 0.f;
+#pragma unroll
+        for (int o = 1; o < TPB; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+        m = guard_zero(m);
+        if (live) {
+            // q = sign(val) * trunc(fma(|val|, scale, 0)) = trunc(val * scale): rounding to nearest is sign-symmetric, truncation is odd
+            const float scale = quant_scale(kQmax, m);
+            const uint64_t sc2 = f2_pack(scale, scale);
+            if (s == 0) sr[blk] = m;
+            int q[EPT];
+#pragma unroll
+            for (int e = 0; e < EPT / 2; ++e) {
+                uint64_t p;
+                asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p) : "l"(val2[e]), "l"(sc2));
+                q[2 * e] = __float2int_rz(f2_lo(p));
+                q[2 * e + 1] = __float2int_rz(f2_hi(p));
+            }
+            uint32_t o[kW];
+#pragma unroll
+            for (int w = 0; w < kW; ++w) {
+                if (BITS == 4) {
+                    uint32_t t = 0;
+#pragma unroll
+                    for (int b = 3; b >= 0; --b) t = pack_s4(q[8 * w + 2 * b], q[8 * w + 2 * b + 1], t);
+                    o[w] = t;
+                } else {
+                    o[w] = pack_s8(q[4 * w + 1], q[4 * w], pack_s8(q[4 * w + 3], q[4 * w + 2], 0u));
+                }
+            }
+            uint32_t *gr = r + blk * kBW + s * kW;
+            if (kW == 2) {
+                *reinterpret_cast<uint2 *>(gr) = make_uint2(o[0], o[1]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < kW / 4; ++i) reinterpret_cast<uint4 *>(gr)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kW; ++i) { wu[i] = nwu[i]; wv[i] = nwv[i]; }
+        su_raw = nsu_raw; sv_raw = nsv_raw;
+    }
+}
+
+template <int BITS, int TPB>
+static void launch_scale_add_pk(const uint32_t *u32, const float *su, const uint32_t *v32, const float *sv, float a, uint64_t nblocks,
+                                uint32_t *r32, float *sr, cudaStream_t stream) {
+    static int ctas_per_sm[kMaxDevices] = {};
+    const int dev = current_device() < 0 ? 0 : current_device();
+    int &cps = ctas_per_sm[dev];
+    if (cps == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vscale_add_pk<BITS, TPB>, 256, 0) != cudaSuccess || cps < 1) cps = 1;
+    }
+    const uint64_t max_groups = (uint64_t)sm_count() * cps * (256 / TPB);                  // one resident wave
+    const uint64_t groups = nblocks < max_groups ? nblocks : max_groups;
+    const unsigned grid = (unsigned)((groups * TPB + 255) / 256);
+    k_vscale_add_pk<BITS, TPB><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, r32, sr, 0u);
+}
+
 template <int BITS>
 static int launch_scale_add(const int8_t *u, const float *su, const int8_t *v, const float *sv, float a, uint64_t n_pad,
                             int8_t *r, float *sr, uint64_t *key_host, cudaStream_t stream) {
@@ -393,36 +367,30 @@ static int launch_scale_add(const int8_t *u, const float *su, const int8_t *v, c
     if (nblocks == 0) return CLOVER_OK;
     const uint32_t *u32 = reinterpret_cast<const uint32_t *>(u), *v32 = reinterpret_cast<const uint32_t *>(v);
     uint32_t *r32 = reinterpret_cast<uint32_t *>(r);
-    // CLOVER_AXPY_IMPL=block selects the thread-per-block kernel (kept for A/B measurements)
-    static const bool per_block = getenv("CLOVER_AXPY_IMPL") && !strcmp(getenv("CLOVER_AXPY_IMPL"), "block");
-    Key4 key = {};
-    const uint64_t *tables = nullptr;
-    if (key_host) {
-        tables = device_jump_tables();
-        if (!tables) { set_error("clover: could not upload PRNG jump tables"); return CLOVER_ERR_CUDA; }
-        key = key_lanes(key_host);
+    if (!key_host) {
+        // threads per block, measured at n = 2^26 on B200 (r02s): 4-bit 37.5 / 39.7 / 45.7 us with 1 / 2 / 4 threads per block
+        // (3.0 TB/s, 46 % of the HBM peak; round 1: 58.7 us), 8-bit 53.5 / 46.2 / 42.9 us (5.0 TB/s, 76 %; round 1: 56 us) -
+        // the 8-bit thread-per-block kernel needs 150 registers
+        if (BITS == 4) launch_scale_add_pk<BITS, 1>(u32, su, v32, sv, a, nblocks, r32, sr, stream);
+        else           launch_scale_add_pk<BITS, 4>(u32, su, v32, sv, a, nblocks, r32, sr, stream);
+        count_launch();
+        return launch_status("k_vscale_add_pk");
     }
-    if (per_block) {
-        const uint64_t want = (nblocks + 255) / 256, cap = (uint64_t)sm_count() * 8;
-        const unsigned grid = (unsigned)(want > cap ? cap : want);
-        if (key_host) k_vscale_add<BITS, true><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, r32, sr, key, tables);
-        else          k_vscale_add<BITS, false><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, r32, sr, key, nullptr);
-    } else {
-        static int ctas_per_sm[2] = {0, 0};
-        int &cps = ctas_per_sm[key_host != nullptr];
-        if (cps == 0) {
-            cudaError_t e = key_host ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vscale_add4t<BITS, true>, 256, 0)
-                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vscale_add4t<BITS, false>, 256, 0);
-            if (e != cudaSuccess || cps < 1) cps = 1;
-        }
-        const uint64_t max_groups = (uint64_t)sm_count() * cps * 64;                       // one resident wave
-        const uint64_t groups = nblocks < max_groups ? nblocks : max_groups;
-        const uint64_t R = (nblocks + groups - 1) / groups;
-        const unsigned grid = (unsigned)((groups * 4 + 255) / 256);
-        if (key_host) k_vscale_add4t<BITS, true><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, R, r32, sr, key, tables, 0u);
-        else          k_vscale_add4t<BITS, false><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, R, r32, sr, key, nullptr, 0u);
+    const uint64_t *tables = device_jump_tables();
+    if (!tables) { set_error("clover: could not upload PRNG jump tables"); return CLOVER_ERR_CUDA; }
+    const Key4 key = key_lanes(key_host);
+    static int ctas_per_sm[kMaxDevices] = {};
+    const int dev = current_device() < 0 ? 0 : current_device();
+    int &cps = ctas_per_sm[dev];
+    if (cps == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vscale_add4t<BITS, true>, 256, 0) != cudaSuccess || cps < 1) cps = 1;
     }
-    if (key_host) host_key_skip(key_host, 2 * nblocks);
+    const uint64_t max_groups = (uint64_t)sm_count() * cps * 64;                       // one resident wave
+    const uint64_t groups = nblocks < max_groups ? nblocks : max_groups;
+    const uint64_t R = (nblocks + groups - 1) / groups;
+    const unsigned grid = (unsigned)((groups * 4 + 255) / 256);
+    k_vscale_add4t<BITS, true><<<grid, 256, 0, stream>>>(u32, su, v32, sv, a, nblocks, R, r32, sr, key, tables, 0u);
+    host_key_skip(key_host, 2 * nblocks);
     count_launch();
     return launch_status("k_vscale_add");
 }

@@ -1,4 +1,4 @@
-"""Time scaleAndAdd at n = 2^26 for both widths (CLOVER_AXPY_IMPL=block selects the thread-per-block kernel)."""
+"""Time scaleAndAdd at n = 2^26 for both widths."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -16,5 +16,5 @@ for bits_, V in ((4, cb.CloverVector4), (8, cb.CloverVector8)):
         k = i[0] % 2; qs[3 * k].scaleAndAdd(qs[3 * k + 1], 0.5, qs[3 * k + 2]); i[0] += 1
     t = min(cuda_time(torch, axpy, 20) for _ in range(3))
     b = 3 * qs[0].getBytes()
-    print(bits_, os.environ.get("CLOVER_AXPY_IMPL", "4t"), round(t * 1e6, 1), "us", round(b / t / 1e9), "GB/s", flush=True)
+    print(bits_, "bit", round(t * 1e6, 1), "us", round(b / t / 1e9), "GB/s", flush=True)
     del qs
