@@ -18,122 +18,13 @@ namespace clover {
 // =============================================================================================
 // quantize
 // =============================================================================================
-// One THREAD owns one block of 64 elements at a time and walks R consecutive blocks, so that
-//   * absmax, scale, all 64 roundings and the 32/64 packed output bytes are thread-local
-//     (no shuffles, no cross-thread packing), and
-//   * in stochastic mode the thread carries its own XORShift state and steps it exactly like the
-//     reference's sequential loop does (two calls per block), after one O(log n) jump to its
-//     starting block.
-// Global loads stay fully coalesced: the CTA stages its 128 blocks (128 x 256 B pieces) through
-// shared memory with a 272 B row pitch, which makes both the cooperative 16 B stores and the
-// per-thread 16 B row reads bank-conflict free.
-constexpr int kQThreads = 128;
-constexpr int kRowFloats = 68;   // 64 data + 4 pad floats -> 272 B pitch
-
-template <int BITS, bool STOCH>
-__global__ void __launch_bounds__(kQThreads)
-k_vquantize(const float *__restrict__ x, uint64_t nblocks, uint64_t R, int8_t *__restrict__ values,
-            float *__restrict__ scales, Key4 key, const uint64_t *__restrict__ tables) {
-    __shared__ __align__(16) float tile[kQThreads * kRowFloats];
-    constexpr float kQmax = BITS == 4 ? 7.0f : 127.0f;
-
-    const int tid = threadIdx.x;
-    const uint64_t cta_first = (uint64_t)blockIdx.x * kQThreads;   // first thread slot of this CTA
-    const uint64_t my_first = (cta_first + tid) * R;               // first block of this thread
-
-    uint64_t lanes[4] = {0, 0, 0, 0};
-    if (STOCH && my_first < nblocks) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) lanes[k] = xs_jump(tables, key.x[k], 2 * my_first);
-    }
-
-    const int sub = tid >> 4, chunk = tid & 15;                    // half-warp per 256 B piece
-    for (uint64_t r = 0; r < R; ++r) {
-        float4 stage[16];
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-            const uint64_t blk = (cta_first + it * 8 + sub) * R + r;
-            stage[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (blk < nblocks) stage[it] = ldg_stream(reinterpret_cast<const float4 *>(x + blk * 64) + chunk);
-        }
-#pragma unroll
-        for (int it = 0; it < 16; ++it)
-            *reinterpret_cast<float4 *>(&tile[(it * 8 + sub) * kRowFloats + chunk * 4]) = stage[it];
-        __syncthreads();
-
-        const uint64_t blk = my_first + r;
-        if (blk < nblocks) {
-            float f[64];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float4 v = *reinterpret_cast<const float4 *>(&tile[tid * kRowFloats + j * 4]);
-                f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
-            }
-            float m = 0.f;
-#pragma unroll
-            for (int e = 0; e < 64; ++e) m = fmaxf(m, fabsf(f[e]));
-            m = guard_zero(m);
-            scales[blk] = m;
-            const float scale = quant_scale(kQmax, m);
-
-            uint32_t w[2][8];
-            if (STOCH) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t o = xs_next(lanes[k]);
-                        w[c][2 * k] = (uint32_t)o;
-                        w[c][2 * k + 1] = (uint32_t)(o >> 32);
-                    }
-            }
-            if (BITS == 4) {
-                uint32_t out[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    int q[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int e = 8 * j + i;   // noise slot: call e/32, byte (e%32)/8, word e%8
-                        const float rnd = STOCH ? noise_from_word(w[e >> 5][e & 7], (e & 31) >> 3) : 0.f;
-                        q[i] = quant_one(f[e], scale, rnd);
-                    }
-                    out[j] = pack8_nibbles(q);
-                }
-                uint4 *dst = reinterpret_cast<uint4 *>(values + blk * 32);
-                dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
-                dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
-            } else {
-                uint4 *dst = reinterpret_cast<uint4 *>(values + blk * 64);
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    uint32_t out[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        int q[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int e = 16 * j4 + 4 * j + i;
-                            const float rnd = STOCH ? noise_from_word(w[e >> 5][e & 7], (e & 31) >> 3) : 0.f;
-                            q[i] = quant_one(f[e], scale, rnd);
-                        }
-                        out[j] = pack4_bytes(q);
-                    }
-                    dst[j4] = make_uint4(out[0], out[1], out[2], out[3]);
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// quantize, second design: FOUR threads per block of 64 (16 contiguous elements each), no shared memory, no
+// quantize: FOUR threads per block of 64 (16 contiguous elements each), no shared memory, no
 // CTA barrier. Thread s of a group loads its 64 bytes with four 16 B loads (the two halves of each 32 B sector
 // are fetched by consecutive instructions and meet in L1), the block absmax is two xor-shuffles away, and the
 // thread's 16 roundings pack into exactly the 8 (4-bit) or 16 (8-bit) contiguous bytes it stores - a warp writes
 // 256 / 512 contiguous bytes. ~45 registers => full occupancy; this is what lifted C2a from 73 % of the HBM
-// roofline (thread-per-block kernel above, kept for reference as k_vquantize) - see DESIGN.md section 3.
+// roofline (a thread-per-block kernel, round 1a) - see DESIGN.md section 3.
 // Stochastic mode: a group walks R consecutive blocks and all four threads step the same XORShift state
 // (two calls per block), so the stream is consumed exactly like the reference's sequential loop.
 // ---------------------------------------------------------------------------------------------
@@ -212,8 +103,6 @@ static int launch_vquantize(const float *x, uint64_t n_pad, int8_t *values, floa
                             cudaStream_t stream) {
     const uint64_t nblocks = n_pad / kBlock;
     if (nblocks == 0) return CLOVER_OK;
-    // CLOVER_QUANTIZE_IMPL=block selects the thread-per-block kernel (kept for A/B measurements)
-    static const bool per_block = getenv("CLOVER_QUANTIZE_IMPL") && !strcmp(getenv("CLOVER_QUANTIZE_IMPL"), "block");
     Key4 key = {};
     const uint64_t *tables = nullptr;
     if (key_host) {
@@ -221,24 +110,10 @@ static int launch_vquantize(const float *x, uint64_t n_pad, int8_t *values, floa
         if (!tables) { set_error("clover: could not upload PRNG jump tables"); return CLOVER_ERR_CUDA; }
         key = key_lanes(key_host);
     }
-    if (per_block) {
-        // exactly ONE wave: as many thread slots as can be resident, then R consecutive blocks per thread
-        static int ctas_per_sm[2] = {0, 0};
-        int &cps = ctas_per_sm[key_host != nullptr];
-        if (cps == 0) {
-            cudaError_t e = key_host ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vquantize<BITS, true>, kQThreads, 0)
-                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vquantize<BITS, false>, kQThreads, 0);
-            if (e != cudaSuccess || cps < 1) cps = 1;
-        }
-        const uint64_t max_threads = (uint64_t)sm_count() * cps * kQThreads;
-        const uint64_t R = (nblocks + max_threads - 1) / max_threads;
-        const uint64_t threads = (nblocks + R - 1) / R;
-        const unsigned grid = (unsigned)((threads + kQThreads - 1) / kQThreads);
-        if (key_host) k_vquantize<BITS, true><<<grid, kQThreads, 0, stream>>>(x, nblocks, R, values, scales, key, tables);
-        else          k_vquantize<BITS, false><<<grid, kQThreads, 0, stream>>>(x, nblocks, R, values, scales, key, nullptr);
-    } else {
-        static int ctas_per_sm[2] = {0, 0};
-        int &cps = ctas_per_sm[key_host != nullptr];
+    {
+        static int ctas_per_sm[kMaxDevices][2] = {};
+        const int dev = current_device() < 0 ? 0 : current_device();
+        int &cps = ctas_per_sm[dev][key_host != nullptr];
         if (cps == 0) {
             cudaError_t e = key_host ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vquantize4t<BITS, true>, kQ4Threads, 0)
                                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k_vquantize4t<BITS, false>, kQ4Threads, 0);
