@@ -356,7 +356,8 @@ def extras(torch, cb, peak):
         k = i[0] % 2; qs[4 * k].scaleAndAdd(qs[4 * k + 1], 0.5, qs[4 * k + 2]); i[0] += 1
     t = cuda_time(torch, axpy, 20)
     b = 3 * qs[0].getBytes()
-    out["scaleAndAdd4_n2^26"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b}
+    out["scaleAndAdd4_n2^26"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b,
+                                 "traffic": ncu_traffic("scaleAndAdd4:2^26")}
     q8 = [cb.CloverVector8(n) for _ in range(2)]
     def quant8():
         q8[i[0] % 2].quantize(xs32[i[0] % 2]); i[0] += 1
@@ -396,6 +397,7 @@ def extras(torch, cb, peak):
     b = m4.getBytes() + 4 * (c8 + r8)
     out["mvm4_f32_32768"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b,
                              "fp32_ops_per_s": 2.0 * r8 * c8 / t,
+                             "traffic": ncu_traffic("mvm4_f32:32768x32768"),
                              "note": "one int->float, one multiply and one fma per matrix element (the reference's order): CUDA-core bound, not HBM bound"}
     del m4
     # CloverMatrix8::mvm(V32,V32) (CloverMatrix8.h:558-661)
@@ -404,7 +406,8 @@ def extras(torch, cb, peak):
     m8.scales.uniform_(0.25, 1.0, generator=g)
     t = cuda_time(torch, lambda: m8.mvm(x32v, y32v), 20)
     b = m8.getBytes() + 4 * (c8 + r8)
-    out["mvm8_f32_32768"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b, "fp32_ops_per_s": 2.0 * r8 * c8 / t}
+    out["mvm8_f32_32768"] = {"ms": t * 1e3, "GBps": b / t / 1e9, "frac_hbm": b / t / 1e9 / peak, "bytes": b, "fp32_ops_per_s": 2.0 * r8 * c8 / t,
+                             "traffic": ncu_traffic("mvm8_f32:32768x32768")}
     del m8
     # transpose of a 16384 x 16384 matrix (every byte read once and written once)
     for bits_, M_ in ((4, cb.CloverMatrix4), (8, cb.CloverMatrix8)):
@@ -451,7 +454,8 @@ def extras(torch, cb, peak):
         "roofline": {"bound": "tensor", "kernel": "k_gemm4_tc", "achieved": ops / tk / 1e12, "peak": INT8_PEAK_TOPS,
                      "unit": "TOP/s", "frac": ops / tk / 1e12 / INT8_PEAK_TOPS,
                      "peak_source": "measured here: tools/mma_probe peak, tcgen05.mma kind::i8 issue loop on 148 SMs "
-                                    "(profiles/r01_mma_probe.txt); kind::f8f6f4, the kind this kernel uses, sustains 3767",
+                                    "(profiles/r01_mma_probe.txt, re-measured profiles/r02_mma_probe_peak.txt: 4565 burst / 4572 sustained); "
+                                    "kind::f8f6f4, the kind this kernel uses, sustains 3788",
                      "frac_of_e4m3_sustained_3767": ops / tk / 1e12 / 3767.0, "frac_of_nominal_4500": ops / tk / 1e12 / 4500.0,
                      "traffic": ncu_traffic("k_gemm4_tc:16384^3")},
         "note": "C[i][j] = rowView(A,i).dot(rowView(Bt,j)); bit-identical to the DP4A kernel (tests/test_gpu_parity.py)"}
@@ -557,7 +561,12 @@ def main():
                          C.c_void_p(x.scales.data_ptr()), C.c_void_p(A.y32.data_ptr()),
                          C.c_void_p(y.values.data_ptr()), C.c_void_p(y.scales.data_ptr()), None,
                          C.c_void_p(torch.cuda.current_stream().cuda_stream))
-    tk = cuda_time(torch, kernel_only, args.steps)
+    if world == 1:
+        # one step IS one launch of this kernel and nothing else runs in the timed region: its average launch duration is the
+        # timed region's own CUDA-event time (a second loop after 400 steps of full HBM load ran up to 5 % slower on warm boxes)
+        tk = secs / args.steps
+    else:
+        tk = cuda_time(torch, kernel_only, args.steps)
     achieved = shard_bytes / tk / 1e9
 
     # ---- e2e: per-step operands in pinned host memory, result read back every step -------------------------------
@@ -662,7 +671,7 @@ def main():
                          "traffic": ncu_traffic(f"C3_mvm4:{rows}x{cols}") if world == 1 else None,
                          "kernel_ms": tk * 1e3, "algorithmic_bytes_per_launch": shard_bytes,
                          "note": "peak is the measured COPY bandwidth (a kernel that reads and writes); this kernel only reads, "
-                                 "so frac may exceed 1 (ncu: 6.86 TB/s of DRAM traffic, profiles/r01d_gemv4_ncu_summary.txt)"},
+                                 "so frac may exceed 1 (ncu: 6.80 TB/s of DRAM traffic, profiles/r02t_gemv4_ncu_summary.txt)"},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
