@@ -608,18 +608,16 @@ constexpr int kG8Consumers = 256;
 constexpr int kG8Threads = kG8Consumers + 64;
 constexpr int kG8ChunkBytes = kG8Rows * 128;
 
-// MBITS = 8: CloverMatrix8 (a 128-byte chunk holds 2 blocks of 64 columns); MBITS = 4: the mixed-precision
-// CloverMatrix4::mvm(V8,V8) (CloverMatrix4.h:1093-1441) - the same chains on a nibble matrix, 4 blocks per chunk
-template <int MBITS>
+// a 128-byte chunk holds 2 blocks of 64 columns
 struct __align__(1024) Gemv8Stage {
-    static constexpr int kBlocksPerChunk = MBITS == 8 ? 2 : 4;
+    static constexpr int kBlocksPerChunk = 2;
     uint8_t rows[kG8Chunks][kG8ChunkBytes];   // chunk c: rows 0..31 x 128 B, SWIZZLE_128B (each 4 KiB, 1024-aligned)
     uint4 units[kG8Chunks * kBlocksPerChunk * 8];   // unit (block, l): x = xa, y = xb, z = bits of prod
 };
 // STAGES = 5: one CTA per SM; STAGES = 3 (105 KiB): two CTAs per SM, grid = 2 x SMs (see Gemv4Smem)
-template <int STAGES, int MBITS>
+template <int STAGES>
 struct Gemv8Smem {
-    Gemv8Stage<MBITS> stage[STAGES];
+    Gemv8Stage stage[STAGES];
     uint64_t full[STAGES];
     uint64_t empty[STAGES];
     float part[kG8Rows][8];
@@ -629,21 +627,19 @@ struct Gemv8Smem {
     unsigned int ticket;
 };
 
-template <bool STOCH, int STAGES, int MBITS>
+template <bool STOCH, int STAGES>
 __global__ void __launch_bounds__(kG8Threads, STAGES == 5 ? 1 : 2)
 k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows_local,
              uint64_t cols, uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
              float *__restrict__ ybuf, unsigned int *__restrict__ counters, int8_t *__restrict__ yv,
              float *__restrict__ ys, Key4 key, const uint64_t *__restrict__ tables) {
     extern __shared__ uint8_t smem_raw8[];
-    Gemv8Smem<STAGES, MBITS> &sm = *reinterpret_cast<Gemv8Smem<STAGES, MBITS> *>((reinterpret_cast<uintptr_t>(smem_raw8) + 1023u) & ~(uintptr_t)1023u);
+    Gemv8Smem<STAGES> &sm = *reinterpret_cast<Gemv8Smem<STAGES> *>((reinterpret_cast<uintptr_t>(smem_raw8) + 1023u) & ~(uintptr_t)1023u);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t hb = cols >> 6, nitems = rows_local / kG8Rows;
-    constexpr int kBPC = Gemv8Stage<MBITS>::kBlocksPerChunk;
-    // 128-byte chunks per row; a nibble row of cols = 128 mod 256 ends half-way through its last chunk: TMA zero-fills the
-    // rest and the x-units of the blocks beyond hb are zero
-    const uint32_t nchunks128 = MBITS == 8 ? (uint32_t)(cols >> 7) : (uint32_t)((cols + 255) >> 8);
+    constexpr int kBPC = Gemv8Stage::kBlocksPerChunk;
+    const uint32_t nchunks128 = (uint32_t)(cols >> 7);                    // 128-byte chunks per row
     const uint32_t steps = (nchunks128 + kG8Chunks - 1) / kG8Chunks;      // stages per work item
 
     if (tid == 0) {
@@ -691,8 +687,7 @@ k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
                     u[j].x = ok ? __ldg(xv + b * 16 + l) : 0u;
                     u[j].y = ok ? __ldg(xv + b * 16 + 8 + l) : 0u;
                     const float sa = ok ? __ldg(su + b) : 0.f, sb = ok ? __ldg(xs + b) : 0.f;
-                    u[j].z = MBITS == 8 ? __float_as_uint(__fmul_rn(__fmul_rn(sa, 1.0f / 127.0f), __fmul_rn(sb, 1.0f / 127.0f)))    // (CloverMatrix8.h:1042-1046)
-                                        : __float_as_uint(__fmul_rn(__fmul_rn(sa, 1.0f / 7.0f), __fmul_rn(sb, 1.0f / 127.0f)));     // (CloverMatrix4.h:1093-1441)
+                    u[j].z = __float_as_uint(__fmul_rn(__fmul_rn(sa, 1.0f / 127.0f), __fmul_rn(sb, 1.0f / 127.0f)));    // (CloverMatrix8.h:1042-1046)
                     u[j].w = 0u;
                 }
                 mbar_wait(&sm.empty[s], ((it / STAGES) & 1) ^ 1);
@@ -709,41 +704,25 @@ k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
         const uint32_t base = (uint32_t)r * 128u + 4u * (uint32_t)(lane & 3);
         const uint32_t oa0 = base + ((uint32_t)((0 + ty) ^ rin) << 4), ob0 = base + ((uint32_t)((2 + ty) ^ rin) << 4);
         const uint32_t oa1 = base + ((uint32_t)((4 + ty) ^ rin) << 4), ob1 = base + ((uint32_t)((6 + ty) ^ rin) << 4);
-        // nibble matrix: block b of a chunk = 16-byte chunks 2b (elements 0..31) and 2b+1 (32..63); lane l owns halfword l of each
-        const uint32_t hbase = (uint32_t)r * 128u + 2u * (uint32_t)l;
         uint32_t it = 0;
         for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
             float acc = 0.f;
             for (uint32_t c = 0; c < steps; ++c, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&sm.full[s], (it / STAGES) & 1);
-                const Gemv8Stage<MBITS> &st = sm.stage[s];
+                const Gemv8Stage &st = sm.stage[s];
                 const int live = (int)min((uint32_t)kG8Chunks, nchunks128 - c * kG8Chunks);
                 auto chunk = [&](int j) {
                     const uint8_t *p = st.rows[j];
-                    if (MBITS == 8) {
-                        const uint32_t wa0 = *reinterpret_cast<const uint32_t *>(p + oa0), wb0 = *reinterpret_cast<const uint32_t *>(p + ob0);
-                        const uint32_t wa1 = *reinterpret_cast<const uint32_t *>(p + oa1), wb1 = *reinterpret_cast<const uint32_t *>(p + ob1);
-                        const uint4 u0 = st.units[(2 * j) * 8 + l], u1 = st.units[(2 * j + 1) * 8 + l];
-                        int d0 = dp4a_ss((int)wa0, (int)u0.x, (int)kMagicBits);
-                        d0 = dp4a_ss((int)wb0, (int)u0.y, d0);
-                        int d1 = dp4a_ss((int)wa1, (int)u1.x, (int)kMagicBits);
-                        d1 = dp4a_ss((int)wb1, (int)u1.y, d1);
-                        acc = __fmaf_rn(__uint_as_float(u0.z), __fsub_rn(__int_as_float(d0), 12582912.0f), acc);   // (:1093-1094)
-                        acc = __fmaf_rn(__uint_as_float(u1.z), __fsub_rn(__int_as_float(d1), 12582912.0f), acc);
-                    } else {
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const uint32_t h0 = *reinterpret_cast<const uint16_t *>(p + hbase + ((uint32_t)((2 * b) ^ rin) << 4));
-                            const uint32_t h1 = *reinterpret_cast<const uint16_t *>(p + hbase + ((uint32_t)((2 * b + 1) ^ rin) << 4));
-                            const uint4 ux = st.units[(4 * j + b) * 8 + l];
-                            // nibbles -> 16*q bytes like the reference (:1150-1166); the sum d = 16 S is a multiple of 16, so
-                            // as_float(magic + d) * 2^-4 - magic * 2^-4 IS float(d >> 4), the reference's srai 4 (:1196)
-                            int d = dp4a_ss((int)nibbles4_to_bytes16(h0), (int)ux.x, (int)kMagicBits);
-                            d = dp4a_ss((int)nibbles4_to_bytes16(h1), (int)ux.y, d);
-                            acc = __fmaf_rn(__uint_as_float(ux.z), __fmaf_rn(__int_as_float(d), 0.0625f, -786432.0f), acc);     // exact: (magic + 16 S) / 16 - magic / 16 = S
-                        }
-                    }
+                    const uint32_t wa0 = *reinterpret_cast<const uint32_t *>(p + oa0), wb0 = *reinterpret_cast<const uint32_t *>(p + ob0);
+                    const uint32_t wa1 = *reinterpret_cast<const uint32_t *>(p + oa1), wb1 = *reinterpret_cast<const uint32_t *>(p + ob1);
+                    const uint4 u0 = st.units[(2 * j) * 8 + l], u1 = st.units[(2 * j + 1) * 8 + l];
+                    int d0 = dp4a_ss((int)wa0, (int)u0.x, (int)kMagicBits);
+                    d0 = dp4a_ss((int)wb0, (int)u0.y, d0);
+                    int d1 = dp4a_ss((int)wa1, (int)u1.x, (int)kMagicBits);
+                    d1 = dp4a_ss((int)wb1, (int)u1.y, d1);
+                    acc = __fmaf_rn(__uint_as_float(u0.z), __fsub_rn(__int_as_float(d0), 12582912.0f), acc);   // (:1093-1094)
+                    acc = __fmaf_rn(__uint_as_float(u1.z), __fsub_rn(__int_as_float(d1), 12582912.0f), acc);
                 };
                 if (live == kG8Chunks) {
 #pragma unroll
@@ -777,6 +756,218 @@ k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
                     if (tid == 0) counters[rb] = 0u;                            // re-armed for the next launch
                 }
             }
+        }
+    }
+}
+
+// =============================================================================================
+// mixed-precision CloverMatrix4::mvm(V8,V8) (CloverMatrix4.h:1093-1441), round-2 kernel: thread = (row, chain PAIR)
+// =============================================================================================
+// k_m8_mvm_tma<.,.,4> gave every (row, AVX lane l) its own thread: two 16-bit shared loads + one 128-bit unit load and a
+// three-instruction nibble expansion per halfword - 24 issue slots per (row, block, lane), LSU pipe 64-77 % busy, 71 % of
+// HBM. Here a thread owns lanes l = 2p and 2p + 1 of one row:
+//   * ONE 32-bit load per 16-byte half block (bytes 4p..4p+3 = the halfwords of lanes 2p and 2p+1), two PRMT sort the
+//     four halfwords by lane: w_l = [A.b0 A.b1 B.b0 B.b1] = elements (e0|e1) (e2|e3) (e32|e33) (e34|e35) of lane l;
+//   * the high nibbles (w & 0xF0F0F0F0 = 16*q of e0, e2, e32, e34) and the low nibbles ((w << 4) & 0xF0F0F0F0 = 16*q of
+//     e1, e3, e33, e35) meet x operands the unit warp has already sorted the same way (xe, xo): LOP3, SHL, LOP3, 2 DP4A;
+//   * units are 8 bytes per (block, lane) - one 128-bit load serves both lanes of the thread - and the block's scale
+//     product is one broadcast word.
+// 10 issue slots per (row, block, lane) instead of 24; 128 consumer threads per 32-row work item, KC 128-byte chunks per
+// stage, so that more CTAs (smaller rings) share an SM. The hadd tree of a row lives in four adjacent lanes (shuffles).
+// Arithmetic, chain order and the re-quantizer are those of k_m8_mvm<4>: results are bit-identical.
+constexpr int kMxRows = 32;
+constexpr int kMxConsumers = 128;
+constexpr int kMxThreads = kMxConsumers + 64;
+constexpr int kMxChunkBytes = kMxRows * 128;
+
+template <int KC>
+struct __align__(1024) MixStage {
+    uint8_t rows[KC][kMxChunkBytes];          // chunk c: rows 0..31 x 128 B (256 nibbles = 4 blocks), SWIZZLE_128B
+    uint2 units[KC * 4 * 8];                  // unit (block, l): x = xe (x0 x2 x32 x34 of the lane), y = xo (x1 x3 x33 x35)
+    float prod[KC * 4];                       // (su * 1/7) * (sv * 1/127) of the block
+};
+template <int STAGES, int KC>
+struct MixSmem {
+    MixStage<KC> stage[STAGES];
+    uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+    float red_f[2];
+    int red_q[64];
+    unsigned int ticket;
+};
+
+template <bool STOCH, int STAGES, int KC, int PER_SM>
+__global__ void __launch_bounds__(kMxThreads, PER_SM)
+k_m4v8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows_local,
+               uint64_t cols, uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
+               float *__restrict__ ybuf, unsigned int *__restrict__ counters, int8_t *__restrict__ yv,
+               float *__restrict__ ys, Key4 key, const uint64_t *__restrict__ tables) {
+    extern __shared__ uint8_t smem_rawx[];
+    MixSmem<STAGES, KC> &sm = *reinterpret_cast<MixSmem<STAGES, KC> *>((reinterpret_cast<uintptr_t>(smem_rawx) + 1023u) & ~(uintptr_t)1023u);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t hb = cols >> 6, nitems = rows_local / kMxRows;
+    const uint32_t nchunks128 = (uint32_t)((cols + 255) >> 8);            // the last chunk may be half outside the row: TMA zero-fills it
+    const uint32_t steps = (nchunks128 + KC - 1) / KC;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&sm.full[s], 1 + 32);              // TMA issuer (posts the tx bytes) + the 32 unit lanes
+            mbar_init(&sm.empty[s], kMxConsumers / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kMxConsumers / 32) {
+        // ------------------------------- TMA issuer -------------------------------
+        if (lane == 0) {
+            tma_prefetch_descriptor(&tmap);
+            const uint64_t policy = policy_evict_first();
+            uint32_t it = 0;
+            for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+                for (uint32_t c = 0; c < steps; ++c, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t live = min((uint32_t)KC, nchunks128 - c * KC);
+                    mbar_wait(&sm.empty[s], ((it / STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&sm.full[s], live * kMxChunkBytes);
+                    for (uint32_t j = 0; j < live; ++j)
+                        tma_load_2d(sm.stage[s].rows[j], &tmap, (int)((c * KC + j) * 128), (int)(item * kMxRows),
+                                    &sm.full[s], policy);
+                }
+            }
+        }
+    } else if (warp == kMxConsumers / 32 + 1) {
+        // ------------------------------- x-unit warp -------------------------------
+        // lane owns units lane + 32j (j = 0..KC-1) of a stage = (block 4j + lane/8, AVX lane lane%8)
+        uint32_t it = 0;
+        const int l = lane & 7;
+        for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const float *su = scales + (item >> 1) * hb;
+            for (uint32_t c = 0; c < steps; ++c, ++it) {
+                const int s = it % STAGES;
+                uint2 u[KC];
+                float pr[KC];
+#pragma unroll
+                for (int j = 0; j < KC; ++j) {
+                    const uint64_t b = (uint64_t)c * (4 * KC) + 4 * j + (lane >> 3);
+                    const bool ok = b < hb;
+                    const uint32_t xa = ok ? __ldg(xv + b * 16 + l) : 0u;            // elements 4l .. 4l+3
+                    const uint32_t xb = ok ? __ldg(xv + b * 16 + 8 + l) : 0u;        // elements 32+4l .. 32+4l+3
+                    u[j].x = __byte_perm(xa, xb, 0x6420);
+                    u[j].y = __byte_perm(xa, xb, 0x7531);
+                    const float sa = ok ? __ldg(su + b) : 0.f, sb = ok ? __ldg(xs + b) : 0.f;
+                    pr[j] = __fmul_rn(__fmul_rn(sa, 1.0f / 7.0f), __fmul_rn(sb, 1.0f / 127.0f));
+                }
+                mbar_wait(&sm.empty[s], ((it / STAGES) & 1) ^ 1);
+#pragma unroll
+                for (int j = 0; j < KC; ++j) {
+                    sm.stage[s].units[lane + 32 * j] = u[j];
+                    if (l == 0) sm.stage[s].prod[4 * j + (lane >> 3)] = pr[j];
+                }
+                mbar_arrive(&sm.full[s]);
+            }
+        }
+    } else {
+        // ------------------------------- consumer warps ------------------------------
+        // warp = 8 rows, lane = (row rin of the eight, pair p): 16-byte chunk c of a row sits at chunk position c ^ (row & 7),
+        // so the 32 words of a warp-wide load fall into 32 different banks
+        const int rin = lane >> 2, p = lane & 3;
+        const int r = 8 * warp + rin;
+        const uint32_t base = (uint32_t)r * 128u + 4u * (uint32_t)p;
+        uint32_t off[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) off[c] = base + ((uint32_t)(c ^ rin) << 4);
+        uint32_t it = 0;
+        for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+            float acc0 = 0.f, acc1 = 0.f;
+            for (uint32_t c = 0; c < steps; ++c, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&sm.full[s], (it / STAGES) & 1);
+                // explicit shared-space loads with immediate offsets (a generic pointer into the aligned struct compiles to LD.E)
+                const uint32_t sbase = smem_u32(&sm.stage[s]);
+                uint32_t ra[8];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) ra[cc] = sbase + off[cc];
+                const uint32_t ubase = sbase + 16u * (uint32_t)p;
+                const int live = (int)min((uint32_t)KC, nchunks128 - c * KC);
+#define CLOVER_MIX_BLOCK(J, B)                                                                                           \
+    {                                                                                                                     \
+        uint32_t wa, wb, pr_;                                                                                             \
+        uint4 u;                                                                                                          \
+        asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(wa) : "r"(ra[2 * (B)]), "n"((J) * kMxChunkBytes));              \
+        asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(wb) : "r"(ra[2 * (B) + 1]), "n"((J) * kMxChunkBytes));          \
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+%5];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)           \
+                     : "r"(ubase), "n"(KC * kMxChunkBytes + (4 * (J) + (B)) * 64));                                       \
+        asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(pr_) : "r"(sbase), "n"(KC * kMxChunkBytes + KC * 256 + (4 * (J) + (B)) * 4)); \
+        const float pr = __uint_as_float(pr_);                                                                            \
+        const uint32_t w0 = __byte_perm(wa, wb, 0x5410), w1 = __byte_perm(wa, wb, 0x7632);                                \
+        /* d = magic + 16 S; as_float(d) / 16 - magic / 16 IS float(S), the reference's srai 4 + cvt (:1196) */           \
+        int d0 = dp4a_ss((int)(w0 & 0xF0F0F0F0u), (int)u.x, (int)kMagicBits);                                             \
+        d0 = dp4a_ss((int)((w0 << 4) & 0xF0F0F0F0u), (int)u.y, d0);                                                       \
+        int d1 = dp4a_ss((int)(w1 & 0xF0F0F0F0u), (int)u.z, (int)kMagicBits);                                             \
+        d1 = dp4a_ss((int)((w1 << 4) & 0xF0F0F0F0u), (int)u.w, d1);                                                       \
+        acc0 = __fmaf_rn(pr, __fmaf_rn(__int_as_float(d0), 0.0625f, -786432.0f), acc0);                                   \
+        acc1 = __fmaf_rn(pr, __fmaf_rn(__int_as_float(d1), 0.0625f, -786432.0f), acc1);                                   \
+    }
+#define CLOVER_MIX_CHUNK(J) { CLOVER_MIX_BLOCK(J, 0) CLOVER_MIX_BLOCK(J, 1) CLOVER_MIX_BLOCK(J, 2) CLOVER_MIX_BLOCK(J, 3) }
+                if (live == KC) {
+                    CLOVER_MIX_CHUNK(0) CLOVER_MIX_CHUNK(1) CLOVER_MIX_CHUNK(2) CLOVER_MIX_CHUNK(3)
+                    if (KC == 8) { CLOVER_MIX_CHUNK(4) CLOVER_MIX_CHUNK(5) CLOVER_MIX_CHUNK(6) CLOVER_MIX_CHUNK(7) }
+                } else {
+                    // ragged last stage: same loads with a run-time chunk offset
+                    for (int j = 0; j < live; ++j) {
+                        uint32_t rj[8];
+#pragma unroll
+                        for (int cc = 0; cc < 8; ++cc) rj[cc] = ra[cc] + (uint32_t)j * kMxChunkBytes;
+                        const uint32_t uj = ubase + (uint32_t)j * 256u, pj = sbase + (uint32_t)j * 16u;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            uint32_t wa, wb, pr_;
+                            uint4 u;
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wa) : "r"(rj[2 * b]));
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wb) : "r"(rj[2 * b + 1]));
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+%5];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                                         : "r"(uj + 64u * (uint32_t)b), "n"(KC * kMxChunkBytes));
+                            asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(pr_) : "r"(pj + 4u * (uint32_t)b), "n"(KC * kMxChunkBytes + KC * 256));
+                            const float pr = __uint_as_float(pr_);
+                            const uint32_t w0 = __byte_perm(wa, wb, 0x5410), w1 = __byte_perm(wa, wb, 0x7632);
+                            int d0 = dp4a_ss((int)(w0 & 0xF0F0F0F0u), (int)u.x, (int)kMagicBits);
+                            d0 = dp4a_ss((int)((w0 << 4) & 0xF0F0F0F0u), (int)u.y, d0);
+                            int d1 = dp4a_ss((int)(w1 & 0xF0F0F0F0u), (int)u.z, (int)kMagicBits);
+                            d1 = dp4a_ss((int)((w1 << 4) & 0xF0F0F0F0u), (int)u.w, d1);
+                            acc0 = __fmaf_rn(pr, __fmaf_rn(__int_as_float(d0), 0.0625f, -786432.0f), acc0);
+                            acc1 = __fmaf_rn(pr, __fmaf_rn(__int_as_float(d1), 0.0625f, -786432.0f), acc1);
+                        }
+                    }
+                }
+#undef CLOVER_MIX_CHUNK
+#undef CLOVER_MIX_BLOCK
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[s]);
+            }
+            // hadd tree ((a4+a0)+(a6+a2))+((a5+a1)+(a7+a3)) (CloverBase.h:149-157): lane p holds a_2p, a_2p+1
+            acc0 = __fadd_rn(acc0, __shfl_xor_sync(0xFFFFFFFFu, acc0, 2));      // p = 0,2: a4+a0   p = 1,3: a6+a2
+            acc1 = __fadd_rn(acc1, __shfl_xor_sync(0xFFFFFFFFu, acc1, 2));      //          a5+a1             a7+a3
+            acc0 = __fadd_rn(acc0, __shfl_xor_sync(0xFFFFFFFFu, acc0, 1));
+            acc1 = __fadd_rn(acc1, __shfl_xor_sync(0xFFFFFFFFu, acc1, 1));
+            const uint64_t rb = item >> 1, grb = rowblock0 + rb;
+            if (p == 0) {
+                ybuf[grb * 64 + (item & 1) * kMxRows + r] = __fadd_rn(acc0, acc1);
+                __threadfence();
+            }
+            named_bar_sync(2, kMxConsumers);
+            if (tid == 0) sm.ticket = yv ? atomicAdd(counters + rb, 1u) : 0u;
+            named_bar_sync(2, kMxConsumers);
+            if (sm.ticket == 1u) {                                              // both halves of the block are in ybuf
+                if (tid < 64) {
+                    __threadfence();
+                    const float y = __ldcg(ybuf + grb * 64 + tid);
+                    requantize_block<8, STOCH>(y, tid, grb, yv, ys, key, tables, sm.red_f, sm.red_q);
+                    if (tid == 0) counters[rb] = 0u;                            // re-armed for the next launch
+                }
+            }
+            named_bar_sync(2, kMxConsumers);                                    // ticket / red_* are free again
         }
     }
 }
@@ -998,8 +1189,7 @@ static int mvm_scratch(cudaStream_t stream, uint64_t nrb_local, uint64_t nrb_glo
     return CLOVER_OK;
 }
 
-// the TMA-ring kernel for an 8-bit product vector; MBITS = 8: CloverMatrix8::mvm, MBITS = 4: CloverMatrix4::mvm(V8,V8)
-template <int MBITS>
+// the TMA-ring kernel of CloverMatrix8::mvm
 static int launch_mvm8_tma(const int8_t *values, const float *scales, uint64_t rows_local, uint64_t cols, uint64_t row0,
                            const uint32_t *x32, const float *xs, float *y32, int8_t *yv, float *ys, bool stoch, Key4 key,
                            const uint64_t *tables, cudaStream_t stream) {
@@ -1016,18 +1206,18 @@ static int launch_mvm8_tma(const int8_t *values, const float *scales, uint64_t r
     // items32x2 force either.
     const char *impl8 = getenv("CLOVER_GEMV_IMPL");
     const bool x2 = impl8 ? !strcmp(impl8, "items32x2") : rows_local / kG8Rows > (uint64_t)sm_count();
-    const int smem = (int)(x2 ? sizeof(Gemv8Smem<3, MBITS>) : sizeof(Gemv8Smem<5, MBITS>)) + 1024;
+    const int smem = (int)(x2 ? sizeof(Gemv8Smem<3>) : sizeof(Gemv8Smem<5>)) + 1024;
     // function attributes and occupancy belong to a device's context: remembered per device (clover_set_device may switch)
     static bool attr_set8[kMaxDevices][2][2] = {};
     const int dev = current_device();
     if (dev < 0) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
-    auto kern = x2 ? (stoch ? k_m8_mvm_tma<true, 3, MBITS> : k_m8_mvm_tma<false, 3, MBITS>) : (stoch ? k_m8_mvm_tma<true, 5, MBITS> : k_m8_mvm_tma<false, 5, MBITS>);
+    auto kern = x2 ? (stoch ? k_m8_mvm_tma<true, 3> : k_m8_mvm_tma<false, 3>) : (stoch ? k_m8_mvm_tma<true, 5> : k_m8_mvm_tma<false, 5>);
     if (!attr_set8[dev][x2][stoch]) {
         CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set8[dev][x2][stoch] = true;
     }
     CUtensorMap tmap;
-    rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows_local, MBITS == 8 ? cols : cols >> 1, kG8Rows);
+    rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows_local, cols, kG8Rows);
     if (rc != CLOVER_OK) return rc;
     const uint64_t nitems = rows_local / kG8Rows;
     uint64_t slots = (uint64_t)sm_count();
@@ -1040,6 +1230,53 @@ static int launch_mvm8_tma(const int8_t *values, const float *scales, uint64_t r
     kern<<<pgrid, kG8Threads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, ybuf, counters, yv, ys,
                                               key, tables);
     return CLOVER_OK;
+}
+
+// the mixed-precision TMA-ring kernel (k_m4v8_mvm_tma): ring geometry by shape
+template <bool STOCH, int STAGES, int KC, int PER_SM>
+static int launch_mix_variant(const CUtensorMap &tmap, const float *scales, uint64_t rows_local, uint64_t cols, uint64_t row0,
+                              const uint32_t *x32, const float *xs, float *ybuf, unsigned int *counters, int8_t *yv, float *ys,
+                              Key4 key, const uint64_t *tables, cudaStream_t stream) {
+    static bool attr_set[kMaxDevices] = {};
+    static int per_sm[kMaxDevices] = {};
+    const int dev = current_device();
+    if (dev < 0) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
+    auto kern = k_m4v8_mvm_tma<STOCH, STAGES, KC, PER_SM>;
+    const int smem = (int)sizeof(MixSmem<STAGES, KC>) + 1024;
+    if (!attr_set[dev]) {
+        CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[dev], kern, kMxThreads, smem));
+        attr_set[dev] = true;
+    }
+    const uint64_t nitems = rows_local / kMxRows;
+    const uint64_t slots = (uint64_t)sm_count() * (uint64_t)std::max(1, std::min(per_sm[dev], PER_SM));
+    const unsigned pgrid = (unsigned)(nitems < slots ? nitems : slots);
+    kern<<<pgrid, kMxThreads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, ybuf, counters, yv, ys, key, tables);
+    return CLOVER_OK;
+}
+
+static int launch_mix_tma(const int8_t *values, const float *scales, uint64_t rows_local, uint64_t cols, uint64_t row0,
+                          const uint32_t *x32, const float *xs, float *y32, int8_t *yv, float *ys, bool stoch, Key4 key,
+                          const uint64_t *tables, cudaStream_t stream) {
+    const uint64_t nrb = rows_local >> 6;
+    float *ybuf = y32;
+    unsigned int *counters = nullptr;
+    int rc = mvm_scratch(stream, nrb, (row0 >> 6) + nrb, y32 ? nullptr : &ybuf, &counters);
+    if (rc != CLOVER_OK) return rc;
+    CUtensorMap tmap;
+    rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows_local, cols >> 1, kMxRows);
+    if (rc != CLOVER_OK) return rc;
+#define CLOVER_MIX(ST, KC, PS)                                                                                                         \
+    (stoch ? launch_mix_variant<true, ST, KC, PS>(tmap, scales, rows_local, cols, row0, x32, xs, ybuf, counters, yv, ys, key, tables, stream) \
+           : launch_mix_variant<false, ST, KC, PS>(tmap, scales, rows_local, cols, row0, x32, xs, ybuf, counters, yv, ys, key, tables, stream))
+    // measured on B200 (tools/mix_sweep.py; us with four 52 KiB CTAs per SM / two 106 KiB CTAs per SM): 32768^2 88.1 / 91.1,
+    // 16384^2 28.9 / 29.9, 32768 x 8192 28.9 / 33.0 - but 8192 x 32768 29.0 / 26.9 and 4096 x 32768 18.8 / 16.7: with fewer
+    // work items than two per SM the deeper ring wins. CLOVER_GEMV_IMPL=ring4 / ring8 force either.
+    const char *impl = getenv("CLOVER_GEMV_IMPL");
+    const bool small_rings = impl && !strcmp(impl, "ring4") ? true : impl && !strcmp(impl, "ring8") ? false
+                                                            : rows_local / kMxRows > 2 * (uint64_t)sm_count();
+    return small_rings ? CLOVER_MIX(3, 4, 4) : CLOVER_MIX(3, 8, 2);
+#undef CLOVER_MIX
 }
 
 template <int BITS>
@@ -1132,7 +1369,7 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
             if (stoch) k_m8_mvm<8, true><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
             else       k_m8_mvm<8, false><<<grid, 512, 0, stream>>>(v32, scales, rows_local, cols, row0 >> 6, x32, xs, y32, yv, ys, key, tables);
         } else {
-            int rc = launch_mvm8_tma<8>(values, scales, rows_local, cols, row0, x32, xs, y32, yv, ys, stoch, key, tables, stream);
+            int rc = launch_mvm8_tma(values, scales, rows_local, cols, row0, x32, xs, y32, yv, ys, stoch, key, tables, stream);
             if (rc != CLOVER_OK) return rc;
         }
     }
@@ -1204,7 +1441,7 @@ int clover_m4_mvm_v8(const int8_t *values, const float *scales, uint64_t rows, u
         if (key_host) k_m8_mvm<4, true><<<(unsigned)nrb, 512, 0, st>>>(v32, scales, rows, cols, 0, x32, xs, y32, yv, ys, key, tables);
         else          k_m8_mvm<4, false><<<(unsigned)nrb, 512, 0, st>>>(v32, scales, rows, cols, 0, x32, xs, y32, yv, ys, key, tables);
     } else {
-        const int rc2 = launch_mvm8_tma<4>(values, scales, rows, cols, 0, x32, xs, y32, yv, ys, key_host != nullptr, key, tables, st);
+        const int rc2 = launch_mix_tma(values, scales, rows, cols, 0, x32, xs, y32, yv, ys, key_host != nullptr, key, tables, st);
         if (rc2 != CLOVER_OK) return rc2;
     }
     count_launch();

@@ -15,6 +15,7 @@
 //   3. writes the result words into a shared-memory image of the output tile, columns rotated by bj so that the 32
 //      lanes of a warp hit 32 different banks;
 //   4. the CTA copies the image out row by row: a warp writes one 128-byte run per instruction.
+#include <stdlib.h>
 #include "common.cuh"
 #include "runtime.cuh"
 
@@ -66,7 +67,7 @@ __device__ __forceinline__ void transpose4x4_bytes(uint32_t (&a)[4]) {
 // A tile is 32 x 32 thread blocks of RB x RB elements (RB = 8 nibbles / 4 bytes = one 32-bit word wide): 256 x 256
 // elements (4-bit) or 128 x 128 (8-bit), i.e. 128-byte runs on the way in and on the way out. 256 threads, thread =
 // word column bj of four thread-block rows bi: all of its 4 * RB loads are in flight together.
-template <int BITS>
+template <int BITS, int RASTER, bool STREAM_ST>
 __global__ void __launch_bounds__(256)
 k_mtranspose(const uint32_t *__restrict__ in, const float *__restrict__ in_scales, uint64_t rows, uint64_t cols,
              uint32_t *__restrict__ out, float *__restrict__ out_scales) {
@@ -80,8 +81,21 @@ k_mtranspose(const uint32_t *__restrict__ in, const float *__restrict__ in_scale
     const uint64_t wpr_in = cols / RB, wpr_out = rows / RB;      // words per row (RB elements per word)
     const uint64_t vb = rows >> 6, hb = cols >> 6;
 
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t ti = tile / tiles_j, tj = tile % tiles_j;
+    // RASTER > 1: tiles are walked in RASTER x RASTER super-blocks, so that the CTAs resident at any moment cover square
+    // regions: their 128-byte runs line up to RASTER * 128 contiguous bytes per row on the way in AND on the way out
+    // (row-major order gives 8 KiB-long reads but isolated 128-byte writes one row pitch apart)
+    const uint64_t sb_j = (tiles_j + RASTER - 1) / RASTER, sb_i = (tiles_i + RASTER - 1) / RASTER;
+    const uint64_t nwalk = RASTER > 1 ? sb_i * sb_j * RASTER * RASTER : ntiles;
+    for (uint64_t walk = blockIdx.x; walk < nwalk; walk += gridDim.x) {
+        uint64_t ti, tj;
+        if (RASTER > 1) {
+            const uint64_t sb = walk / (RASTER * RASTER), in_sb = walk % (RASTER * RASTER);
+            ti = (sb / sb_j) * RASTER + in_sb / RASTER;
+            tj = (sb % sb_j) * RASTER + in_sb % RASTER;
+            if (ti >= tiles_i || tj >= tiles_j) continue;
+        } else {
+            ti = walk / tiles_j; tj = walk % tiles_j;
+        }
         const bool col_ok = tj * 32 + bj < wpr_in;                // rows/cols are multiples of 128: a word is all in or all out
         uint32_t a[4][RB];
 #pragma unroll
@@ -111,7 +125,10 @@ k_mtranspose(const uint32_t *__restrict__ in, const float *__restrict__ in_scale
 #pragma unroll 8
         for (int it = 0; it < TILE / 8; ++it) {
             const int r = bi0 + 8 * it;                           // output row of the tile; this thread writes word bj
-            if (word_ok && tj * TILE + r < cols) __stcs(dst + (uint64_t)r * wpr_out, img[r * 32 + ((bj + r / RB) & 31)]);
+            if (word_ok && tj * TILE + r < cols) {
+                if (STREAM_ST) __stcs(dst + (uint64_t)r * wpr_out, img[r * 32 + ((bj + r / RB) & 31)]);
+                else           dst[(uint64_t)r * wpr_out] = img[r * 32 + ((bj + r / RB) & 31)];
+            }
         }
         __syncthreads();
     }
@@ -123,10 +140,24 @@ static int launch_transpose(const int8_t *values, const float *scales, uint64_t 
     constexpr uint64_t TILE = BITS == 4 ? 256 : 128;
     const uint64_t ntiles = ((rows + TILE - 1) / TILE) * ((cols + TILE - 1) / TILE);
     if (ntiles == 0) return CLOVER_OK;
+    const char *v = getenv("CLOVER_TRANSPOSE_IMPL");
+    const int variant = v ? atoi(v) : 0;
+    const uint64_t R = variant % 10 == 1 ? 4 : variant % 10 == 2 ? 8 : variant % 10 == 3 ? 16 : 1;
+    const uint64_t nwalk = R > 1 ? (((rows + TILE - 1) / TILE + R - 1) / R) * (((cols + TILE - 1) / TILE + R - 1) / R) * R * R : ntiles;
     const uint64_t cap = (uint64_t)sm_count() * 16;
-    const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
-    k_mtranspose<BITS><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint32_t *>(values), scales, rows, cols,
-                                                 reinterpret_cast<uint32_t *>(out_values), out_scales);
+    const unsigned grid = (unsigned)(nwalk < cap ? nwalk : cap);
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(values);
+    uint32_t *out = reinterpret_cast<uint32_t *>(out_values);
+    switch (variant) {
+        case 1:  k_mtranspose<BITS, 4, true><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
+        case 2:  k_mtranspose<BITS, 8, true><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
+        case 3:  k_mtranspose<BITS, 16, true><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
+        case 10: k_mtranspose<BITS, 1, false><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
+        case 11: k_mtranspose<BITS, 4, false><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
+        case 12: k_mtranspose<BITS, 8, false><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
+        case 13: k_mtranspose<BITS, 16, false><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
+        default: k_mtranspose<BITS, 1, true><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
+    }
     count_launch();
     return launch_status("k_mtranspose");
 }

@@ -98,11 +98,16 @@ def test_mvm4_default_dispatch_long_rows_vs_oracle(cb, oracle, shape, keyed, mon
     _check_mvm4(cb, oracle, _random_m4(cb, rows, cols, 71), _random_v4(cb, cols, 72), rows, cols, keyed)
 
 
+@pytest.mark.parametrize("impl", [None, "ring4", "ring8"])
 @pytest.mark.parametrize("shape", [(9728, 4224), (4992, 640), (32768, 2048 + 128)])
-def test_mvm4_v8_many_items_vs_oracle(cb, oracle, shape, monkeypatch):
-    """The mixed 4-bit matrix x CloverVector8 kernel at two CTAs per SM (rows / 32 > 148: k_m8_mvm_tma<.,3,4>, the
-    instantiation behind extras.mvm4_v8_mixed_32768), half chunks at the row end included."""
-    monkeypatch.delenv("CLOVER_GEMV_IMPL", raising=False)
+def test_mvm4_v8_many_items_vs_oracle(cb, oracle, shape, impl, monkeypatch):
+    """The mixed 4-bit matrix x CloverVector8 kernel k_m4v8_mvm_tma under default dispatch (rows / 32 > 2 * 148: four
+    CTAs per SM with 4-chunk stages, the instantiation behind extras.mvm4_v8_mixed_32768; else two CTAs per SM with
+    8-chunk stages) and with either ring forced, half chunks at the row end included."""
+    if impl is None:
+        monkeypatch.delenv("CLOVER_GEMV_IMPL", raising=False)
+    else:
+        monkeypatch.setenv("CLOVER_GEMV_IMPL", impl)          # read per call by the launcher
     rows, cols = shape
     A = _random_m4(cb, rows, cols, 81)
     g = torch.Generator(device="cuda").manual_seed(82)
