@@ -8,14 +8,9 @@
 // those to ippiTranspose_32f_C1R). HBM-bound: every byte is read once and written once (0.5 + 0.5 B/element for
 // 4-bit, 1 + 1 for 8-bit, plus the scales).
 //
-// One CTA of 256 threads per tile (4-bit: 256x256 elements, 8-bit: 128x128; either way 128 bytes wide on the way in
-// and on the way out):
-//   1. thread (bi, bj) loads word bj of 8 (4) consecutive rows - a warp reads one 128-byte run per instruction;
-//   2. transposes its 8x8 nibbles (three masked-swap stages) / 4x4 bytes (six PRMT) in registers;
-//   3. writes the result words into a shared-memory image of the output tile, columns rotated by bj so that the 32
-//      lanes of a warp hit 32 different banks;
-//   4. the CTA copies the image out row by row: a warp writes one 128-byte run per instruction.
-#include <stdlib.h>
+// One CTA of 256 threads per tile (4-bit: 256x256 elements, 8-bit: 128x128; either way 128 bytes wide on the way in and
+// on the way out); 128-bit global loads, register transposes (8x8 nibbles: 16 PRMT + 8 shift/LOP3 pairs; 4x4 bytes: 8 PRMT),
+// an XOR-swizzled shared-memory image of the output tile, 128-bit copy-out. See k_mtranspose.
 #include "common.cuh"
 #include "runtime.cuh"
 
@@ -29,27 +24,31 @@ __device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t se
 
 // a[r] = word of row r holding 8 nibbles in the reference order (element e at nibble position e ^ 1).
 // On return a[c] = word of output row c (element r of it = element c of input row r).
+// Position-space transpose of W'[k] = in[k ^ 1]; output row c = T[c ^ 1] (both index swaps are free). The 16-bit and
+// 8-bit exchange stages are one PRMT per word, the nibble stage a shift and a LOP3 per word: 32 instructions per block.
 __device__ __forceinline__ void transpose8x8_nibbles(uint32_t (&a)[8]) {
-    // position-space transpose of W'[k] = in[k ^ 1]; output row c = T[c ^ 1] (both index swaps are free)
     uint32_t w[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) w[k] = a[k ^ 1];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t t = ((w[i] >> 16) ^ w[i + 4]) & 0x0000FFFFu;
-        w[i + 4] ^= t; w[i] ^= t << 16;
+    for (int i = 0; i < 4; ++i) {                     // high half of w[i] <-> low half of w[i+4]
+        const uint32_t x = w[i], y = w[i + 4];
+        w[i] = prmt_b32(x, y, 0x5410u);
+        w[i + 4] = prmt_b32(x, y, 0x7632u);
     }
 #pragma unroll
     for (int g = 0; g < 2; ++g)
 #pragma unroll
-        for (int i = 4 * g; i < 4 * g + 2; ++i) {
-            const uint32_t t = ((w[i] >> 8) ^ w[i + 2]) & 0x00FF00FFu;
-            w[i + 2] ^= t; w[i] ^= t << 8;
+        for (int i = 4 * g; i < 4 * g + 2; ++i) {     // bytes 1, 3 of w[i] <-> bytes 0, 2 of w[i+2]
+            const uint32_t x = w[i], y = w[i + 2];
+            w[i] = prmt_b32(x, y, 0x6240u);
+            w[i + 2] = prmt_b32(x, y, 0x7351u);
         }
 #pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-        const uint32_t t = ((w[i] >> 4) ^ w[i + 1]) & 0x0F0F0F0Fu;
-        w[i + 1] ^= t; w[i] ^= t << 4;
+    for (int i = 0; i < 8; i += 2) {                  // high nibbles of w[i] <-> low nibbles of w[i+1]
+        const uint32_t x = w[i], y = w[i + 1];
+        w[i] = (x & 0x0F0F0F0Fu) | ((y << 4) & 0xF0F0F0F0u);
+        w[i + 1] = ((x >> 4) & 0x0F0F0F0Fu) | (y & 0xF0F0F0F0u);
     }
 #pragma unroll
     for (int c = 0; c < 8; ++c) a[c] = w[c ^ 1];
@@ -64,71 +63,69 @@ __device__ __forceinline__ void transpose4x4_bytes(uint32_t (&a)[4]) {
     a[3] = prmt_b32(t1, u1, 0x7632u);
 }
 
-// A tile is 32 x 32 thread blocks of RB x RB elements (RB = 8 nibbles / 4 bytes = one 32-bit word wide): 256 x 256
-// elements (4-bit) or 128 x 128 (8-bit), i.e. 128-byte runs on the way in and on the way out. 256 threads, thread =
-// word column bj of four thread-block rows bi: all of its 4 * RB loads are in flight together.
-template <int BITS, int RASTER, bool STREAM_ST>
+// A tile is 32 x 32 register blocks of RB x RB elements (RB = 8 nibbles / 4 bytes = one 32-bit word wide): 256 x 256
+// elements (4-bit) or 128 x 128 (8-bit), i.e. 128-byte runs on the way in and on the way out. 256 threads.
+//   in:   thread (bi, q) reads 16 bytes (word columns 4q..4q+3) of the RB rows of block row bi: RB LDG.128, all in flight;
+//   regs: four RB x RB transposes (one per word column);
+//   img:  block (bi, bj = 4q + j) becomes words `bi` of output rows R = bj * RB + c. The image keeps 128-byte rows with
+//         the 16-byte chunk index XORed by (R / (4 RB)) & 7 = q: the 32 lanes of a warp (4 bi x 8 q) hit 32 banks;
+//   out:  thread (row, chunk) copies 16 bytes per iteration: LDS.128 + STG.128, a warp writes four 128-byte runs.
+// Round 1 moved single words everywhere (42 issue slots per word, ALU pipe 65 % busy, 71 / 77 % of HBM).
+template <int BITS>
 __global__ void __launch_bounds__(256)
 k_mtranspose(const uint32_t *__restrict__ in, const float *__restrict__ in_scales, uint64_t rows, uint64_t cols,
              uint32_t *__restrict__ out, float *__restrict__ out_scales) {
-    constexpr int RB = BITS == 4 ? 8 : 4;             // rows (and columns) per thread block
+    constexpr int RB = BITS == 4 ? 8 : 4;             // rows (and columns) per register block
     constexpr int TILE = 32 * RB;                     // 256 / 128
     constexpr int ST = TILE / 64;                     // scale tiles per tile edge
-    __shared__ uint32_t img[TILE * 32];
+    __shared__ uint4 img4[TILE * 8];
+    uint32_t *img = reinterpret_cast<uint32_t *>(img4);
 
-    const int t = threadIdx.x, bj = t & 31, bi0 = t >> 5;
+    const int t = threadIdx.x, q = t & 7, bi = t >> 3;
     const uint64_t tiles_i = (rows + TILE - 1) / TILE, tiles_j = (cols + TILE - 1) / TILE, ntiles = tiles_i * tiles_j;
-    const uint64_t wpr_in = cols / RB, wpr_out = rows / RB;      // words per row (RB elements per word)
+    const uint64_t cpr_in = cols / (4 * RB), cpr_out = rows / (4 * RB);      // 16-byte chunks per row
     const uint64_t vb = rows >> 6, hb = cols >> 6;
+    const uint4 *in4 = reinterpret_cast<const uint4 *>(in);
+    uint4 *out4 = reinterpret_cast<uint4 *>(out);
 
-    // RASTER > 1: tiles are walked in RASTER x RASTER super-blocks, so that the CTAs resident at any moment cover square
-    // regions: their 128-byte runs line up to RASTER * 128 contiguous bytes per row on the way in AND on the way out
-    // (row-major order gives 8 KiB-long reads but isolated 128-byte writes one row pitch apart)
-    const uint64_t sb_j = (tiles_j + RASTER - 1) / RASTER, sb_i = (tiles_i + RASTER - 1) / RASTER;
-    const uint64_t nwalk = RASTER > 1 ? sb_i * sb_j * RASTER * RASTER : ntiles;
-    for (uint64_t walk = blockIdx.x; walk < nwalk; walk += gridDim.x) {
-        uint64_t ti, tj;
-        if (RASTER > 1) {
-            const uint64_t sb = walk / (RASTER * RASTER), in_sb = walk % (RASTER * RASTER);
-            ti = (sb / sb_j) * RASTER + in_sb / RASTER;
-            tj = (sb % sb_j) * RASTER + in_sb % RASTER;
-            if (ti >= tiles_i || tj >= tiles_j) continue;
-        } else {
-            ti = walk / tiles_j; tj = walk % tiles_j;
-        }
-        const bool col_ok = tj * 32 + bj < wpr_in;                // rows/cols are multiples of 128: a word is all in or all out
-        uint32_t a[4][RB];
+    // rows and cols are multiples of 128: a 16-byte chunk and a block row are entirely inside or outside
+    uint4 v[RB];
+    auto load_tile = [&](uint64_t tile) {
+        const uint64_t ti = tile / tiles_j, tj = tile % tiles_j;
+        const uint64_t row0 = ti * TILE + (uint64_t)bi * RB;
+        const bool ok = tj * 8 + q < cpr_in && row0 < rows;
+        const uint4 *src = in4 + row0 * cpr_in + tj * 8 + q;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint64_t row0 = ti * TILE + (uint64_t)(bi0 + 8 * k) * RB;
-            const bool ok = col_ok && row0 < rows;
-            const uint32_t *src = in + row0 * wpr_in + tj * 32 + bj;
+        for (int r = 0; r < RB; ++r) v[r] = ok ? ldg_stream(src + (uint64_t)r * cpr_in) : make_uint4(0u, 0u, 0u, 0u);
+    };
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t ti = tile / tiles_j, tj = tile % tiles_j;
+        load_tile(tile);
 #pragma unroll
-            for (int r = 0; r < RB; ++r) a[k][r] = ok ? ldg_stream(src + (uint64_t)r * wpr_in) : 0u;
-        }
+        for (int j = 0; j < 4; ++j) {
+            uint32_t a[RB];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if constexpr (BITS == 4) transpose8x8_nibbles(a[k]);
-            else                     transpose4x4_bytes(a[k]);
-            const int bi = bi0 + 8 * k;
-            // output row (bj * RB + c) of the tile, word bi; columns rotated by bj: the 32 lanes hit 32 banks
+            for (int r = 0; r < RB; ++r) a[r] = j == 0 ? v[r].x : j == 1 ? v[r].y : j == 2 ? v[r].z : v[r].w;
+            if constexpr (BITS == 4) transpose8x8_nibbles(a);
+            else                     transpose4x4_bytes(a);
+            // output rows R = (4q + j) * RB + c, word bi: chunk (bi >> 2) ^ q, word bi & 3
+            uint32_t *dst = img + ((4 * q + j) * RB) * 32 + ((((bi >> 2) ^ q) << 2) | (bi & 3));
 #pragma unroll
-            for (int c = 0; c < RB; ++c) img[(bj * RB + c) * 32 + ((bi + bj) & 31)] = a[k][c];
+            for (int c = 0; c < RB; ++c) dst[c * 32] = a[c];
         }
         if (t < ST * ST) {                                        // the tile's 64x64-block scales
             const uint64_t si = ti * ST + t / ST, sj = tj * ST + t % ST;
             if (si < vb && sj < hb) out_scales[sj * vb + si] = in_scales[si * hb + sj];
         }
         __syncthreads();
-        const bool word_ok = ti * 32 + bj < wpr_out;
-        uint32_t *dst = out + (tj * TILE) * wpr_out + ti * 32 + bj;
-#pragma unroll 8
-        for (int it = 0; it < TILE / 8; ++it) {
-            const int r = bi0 + 8 * it;                           // output row of the tile; this thread writes word bj
-            if (word_ok && tj * TILE + r < cols) {
-                if (STREAM_ST) __stcs(dst + (uint64_t)r * wpr_out, img[r * 32 + ((bj + r / RB) & 31)]);
-                else           dst[(uint64_t)r * wpr_out] = img[r * 32 + ((bj + r / RB) & 31)];
-            }
+        const int rr = t >> 3;
+        const int64_t rlim = (int64_t)cols - (int64_t)(tj * TILE), clim = (int64_t)cpr_out - (int64_t)(ti * 8);
+        uint4 *orow = out4 + (tj * TILE + rr) * cpr_out + ti * 8;
+#pragma unroll
+        for (int it = 0; it < TILE / 32; ++it) {
+            const int R = rr + 32 * it;                           // output row of the tile
+            const int ch = q ^ ((R / (4 * RB)) & 7);              // logical chunk held at physical chunk q
+            if (ch < clim && R < rlim) __stcs(orow + (uint64_t)it * 32 * cpr_out + ch, img4[R * 8 + q]);
         }
         __syncthreads();
     }
@@ -140,24 +137,13 @@ static int launch_transpose(const int8_t *values, const float *scales, uint64_t 
     constexpr uint64_t TILE = BITS == 4 ? 256 : 128;
     const uint64_t ntiles = ((rows + TILE - 1) / TILE) * ((cols + TILE - 1) / TILE);
     if (ntiles == 0) return CLOVER_OK;
-    const char *v = getenv("CLOVER_TRANSPOSE_IMPL");
-    const int variant = v ? atoi(v) : 0;
-    const uint64_t R = variant % 10 == 1 ? 4 : variant % 10 == 2 ? 8 : variant % 10 == 3 ? 16 : 1;
-    const uint64_t nwalk = R > 1 ? (((rows + TILE - 1) / TILE + R - 1) / R) * (((cols + TILE - 1) / TILE + R - 1) / R) * R * R : ntiles;
-    const uint64_t cap = (uint64_t)sm_count() * 16;
-    const unsigned grid = (unsigned)(nwalk < cap ? nwalk : cap);
-    const uint32_t *in = reinterpret_cast<const uint32_t *>(values);
-    uint32_t *out = reinterpret_cast<uint32_t *>(out_values);
-    switch (variant) {
-        case 1:  k_mtranspose<BITS, 4, true><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
-        case 2:  k_mtranspose<BITS, 8, true><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
-        case 3:  k_mtranspose<BITS, 16, true><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
-        case 10: k_mtranspose<BITS, 1, false><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
-        case 11: k_mtranspose<BITS, 4, false><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
-        case 12: k_mtranspose<BITS, 8, false><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
-        case 13: k_mtranspose<BITS, 16, false><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
-        default: k_mtranspose<BITS, 1, true><<<grid, 256, 0, stream>>>(in, scales, rows, cols, out, out_scales); break;
-    }
+    // CTAs per SM the tile loop is spread over, measured on B200 (tools/transpose_sweep.py, 16384^2): 4-bit 47.4 us with 16
+    // (49.6 / 53.6 / 50.9 with 3 / 4 / 6), 8-bit 94.5 us with 4 (99.1 / 106 / 106 with 16 / 3 / 6); loading the next tile
+    // before the copy-out of the current one (110 registers) was slower for both
+    const uint64_t cap = (uint64_t)sm_count() * (BITS == 4 ? 16 : 4);
+    const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
+    k_mtranspose<BITS><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint32_t *>(values), scales, rows, cols,
+                                                 reinterpret_cast<uint32_t *>(out_values), out_scales);
     count_launch();
     return launch_status("k_mtranspose");
 }

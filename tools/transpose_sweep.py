@@ -1,5 +1,4 @@
-"""Time CloverMatrix4/8::transpose under every tile-walk / store variant (CLOVER_TRANSPOSE_IMPL is read per call); checks
-that every variant writes the same bytes.
+"""Time CloverMatrix4/8::transpose on a few shapes and check the result against torch's transpose of the unpacked matrix.
 
 usage: python tools/transpose_sweep.py [reps=30]
 """
@@ -15,7 +14,7 @@ def main():
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev).manual_seed(1)
     peak = measured_peaks()[0]
-    variants = os.environ.get("TRANSPOSE_VARIANTS", "0,1,2,3,10,11,12,13").split(",")
+    variants = ("default",)
     for bits in (4, 8):
         for rows, cols in ((16384, 16384), (8192, 32768), (32768, 8192), (4096, 4096 + 128)):
             M = (cb.CloverMatrix4 if bits == 4 else cb.CloverMatrix8)(rows, cols)
@@ -28,7 +27,6 @@ def main():
             ref = None
             by = 2 * M.getBytes()
             for impl in variants:
-                os.environ["CLOVER_TRANSPOSE_IMPL"] = impl
                 T.values.zero_(); T.scales.zero_()
                 for _ in range(3):
                     M.transpose(T)
@@ -42,9 +40,15 @@ def main():
                     e1.record(); e1.synchronize()
                     ts.append(e0.elapsed_time(e1) / reps)
                 ms = min(ts)
-                same = "ref" if ref is None else ("same" if torch.equal(ref[0], T.values) and torch.equal(ref[1], T.scales) else "DIFFERENT")
-                if ref is None:
-                    ref = (T.values.clone(), T.scales.clone())
+                if bits == 8:
+                    good = torch.equal(T.values.view(cols, rows), M.values.view(rows, cols).t())
+                else:
+                    def unpack(m, r, c):
+                        b = m.values.view(torch.uint8).view(r, c // 2)
+                        return torch.stack((b >> 4, b & 0xF), dim=2).view(r, c)
+                    good = torch.equal(unpack(T, cols, rows), unpack(M, rows, cols).t())
+                good = good and torch.equal(T.scales.view(cols // 64, rows // 64), M.scales.view(rows // 64, cols // 64).t())
+                same = "ok" if good else "WRONG"
                 print(json.dumps({"bits": bits, "rows": rows, "cols": cols, "impl": impl, "us": round(ms * 1e3, 2),
                                   "GBps": round(by / ms * 1e-6, 1), "frac_hbm": round(by / ms * 1e-6 / peak, 3), "check": same}), flush=True)
             del M, T
