@@ -471,7 +471,7 @@ def main():
     ap.add_argument("--impl", default="clover_b200", choices=["clover_b200", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS)
     ap.add_argument("--cols", type=int, default=COLS)
-    ap.add_argument("--exchange", default="fused", choices=["fused", "allgather", "allreduce"])
+    ap.add_argument("--exchange", default="fused", choices=["fused", "fused_sync", "fused_pipelined", "allgather", "allreduce"])
     ap.add_argument("--cpu-sample-rows", type=int, default=0, help="rows of the matrix the CPU reference times (0 = all)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -520,8 +520,9 @@ def main():
     def step():
         if world == 1:
             A.local.mvm(x, y)          # the reference-facing call: CloverMatrix4::mvm(V4, V4), one fused kernel
-        elif args.exchange == "fused":
-            out["y"] = A.mvm(x)        # one kernel: shard GEMV + NVLink-store epilogue; result = view of the shared vector
+        elif args.exchange.startswith("fused"):
+            out["y"] = A.mvm(x, wait=False)   # one kernel: shard GEMV + NVLink-store epilogue + flags; result = view of the shared
+                                              # vector. From 8 ranks on pipelined: the NEXT step's kernel waits for this step's flags
         else:
             A.mvm(x, y)                # shard kernel + NCCL exchange + re-quantize
 
@@ -531,9 +532,14 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def finish():                      # fused exchange: the last step's result is complete on this rank (stream order)
+        if world > 1 and args.exchange.startswith("fused"):
+            A.wait()
+
     total_bytes = gemv_bytes(rows, cols)
     for _ in range(args.warmup):
         step()
+    finish()
     barrier()
     l0 = L.clover_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -543,6 +549,7 @@ def main():
         e0.record()
         for _ in range(args.steps):
             step()
+        finish()
         e1.record()
         barrier()
         clk.mark()
@@ -591,7 +598,10 @@ def main():
                  C.c_uint64(rows), C.c_uint64(cols), hx, C.c_void_p(hx.value + xvb), hy, C.c_void_p(hy.value + yvb), None)
             return
         call("clover_copy_h2d", C.c_void_p(x.storage.data_ptr()), hx, C.c_size_t(xb), stream)
-        step()
+        if world > 1 and args.exchange.startswith("fused"):
+            out["y"] = A.mvm(x, wait=True)                # every step's result is read back: the kernel waits for the peers' slices
+        else:
+            step()
         r = out["y"]
         if getattr(r, "storage", None) is not None:
             call("clover_copy_d2h", hy, C.c_void_p(r.storage.data_ptr()), C.c_size_t(yb), stream)
@@ -620,7 +630,7 @@ def main():
     # ---- north_star's wording, measured beside the fused exchange in the same run: the shard kernel,
     # ONE ncclAllReduce of the fp32 output, the re-quantize pass - same shards, same x, same timing protocol
     nccl = None
-    if world > 1 and args.exchange == "fused":
+    if world > 1 and args.exchange.startswith("fused"):
         B = ShardedCloverMatrix4.__new__(ShardedCloverMatrix4)
         B.__dict__.update(A.__dict__)
         B.exchange, B._peer = "allreduce", None
@@ -653,12 +663,17 @@ def main():
                        "l2_policy": "inputs larger than L2 (2 GiB matrix streamed per step vs 126 MB L2)",
                        "parallelism": "1 GPU" if world == 1 else
                                       (f"rows sharded over {world} GPUs in 64-row blocks; fused exchange: the GEMV epilogue stores each "
-                                       f"re-quantized block into every peer's result vector over NVLink (no NCCL call)"
-                                       if args.exchange == "fused" else
+                                       f"re-quantized block into every peer's result vector over NVLink and raises a flag word per peer (no NCCL call); "
+                                       + ("pipelined: the wait for the peers' flags of step e sits in the prologue of step e+1's kernel (before it reads x "
+                                          "or stores to a peer), the last step's wait (clover_m4_shard_fused_wait) inside the timed region"
+                                          if (args.exchange == "fused_pipelined" or (args.exchange == "fused" and world >= 8)) else
+                                          "every kernel waits for the peers' flags at its end")
+                                       if args.exchange.startswith("fused") else
                                        f"rows sharded over {world} GPUs in 64-row blocks + one NCCL {args.exchange} of the fp32 output"),
                        "e2e": ("clover_host_m4_mvm: x copied from pinned host memory, kernel, y copied back, host sync - every step; "
                                "matrix resident in HBM") if world == 1 else
-                              "clover_copy_h2d(x) + sharded step + clover_copy_d2h(y) + clover_stream_sync every step; matrix shards resident in HBM"},
+                              "clover_copy_h2d(x) + sharded step (complete when its kernel ends) + clover_copy_d2h(y) + clover_stream_sync every step; "
+                              "matrix shards resident in HBM"},
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(ms2.item()) / args.steps, "wall_ms_per_step": wall / args.steps * 1e3},
             "gpu_launches": launches,

@@ -120,6 +120,7 @@ struct PeerOut {
     int8_t *yv[kMaxPeers] = {};              // peer p's result values / scales (entry `rank` unused: yv/ys are local)
     float *ys[kMaxPeers] = {};
     uint32_t *flags[kMaxPeers] = {};         // peer p's flag array, one word per source rank
+    int defer = 0;                           // 1: pipelined form - wait for the PREVIOUS epoch before x is read, none at the end
 };
 
 template <int BITS, bool STOCH>
@@ -161,29 +162,58 @@ __device__ __forceinline__ void requantize_block(float y, int i, uint64_t rb, in
             if (p != peers->rank) peers->ys[p][rb] = m;
 }
 
-// Tail of the fused exchange, one thread per CTA, after the CTA's peer stores have been fenced at system scope: take a
-// ticket; the LAST CTA of this rank raises flags[peer][rank] = epoch on every peer and waits until every peer has
-// raised its flag here - when the kernel ends, the slices of all ranks have landed in the local result vector.
-// ONE system-scope fence covers all flag stores (round 1 used st.release.sys per peer: a full fence per store, i.e.
-// 7 serialised NVLink round trips at 8 GPUs - the 8 / 19 / 27 us per step of VERDICT r01 weak #4); the flags are
-// polled with relaxed loads and acquired once at the end.
-__device__ __forceinline__ void peer_signal_and_wait(const PeerOut &peers) {
-    const unsigned int t = atomicAdd(peers.ticket, 1u);
-    if (t != gridDim.x - 1) return;
-    *peers.ticket = 0u;                                          // re-armed for the next launch (stream order)
-    asm volatile("fence.acq_rel.sys;" ::: "memory");             // acquires the other CTAs' tickets, releases everything to the peers
-    for (int p = 0; p < peers.world; ++p)
-        if (p != peers.rank)
-            asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(peers.flags[p] + peers.rank), "r"(peers.epoch) : "memory");
-    for (int q = 0; q < peers.world; ++q) {
-        if (q == peers.rank) continue;
-        uint32_t seen;
-        do {
-            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(peers.flags[peers.rank] + q) : "memory");
-        } while ((int32_t)(seen - peers.epoch) < 0);
-    }
-    asm volatile("fence.acq_rel.sys;" ::: "memory");             // the peers' stores before their flags are visible to whatever runs next
+// Wait until every peer has raised its flag here to at least `epoch`, then acquire at system scope: the peers' result stores
+// before their flags are visible to whatever this warp - and, through barriers, its CTA - does next. The flags live in LOCAL
+// memory and are written by the peers over NVLink. Called by ALL 32 lanes of a converged warp: lane q polls peer q's flag, so
+// one load instruction covers all peers (one L2 round trip per poll instead of world - 1) and the loop condition is
+// warp-uniform. Two things this form avoids on purpose (tools/exchange_probe.py, profiles/r02u_exchange_notes.md):
+//   * `if (lane == 0) wait(); __syncwarp();` in a kernel prologue: the warp left the wait diverged and stayed slow for the
+//     rest of the kernel - 273 instead of 201 us per step at 32768 x 65536 on 2 GPUs;
+//   * nanosleep back-off: a unit warp that slept ONCE at kernel start slowed the whole kernel by 35 % (182 -> 249 us for a
+//     5 us sleep; the same 5 us as a busy-wait on clock64: 184 us).
+__device__ __forceinline__ void peer_wait_flags(const PeerOut &peers, uint32_t epoch) {
+    const int q = threadIdx.x & 31;
+    const bool mine = q < peers.world && q != peers.rank;
+    const uint32_t *flag = peers.flags[peers.rank] + (mine ? q : 0);
+    bool ok;
+    do {
+        uint32_t seen = epoch;
+        if (mine) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        ok = (int32_t)(seen - epoch) >= 0;
+    } while (!__all_sync(0xFFFFFFFFu, ok));
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
 }
+
+// Tail of the fused exchange, one WARP per CTA (all 32 lanes), after the CTA's peer stores have been fenced at system scope:
+// take a ticket; the LAST CTA of this rank raises flags[peer][rank] = epoch on every peer (lane p stores to peer p) and
+// (synchronous form) waits until every peer has raised its flag here - when the kernel ends, the slices of all ranks have
+// landed in the local result vector. ONE system-scope fence covers all flag stores (round 1 used st.release.sys per peer: a
+// full fence per store, i.e. 7 serialised NVLink round trips at 8 GPUs - the 8 / 19 / 27 us per step of VERDICT r01 weak #4);
+// the flags are polled with relaxed loads and acquired once at the end.
+// Pipelined form (peers.defer): the kernel ends right after its flag stores. The wait moves to where the result is consumed:
+// the prologue of the NEXT step's kernel (peer_wait_flags(epoch - 1) before x is read and before any peer store - which is
+// also what makes re-using the result buffer of two steps ago safe) or k_peer_wait for any other consumer. The flag flight,
+// the spin and the spread of the ranks' finishing times then overlap the next kernel's launch and ring fill.
+__device__ __forceinline__ void peer_signal_and_wait(const PeerOut &peers) {
+    const int p = threadIdx.x & 31;
+    unsigned int t = 0;
+    if (p == 0) t = atomicAdd(peers.ticket, 1u);
+    t = __shfl_sync(0xFFFFFFFFu, t, 0);
+    if (t != gridDim.x - 1) return;                              // warp-uniform
+    if (p == 0) *peers.ticket = 0u;                              // re-armed for the next launch (stream order)
+    __syncwarp();
+    asm volatile("fence.acq_rel.sys;" ::: "memory");             // acquires the other CTAs' tickets, releases everything to the peers
+    if (p < peers.world && p != peers.rank)
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(peers.flags[p] + peers.rank), "r"(peers.epoch) : "memory");
+    if (!peers.defer) peer_wait_flags(peers, peers.epoch);
+}
+
+__global__ void __launch_bounds__(32) k_peer_wait(const __grid_constant__ PeerOut peers) { peer_wait_flags(peers, peers.epoch); }
+
+// x of a pipelined step may be the previous step's result, i.e. written by the peers while this kernel is already
+// running (before their flags): read it through L2 (ld.global.cg), never through the non-coherent path
+__device__ __forceinline__ uint32_t ld_x(const uint32_t *p, bool coherent) { return coherent ? __ldcg(p) : __ldg(p); }
+__device__ __forceinline__ float ld_x(const float *p, bool coherent) { return coherent ? __ldcg(p) : __ldg(p); }
 
 // =============================================================================================
 // mvm(V4,V4): exact-order 4-bit GEMV
@@ -396,14 +426,19 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
         uint32_t it = 0;
         uint32_t w[4] = {0, 0, 0, 0};
         float sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+        const bool piped = peers.world > 1 && peers.defer;
+        if (piped) {                                  // pipelined exchange: the previous epoch is complete here before x is read
+            peer_wait_flags(peers, peers.epoch - 1u);          // all 32 lanes, converged
+            __syncwarp();
+        }
         auto prefetch = [&](uint64_t rb, uint32_t c) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint64_t b = (uint64_t)c * kKC + 4 * j + (lane >> 3);
                 const bool ok = b < hb;
-                w[j] = ok ? __ldg(xv + b * 8 + (lane & 7)) : 0u;
+                w[j] = ok ? ld_x(xv + b * 8 + (lane & 7), piped) : 0u;
                 sa[j] = ok ? __ldg(scales + rb * hb + b) : 0.f;
-                sb[j] = ok ? __ldg(xs + b) : 0.f;
+                sb[j] = ok ? ld_x(xs + b, piped) : 0.f;
             }
         };
         if (blockIdx.x < nrb) prefetch(blockIdx.x, 0);
@@ -472,7 +507,7 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
         if (peers.world > 1) {
             if (tid < 64) __threadfence_system();                // this CTA's peer stores are visible system-wide ...
             named_bar_sync(2, kGemvConsumers);                   // ... before its ticket is taken
-            if (tid == 0) peer_signal_and_wait(peers);
+            if (warp == 0) peer_signal_and_wait(peers);        // all 32 lanes of consumer warp 0
         }
     }
 }
@@ -1056,24 +1091,46 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
         // lane owns units lane + 32j (j = 0..7) of a stage = (block 4j + lane/8, AVX lane lane%8)
         uint32_t it = 0;
         const int l = lane & 7;
-        for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const bool piped = peers.world > 1 && peers.defer;
+        if (piped) {                                  // pipelined exchange: the previous epoch is complete here before x is read
+            peer_wait_flags(peers, peers.epoch - 1u);          // all 32 lanes, converged
+            __syncwarp();
+        }
+        // The raw operands of a stage (x word, matrix-tile scale, x scale per unit) are requested ONE STAGE AHEAD, before this
+        // warp blocks on the slot: their L2 latency (~1 us while the matrix streams at the HBM rate) never adds to the
+        // consumers' stage time. Without it a unit warp that once falls behind the TMA ring (a late start is enough: the
+        // pipelined exchange waits here) stays behind for the whole kernel, because every stage then costs (load latency +
+        // consume) instead of max(load latency, consume).
+        uint32_t w[8];
+        float sa[8], sb[8];
+        auto prefetch = [&](uint64_t item, uint32_t c) {
             const float *su = scales + (item >> 1) * hb;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint64_t b = (uint64_t)c * (4 * kG4Chunks) + 4 * j + (lane >> 3);
+                const bool ok = b < hb;
+                w[j] = ok ? ld_x(xv + b * 8 + l, piped) : 0u;
+                sa[j] = ok ? __ldg(su + b) : 0.f;
+                sb[j] = ok ? ld_x(xs + b, piped) : 0.f;
+            }
+        };
+        if (blockIdx.x < nitems) prefetch(blockIdx.x, 0);
+        for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
             for (uint32_t c = 0; c < steps; ++c, ++it) {
                 const int s = it % STAGES;
                 XUnit u[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const uint64_t b = (uint64_t)c * (4 * kG4Chunks) + 4 * j + (lane >> 3);
-                    const bool ok = b < hb;
-                    const uint32_t w = ok ? __ldg(xv + b * 8 + l) : 0u;
-                    const float sa = ok ? __ldg(su + b) : 0.f, sb = ok ? __ldg(xs + b) : 0.f;
-                    const int xh = sext_nibbles((w >> 4) & 0x0F0F0F0Fu);
-                    const int xl = sext_nibbles(w & 0x0F0F0F0Fu);
+                    const int xh = sext_nibbles((w[j] >> 4) & 0x0F0F0F0Fu);
+                    const int xl = sext_nibbles(w[j] & 0x0F0F0F0Fu);
                     u[j].xh = xh;
-                    u[j].xl16 = (int)((w << 4) & 0xF0F0F0F0u);
+                    u[j].xl16 = (int)((w[j] << 4) & 0xF0F0F0F0u);
                     u[j].cneg = -(786432.0f + 8.0f * (float)(dp4a_ss(xh, 0x01010101, 0) + dp4a_ss(xl, 0x01010101, 0)));
-                    u[j].prod = __fmul_rn(__fmul_rn(sa, 1.0f / 49.0f), sb);                       // (:834-837)
+                    u[j].prod = __fmul_rn(__fmul_rn(sa[j], 1.0f / 49.0f), sb[j]);                 // (:834-837)
                 }
+                uint32_t nc = c + 1; uint64_t nitem = item;
+                if (nc == steps) { nc = 0; nitem = item + gridDim.x; }
+                if (nitem < nitems) prefetch(nitem, nc);
                 mbar_wait(&sm.empty[s], ((it / STAGES) & 1) ^ 1);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) sm.stage[s].units[lane + 32 * j] = u[j];
@@ -1155,7 +1212,7 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
         if (peers.world > 1) {
             if (tid < 64) __threadfence_system();                // this CTA's peer stores are visible system-wide ...
             named_bar_sync(2, kG4Consumers);                     // ... before its ticket is taken
-            if (tid == 0) peer_signal_and_wait(peers);
+            if (warp == 0) peer_signal_and_wait(peers);        // all 32 lanes of consumer warp 0
         }
     }
 }
@@ -1463,10 +1520,10 @@ int clover_m4_mvm_shard(const int8_t *values_local, const float *scales_local, u
                          yv_full, ys_full, key_host, (cudaStream_t)stream);
 }
 
-int clover_m4_mvm_shard_fused(const int8_t *values_local, const float *scales_local, uint64_t rows_local, uint64_t cols,
+static int launch_shard_fused(const int8_t *values_local, const float *scales_local, uint64_t rows_local, uint64_t cols,
                               uint64_t row0, const int8_t *xv, const float *xs, int8_t *const *peer_yv_host,
                               float *const *peer_ys_host, uint32_t *const *peer_flags_host, unsigned int *ticket,
-                              int world, int rank, uint32_t epoch, uint64_t *key_host, void *stream) {
+                              int world, int rank, uint32_t epoch, uint64_t *key_host, void *stream, int defer) {
     CLOVER_REQUIRE(values_local && scales_local && xv && xs && peer_yv_host && peer_ys_host && peer_flags_host && ticket,
                    CLOVER_ERR_INVALID, "null pointer");
     CLOVER_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, CLOVER_ERR_INVALID, "bad world / rank (at most 8 peers)");
@@ -1475,7 +1532,7 @@ int clover_m4_mvm_shard_fused(const int8_t *values_local, const float *scales_lo
     CLOVER_REQUIRE(rows_local > 0, CLOVER_ERR_UNSUPPORTED, "every rank must own at least one 64-row block (a rank without work could not signal)");
     CLOVER_REQUIRE((reinterpret_cast<uintptr_t>(values_local) & 15u) == 0, CLOVER_ERR_UNSUPPORTED, "values_local must be 16-byte aligned");
     PeerOut peers;
-    peers.world = world; peers.rank = rank; peers.epoch = epoch; peers.ticket = ticket;
+    peers.world = world; peers.rank = rank; peers.epoch = epoch; peers.ticket = ticket; peers.defer = defer;
     for (int p = 0; p < world; ++p) {
         CLOVER_REQUIRE(peer_yv_host[p] && peer_ys_host[p] && peer_flags_host[p], CLOVER_ERR_INVALID, "null peer pointer");
         peers.yv[p] = peer_yv_host[p]; peers.ys[p] = peer_ys_host[p]; peers.flags[p] = peer_flags_host[p];
@@ -1483,6 +1540,34 @@ int clover_m4_mvm_shard_fused(const int8_t *values_local, const float *scales_lo
     // own slice goes through the ordinary local pointers; the stream position of key_host follows clover_m4_mvm_shard
     return launch_mvm<4>(values_local, scales_local, rows_local, cols, row0, xv, xs, nullptr, peers.yv[rank], peers.ys[rank],
                          key_host, (cudaStream_t)stream, &peers);
+}
+
+int clover_m4_mvm_shard_fused(const int8_t *values_local, const float *scales_local, uint64_t rows_local, uint64_t cols,
+                              uint64_t row0, const int8_t *xv, const float *xs, int8_t *const *peer_yv_host,
+                              float *const *peer_ys_host, uint32_t *const *peer_flags_host, unsigned int *ticket,
+                              int world, int rank, uint32_t epoch, uint64_t *key_host, void *stream) {
+    return launch_shard_fused(values_local, scales_local, rows_local, cols, row0, xv, xs, peer_yv_host, peer_ys_host,
+                              peer_flags_host, ticket, world, rank, epoch, key_host, stream, 0);
+}
+
+int clover_m4_mvm_shard_fused_async(const int8_t *values_local, const float *scales_local, uint64_t rows_local, uint64_t cols,
+                                    uint64_t row0, const int8_t *xv, const float *xs, int8_t *const *peer_yv_host,
+                                    float *const *peer_ys_host, uint32_t *const *peer_flags_host, unsigned int *ticket,
+                                    int world, int rank, uint32_t epoch, uint64_t *key_host, void *stream) {
+    return launch_shard_fused(values_local, scales_local, rows_local, cols, row0, xv, xs, peer_yv_host, peer_ys_host,
+                              peer_flags_host, ticket, world, rank, epoch, key_host, stream, 1);
+}
+
+int clover_m4_shard_fused_wait(uint32_t *flags_local, int world, int rank, uint32_t epoch, void *stream) {
+    CLOVER_REQUIRE(flags_local, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, CLOVER_ERR_INVALID, "bad world / rank (at most 8 peers)");
+    if (world == 1) return CLOVER_OK;
+    PeerOut peers;
+    peers.world = world; peers.rank = rank; peers.epoch = epoch;
+    peers.flags[rank] = flags_local;
+    k_peer_wait<<<1, 32, 0, (cudaStream_t)stream>>>(peers);
+    count_launch();
+    return launch_status("k_peer_wait");
 }
 
 int clover_v4_requantize_mvm(const float *y32, uint64_t rows, int8_t *yv, float *ys, uint64_t *key_host, void *stream) {

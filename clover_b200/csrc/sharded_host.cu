@@ -4,7 +4,7 @@
 // SURVEY.md 8e / 8b (`clover_mvm4_sharded(handles, ...)`): rows are sharded in whole 64-row blocks, x is replicated,
 // every GPU runs the GEMV kernel on its rows and its epilogue stores each re-quantized block (32 B of nibbles + one fp32
 // scale) into the result vector of EVERY GPU through peer pointers (cudaDeviceEnablePeerAccess: NVLink / NVSwitch), then
-// the GPUs signal each other with flag words - clover_m4_mvm_shard_fused, one kernel per GPU and call, no NCCL. The
+// the GPUs signal each other with flag words - clover_m4_mvm_shard_fused_async, one kernel per GPU and call, no NCCL. The
 // Python host (clover_b200/sharded.py) does the same with one process per GPU and CUDA IPC; the kernels are shared.
 #include <vector>
 #include "runtime.cuh"
@@ -157,14 +157,20 @@ int clover_m4_sharded_mvm_host(clover_m4_sharded *h, const int8_t *xv_host, cons
         CLOVER_CUDA_CHECK(cudaMemcpyAsync(k.x, xv_host, xvb, cudaMemcpyHostToDevice, k.stream));
         CLOVER_CUDA_CHECK(cudaMemcpyAsync(k.x + xvb, xs_host, xsb, cudaMemcpyHostToDevice, k.stream));
         // the key is read at each block's GLOBAL position by every GPU and advanced once below, like the reference's stream
-        int rc = clover_m4_mvm_shard_fused(k.values, k.scales, k.rows_local, h->cols, k.row0, reinterpret_cast<const int8_t *>(k.x),
+        int rc = clover_m4_mvm_shard_fused_async(k.values, k.scales, k.rows_local, h->cols, k.row0, reinterpret_cast<const int8_t *>(k.x),
                                            reinterpret_cast<const float *>(k.x + xvb), peer_yv, peer_ys, peer_flags,
                                            reinterpret_cast<unsigned int *>(k.block + h->off_ticket), h->world, r, epoch, key_host, k.stream);
         if (rc != CLOVER_OK) return rc;
     }
     if (key_host) host_key_skip(key_host, 2 * (h->rows / 64));
-    clover_m4_sharded::Rank &k0 = h->ranks[0];       // every GPU holds the full result when its kernel has ended: read GPU 0's
+    // pipelined exchange: no kernel waits for its peers at its end; GPU 0 waits for their flags in front of the read-back,
+    // the other GPUs in the prologue of their next call's kernel
+    clover_m4_sharded::Rank &k0 = h->ranks[0];
     CLOVER_CUDA_CHECK(cudaSetDevice(k0.device));
+    {
+        int rc = clover_m4_shard_fused_wait(peer_flags[0], h->world, 0, epoch, k0.stream);
+        if (rc != CLOVER_OK) return rc;
+    }
     CLOVER_CUDA_CHECK(cudaMemcpyAsync(yv_host, k0.block + h->off_yv[b], h->rows / 2, cudaMemcpyDeviceToHost, k0.stream));
     CLOVER_CUDA_CHECK(cudaMemcpyAsync(ys_host, k0.block + h->off_ys[b], h->rows / 64 * sizeof(float), cudaMemcpyDeviceToHost, k0.stream));
     for (auto &k : h->ranks) { CLOVER_CUDA_CHECK(cudaSetDevice(k.device)); CLOVER_CUDA_CHECK(cudaStreamSynchronize(k.stream)); }

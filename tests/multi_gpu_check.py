@@ -18,6 +18,8 @@ from clover_b200.sharded import ShardedCloverMatrix4  # noqa: E402
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(150, exit=True)        # a flag protocol that deadlocks must not hold the GPUs
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -54,6 +56,37 @@ def main():
             if rank == 0:
                 print(f"multi-gpu check: {rows} x {cols}, exchange={mode}: 5 steps identical to the single-GPU mvm on every rank ({world} ranks)", flush=True)
         dist.barrier()
+    # pipelined fused exchange: a chain y_{e+1} = A y_e on a square matrix, every step consuming the previous step's result
+    # VIEW (written by the peers over NVLink) with no host synchronisation and no wait kernel in between - the next kernel's
+    # prologue is the only wait. Compared with the same chain on one GPU; 3 rounds so that both result buffers are re-used.
+    for n in (2048, 16384 + 128):
+        n += (-n) % 128
+        g = torch.Generator(device=dev).manual_seed(11)
+        full = cb.CloverMatrix4(n, n)
+        full.values.copy_(random_nibbles(torch, n * n // 2, g, dev))
+        full.scales.uniform_(0.05, 4.0, generator=g)
+        v = cb.CloverVector32(n); v.values.uniform_(-1, 1, generator=g)
+        x0 = cb.CloverVector4(n); x0.quantize(v)
+        steps = 7
+        want, cur = [], x0
+        for _ in range(steps):
+            y = cb.CloverVector4(n); full.mvm(cur, y); want.append(y); cur = y
+        A = ShardedCloverMatrix4(n, n, exchange="fused_pipelined")
+        hb = n // 64
+        A.load_shard(full.values[A.row0 * n // 2:(A.row0 + A.rows_local) * n // 2],
+                     full.scales[(A.row0 // 64) * hb:((A.row0 + A.rows_local) // 64) * hb])
+        for rnd in range(3):
+            cur = x0
+            for e in range(steps):
+                cur = A.mvm(cur, wait=(rnd == 2 and e % 3 == 1))      # round 2 mixes synchronous steps into the pipelined chain
+            A.wait()
+            torch.cuda.synchronize()
+            assert torch.equal(cur.values, want[-1].values), ("pipelined chain", n, rank, "values")
+            assert torch.equal(cur.scales.view(torch.int32)[: n // 64], want[-1].scales.view(torch.int32)[: n // 64]), ("pipelined chain", n, rank, "scales")
+            dist.barrier()
+        A.close()
+        if rank == 0:
+            print(f"multi-gpu check: {n} x {n}, pipelined fused chain of {steps} steps x 3 identical to the single-GPU chain on every rank ({world} ranks)", flush=True)
     if rank == 0:
         print("multi-gpu ok: fused / allgather / allreduce == single-GPU mvm on", world, "ranks")
     dist.destroy_process_group()

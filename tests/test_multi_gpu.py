@@ -44,7 +44,7 @@ def test_exchange_modes_two_gpus():
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29511", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=200, cwd=ROOT)
     assert out.returncode == 0 and "multi-gpu ok" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
