@@ -212,8 +212,10 @@ __global__ void __launch_bounds__(32) k_peer_wait(const __grid_constant__ PeerOu
 
 // x of a pipelined step may be the previous step's result, i.e. written by the peers while this kernel is already
 // running (before their flags): read it through L2 (ld.global.cg), never through the non-coherent path
-__device__ __forceinline__ uint32_t ld_x(const uint32_t *p, bool coherent) { return coherent ? __ldcg(p) : __ldg(p); }
-__device__ __forceinline__ float ld_x(const float *p, bool coherent) { return coherent ? __ldcg(p) : __ldg(p); }
+// (a compile-time choice: as a run-time `coherent ? __ldcg(p) : __ldg(p)` every load of the unit warp became its own branch
+// region and the C3 kernel lost 12 % - tools/ab, r02u)
+template <bool COHERENT> __device__ __forceinline__ uint32_t ld_x(const uint32_t *p) { return COHERENT ? __ldcg(p) : __ldg(p); }
+template <bool COHERENT> __device__ __forceinline__ float ld_x(const float *p) { return COHERENT ? __ldcg(p) : __ldg(p); }
 
 // =============================================================================================
 // mvm(V4,V4): exact-order 4-bit GEMV
@@ -381,7 +383,7 @@ __device__ __forceinline__ void gemv4_step(const uint8_t *r0, const uint8_t *r1,
     acc1 = __fmaf_rn(u.prod, __fmaf_rn(__int_as_float(s1), 0.0625f, u.cneg), acc1);
 }
 
-template <bool STOCH>
+template <bool STOCH, bool PIPED>
 __global__ void __launch_bounds__(kGemvThreads, 1)
 k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows_local,
              uint64_t cols, uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
@@ -426,8 +428,7 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
         uint32_t it = 0;
         uint32_t w[4] = {0, 0, 0, 0};
         float sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
-        const bool piped = peers.world > 1 && peers.defer;
-        if (piped) {                                  // pipelined exchange: the previous epoch is complete here before x is read
+        if (PIPED) {                                  // pipelined exchange: the previous epoch is complete here before x is read
             peer_wait_flags(peers, peers.epoch - 1u);          // all 32 lanes, converged
             __syncwarp();
         }
@@ -436,9 +437,9 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
             for (int j = 0; j < 4; ++j) {
                 const uint64_t b = (uint64_t)c * kKC + 4 * j + (lane >> 3);
                 const bool ok = b < hb;
-                w[j] = ok ? ld_x(xv + b * 8 + (lane & 7), piped) : 0u;
+                w[j] = ok ? ld_x<PIPED>(xv + b * 8 + (lane & 7)) : 0u;
                 sa[j] = ok ? __ldg(scales + rb * hb + b) : 0.f;
-                sb[j] = ok ? ld_x(xs + b, piped) : 0.f;
+                sb[j] = ok ? ld_x<PIPED>(xs + b) : 0.f;
             }
         };
         if (blockIdx.x < nrb) prefetch(blockIdx.x, 0);
@@ -706,25 +707,40 @@ k_m8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
         }
     } else if (warp == kG8Consumers / 32 + 1) {
         // ------------------------------- x-unit warp -------------------------------
-        // lane owns units lane + 32j (j = 0..4*kBPC/2-1) of a stage = (block 4j + lane/8, AVX lane lane%8)
+        // lane owns units lane + 32j (j = 0..4*kBPC/2-1) of a stage = (block 4j + lane/8, AVX lane lane%8); the raw operands
+        // of a stage are requested one stage ahead, before the warp blocks on the slot (see k_m4_mvm_tma2)
         constexpr int kUnitsPerLane = kG8Chunks * kBPC / 4;
         uint32_t it = 0;
         const int l = lane & 7;
-        for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        uint32_t xa[kUnitsPerLane], xb[kUnitsPerLane];
+        float sa[kUnitsPerLane], sb[kUnitsPerLane];
+        auto prefetch = [&](uint64_t item, uint32_t c) {
             const float *su = scales + (item >> 1) * hb;
+#pragma unroll
+            for (int j = 0; j < kUnitsPerLane; ++j) {
+                const uint64_t b = (uint64_t)c * (kBPC * kG8Chunks) + 4 * j + (lane >> 3);
+                const bool ok = b < hb;
+                xa[j] = ok ? __ldg(xv + b * 16 + l) : 0u;
+                xb[j] = ok ? __ldg(xv + b * 16 + 8 + l) : 0u;
+                sa[j] = ok ? __ldg(su + b) : 0.f;
+                sb[j] = ok ? __ldg(xs + b) : 0.f;
+            }
+        };
+        if (blockIdx.x < nitems) prefetch(blockIdx.x, 0);
+        for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
             for (uint32_t c = 0; c < steps; ++c, ++it) {
                 const int s = it % STAGES;
                 uint4 u[kUnitsPerLane];
 #pragma unroll
                 for (int j = 0; j < kUnitsPerLane; ++j) {
-                    const uint64_t b = (uint64_t)c * (kBPC * kG8Chunks) + 4 * j + (lane >> 3);
-                    const bool ok = b < hb;
-                    u[j].x = ok ? __ldg(xv + b * 16 + l) : 0u;
-                    u[j].y = ok ? __ldg(xv + b * 16 + 8 + l) : 0u;
-                    const float sa = ok ? __ldg(su + b) : 0.f, sb = ok ? __ldg(xs + b) : 0.f;
-                    u[j].z = __float_as_uint(__fmul_rn(__fmul_rn(sa, 1.0f / 127.0f), __fmul_rn(sb, 1.0f / 127.0f)));    // (CloverMatrix8.h:1042-1046)
+                    u[j].x = xa[j];
+                    u[j].y = xb[j];
+                    u[j].z = __float_as_uint(__fmul_rn(__fmul_rn(sa[j], 1.0f / 127.0f), __fmul_rn(sb[j], 1.0f / 127.0f)));    // (CloverMatrix8.h:1042-1046)
                     u[j].w = 0u;
                 }
+                uint32_t nc = c + 1; uint64_t nitem = item;
+                if (nc == steps) { nc = 0; nitem = item + gridDim.x; }
+                if (nitem < nitems) prefetch(nitem, nc);
                 mbar_wait(&sm.empty[s], ((it / STAGES) & 1) ^ 1);
 #pragma unroll
                 for (int j = 0; j < kUnitsPerLane; ++j) sm.stage[s].units[lane + 32 * j] = u[j];
@@ -874,26 +890,39 @@ k_m4v8_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict
         }
     } else if (warp == kMxConsumers / 32 + 1) {
         // ------------------------------- x-unit warp -------------------------------
-        // lane owns units lane + 32j (j = 0..KC-1) of a stage = (block 4j + lane/8, AVX lane lane%8)
+        // lane owns units lane + 32j (j = 0..KC-1) of a stage = (block 4j + lane/8, AVX lane lane%8); the raw operands of a
+        // stage are requested one stage ahead, before the warp blocks on the slot (see k_m4_mvm_tma2)
         uint32_t it = 0;
         const int l = lane & 7;
-        for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        uint32_t xa[KC], xb[KC];
+        float sa[KC], sb[KC];
+        auto prefetch = [&](uint64_t item, uint32_t c) {
             const float *su = scales + (item >> 1) * hb;
+#pragma unroll
+            for (int j = 0; j < KC; ++j) {
+                const uint64_t b = (uint64_t)c * (4 * KC) + 4 * j + (lane >> 3);
+                const bool ok = b < hb;
+                xa[j] = ok ? __ldg(xv + b * 16 + l) : 0u;            // elements 4l .. 4l+3
+                xb[j] = ok ? __ldg(xv + b * 16 + 8 + l) : 0u;        // elements 32+4l .. 32+4l+3
+                sa[j] = ok ? __ldg(su + b) : 0.f;
+                sb[j] = ok ? __ldg(xs + b) : 0.f;
+            }
+        };
+        if (blockIdx.x < nitems) prefetch(blockIdx.x, 0);
+        for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
             for (uint32_t c = 0; c < steps; ++c, ++it) {
                 const int s = it % STAGES;
                 uint2 u[KC];
                 float pr[KC];
 #pragma unroll
                 for (int j = 0; j < KC; ++j) {
-                    const uint64_t b = (uint64_t)c * (4 * KC) + 4 * j + (lane >> 3);
-                    const bool ok = b < hb;
-                    const uint32_t xa = ok ? __ldg(xv + b * 16 + l) : 0u;            // elements 4l .. 4l+3
-                    const uint32_t xb = ok ? __ldg(xv + b * 16 + 8 + l) : 0u;        // elements 32+4l .. 32+4l+3
-                    u[j].x = __byte_perm(xa, xb, 0x6420);
-                    u[j].y = __byte_perm(xa, xb, 0x7531);
-                    const float sa = ok ? __ldg(su + b) : 0.f, sb = ok ? __ldg(xs + b) : 0.f;
-                    pr[j] = __fmul_rn(__fmul_rn(sa, 1.0f / 7.0f), __fmul_rn(sb, 1.0f / 127.0f));
+                    u[j].x = __byte_perm(xa[j], xb[j], 0x6420);
+                    u[j].y = __byte_perm(xa[j], xb[j], 0x7531);
+                    pr[j] = __fmul_rn(__fmul_rn(sa[j], 1.0f / 7.0f), __fmul_rn(sb[j], 1.0f / 127.0f));
                 }
+                uint32_t nc = c + 1; uint64_t nitem = item;
+                if (nc == steps) { nc = 0; nitem = item + gridDim.x; }
+                if (nitem < nitems) prefetch(nitem, nc);
                 mbar_wait(&sm.empty[s], ((it / STAGES) & 1) ^ 1);
 #pragma unroll
                 for (int j = 0; j < KC; ++j) {
@@ -1044,7 +1073,7 @@ struct Gemv4Smem {
     unsigned int ticket;
 };
 
-template <bool STOCH, int STAGES>
+template <bool STOCH, int STAGES, bool PIPED>
 __global__ void __launch_bounds__(kG4Threads, STAGES == 5 ? 1 : 2)
 k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows_local,
               uint64_t cols, uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
@@ -1091,8 +1120,7 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
         // lane owns units lane + 32j (j = 0..7) of a stage = (block 4j + lane/8, AVX lane lane%8)
         uint32_t it = 0;
         const int l = lane & 7;
-        const bool piped = peers.world > 1 && peers.defer;
-        if (piped) {                                  // pipelined exchange: the previous epoch is complete here before x is read
+        if (PIPED) {                                  // pipelined exchange: the previous epoch is complete here before x is read
             peer_wait_flags(peers, peers.epoch - 1u);          // all 32 lanes, converged
             __syncwarp();
         }
@@ -1109,9 +1137,9 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
             for (int j = 0; j < 8; ++j) {
                 const uint64_t b = (uint64_t)c * (4 * kG4Chunks) + 4 * j + (lane >> 3);
                 const bool ok = b < hb;
-                w[j] = ok ? ld_x(xv + b * 8 + l, piped) : 0u;
+                w[j] = ok ? ld_x<PIPED>(xv + b * 8 + l) : 0u;
                 sa[j] = ok ? __ldg(su + b) : 0.f;
-                sb[j] = ok ? ld_x(xs + b, piped) : 0.f;
+                sb[j] = ok ? ld_x<PIPED>(xs + b) : 0.f;
             }
         };
         if (blockIdx.x < nitems) prefetch(blockIdx.x, 0);
@@ -1381,13 +1409,15 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
             int rc = mvm_scratch(stream, nrb, (row0 >> 6) + nrb, y32 ? nullptr : &ybuf, &counters);
             if (rc != CLOVER_OK) return rc;
             const int smem = (int)(x2 ? sizeof(Gemv4Smem<3>) : sizeof(Gemv4Smem<5>)) + 1024;
-            static bool attr_set2[kMaxDevices][2][2] = {};      // per device: function attributes belong to a device's context
+            static bool attr_set2[kMaxDevices][2][2][2] = {};   // per device: function attributes belong to a device's context
             const int dev = current_device();
             if (dev < 0) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
-            auto kern = x2 ? (stoch ? k_m4_mvm_tma2<true, 3> : k_m4_mvm_tma2<false, 3>) : (stoch ? k_m4_mvm_tma2<true, 5> : k_m4_mvm_tma2<false, 5>);
-            if (!attr_set2[dev][x2][stoch]) {
+            const bool piped = peers && peers->world > 1 && peers->defer;      // pipelined exchange: its own instantiation
+            auto kern = piped ? (x2 ? (stoch ? k_m4_mvm_tma2<true, 3, true> : k_m4_mvm_tma2<false, 3, true>) : (stoch ? k_m4_mvm_tma2<true, 5, true> : k_m4_mvm_tma2<false, 5, true>))
+                              : (x2 ? (stoch ? k_m4_mvm_tma2<true, 3, false> : k_m4_mvm_tma2<false, 3, false>) : (stoch ? k_m4_mvm_tma2<true, 5, false> : k_m4_mvm_tma2<false, 5, false>));
+            if (!attr_set2[dev][x2][stoch][piped]) {
                 CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                attr_set2[dev][x2][stoch] = true;
+                attr_set2[dev][x2][stoch][piped] = true;
             }
             CUtensorMap tmap;
             rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows_local, cols >> 1, kG4Rows);
@@ -1395,22 +1425,23 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
             const uint64_t nitems = rows_local / kG4Rows;
             uint64_t slots = (uint64_t)sm_count();
             if (x2) {
-                static int per_sm4[kMaxDevices][2] = {};      // asked once per template instance and device
-                if (!per_sm4[dev][stoch]) CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4[dev][stoch], kern, kG4Threads, smem));
-                slots *= (uint64_t)std::max(1, std::min(per_sm4[dev][stoch], 2));
+                static int per_sm4[kMaxDevices][2][2] = {};   // asked once per template instance and device
+                if (!per_sm4[dev][stoch][piped]) CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4[dev][stoch][piped], kern, kG4Threads, smem));
+                slots *= (uint64_t)std::max(1, std::min(per_sm4[dev][stoch][piped], 2));
             }
             const unsigned pgrid = (unsigned)(nitems < slots ? nitems : slots);
             kern<<<pgrid, kG4Threads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, ybuf, counters, yv, ys,
                                                       key, tables, peers ? *peers : PeerOut());
         } else {
             const int smem = (int)sizeof(GemvSmem);
-            static bool attr_set[kMaxDevices][2] = {};      // per template instance and device
+            static bool attr_set[kMaxDevices][2][2] = {};   // per template instance and device
             const int dev = current_device();
             if (dev < 0) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
-            auto kern = stoch ? k_m4_mvm_tma<true> : k_m4_mvm_tma<false>;
-            if (!attr_set[dev][stoch]) {
+            const bool piped = peers && peers->world > 1 && peers->defer;
+            auto kern = piped ? (stoch ? k_m4_mvm_tma<true, true> : k_m4_mvm_tma<false, true>) : (stoch ? k_m4_mvm_tma<true, false> : k_m4_mvm_tma<false, false>);
+            if (!attr_set[dev][stoch][piped]) {
                 CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                attr_set[dev][stoch] = true;
+                attr_set[dev][stoch][piped] = true;
             }
             CUtensorMap tmap;
             int rc = make_tensor_map_u32_2d(&tmap, values, rows_local, cols >> 3, cols >> 1, 32, kKC * 8);
