@@ -686,7 +686,7 @@ def main():
                          "traffic": ncu_traffic(f"C3_mvm4:{rows}x{cols}") if world == 1 else None,
                          "kernel_ms": tk * 1e3, "algorithmic_bytes_per_launch": shard_bytes,
                          "note": "peak is the measured COPY bandwidth (a kernel that reads and writes); this kernel only reads, "
-                                 "so frac may exceed 1 (ncu: 6.80 TB/s of DRAM traffic, profiles/r02t_gemv4_ncu_summary.txt)"},
+                                 "so frac may exceed 1 (ncu: 6.86 TB/s of DRAM traffic, profiles/r02u_gemv4_ncu_summary.txt)"},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -80,16 +80,17 @@ __device__ __forceinline__ void pair4(uint64_t &acc, uint64_t x2, uint32_t hi, u
         "fma.rn.f32x2 %0, %1, m, %0;\n\t}"
         : "+l"(acc) : "l"(x2), "r"(hi), "r"(lo), "r"(magic), "l"(neg), "l"(ss), "n"(0x7650 + P));
 }
+// (t2 = x2 * s is the same for all 16 rows of a work item - one 64x64 tile scale per block - so the warp multiplies the
+//  stage's x slice ONCE, in place, before the block steps: one mul.f32x2 per 32 elements instead of one per 2)
 template <int P>
-__device__ __forceinline__ void pair8(uint64_t &acc, uint64_t x2, uint32_t u, uint32_t magic, uint64_t neg, uint64_t ss) {
-    asm("{\n\t.reg .b32 a, b;\n\t.reg .b64 m, t;\n\t"
-        "prmt.b32 a, %2, %3, %6;\n\t"
-        "prmt.b32 b, %2, %3, %7;\n\t"
+__device__ __forceinline__ void pair8(uint64_t &acc, uint64_t t2, uint32_t u, uint32_t magic, uint64_t neg) {
+    asm("{\n\t.reg .b32 a, b;\n\t.reg .b64 m;\n\t"
+        "prmt.b32 a, %2, %3, %5;\n\t"
+        "prmt.b32 b, %2, %3, %6;\n\t"
         "mov.b64 m, {a, b};\n\t"
         "add.rn.f32x2 m, m, %4;\n\t"
-        "mul.rn.f32x2 t, %1, %5;\n\t"
-        "fma.rn.f32x2 %0, t, m, %0;\n\t}"
-        : "+l"(acc) : "l"(x2), "r"(u), "r"(magic), "l"(neg), "l"(ss), "n"(0x7650 + P), "n"(0x7651 + P));
+        "fma.rn.f32x2 %0, %1, m, %0;\n\t}"
+        : "+l"(acc) : "l"(t2), "r"(u), "r"(magic), "l"(neg), "n"(0x7650 + P), "n"(0x7651 + P));
 }
 
 // x as packed f32x2 operands straight from shared memory (immediate offsets: no address arithmetic per load)
@@ -111,14 +112,14 @@ __device__ __forceinline__ void word4(uint32_t w, uint32_t xaddr, uint64_t ss, u
     pair4<2>(acc[2], x2, hi, lo, rc.magic, neg, ss);
     pair4<3>(acc[3], x3, hi, lo, rc.magic, neg, ss);
 }
-// one 32-bit word of the 8-bit matrix (elements e..e+3) against x[e..e+3] at shared address xaddr + XOFF
+// one 32-bit word of the 8-bit matrix (elements e..e+3) against t[e..e+3] = x * s at shared address xaddr + XOFF
 template <int XOFF>
-__device__ __forceinline__ void word8(uint32_t w, uint32_t xaddr, uint64_t ss, uint64_t neg, const RegConsts &rc, uint64_t *acc) {
+__device__ __forceinline__ void word8(uint32_t w, uint32_t xaddr, uint64_t neg, const RegConsts &rc, uint64_t *acc) {
     const uint32_t u = w ^ rc.c80;                                    // byte i: q + 128
     uint64_t x0, x1;
     lds_x4<XOFF>(xaddr, x0, x1);
-    pair8<0>(acc[0], x0, u, rc.magic, neg, ss);
-    pair8<2>(acc[1], x1, u, rc.magic, neg, ss);
+    pair8<0>(acc[0], x0, u, rc.magic, neg);
+    pair8<2>(acc[1], x1, u, rc.magic, neg);
 }
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -214,6 +215,18 @@ k_mvm_f32_ring(const __grid_constant__ CUtensorMap tmap, const float *__restrict
             float sjs[4];
 #pragma unroll
             for (int j = 0; j < kBPC; ++j) sjs[j] = __shfl_sync(0xFFFFFFFFu, sdiv, (int)(c % kCPG) * kBPC + j);
+            if (MBITS == 8) {
+                // t = x * s (CloverMatrix8.h:632-639) for the chunk's 128 elements, in place: lane L owns floats 4L .. 4L+3
+                // (block L / 16). Padding blocks beyond hb hold stale bytes - they are multiplied but never read.
+                const uint32_t ta = st + kF32Rows * 128u + 16u * (uint32_t)lane;
+                const float sj = lane < 16 ? sjs[0] : sjs[1];
+                const uint64_t s2 = pack2f(sj, sj);
+                uint64_t a, b;
+                asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(ta));
+                a = mul2(a, s2); b = mul2(b, s2);
+                asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(ta), "l"(a), "l"(b) : "memory");
+                __syncwarp();
+            }
             auto block_step = [&](auto J) {
                 constexpr int j = decltype(J)::value;
                 if (j < kBPC) {
@@ -229,17 +242,17 @@ k_mvm_f32_ring(const __grid_constant__ CUtensorMap tmap, const float *__restrict
                     } else {
                         {   // half 0: this thread's 16 bytes = 16-byte chunk 4j + kh
                             const uint4 w = lds128(rowp + ((((uint32_t)(4 * j) + (uint32_t)kh) ^ rsw) << 4));
-                            word8<256 * j>(w.x, xs, ss, neg, rc, &acc[0][0]);          // accumulator 2kh, lanes 0..3
-                            word8<256 * j + 16>(w.y, xs, ss, neg, rc, &acc[0][2]);     //                   lanes 4..7
-                            word8<256 * j + 32>(w.z, xs, ss, neg, rc, &acc[1][0]);     // accumulator 2kh+1
-                            word8<256 * j + 48>(w.w, xs, ss, neg, rc, &acc[1][2]);
+                            word8<256 * j>(w.x, xs, neg, rc, &acc[0][0]);          // accumulator 2kh, lanes 0..3
+                            word8<256 * j + 16>(w.y, xs, neg, rc, &acc[0][2]);     //                   lanes 4..7
+                            word8<256 * j + 32>(w.z, xs, neg, rc, &acc[1][0]);     // accumulator 2kh+1
+                            word8<256 * j + 48>(w.w, xs, neg, rc, &acc[1][2]);
                         }
                         {   // half 1: chunk 4j + 2 + kh, x 128 bytes further
                             const uint4 w = lds128(rowp + ((((uint32_t)(4 * j + 2) + (uint32_t)kh) ^ rsw) << 4));
-                            word8<256 * j + 128>(w.x, xs, ss, neg, rc, &acc[0][0]);
-                            word8<256 * j + 144>(w.y, xs, ss, neg, rc, &acc[0][2]);
-                            word8<256 * j + 160>(w.z, xs, ss, neg, rc, &acc[1][0]);
-                            word8<256 * j + 176>(w.w, xs, ss, neg, rc, &acc[1][2]);
+                            word8<256 * j + 128>(w.x, xs, neg, rc, &acc[0][0]);
+                            word8<256 * j + 144>(w.y, xs, neg, rc, &acc[0][2]);
+                            word8<256 * j + 160>(w.z, xs, neg, rc, &acc[1][0]);
+                            word8<256 * j + 176>(w.w, xs, neg, rc, &acc[1][2]);
                         }
                     }
                 }
@@ -257,7 +270,10 @@ k_mvm_f32_ring(const __grid_constant__ CUtensorMap tmap, const float *__restrict
                 if (nb > 2) block_step(std::integral_constant<int, 2>{});
             }
             __syncwarp();
-            if (lane == 0) issue();
+            if (lane == 0) {
+                if (MBITS == 8) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this warp WROTE the stage (t = x * s) before the async-proxy refill
+                issue();
+            }
             if (++s == kF32Stages) { s = 0; phase ^= 1; }
         }
         // (acc_1 + acc_2) resp. (acc_3 + acc_4) in this thread, their sum across the thread pair, then the hadd tree
