@@ -218,7 +218,7 @@ constexpr int kDotThreads = 256;
 
 struct DotWorkspace { double *partials; unsigned int *ticket; int capacity; };
 
-template <int BITS>
+template <int BITS, int UNROLL>
 __global__ void __launch_bounds__(kDotThreads)
 k_vdot_fast(const uint4 *__restrict__ u, const float *__restrict__ su, const uint4 *__restrict__ v,
             const float *__restrict__ sv, uint64_t nchunks, double *__restrict__ partials,
@@ -227,32 +227,40 @@ k_vdot_fast(const uint4 *__restrict__ u, const float *__restrict__ su, const uin
     const uint64_t stride = (uint64_t)gridDim.x * kDotThreads;
     double acc = 0.0;
     // all 32 lanes of a warp run the same trip count (nchunks is a multiple of 32: n_pad % 128 == 0
-    // gives nchunks % 4 == 0 only, so guard lanes individually but keep shuffles warp-uniform)
+    // gives nchunks % 4 == 0 only, so guard lanes individually but keep shuffles warp-uniform).
+    // UNROLL chunks per operand and thread are requested before the first is consumed.
     const uint64_t first = (uint64_t)blockIdx.x * kDotThreads + threadIdx.x;
     const uint64_t warp_first = first - (threadIdx.x & 31);
-    for (uint64_t base = warp_first; base < nchunks; base += stride) {
-        const uint64_t i = base + (threadIdx.x & 31);
-        int part = 0;
-        if (i < nchunks) {
-            const uint4 a = ldg_stream(u + i), b = ldg_stream(v + i);
-            if (BITS == 4) {
-                part = nibble_dot_word(a.x, b.x) + nibble_dot_word(a.y, b.y) + nibble_dot_word(a.z, b.z) +
-                       nibble_dot_word(a.w, b.w);
-            } else {
-                part = dp4a_ss((int)a.x, (int)b.x, 0);
-                part = dp4a_ss((int)a.y, (int)b.y, part);
-                part = dp4a_ss((int)a.z, (int)b.z, part);
-                part = dp4a_ss((int)a.w, (int)b.w, part);
-            }
+    for (uint64_t base = warp_first; base < nchunks; base += stride * UNROLL) {
+        uint4 a[UNROLL], b[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const uint64_t i = base + (uint64_t)k * stride + (threadIdx.x & 31);
+            if (i < nchunks) { a[k] = ldg_stream(u + i); b[k] = ldg_stream(v + i); }
+            else             { a[k] = make_uint4(0u, 0u, 0u, 0u); b[k] = a[k]; }
         }
-        part += __shfl_xor_sync(0xFFFFFFFFu, part, 1);
-        if (BITS == 8) part += __shfl_xor_sync(0xFFFFFFFFu, part, 2);
-        if (i < nchunks && (i % kChunksPerBlock) == 0) {
-            const uint64_t blk = i / kChunksPerBlock;
-            float s;
-            if (BITS == 4) s = __fmul_rn(__fmul_rn(su[blk], 1.0f / 49.0f), sv[blk]);
-            else           s = __fmul_rn(__fmul_rn(su[blk], 1.0f / 127.0f), __fmul_rn(sv[blk], 1.0f / 127.0f));
-            acc += (double)s * (double)part;
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const uint64_t i = base + (uint64_t)k * stride + (threadIdx.x & 31);
+            int part;
+            if (BITS == 4) {
+                part = nibble_dot_word(a[k].x, b[k].x) + nibble_dot_word(a[k].y, b[k].y) + nibble_dot_word(a[k].z, b[k].z) +
+                       nibble_dot_word(a[k].w, b[k].w);
+            } else {
+                part = dp4a_ss((int)a[k].x, (int)b[k].x, 0);
+                part = dp4a_ss((int)a[k].y, (int)b[k].y, part);
+                part = dp4a_ss((int)a[k].z, (int)b[k].z, part);
+                part = dp4a_ss((int)a[k].w, (int)b[k].w, part);
+            }
+            part += __shfl_xor_sync(0xFFFFFFFFu, part, 1);
+            if (BITS == 8) part += __shfl_xor_sync(0xFFFFFFFFu, part, 2);
+            if (i < nchunks && (i % kChunksPerBlock) == 0) {
+                const uint64_t blk = i / kChunksPerBlock;
+                float s;
+                if (BITS == 4) s = __fmul_rn(__fmul_rn(su[blk], 1.0f / 49.0f), sv[blk]);
+                else           s = __fmul_rn(__fmul_rn(su[blk], 1.0f / 127.0f), __fmul_rn(sv[blk], 1.0f / 127.0f));
+                acc += (double)s * (double)part;
+            }
         }
     }
     // fixed reduction tree
@@ -319,14 +327,16 @@ static int launch_vdot(const int8_t *u, const float *su, const int8_t *v, const 
     }
     const uint64_t nchunks = BITS == 4 ? n_pad / 32 : n_pad / 16;
     uint64_t want = (nchunks + kDotThreads * 4 - 1) / (kDotThreads * 4);       // >= 4 chunks per thread
+    // 8 CTAs per SM, two chunks per operand and thread in flight: measured on B200 at n = 2^26 (tools/dot_sweep.py, us for
+    // unroll 1 / 2 / 4): 4-bit 16.4 / 16.4 / 18.5, 8-bit 24.3 / 23.3 / 26.7; 2 or 4 CTAs per SM are slower for every unroll
     const uint64_t cap = (uint64_t)sm_count() * 8;
     const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     DotWorkspace ws;
     int rc = dot_workspace(stream, (int)cap, &ws);
     if (rc != CLOVER_OK) return rc;
-    k_vdot_fast<BITS><<<grid, kDotThreads, 0, stream>>>(reinterpret_cast<const uint4 *>(u), su,
-                                                        reinterpret_cast<const uint4 *>(v), sv, nchunks,
-                                                        ws.partials, ws.ticket, result);
+    k_vdot_fast<BITS, 2><<<grid, kDotThreads, 0, stream>>>(reinterpret_cast<const uint4 *>(u), su,
+                                                           reinterpret_cast<const uint4 *>(v), sv, nchunks,
+                                                           ws.partials, ws.ticket, result);
     count_launch();
     return launch_status("k_vdot_fast");
 }
