@@ -121,7 +121,11 @@ struct PeerOut {
     float *ys[kMaxPeers] = {};
     uint32_t *flags[kMaxPeers] = {};         // peer p's flag array, one word per source rank
     int defer = 0;                           // 1: pipelined form - wait for the PREVIOUS epoch before x is read, none at the end
+                                             // 2: stamped form - no flags, no fence: every word travels with its epoch (see below)
+    uint64_t *msg[kMaxPeers] = {};           // stamped: peer p's message area of this epoch's parity, 9 x 8 bytes per 64-row block
+    uint32_t *started[kMaxPeers] = {};       // stamped: peer p's "rank r has started call e" words (flow control)
 };
+constexpr int kXchgFlags = 0, kXchgPiped = 1, kXchgStamped = 2;   // template values = PeerOut::defer
 
 template <int BITS, bool STOCH>
 __device__ __forceinline__ void requantize_block(float y, int i, uint64_t rb, int8_t *__restrict__ yv,
@@ -150,16 +154,31 @@ __device__ __forceinline__ void requantize_block(float y, int i, uint64_t rb, in
         if (i < 8) {
             const uint32_t w = pack8_nibbles(smem_q + 8 * i);
             reinterpret_cast<uint32_t *>(yv + rb * 32)[i] = w;
-            if (peers)
+            if (peers && peers->defer == kXchgStamped) {
+                // stamped exchange: ONE naturally aligned 8-byte store {word, epoch} per peer - data and validity arrive together
+                const uint64_t stamped = ((uint64_t)peers->epoch << 32) | w;
+                for (int p = 0; p < peers->world; ++p)
+                    if (p != peers->rank)
+                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(peers->msg[p] + rb * 9 + i), "l"(stamped) : "memory");
+            } else if (peers) {
                 for (int p = 0; p < peers->world; ++p)
                     if (p != peers->rank) reinterpret_cast<uint32_t *>(peers->yv[p] + rb * 32)[i] = w;     // NVLink store
+            }
         }
     } else {
         if (i < 16) reinterpret_cast<uint32_t *>(yv + rb * 64)[i] = pack4_bytes(smem_q + 4 * i);
     }
-    if (peers && i == 0)
-        for (int p = 0; p < peers->world; ++p)
-            if (p != peers->rank) peers->ys[p][rb] = m;
+    if (peers && i == 0) {
+        if (peers->defer == kXchgStamped) {
+            const uint64_t stamped = ((uint64_t)peers->epoch << 32) | __float_as_uint(m);
+            for (int p = 0; p < peers->world; ++p)
+                if (p != peers->rank)
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(peers->msg[p] + rb * 9 + 8), "l"(stamped) : "memory");
+        } else {
+            for (int p = 0; p < peers->world; ++p)
+                if (p != peers->rank) peers->ys[p][rb] = m;
+        }
+    }
 }
 
 // Wait until every peer has raised its flag here to at least `epoch`, then acquire at system scope: the peers' result stores
@@ -171,10 +190,10 @@ __device__ __forceinline__ void requantize_block(float y, int i, uint64_t rb, in
 //     rest of the kernel - 273 instead of 201 us per step at 32768 x 65536 on 2 GPUs;
 //   * nanosleep back-off: a unit warp that slept ONCE at kernel start slowed the whole kernel by 35 % (182 -> 249 us for a
 //     5 us sleep; the same 5 us as a busy-wait on clock64: 184 us).
-__device__ __forceinline__ void peer_wait_flags(const PeerOut &peers, uint32_t epoch) {
+__device__ __forceinline__ void peer_wait_words(const uint32_t *words, int world, int rank, uint32_t epoch) {
     const int q = threadIdx.x & 31;
-    const bool mine = q < peers.world && q != peers.rank;
-    const uint32_t *flag = peers.flags[peers.rank] + (mine ? q : 0);
+    const bool mine = q < world && q != rank;
+    const uint32_t *flag = words + (mine ? q : 0);
     bool ok;
     do {
         uint32_t seen = epoch;
@@ -182,6 +201,46 @@ __device__ __forceinline__ void peer_wait_flags(const PeerOut &peers, uint32_t e
         ok = (int32_t)(seen - epoch) >= 0;
     } while (!__all_sync(0xFFFFFFFFu, ok));
     asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
+__device__ __forceinline__ void peer_wait_flags(const PeerOut &peers, uint32_t epoch) {
+    peer_wait_words(peers.flags[peers.rank], peers.world, peers.rank, epoch);
+}
+
+// ---- stamped exchange (peers.defer == kXchgStamped) -------------------------------------------------------------------
+// What the flag protocols pay at the end of every kernel is ORDER: a system-scope fence in every CTA between its peer
+// stores and its ticket (an NVLink round trip), the last CTA's fence, the flag flight, the poll. The stamped form needs no
+// order at all: every 32-bit word of the result (8 words of nibbles + the scale per 64-row block) travels in ONE naturally
+// aligned 8-byte store {word, epoch} into a message area on the peer - a single-copy-atomic access, so whoever reads the
+// epoch has the word. The producer kernel just ends. The consumer side (k_unpack_stamped, in front of whatever reads the
+// result) polls the stamps of the blocks the other ranks own and writes the words into the reference layout.
+// Flow control instead of flags: a message area is re-used every second call, so a kernel may only store epoch e once every
+// peer has STARTED its call e (whatever consumed epoch e-2 there precedes that call in stream order). One warp of CTA 0
+// announces the start on all peers when the kernel begins; consumer warp 0 of every CTA checks the local words before the
+// item loop - in the shadow of the first TMA round trip, ~40 us before its first message store.
+__device__ __forceinline__ void stamped_announce_start(const PeerOut &peers, int lane_p) {     // lanes of one warp, lane_p = 0..
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    if (lane_p >= 0 && lane_p < peers.world && lane_p != peers.rank)
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(peers.started[lane_p] + peers.rank), "r"(peers.epoch) : "memory");
+}
+__device__ __forceinline__ void stamped_wait_peers_started(const PeerOut &peers) {              // all 32 lanes of a converged warp
+    peer_wait_words(peers.started[peers.rank], peers.world, peers.rank, peers.epoch);
+}
+
+// msg: this rank's message area of the epoch's parity; every (block, word) another rank owns is polled until its stamp is
+// the epoch, then stored into the reference layout: yv32[rb * 8 + j] (j < 8), ys[rb] (j = 8)
+__global__ void __launch_bounds__(256)
+k_unpack_stamped(const uint64_t *__restrict__ msg, uint64_t nblocks, uint64_t own0, uint64_t ownn, uint32_t epoch,
+                 uint32_t *__restrict__ yv32, float *__restrict__ ys) {
+    for (uint64_t idx = (uint64_t)blockIdx.x * 256 + threadIdx.x; idx < nblocks * 9; idx += (uint64_t)gridDim.x * 256) {
+        const uint64_t rb = idx / 9, j = idx % 9;
+        if (rb >= own0 && rb < own0 + ownn) continue;            // written in place by this rank's own kernel
+        uint64_t v;
+        do {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(msg + idx) : "memory");
+        } while ((uint32_t)(v >> 32) != epoch);
+        if (j < 8) yv32[rb * 8 + j] = (uint32_t)v;
+        else       ys[rb] = __uint_as_float((uint32_t)v);
+    }
 }
 
 // Tail of the fused exchange, one WARP per CTA (all 32 lanes), after the CTA's peer stores have been fenced at system scope:
@@ -383,7 +442,7 @@ __device__ __forceinline__ void gemv4_step(const uint8_t *r0, const uint8_t *r1,
     acc1 = __fmaf_rn(u.prod, __fmaf_rn(__int_as_float(s1), 0.0625f, u.cneg), acc1);
 }
 
-template <bool STOCH, bool PIPED>
+template <bool STOCH, int XCHG>
 __global__ void __launch_bounds__(kGemvThreads, 1)
 k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows_local,
              uint64_t cols, uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
@@ -421,6 +480,8 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
                                 &sm.full[s], policy);
                 }
             }
+        } else if (XCHG == kXchgStamped && blockIdx.x == 0 && peers.world > 1) {
+            stamped_announce_start(peers, lane - 1);          // idle lanes of CTA 0's issuer warp: this rank has started call `epoch`
         }
     } else if (warp == kGemvConsumers / 32 + 1) {
         // ------------------------------- x-unit warp -------------------------------
@@ -428,6 +489,7 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
         uint32_t it = 0;
         uint32_t w[4] = {0, 0, 0, 0};
         float sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+        constexpr bool PIPED = XCHG == kXchgPiped;
         if (PIPED) {                                  // pipelined exchange: the previous epoch is complete here before x is read
             peer_wait_flags(peers, peers.epoch - 1u);          // all 32 lanes, converged
             __syncwarp();
@@ -472,6 +534,7 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
         const int h = lane >> 4, a = (lane >> 3) & 1, l = lane & 7;
         const int row_a = 32 * h + warp, row_b = row_a + 16;
         uint32_t it = 0;
+        if (XCHG == kXchgStamped && warp == 0 && peers.world > 1) stamped_wait_peers_started(peers);   // before any message store (barriers order it)
         for (uint64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
             float acc0 = 0.f, acc1 = 0.f;
             for (uint32_t c = 0; c < chunks; ++c, ++it) {
@@ -505,7 +568,7 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
                                                    peers.world > 1 ? &peers : nullptr);
             }
         }
-        if (peers.world > 1) {
+        if (XCHG != kXchgStamped && peers.world > 1) {
             if (tid < 64) __threadfence_system();                // this CTA's peer stores are visible system-wide ...
             named_bar_sync(2, kGemvConsumers);                   // ... before its ticket is taken
             if (warp == 0) peer_signal_and_wait(peers);        // all 32 lanes of consumer warp 0
@@ -1073,7 +1136,7 @@ struct Gemv4Smem {
     unsigned int ticket;
 };
 
-template <bool STOCH, int STAGES, bool PIPED>
+template <bool STOCH, int STAGES, int XCHG>
 __global__ void __launch_bounds__(kG4Threads, STAGES == 5 ? 1 : 2)
 k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows_local,
               uint64_t cols, uint64_t rowblock0, const uint32_t *__restrict__ xv, const float *__restrict__ xs,
@@ -1114,12 +1177,15 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
                                     &sm.full[s], policy);
                 }
             }
+        } else if (XCHG == kXchgStamped && blockIdx.x == 0 && peers.world > 1) {
+            stamped_announce_start(peers, lane - 1);          // idle lanes of CTA 0's issuer warp: this rank has started call `epoch`
         }
     } else if (warp == kG4Consumers / 32 + 1) {
         // ------------------------------- x-unit warp -------------------------------
         // lane owns units lane + 32j (j = 0..7) of a stage = (block 4j + lane/8, AVX lane lane%8)
         uint32_t it = 0;
         const int l = lane & 7;
+        constexpr bool PIPED = XCHG == kXchgPiped;
         if (PIPED) {                                  // pipelined exchange: the previous epoch is complete here before x is read
             peer_wait_flags(peers, peers.epoch - 1u);          // all 32 lanes, converged
             __syncwarp();
@@ -1175,6 +1241,7 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
         // this chain's two blocks of a 128-byte chunk: b = a and b = a + 2 -> 16-byte chunks 2b + ty, swizzled by (row & 7)
         const uint32_t o0 = base + ((uint32_t)((2 * a + ty) ^ rin) << 4), o1 = base + ((uint32_t)((2 * a + 4 + ty) ^ rin) << 4);
         uint32_t it = 0;
+        if (XCHG == kXchgStamped && warp == 0 && peers.world > 1) stamped_wait_peers_started(peers);   // before any message store (barriers order it)
         for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
             float acc = 0.f, acc2 = 0.f;
             for (uint32_t c = 0; c < steps; ++c, ++it) {
@@ -1237,7 +1304,7 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
                 }
             }
         }
-        if (peers.world > 1) {
+        if (XCHG != kXchgStamped && peers.world > 1) {
             if (tid < 64) __threadfence_system();                // this CTA's peer stores are visible system-wide ...
             named_bar_sync(2, kG4Consumers);                     // ... before its ticket is taken
             if (warp == 0) peer_signal_and_wait(peers);        // all 32 lanes of consumer warp 0
@@ -1409,15 +1476,22 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
             int rc = mvm_scratch(stream, nrb, (row0 >> 6) + nrb, y32 ? nullptr : &ybuf, &counters);
             if (rc != CLOVER_OK) return rc;
             const int smem = (int)(x2 ? sizeof(Gemv4Smem<3>) : sizeof(Gemv4Smem<5>)) + 1024;
-            static bool attr_set2[kMaxDevices][2][2][2] = {};   // per device: function attributes belong to a device's context
+            static bool attr_set2[kMaxDevices][2][2][3] = {};   // per device: function attributes belong to a device's context
             const int dev = current_device();
             if (dev < 0) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
-            const bool piped = peers && peers->world > 1 && peers->defer;      // pipelined exchange: its own instantiation
-            auto kern = piped ? (x2 ? (stoch ? k_m4_mvm_tma2<true, 3, true> : k_m4_mvm_tma2<false, 3, true>) : (stoch ? k_m4_mvm_tma2<true, 5, true> : k_m4_mvm_tma2<false, 5, true>))
-                              : (x2 ? (stoch ? k_m4_mvm_tma2<true, 3, false> : k_m4_mvm_tma2<false, 3, false>) : (stoch ? k_m4_mvm_tma2<true, 5, false> : k_m4_mvm_tma2<false, 5, false>));
-            if (!attr_set2[dev][x2][stoch][piped]) {
+            // the pipelined and the stamped exchange are their own instantiations (the local / synchronous kernel stays as it was)
+            const int xchg = peers && peers->world > 1 ? peers->defer : kXchgFlags;
+            using KernT = void (*)(const CUtensorMap, const float *, uint64_t, uint64_t, uint64_t, const uint32_t *, const float *, float *,
+                                   unsigned int *, int8_t *, float *, Key4, const uint64_t *, const PeerOut);
+            static const KernT kerns[2][2][3] = {     // [x2][stoch][xchg]
+                {{k_m4_mvm_tma2<false, 5, 0>, k_m4_mvm_tma2<false, 5, 1>, k_m4_mvm_tma2<false, 5, 2>},
+                 {k_m4_mvm_tma2<true, 5, 0>, k_m4_mvm_tma2<true, 5, 1>, k_m4_mvm_tma2<true, 5, 2>}},
+                {{k_m4_mvm_tma2<false, 3, 0>, k_m4_mvm_tma2<false, 3, 1>, k_m4_mvm_tma2<false, 3, 2>},
+                 {k_m4_mvm_tma2<true, 3, 0>, k_m4_mvm_tma2<true, 3, 1>, k_m4_mvm_tma2<true, 3, 2>}}};
+            const KernT kern = kerns[x2][stoch][xchg];
+            if (!attr_set2[dev][x2][stoch][xchg]) {
                 CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                attr_set2[dev][x2][stoch][piped] = true;
+                attr_set2[dev][x2][stoch][xchg] = true;
             }
             CUtensorMap tmap;
             rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows_local, cols >> 1, kG4Rows);
@@ -1425,23 +1499,27 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
             const uint64_t nitems = rows_local / kG4Rows;
             uint64_t slots = (uint64_t)sm_count();
             if (x2) {
-                static int per_sm4[kMaxDevices][2][2] = {};   // asked once per template instance and device
-                if (!per_sm4[dev][stoch][piped]) CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4[dev][stoch][piped], kern, kG4Threads, smem));
-                slots *= (uint64_t)std::max(1, std::min(per_sm4[dev][stoch][piped], 2));
+                static int per_sm4[kMaxDevices][2][3] = {};   // asked once per template instance and device
+                if (!per_sm4[dev][stoch][xchg]) CLOVER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4[dev][stoch][xchg], kern, kG4Threads, smem));
+                slots *= (uint64_t)std::max(1, std::min(per_sm4[dev][stoch][xchg], 2));
             }
             const unsigned pgrid = (unsigned)(nitems < slots ? nitems : slots);
             kern<<<pgrid, kG4Threads, smem, stream>>>(tmap, scales, rows_local, cols, row0 >> 6, x32, xs, ybuf, counters, yv, ys,
                                                       key, tables, peers ? *peers : PeerOut());
         } else {
             const int smem = (int)sizeof(GemvSmem);
-            static bool attr_set[kMaxDevices][2][2] = {};   // per template instance and device
+            static bool attr_set[kMaxDevices][2][3] = {};   // per template instance and device
             const int dev = current_device();
             if (dev < 0) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
-            const bool piped = peers && peers->world > 1 && peers->defer;
-            auto kern = piped ? (stoch ? k_m4_mvm_tma<true, true> : k_m4_mvm_tma<false, true>) : (stoch ? k_m4_mvm_tma<true, false> : k_m4_mvm_tma<false, false>);
-            if (!attr_set[dev][stoch][piped]) {
+            const int xchg = peers && peers->world > 1 ? peers->defer : kXchgFlags;
+            using KernT = void (*)(const CUtensorMap, const float *, uint64_t, uint64_t, uint64_t, const uint32_t *, const float *, float *,
+                                   int8_t *, float *, Key4, const uint64_t *, const PeerOut);
+            static const KernT kerns[2][3] = {{k_m4_mvm_tma<false, 0>, k_m4_mvm_tma<false, 1>, k_m4_mvm_tma<false, 2>},
+                                              {k_m4_mvm_tma<true, 0>, k_m4_mvm_tma<true, 1>, k_m4_mvm_tma<true, 2>}};
+            const KernT kern = kerns[stoch][xchg];
+            if (!attr_set[dev][stoch][xchg]) {
                 CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                attr_set[dev][stoch][piped] = true;
+                attr_set[dev][stoch][xchg] = true;
             }
             CUtensorMap tmap;
             int rc = make_tensor_map_u32_2d(&tmap, values, rows_local, cols >> 3, cols >> 1, 32, kKC * 8);
@@ -1587,6 +1665,42 @@ int clover_m4_mvm_shard_fused_async(const int8_t *values_local, const float *sca
                                     int world, int rank, uint32_t epoch, uint64_t *key_host, void *stream) {
     return launch_shard_fused(values_local, scales_local, rows_local, cols, row0, xv, xs, peer_yv_host, peer_ys_host,
                               peer_flags_host, ticket, world, rank, epoch, key_host, stream, 1);
+}
+
+int clover_m4_mvm_shard_stamped(const int8_t *values_local, const float *scales_local, uint64_t rows_local, uint64_t cols,
+                                uint64_t row0, const int8_t *xv, const float *xs, int8_t *yv_full, float *ys_full,
+                                uint64_t *const *peer_msg_host, uint32_t *const *peer_started_host,
+                                int world, int rank, uint32_t epoch, uint64_t *key_host, void *stream) {
+    CLOVER_REQUIRE(values_local && scales_local && xv && xs && yv_full && ys_full && peer_msg_host && peer_started_host,
+                   CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, CLOVER_ERR_INVALID, "bad world / rank (at most 8 peers)");
+    CLOVER_REQUIRE(rows_local % 64u == 0 && row0 % 64u == 0 && cols % 128u == 0, CLOVER_ERR_INVALID,
+                   "shards are whole 64-row blocks; cols a multiple of 128");
+    CLOVER_REQUIRE(rows_local > 0, CLOVER_ERR_UNSUPPORTED, "every rank must own at least one 64-row block");
+    CLOVER_REQUIRE((reinterpret_cast<uintptr_t>(values_local) & 15u) == 0, CLOVER_ERR_UNSUPPORTED, "values_local must be 16-byte aligned");
+    PeerOut peers;
+    peers.world = world; peers.rank = rank; peers.epoch = epoch; peers.defer = kXchgStamped;
+    for (int p = 0; p < world; ++p) {
+        CLOVER_REQUIRE(peer_msg_host[p] && peer_started_host[p], CLOVER_ERR_INVALID, "null peer pointer");
+        CLOVER_REQUIRE((reinterpret_cast<uintptr_t>(peer_msg_host[p]) & 7u) == 0, CLOVER_ERR_INVALID, "message areas must be 8-byte aligned");
+        peers.msg[p] = peer_msg_host[p]; peers.started[p] = peer_started_host[p];
+    }
+    return launch_mvm<4>(values_local, scales_local, rows_local, cols, row0, xv, xs, nullptr, yv_full, ys_full,
+                         key_host, (cudaStream_t)stream, &peers);
+}
+
+int clover_m4_shard_stamped_unpack(const uint64_t *msg_local, uint64_t rows, uint64_t row0, uint64_t rows_local, uint32_t epoch,
+                                   int8_t *yv_full, float *ys_full, void *stream) {
+    CLOVER_REQUIRE(msg_local && yv_full && ys_full, CLOVER_ERR_INVALID, "null pointer");
+    CLOVER_REQUIRE(rows % 64u == 0 && row0 % 64u == 0 && rows_local % 64u == 0 && row0 + rows_local <= rows, CLOVER_ERR_INVALID,
+                   "rows, row0 and rows_local are whole 64-row blocks");
+    const uint64_t nblocks = rows >> 6;
+    if (nblocks == 0 || rows_local == rows) return CLOVER_OK;
+    const uint64_t want = (nblocks * 9 + 255) / 256, cap = (uint64_t)sm_count() * 8;
+    k_unpack_stamped<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        msg_local, nblocks, row0 >> 6, rows_local >> 6, epoch, reinterpret_cast<uint32_t *>(yv_full), ys_full);
+    count_launch();
+    return launch_status("k_unpack_stamped");
 }
 
 int clover_m4_shard_fused_wait(uint32_t *flags_local, int world, int rank, uint32_t epoch, void *stream) {

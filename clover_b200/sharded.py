@@ -23,6 +23,11 @@ bit-for-bit, because the fp32 row results do not depend on the sharding.
     (``clover_m4_shard_fused_wait``) in front of any other consumer (``clover_m4_mvm_shard_fused_async``).
     Measured on B200s (tools/exchange_probe.py, C3 sharded, us per step synchronous / pipelined): 2 GPUs
     193.4 / 197.0, 4 GPUs 108.0 / 108.0, 8 GPUs 65.1 / 63.1 - the pipelined form is therefore used from 8 ranks on.
+  * ``exchange="stamped"``: the fused epilogue without ANY ordering between stores - every 32-bit word of a finished
+    block travels to every peer in one 8-byte store {word, epoch} into a message area (``clover_m4_mvm_shard_stamped``),
+    no per-CTA system fence, no flags; the consumer side (``wait()`` = ``clover_m4_shard_stamped_unpack``) polls the
+    stamps and writes the words into the reference layout. ``mvm(x, wait=True)`` = kernel + unpack;
+    ``mvm(x, wait=False)`` = kernel only, ``wait()`` in front of whatever reads the result.
 """
 from __future__ import annotations
 
@@ -89,7 +94,7 @@ class ShardedCloverMatrix4:
         self.key = None
         self._peer = None
         self._pending_wait = False                     # the last step was pipelined and nobody has waited for it yet
-        if exchange in ("fused", "fused_sync", "fused_pipelined"):   # _sync / _pipelined force either form of the wait
+        if exchange in ("fused", "fused_sync", "fused_pipelined", "stamped"):   # _sync / _pipelined force either form of the wait
             self._setup_peer_memory()
 
     # ---- fused exchange: one IPC-shared block per rank = [values x2 | scales x2 | flags | ticket] ------------------
@@ -100,7 +105,11 @@ class ShardedCloverMatrix4:
         vb, sb = al(rows // 2), al(rows // 64 * 4)
         off = {"yv": (0, vb), "ys": (2 * vb, 2 * vb + sb), "flags": 2 * vb + 2 * sb}
         off["ticket"] = off["flags"] + al(4 * world)
-        off["bytes"] = off["ticket"] + 256
+        # stamped exchange: two message areas (9 x 8 bytes per 64-row block of the whole vector) and the started words
+        mb = al(rows // 64 * 72)
+        off["msg"] = (off["ticket"] + 256, off["ticket"] + 256 + mb)
+        off["started"] = off["msg"][1] + mb
+        off["bytes"] = off["started"] + al(4 * world)
         return off
 
     def _setup_peer_memory(self) -> None:
@@ -150,6 +159,8 @@ class ShardedCloverMatrix4:
             "ys": [arr(lambda b, k=k: b + lay["ys"][k]) for k in (0, 1)],
             "flags": arr(lambda b: b + lay["flags"]),
             "ticket": C.c_void_p(base.value + lay["ticket"]),
+            "msg": [arr(lambda b, k=k: b + lay["msg"][k]) for k in (0, 1)],
+            "started": arr(lambda b: b + lay["started"]),
         }
 
     def close(self) -> None:
@@ -175,6 +186,12 @@ class ShardedCloverMatrix4:
         if pr is None or self.world == 1 or pr["epoch"] == 0 or not self._pending_wait:
             return
         self._pending_wait = False
+        if self.exchange == "stamped":
+            k = pr["epoch"] & 1
+            call("clover_m4_shard_stamped_unpack", C.c_void_p(pr["base"] + pr["lay"]["msg"][k]), C.c_uint64(self.rows),
+                 C.c_uint64(self.row0), C.c_uint64(self.rows_local), C.c_uint32(pr["epoch"]),
+                 C.c_void_p(pr["base"] + pr["lay"]["yv"][k]), C.c_void_p(pr["base"] + pr["lay"]["ys"][k]), _stream())
+            return
         call("clover_m4_shard_fused_wait", C.c_void_p(pr["base"] + pr["lay"]["flags"]), self.world, self.rank,
              C.c_uint32(pr["epoch"]), _stream())
 
@@ -185,6 +202,8 @@ class ShardedCloverMatrix4:
         kernel does not wait for the peers - the next step's kernel does, before it reads its x (which may be this
         view), and ``wait()`` does for every other consumer."""
         pr = self._peer
+        if self.exchange == "stamped":
+            return self._mvm_stamped(x, y, key_ptr, wait)
         # pipelined only where it pays (see the module docstring); a step that must be complete when it ends uses the
         # synchronous kernel - after a pipelined step that nobody waited for, the wait kernel first (the synchronous kernel
         # has no prologue wait, and it may not store into a peer's buffer before that peer has finished the step before)
@@ -200,6 +219,29 @@ class ShardedCloverMatrix4:
         lay = pr["lay"]
         if key_ptr is not None:      # the kernel read the key at each block's global position; advance it like the reference
             call("clover_prng_skip", key_ptr, C.c_uint64(2 * (self.rows // 64)))
+        if y is None:
+            return pr["views"][k]
+        call("clover_copy_d2d", _ptr(y.values), C.c_void_p(pr["base"] + lay["yv"][k]), C.c_size_t(self.rows // 2), _stream())
+        call("clover_copy_d2d", _ptr(y.scales), C.c_void_p(pr["base"] + lay["ys"][k]), C.c_size_t(self.rows // 64 * 4), _stream())
+        return y
+
+    def _mvm_stamped(self, x: CloverVector4, y, key_ptr, wait: bool):
+        """The stamped exchange: kernel (messages to every peer, own blocks in place), then - unless wait is False - the
+        unpack pass. The unpack of call e must precede call e + 2 in this stream (same message area): a pending one is
+        issued here before the epoch advances past it."""
+        pr = self._peer
+        lay = pr["lay"]
+        pr["epoch"] += 1
+        k = pr["epoch"] & 1
+        call("clover_m4_mvm_shard_stamped", _ptr(self.local.values), _ptr(self.local.scales), C.c_uint64(self.rows_local),
+             C.c_uint64(self.cols), C.c_uint64(self.row0), _ptr(x.values), _ptr(x.scales),
+             C.c_void_p(pr["base"] + lay["yv"][k]), C.c_void_p(pr["base"] + lay["ys"][k]), pr["msg"][k], pr["started"],
+             self.world, self.rank, C.c_uint32(pr["epoch"]), key_ptr, _stream())
+        if key_ptr is not None:
+            call("clover_prng_skip", key_ptr, C.c_uint64(2 * (self.rows // 64)))
+        self._pending_wait = True
+        if wait or y is not None:
+            self.wait()
         if y is None:
             return pr["views"][k]
         call("clover_copy_d2d", _ptr(y.values), C.c_void_p(pr["base"] + lay["yv"][k]), C.c_size_t(self.rows // 2), _stream())

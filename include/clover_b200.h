@@ -195,6 +195,24 @@ int clover_m4_mvm_shard_fused_async(const int8_t *values_local, const float *sca
                                     float *const *peer_ys_host, uint32_t *const *peer_flags_host, unsigned int *ticket,
                                     int world, int rank, uint32_t epoch, uint64_t *key_host, void *stream);
 int clover_m4_shard_fused_wait(uint32_t *flags_local, int world, int rank, uint32_t epoch, void *stream);
+/* Stamped exchange: the same fused epilogue without any ordering between stores. Every 32-bit word of a finished block (8
+ * words of nibbles + the scale) travels to every peer in ONE naturally aligned 8-byte store {word, epoch} into that peer's
+ * message area (9 x 8 bytes per 64-row block of the WHOLE vector, i.e. rows / 64 * 72 bytes; use two areas alternately,
+ * peer_msg_host[p] = rank p's area of this epoch's parity). No system-scope fence per CTA, no flags, the kernel just ends;
+ * this rank's own blocks go straight into yv_full / ys_full (reference layout).
+ *   clover_m4_shard_stamped_unpack(msg_local, rows, row0, rows_local, epoch, yv_full, ys_full, stream): the consumer side -
+ *     polls the stamps of the blocks the OTHER ranks own and writes their words into yv_full / ys_full. When it has completed
+ *     in stream order the full CloverVector4 result of call `epoch` is present on this rank.
+ * Flow control: peer_started_host[p] = rank p's `world`-word array; a kernel announces "rank r has started call e" on every
+ * peer and stores messages only after every peer has started call e too - so whatever consumes the result of call e - 2
+ * (same message area) must precede call e in this rank's stream. `epoch` increases by one per call and must be the same on
+ * all ranks; zero-initialise message areas and started words once. */
+int clover_m4_mvm_shard_stamped(const int8_t *values_local, const float *scales_local, uint64_t rows_local, uint64_t cols,
+                                uint64_t row0, const int8_t *xv, const float *xs, int8_t *yv_full, float *ys_full,
+                                uint64_t *const *peer_msg_host, uint32_t *const *peer_started_host,
+                                int world, int rank, uint32_t epoch, uint64_t *key_host, void *stream);
+int clover_m4_shard_stamped_unpack(const uint64_t *msg_local, uint64_t rows, uint64_t row0, uint64_t rows_local, uint32_t epoch,
+                                   int8_t *yv_full, float *ys_full, void *stream);
 /* Requantize a full-length fp32 vector exactly like the tail of mvm (include/CloverMatrix4.h:925-1080):
  * used after the collective so that every rank holds the same CloverVector4 result. */
 int clover_v4_requantize_mvm(const float *y32, uint64_t rows, int8_t *yv, float *ys, uint64_t *key_host, void *stream);

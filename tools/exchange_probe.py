@@ -26,7 +26,7 @@ def main():
     x.scales.uniform_(0.25, 1.0, generator=torch.Generator(device=dev).manual_seed(6))
     res = {}
     mats = {}
-    for mode in ("fused_sync", "fused_pipelined"):
+    for mode in ("fused_sync", "fused_pipelined", "stamped"):
         A = ShardedCloverMatrix4(rows, cols, exchange=mode)
         if mode == "fused_sync":
             A.local.values[: A.rows_local * cols // 2].copy_(random_nibbles(torch, A.rows_local * cols // 2, g, dev))
@@ -49,12 +49,17 @@ def main():
         torch.cuda.synchronize(); dist.barrier()
         res[name] = e0.elapsed_time(e1) / steps * 1e3
 
-    S, P = mats["fused_sync"], mats["fused_pipelined"]
+    S, P, T = mats["fused_sync"], mats["fused_pipelined"], mats["stamped"]
     y = cb.CloverVector4(rows)
     for rep in range(1):
         timed(f"sync_{rep}", lambda: S.mvm(x, wait=False))
         timed(f"pipelined_{rep}", lambda: P.mvm(x, wait=False), P.wait)
         timed(f"pipelined_wait_each_{rep}", lambda: P.mvm(x, wait=True))
+        timed(f"stamped_{rep}", lambda: T.mvm(x, wait=False), T.wait)
+        timed(f"stamped_unpack_each_{rep}", lambda: T.mvm(x, wait=True))
+        ys_, yt_ = S.mvm(x, wait=True), T.mvm(x, wait=True)
+        torch.cuda.synchronize()
+        res[f"stamped_equals_sync_{rep}"] = float(torch.equal(ys_.values, yt_.values) and torch.equal(ys_.scales.view(torch.int32)[: rows // 64], yt_.scales.view(torch.int32)[: rows // 64]))
     import ctypes as C
     import clover_b200
     def shard():
@@ -68,7 +73,7 @@ def main():
     if rank == 0:
         for k in res:
             print(k, "us per step by rank:", [round(r[k], 1) for r in allres], flush=True)
-    S.close(); P._peer and P.close()
+    S.close(); P.close(); T.close()
     dist.destroy_process_group()
 
 

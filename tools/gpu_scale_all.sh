@@ -4,11 +4,11 @@
 set -u
 TAG=$1
 mkdir -p gpurun_out
-python -m pytest tests/test_multi_gpu.py tests/test_cpp_containers.py -x -q 2>&1 | tail -3
+timeout 400 python -m pytest tests/test_multi_gpu.py tests/test_cpp_containers.py -x -q 2>&1 | tail -3
 for N in 2 4 8; do
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py 2>&1 \
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py 2>&1 \
       | grep "multi-gpu" | tee gpurun_out/multi_gpu_check_${TAG}_n${N}.log | tail -2
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 400 --warmup 10 2>&1 \
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 400 --warmup 10 2>&1 \
       | grep "^{" > gpurun_out/bench_${TAG}_n${N}_fused.json
 done
 python bench.py --steps 400 --warmup 10 --no-extras --no-cpu-baseline 2>/dev/null | grep "^{" > gpurun_out/bench_${TAG}_n1_quick.json
