@@ -471,7 +471,7 @@ def main():
     ap.add_argument("--impl", default="clover_b200", choices=["clover_b200", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS)
     ap.add_argument("--cols", type=int, default=COLS)
-    ap.add_argument("--exchange", default="fused", choices=["fused", "fused_sync", "fused_pipelined", "allgather", "allreduce"])
+    ap.add_argument("--exchange", default="fused", choices=["fused", "fused_sync", "stamped", "allgather", "allreduce"])
     ap.add_argument("--cpu-sample-rows", type=int, default=0, help="rows of the matrix the CPU reference times (0 = all)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -520,11 +520,13 @@ def main():
     def step():
         if world == 1:
             A.local.mvm(x, y)          # the reference-facing call: CloverMatrix4::mvm(V4, V4), one fused kernel
-        elif args.exchange.startswith("fused"):
-            out["y"] = A.mvm(x, wait=False)   # one kernel: shard GEMV + NVLink-store epilogue + flags; result = view of the shared
-                                              # vector. From 8 ranks on pipelined: the NEXT step's kernel waits for this step's flags
+        elif fused:
+            out["y"] = A.mvm(x, wait=False)   # ONE kernel: shard GEMV + stamped NVLink-store epilogue (every result word reaches every
+                                              # rank's message area); the unpack into the reference layout is the consumer's (finish())
         else:
             A.mvm(x, y)                # shard kernel + NCCL exchange + re-quantize
+
+    fused = args.exchange in ("fused", "fused_sync", "stamped")
 
     def barrier():
         torch.cuda.synchronize()
@@ -533,7 +535,7 @@ def main():
             torch.cuda.synchronize()
 
     def finish():                      # fused exchange: the last step's result is complete on this rank (stream order)
-        if world > 1 and args.exchange.startswith("fused"):
+        if world > 1 and fused:
             A.wait()
 
     total_bytes = gemv_bytes(rows, cols)
@@ -598,8 +600,8 @@ def main():
                  C.c_uint64(rows), C.c_uint64(cols), hx, C.c_void_p(hx.value + xvb), hy, C.c_void_p(hy.value + yvb), None)
             return
         call("clover_copy_h2d", C.c_void_p(x.storage.data_ptr()), hx, C.c_size_t(xb), stream)
-        if world > 1 and args.exchange.startswith("fused"):
-            out["y"] = A.mvm(x, wait=True)                # every step's result is read back: the kernel waits for the peers' slices
+        if world > 1 and fused:
+            out["y"] = A.mvm(x, wait=True)                # every step's result is read back: complete (unpacked) when the call ends
         else:
             step()
         r = out["y"]
@@ -630,7 +632,22 @@ def main():
     # ---- north_star's wording, measured beside the fused exchange in the same run: the shard kernel,
     # ONE ncclAllReduce of the fp32 output, the re-quantize pass - same shards, same x, same timing protocol
     nccl = None
-    if world > 1 and args.exchange.startswith("fused"):
+    unpack_each = None
+    if world > 1 and fused:
+        # the same loop with the result of EVERY step complete in the reference layout on every rank (mvm(x, wait=True))
+        for _ in range(args.warmup):
+            A.mvm(x, wait=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            out["y"] = A.mvm(x, wait=True)
+        e1.record()
+        barrier()
+        ms4 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms4, op=dist.ReduceOp.MAX)
+        unpack_each = {"what": "every step's result complete in the reference layout on every rank (mvm(x, wait=True))",
+                       "value": total_bytes * args.steps / (float(ms4.item()) * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": float(ms4.item()) / args.steps}
+    if world > 1 and fused:
         B = ShardedCloverMatrix4.__new__(ShardedCloverMatrix4)
         B.__dict__.update(A.__dict__)
         B.exchange, B._peer = "allreduce", None
@@ -662,13 +679,13 @@ def main():
                                  "matrix: uniform nibbles in [-7, 7] and scales in [0.25, 1) generated on the device",
                        "l2_policy": "inputs larger than L2 (2 GiB matrix streamed per step vs 126 MB L2)",
                        "parallelism": "1 GPU" if world == 1 else
-                                      (f"rows sharded over {world} GPUs in 64-row blocks; fused exchange: the GEMV epilogue stores each "
-                                       f"re-quantized block into every peer's result vector over NVLink and raises a flag word per peer (no NCCL call); "
-                                       + ("pipelined: the wait for the peers' flags of step e sits in the prologue of step e+1's kernel (before it reads x "
-                                          "or stores to a peer), the last step's wait (clover_m4_shard_fused_wait) inside the timed region"
-                                          if (args.exchange == "fused_pipelined" or (args.exchange == "fused" and world >= 8)) else
-                                          "every kernel waits for the peers' flags at its end")
-                                       if args.exchange.startswith("fused") else
+                                      (f"rows sharded over {world} GPUs in 64-row blocks; fused exchange: the GEMV epilogue stores every word of each "
+                                       f"re-quantized block into every peer's message area over NVLink as one 8-byte {{word, epoch}} store (no NCCL call, no "
+                                       f"fence, no flags); the unpack into the reference layout (clover_m4_shard_stamped_unpack) belongs to the consumer: "
+                                       f"once, for the last step, inside the timed region (exchange.unpack_every_step: the same loop with it in every step)"
+                                       if args.exchange in ("fused", "stamped") else
+                                       f"rows sharded over {world} GPUs in 64-row blocks; fused exchange, flag form: plain peer stores, a system-scope fence "
+                                       f"per CTA, one flag per peer, every kernel waits for the peers' flags at its end" if args.exchange == "fused_sync" else
                                        f"rows sharded over {world} GPUs in 64-row blocks + one NCCL {args.exchange} of the fp32 output"),
                        "e2e": ("clover_host_m4_mvm: x copied from pinned host memory, kernel, y copied back, host sync - every step; "
                                "matrix resident in HBM") if world == 1 else
@@ -680,6 +697,7 @@ def main():
             "clocks": clk.summary(),
             "exchange": {"mode": args.exchange if world > 1 else "none (1 GPU)",
                          "step_minus_kernel_us": (secs / args.steps - tk) * 1e6,      # what the exchange + launch gaps cost per step
+                         "unpack_every_step": unpack_each,
                          "nccl_allreduce": nccl},
             "roofline": {"bound": "hbm", "kernel": "k_m4_mvm_tma2 (32-row items, 2 CTAs/SM)" if cols >= 16384 else "k_m4_mvm_tma", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,

@@ -63,8 +63,6 @@ _SIGNATURES = {
     "clover_m8_mvm_f32": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     "clover_m4_mvm_shard": (_int, [_vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "clover_m4_mvm_shard_fused": (_int, [_vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, C.c_uint32, _vp, _vp]),
-    "clover_m4_mvm_shard_fused_async": (_int, [_vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, C.c_uint32, _vp, _vp]),
-    "clover_m4_shard_fused_wait": (_int, [_vp, _int, _int, C.c_uint32, _vp]),
     "clover_m4_mvm_shard_stamped": (_int, [_vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, C.c_uint32, _vp, _vp]),
     "clover_m4_shard_stamped_unpack": (_int, [_vp, _u64, _u64, _u64, C.c_uint32, _vp, _vp, _vp]),
     "clover_v4_requantize_mvm": (_int, [_vp, _u64, _vp, _vp, _vp, _vp]),

@@ -120,12 +120,11 @@ struct PeerOut {
     int8_t *yv[kMaxPeers] = {};              // peer p's result values / scales (entry `rank` unused: yv/ys are local)
     float *ys[kMaxPeers] = {};
     uint32_t *flags[kMaxPeers] = {};         // peer p's flag array, one word per source rank
-    int defer = 0;                           // 1: pipelined form - wait for the PREVIOUS epoch before x is read, none at the end
-                                             // 2: stamped form - no flags, no fence: every word travels with its epoch (see below)
+    int defer = 0;                           // 2 (kXchgStamped): stamped form - no flags, no fence: every word travels with its epoch
     uint64_t *msg[kMaxPeers] = {};           // stamped: peer p's message area of this epoch's parity, 9 x 8 bytes per 64-row block
     uint32_t *started[kMaxPeers] = {};       // stamped: peer p's "rank r has started call e" words (flow control)
 };
-constexpr int kXchgFlags = 0, kXchgPiped = 1, kXchgStamped = 2;   // template values = PeerOut::defer
+constexpr int kXchgFlags = 0, kXchgStamped = 2;                   // PeerOut::defer
 
 template <int BITS, bool STOCH>
 __device__ __forceinline__ void requantize_block(float y, int i, uint64_t rb, int8_t *__restrict__ yv,
@@ -185,21 +184,23 @@ __device__ __forceinline__ void requantize_block(float y, int i, uint64_t rb, in
 // before their flags are visible to whatever this warp - and, through barriers, its CTA - does next. The flags live in LOCAL
 // memory and are written by the peers over NVLink. Called by ALL 32 lanes of a converged warp: lane q polls peer q's flag, so
 // one load instruction covers all peers (one L2 round trip per poll instead of world - 1) and the loop condition is
-// warp-uniform. Two things this form avoids on purpose (tools/exchange_probe.py, profiles/r02u_exchange_notes.md):
-//   * `if (lane == 0) wait(); __syncwarp();` in a kernel prologue: the warp left the wait diverged and stayed slow for the
-//     rest of the kernel - 273 instead of 201 us per step at 32768 x 65536 on 2 GPUs;
+// warp-uniform. Two things this form avoids on purpose (measured with in-kernel prologue waits in round 2,
+// profiles/r02u_exchange_notes.md):
+//   * `if (lane == 0) wait(); __syncwarp();` in a warp that works afterwards: the warp left the wait diverged and stayed
+//     slow for the rest of the kernel - 273 instead of 201 us per step at 32768 x 65536 on 2 GPUs;
 //   * nanosleep back-off: a unit warp that slept ONCE at kernel start slowed the whole kernel by 35 % (182 -> 249 us for a
 //     5 us sleep; the same 5 us as a busy-wait on clock64: 184 us).
-__device__ __forceinline__ void peer_wait_words(const uint32_t *words, int world, int rank, uint32_t epoch) {
-    const int q = threadIdx.x & 31;
-    const bool mine = q < world && q != rank;
+__device__ __forceinline__ void peer_wait_words(const uint32_t *words, int world, int rank, uint32_t epoch,
+                                                unsigned mask = 0xFFFFFFFFu, int lane0 = 0) {     // lanes lane0 .. 31 of the warp take part
+    const int q = (int)(threadIdx.x & 31) - lane0;
+    const bool mine = q >= 0 && q < world && q != rank;
     const uint32_t *flag = words + (mine ? q : 0);
     bool ok;
     do {
         uint32_t seen = epoch;
         if (mine) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
         ok = (int32_t)(seen - epoch) >= 0;
-    } while (!__all_sync(0xFFFFFFFFu, ok));
+    } while (!__all_sync(mask, ok));
     asm volatile("fence.acq_rel.sys;" ::: "memory");
 }
 __device__ __forceinline__ void peer_wait_flags(const PeerOut &peers, uint32_t epoch) {
@@ -214,16 +215,19 @@ __device__ __forceinline__ void peer_wait_flags(const PeerOut &peers, uint32_t e
 // epoch has the word. The producer kernel just ends. The consumer side (k_unpack_stamped, in front of whatever reads the
 // result) polls the stamps of the blocks the other ranks own and writes the words into the reference layout.
 // Flow control instead of flags: a message area is re-used every second call, so a kernel may only store epoch e once every
-// peer has STARTED its call e (whatever consumed epoch e-2 there precedes that call in stream order). One warp of CTA 0
-// announces the start on all peers when the kernel begins; consumer warp 0 of every CTA checks the local words before the
-// item loop - in the shadow of the first TMA round trip, ~40 us before its first message store.
-__device__ __forceinline__ void stamped_announce_start(const PeerOut &peers, int lane_p) {     // lanes of one warp, lane_p = 0..
-    asm volatile("fence.acq_rel.sys;" ::: "memory");
-    if (lane_p >= 0 && lane_p < peers.world && lane_p != peers.rank)
-        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(peers.started[lane_p] + peers.rank), "r"(peers.epoch) : "memory");
-}
-__device__ __forceinline__ void stamped_wait_peers_started(const PeerOut &peers) {              // all 32 lanes of a converged warp
-    peer_wait_words(peers.started[peers.rank], peers.world, peers.rank, peers.epoch);
+// peer has STARTED its call e (whatever consumed epoch e-2 there precedes that call in stream order). The idle lanes
+// 1..31 of the TMA issuer warp do both, off every critical path: in CTA 0 they announce the start on all peers, in every CTA
+// they poll the local words and then raise a shared-memory flag the epilogue threads check before their first message store
+// (~40 us later; a wait in a consumer or unit warp at kernel start costs 2 us per kernel - tools/exchange_probe.py).
+__device__ __forceinline__ void stamped_flow_control(const PeerOut &peers, volatile int *started_flag) {   // lanes 1..31 of one warp
+    const int p = (int)(threadIdx.x & 31) - 1;
+    if (blockIdx.x == 0) {
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        if (p < peers.world && p != peers.rank)
+            asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(peers.started[p] + peers.rank), "r"(peers.epoch) : "memory");
+    }
+    peer_wait_words(peers.started[peers.rank], peers.world, peers.rank, peers.epoch, 0xFFFFFFFEu, 1);
+    if (p == 0) { *started_flag = 1; __threadfence_block(); }
 }
 
 // msg: this rank's message area of the epoch's parity; every (block, word) another rank owns is polled until its stamp is
@@ -243,16 +247,12 @@ k_unpack_stamped(const uint64_t *__restrict__ msg, uint64_t nblocks, uint64_t ow
     }
 }
 
-// Tail of the fused exchange, one WARP per CTA (all 32 lanes), after the CTA's peer stores have been fenced at system scope:
-// take a ticket; the LAST CTA of this rank raises flags[peer][rank] = epoch on every peer (lane p stores to peer p) and
-// (synchronous form) waits until every peer has raised its flag here - when the kernel ends, the slices of all ranks have
-// landed in the local result vector. ONE system-scope fence covers all flag stores (round 1 used st.release.sys per peer: a
-// full fence per store, i.e. 7 serialised NVLink round trips at 8 GPUs - the 8 / 19 / 27 us per step of VERDICT r01 weak #4);
+// Tail of the flag-synchronised fused exchange, one WARP per CTA (all 32 lanes), after the CTA's peer stores have been fenced
+// at system scope: take a ticket; the LAST CTA of this rank raises flags[peer][rank] = epoch on every peer (lane p stores to
+// peer p) and waits until every peer has raised its flag here - when the kernel ends, the slices of all ranks have landed
+// in the local result vector. ONE system-scope fence covers all flag stores (round 1 used st.release.sys per peer: a full
+// fence per store, i.e. 7 serialised NVLink round trips at 8 GPUs - the 8 / 19 / 27 us per step of VERDICT r01 weak #4);
 // the flags are polled with relaxed loads and acquired once at the end.
-// Pipelined form (peers.defer): the kernel ends right after its flag stores. The wait moves to where the result is consumed:
-// the prologue of the NEXT step's kernel (peer_wait_flags(epoch - 1) before x is read and before any peer store - which is
-// also what makes re-using the result buffer of two steps ago safe) or k_peer_wait for any other consumer. The flag flight,
-// the spin and the spread of the ranks' finishing times then overlap the next kernel's launch and ring fill.
 __device__ __forceinline__ void peer_signal_and_wait(const PeerOut &peers) {
     const int p = threadIdx.x & 31;
     unsigned int t = 0;
@@ -264,17 +264,8 @@ __device__ __forceinline__ void peer_signal_and_wait(const PeerOut &peers) {
     asm volatile("fence.acq_rel.sys;" ::: "memory");             // acquires the other CTAs' tickets, releases everything to the peers
     if (p < peers.world && p != peers.rank)
         asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(peers.flags[p] + peers.rank), "r"(peers.epoch) : "memory");
-    if (!peers.defer) peer_wait_flags(peers, peers.epoch);
+    peer_wait_flags(peers, peers.epoch);
 }
-
-__global__ void __launch_bounds__(32) k_peer_wait(const __grid_constant__ PeerOut peers) { peer_wait_flags(peers, peers.epoch); }
-
-// x of a pipelined step may be the previous step's result, i.e. written by the peers while this kernel is already
-// running (before their flags): read it through L2 (ld.global.cg), never through the non-coherent path
-// (a compile-time choice: as a run-time `coherent ? __ldcg(p) : __ldg(p)` every load of the unit warp became its own branch
-// region and the C3 kernel lost 12 % - tools/ab, r02u)
-template <bool COHERENT> __device__ __forceinline__ uint32_t ld_x(const uint32_t *p) { return COHERENT ? __ldcg(p) : __ldg(p); }
-template <bool COHERENT> __device__ __forceinline__ float ld_x(const float *p) { return COHERENT ? __ldcg(p) : __ldg(p); }
 
 // =============================================================================================
 // mvm(V4,V4): exact-order 4-bit GEMV
@@ -427,6 +418,7 @@ struct GemvSmem {
     float ysm[64];
     float red_f[2];
     int red_q[64];
+    int peers_started;                                // stamped exchange: every peer has started this call
 };
 
 __device__ __forceinline__ void gemv4_step(const uint8_t *r0, const uint8_t *r1, const XUnit *units, int blk, int l,
@@ -460,6 +452,7 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
             mbar_init(&sm.full[s], 1 + 32);              // TMA issuer (posts the tx bytes) + the 32 unit lanes
             mbar_init(&sm.empty[s], kGemvConsumers / 32);
         }
+        sm.peers_started = 0;
         mbar_fence_init();
     }
     __syncthreads();
@@ -480,8 +473,8 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
                                 &sm.full[s], policy);
                 }
             }
-        } else if (XCHG == kXchgStamped && blockIdx.x == 0 && peers.world > 1) {
-            stamped_announce_start(peers, lane - 1);          // idle lanes of CTA 0's issuer warp: this rank has started call `epoch`
+        } else if (XCHG == kXchgStamped && peers.world > 1) {
+            stamped_flow_control(peers, &sm.peers_started);   // the issuer warp's idle lanes
         }
     } else if (warp == kGemvConsumers / 32 + 1) {
         // ------------------------------- x-unit warp -------------------------------
@@ -489,19 +482,14 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
         uint32_t it = 0;
         uint32_t w[4] = {0, 0, 0, 0};
         float sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
-        constexpr bool PIPED = XCHG == kXchgPiped;
-        if (PIPED) {                                  // pipelined exchange: the previous epoch is complete here before x is read
-            peer_wait_flags(peers, peers.epoch - 1u);          // all 32 lanes, converged
-            __syncwarp();
-        }
         auto prefetch = [&](uint64_t rb, uint32_t c) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint64_t b = (uint64_t)c * kKC + 4 * j + (lane >> 3);
                 const bool ok = b < hb;
-                w[j] = ok ? ld_x<PIPED>(xv + b * 8 + (lane & 7)) : 0u;
+                w[j] = ok ? __ldg(xv + b * 8 + (lane & 7)) : 0u;
                 sa[j] = ok ? __ldg(scales + rb * hb + b) : 0.f;
-                sb[j] = ok ? ld_x<PIPED>(xs + b) : 0.f;
+                sb[j] = ok ? __ldg(xs + b) : 0.f;
             }
         };
         if (blockIdx.x < nrb) prefetch(blockIdx.x, 0);
@@ -534,7 +522,6 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
         const int h = lane >> 4, a = (lane >> 3) & 1, l = lane & 7;
         const int row_a = 32 * h + warp, row_b = row_a + 16;
         uint32_t it = 0;
-        if (XCHG == kXchgStamped && warp == 0 && peers.world > 1) stamped_wait_peers_started(peers);   // before any message store (barriers order it)
         for (uint64_t rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
             float acc0 = 0.f, acc1 = 0.f;
             for (uint32_t c = 0; c < chunks; ++c, ++it) {
@@ -564,6 +551,7 @@ k_m4_mvm_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
             if (tid < 64) {
                 const float y = sm.ysm[tid];
                 if (y32) y32[(rowblock0 + rb) * 64 + tid] = y;
+                if (XCHG == kXchgStamped && peers.world > 1) { while (*(volatile int *)&sm.peers_started == 0) { } }
                 if (yv) requantize_block<4, STOCH>(y, tid, rowblock0 + rb, yv, ys, key, tables, sm.red_f, sm.red_q,
                                                    peers.world > 1 ? &peers : nullptr);
             }
@@ -1134,6 +1122,7 @@ struct Gemv4Smem {
     float red_f[2];
     int red_q[64];
     unsigned int ticket;
+    int peers_started;                       // stamped exchange: every peer has started this call
 };
 
 template <bool STOCH, int STAGES, int XCHG>
@@ -1156,6 +1145,7 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
             mbar_init(&sm.full[s], 1 + 32);
             mbar_init(&sm.empty[s], kG4Consumers / 32);
         }
+        sm.peers_started = 0;
         mbar_fence_init();
     }
     __syncthreads();
@@ -1177,23 +1167,18 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
                                     &sm.full[s], policy);
                 }
             }
-        } else if (XCHG == kXchgStamped && blockIdx.x == 0 && peers.world > 1) {
-            stamped_announce_start(peers, lane - 1);          // idle lanes of CTA 0's issuer warp: this rank has started call `epoch`
+        } else if (XCHG == kXchgStamped && peers.world > 1) {
+            stamped_flow_control(peers, &sm.peers_started);   // the issuer warp's idle lanes
         }
     } else if (warp == kG4Consumers / 32 + 1) {
         // ------------------------------- x-unit warp -------------------------------
         // lane owns units lane + 32j (j = 0..7) of a stage = (block 4j + lane/8, AVX lane lane%8)
         uint32_t it = 0;
         const int l = lane & 7;
-        constexpr bool PIPED = XCHG == kXchgPiped;
-        if (PIPED) {                                  // pipelined exchange: the previous epoch is complete here before x is read
-            peer_wait_flags(peers, peers.epoch - 1u);          // all 32 lanes, converged
-            __syncwarp();
-        }
         // The raw operands of a stage (x word, matrix-tile scale, x scale per unit) are requested ONE STAGE AHEAD, before this
         // warp blocks on the slot: their L2 latency (~1 us while the matrix streams at the HBM rate) never adds to the
-        // consumers' stage time. Without it a unit warp that once falls behind the TMA ring (a late start is enough: the
-        // pipelined exchange waits here) stays behind for the whole kernel, because every stage then costs (load latency +
+        // consumers' stage time. Without it a unit warp that once falls behind the TMA ring (a late start is enough)
+        // stays behind for the whole kernel, because every stage then costs (load latency +
         // consume) instead of max(load latency, consume).
         uint32_t w[8];
         float sa[8], sb[8];
@@ -1203,9 +1188,9 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
             for (int j = 0; j < 8; ++j) {
                 const uint64_t b = (uint64_t)c * (4 * kG4Chunks) + 4 * j + (lane >> 3);
                 const bool ok = b < hb;
-                w[j] = ok ? ld_x<PIPED>(xv + b * 8 + l) : 0u;
+                w[j] = ok ? __ldg(xv + b * 8 + l) : 0u;
                 sa[j] = ok ? __ldg(su + b) : 0.f;
-                sb[j] = ok ? ld_x<PIPED>(xs + b) : 0.f;
+                sb[j] = ok ? __ldg(xs + b) : 0.f;
             }
         };
         if (blockIdx.x < nitems) prefetch(blockIdx.x, 0);
@@ -1241,7 +1226,6 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
         // this chain's two blocks of a 128-byte chunk: b = a and b = a + 2 -> 16-byte chunks 2b + ty, swizzled by (row & 7)
         const uint32_t o0 = base + ((uint32_t)((2 * a + ty) ^ rin) << 4), o1 = base + ((uint32_t)((2 * a + 4 + ty) ^ rin) << 4);
         uint32_t it = 0;
-        if (XCHG == kXchgStamped && warp == 0 && peers.world > 1) stamped_wait_peers_started(peers);   // before any message store (barriers order it)
         for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
             float acc = 0.f, acc2 = 0.f;
             for (uint32_t c = 0; c < steps; ++c, ++it) {
@@ -1298,6 +1282,7 @@ k_m4_mvm_tma2(const __grid_constant__ CUtensorMap tmap, const float *__restrict_
                 if (tid < 64) {
                     __threadfence();
                     const float y = __ldcg(ybuf + grb * 64 + tid);
+                    if (XCHG == kXchgStamped && peers.world > 1) { while (*(volatile int *)&sm.peers_started == 0) { } }
                     requantize_block<4, STOCH>(y, tid, grb, yv, ys, key, tables, sm.red_f, sm.red_q,
                                                peers.world > 1 ? &peers : nullptr);
                     if (tid == 0) counters[rb] = 0u;
@@ -1479,16 +1464,16 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
             static bool attr_set2[kMaxDevices][2][2][3] = {};   // per device: function attributes belong to a device's context
             const int dev = current_device();
             if (dev < 0) { set_error("device index out of range"); return CLOVER_ERR_INVALID; }
-            // the pipelined and the stamped exchange are their own instantiations (the local / synchronous kernel stays as it was)
+            // the stamped exchange is its own instantiation (the local / flag-synchronised kernel stays as it was)
             const int xchg = peers && peers->world > 1 ? peers->defer : kXchgFlags;
             using KernT = void (*)(const CUtensorMap, const float *, uint64_t, uint64_t, uint64_t, const uint32_t *, const float *, float *,
                                    unsigned int *, int8_t *, float *, Key4, const uint64_t *, const PeerOut);
-            static const KernT kerns[2][2][3] = {     // [x2][stoch][xchg]
-                {{k_m4_mvm_tma2<false, 5, 0>, k_m4_mvm_tma2<false, 5, 1>, k_m4_mvm_tma2<false, 5, 2>},
-                 {k_m4_mvm_tma2<true, 5, 0>, k_m4_mvm_tma2<true, 5, 1>, k_m4_mvm_tma2<true, 5, 2>}},
-                {{k_m4_mvm_tma2<false, 3, 0>, k_m4_mvm_tma2<false, 3, 1>, k_m4_mvm_tma2<false, 3, 2>},
-                 {k_m4_mvm_tma2<true, 3, 0>, k_m4_mvm_tma2<true, 3, 1>, k_m4_mvm_tma2<true, 3, 2>}}};
-            const KernT kern = kerns[x2][stoch][xchg];
+            static const KernT kerns[2][2][2] = {     // [x2][stoch][stamped]
+                {{k_m4_mvm_tma2<false, 5, kXchgFlags>, k_m4_mvm_tma2<false, 5, kXchgStamped>},
+                 {k_m4_mvm_tma2<true, 5, kXchgFlags>, k_m4_mvm_tma2<true, 5, kXchgStamped>}},
+                {{k_m4_mvm_tma2<false, 3, kXchgFlags>, k_m4_mvm_tma2<false, 3, kXchgStamped>},
+                 {k_m4_mvm_tma2<true, 3, kXchgFlags>, k_m4_mvm_tma2<true, 3, kXchgStamped>}}};
+            const KernT kern = kerns[x2][stoch][xchg == kXchgStamped];
             if (!attr_set2[dev][x2][stoch][xchg]) {
                 CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
                 attr_set2[dev][x2][stoch][xchg] = true;
@@ -1514,9 +1499,9 @@ static int launch_mvm(const int8_t *values, const float *scales, uint64_t rows_l
             const int xchg = peers && peers->world > 1 ? peers->defer : kXchgFlags;
             using KernT = void (*)(const CUtensorMap, const float *, uint64_t, uint64_t, uint64_t, const uint32_t *, const float *, float *,
                                    int8_t *, float *, Key4, const uint64_t *, const PeerOut);
-            static const KernT kerns[2][3] = {{k_m4_mvm_tma<false, 0>, k_m4_mvm_tma<false, 1>, k_m4_mvm_tma<false, 2>},
-                                              {k_m4_mvm_tma<true, 0>, k_m4_mvm_tma<true, 1>, k_m4_mvm_tma<true, 2>}};
-            const KernT kern = kerns[stoch][xchg];
+            static const KernT kerns[2][2] = {{k_m4_mvm_tma<false, kXchgFlags>, k_m4_mvm_tma<false, kXchgStamped>},
+                                              {k_m4_mvm_tma<true, kXchgFlags>, k_m4_mvm_tma<true, kXchgStamped>}};
+            const KernT kern = kerns[stoch][xchg == kXchgStamped];
             if (!attr_set[dev][stoch][xchg]) {
                 CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
                 attr_set[dev][stoch][xchg] = true;
@@ -1656,15 +1641,7 @@ int clover_m4_mvm_shard_fused(const int8_t *values_local, const float *scales_lo
                               float *const *peer_ys_host, uint32_t *const *peer_flags_host, unsigned int *ticket,
                               int world, int rank, uint32_t epoch, uint64_t *key_host, void *stream) {
     return launch_shard_fused(values_local, scales_local, rows_local, cols, row0, xv, xs, peer_yv_host, peer_ys_host,
-                              peer_flags_host, ticket, world, rank, epoch, key_host, stream, 0);
-}
-
-int clover_m4_mvm_shard_fused_async(const int8_t *values_local, const float *scales_local, uint64_t rows_local, uint64_t cols,
-                                    uint64_t row0, const int8_t *xv, const float *xs, int8_t *const *peer_yv_host,
-                                    float *const *peer_ys_host, uint32_t *const *peer_flags_host, unsigned int *ticket,
-                                    int world, int rank, uint32_t epoch, uint64_t *key_host, void *stream) {
-    return launch_shard_fused(values_local, scales_local, rows_local, cols, row0, xv, xs, peer_yv_host, peer_ys_host,
-                              peer_flags_host, ticket, world, rank, epoch, key_host, stream, 1);
+                              peer_flags_host, ticket, world, rank, epoch, key_host, stream, kXchgFlags);
 }
 
 int clover_m4_mvm_shard_stamped(const int8_t *values_local, const float *scales_local, uint64_t rows_local, uint64_t cols,
@@ -1701,18 +1678,6 @@ int clover_m4_shard_stamped_unpack(const uint64_t *msg_local, uint64_t rows, uin
         msg_local, nblocks, row0 >> 6, rows_local >> 6, epoch, reinterpret_cast<uint32_t *>(yv_full), ys_full);
     count_launch();
     return launch_status("k_unpack_stamped");
-}
-
-int clover_m4_shard_fused_wait(uint32_t *flags_local, int world, int rank, uint32_t epoch, void *stream) {
-    CLOVER_REQUIRE(flags_local, CLOVER_ERR_INVALID, "null pointer");
-    CLOVER_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, CLOVER_ERR_INVALID, "bad world / rank (at most 8 peers)");
-    if (world == 1) return CLOVER_OK;
-    PeerOut peers;
-    peers.world = world; peers.rank = rank; peers.epoch = epoch;
-    peers.flags[rank] = flags_local;
-    k_peer_wait<<<1, 32, 0, (cudaStream_t)stream>>>(peers);
-    count_launch();
-    return launch_status("k_peer_wait");
 }
 
 int clover_v4_requantize_mvm(const float *y32, uint64_t rows, int8_t *yv, float *ys, uint64_t *key_host, void *stream) {

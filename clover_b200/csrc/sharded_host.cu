@@ -2,9 +2,10 @@
 // reference's own model: a C++ program calling container methods) drives all GPUs of the node.
 //
 // SURVEY.md 8e / 8b (`clover_mvm4_sharded(handles, ...)`): rows are sharded in whole 64-row blocks, x is replicated,
-// every GPU runs the GEMV kernel on its rows and its epilogue stores each re-quantized block (32 B of nibbles + one fp32
-// scale) into the result vector of EVERY GPU through peer pointers (cudaDeviceEnablePeerAccess: NVLink / NVSwitch), then
-// the GPUs signal each other with flag words - clover_m4_mvm_shard_fused_async, one kernel per GPU and call, no NCCL. The
+// every GPU runs the GEMV kernel on its rows and its epilogue stores each re-quantized block (8 words of nibbles + one fp32
+// scale) into the message area of EVERY GPU through peer pointers (cudaDeviceEnablePeerAccess: NVLink / NVSwitch) as
+// self-validating 8-byte {word, epoch} stores - clover_m4_mvm_shard_stamped, one kernel per GPU and call, no NCCL, no flags;
+// GPU 0 unpacks the messages into the reference layout in front of the read-back (clover_m4_shard_stamped_unpack). The
 // Python host (clover_b200/sharded.py) does the same with one process per GPU and CUDA IPC; the kernels are shared.
 #include <vector>
 #include "runtime.cuh"
@@ -20,10 +21,10 @@ struct clover_m4_sharded {
         int8_t *values = nullptr;        // rows_local * cols / 2
         float *scales = nullptr;         // (rows_local / 64) * (cols / 64)
         unsigned char *x = nullptr;      // [values cols/2 | scales cols/64 fp32]
-        unsigned char *block = nullptr;  // [yv x2 | ys x2 | flags | ticket], see offsets below
+        unsigned char *block = nullptr;  // [yv x2 | ys x2 | messages x2 | started words], see offsets below
     };
     std::vector<Rank> ranks;
-    size_t off_yv[2] = {0, 0}, off_ys[2] = {0, 0}, off_flags = 0, off_ticket = 0, block_bytes = 0;
+    size_t off_yv[2] = {0, 0}, off_ys[2] = {0, 0}, off_msg[2] = {0, 0}, off_started = 0, block_bytes = 0;
 };
 
 namespace {
@@ -61,7 +62,9 @@ int clover_m4_sharded_create(clover_m4_sharded **out, uint64_t rows, uint64_t co
     h->rows = rows; h->cols = cols; h->world = ngpus;
     const size_t vb = al256(rows / 2), sb = al256(rows / 64 * sizeof(float));
     h->off_yv[0] = 0; h->off_yv[1] = vb; h->off_ys[0] = 2 * vb; h->off_ys[1] = 2 * vb + sb;
-    h->off_flags = 2 * vb + 2 * sb; h->off_ticket = h->off_flags + al256(4 * (size_t)ngpus); h->block_bytes = h->off_ticket + 256;
+    const size_t mb = al256(rows / 64 * 72);             // 9 x 8 bytes per 64-row block of the whole vector
+    h->off_msg[0] = 2 * vb + 2 * sb; h->off_msg[1] = h->off_msg[0] + mb;
+    h->off_started = h->off_msg[1] + mb; h->block_bytes = h->off_started + al256(4 * (size_t)ngpus);
     h->ranks.resize(ngpus);
     int rc = CLOVER_OK;
     for (int r = 0; r < ngpus && rc == CLOVER_OK; ++r) {
@@ -144,12 +147,11 @@ int clover_m4_sharded_mvm_host(clover_m4_sharded *h, const int8_t *xv_host, cons
     const uint32_t epoch = ++h->epoch;
     const int b = (int)(epoch & 1);                    // the two result buffers alternate: a fast GPU may already run the next call
     const size_t xvb = h->cols / 2, xsb = h->cols / 64 * sizeof(float);
-    int8_t *peer_yv[8]; float *peer_ys[8]; uint32_t *peer_flags[8];
+    uint64_t *peer_msg[8]; uint32_t *peer_started[8];
     for (int r = 0; r < h->world; ++r) {
         unsigned char *blk = h->ranks[r].block;
-        peer_yv[r] = reinterpret_cast<int8_t *>(blk + h->off_yv[b]);
-        peer_ys[r] = reinterpret_cast<float *>(blk + h->off_ys[b]);
-        peer_flags[r] = reinterpret_cast<uint32_t *>(blk + h->off_flags);
+        peer_msg[r] = reinterpret_cast<uint64_t *>(blk + h->off_msg[b]);
+        peer_started[r] = reinterpret_cast<uint32_t *>(blk + h->off_started);
     }
     for (int r = 0; r < h->world; ++r) {
         clover_m4_sharded::Rank &k = h->ranks[r];
@@ -157,18 +159,20 @@ int clover_m4_sharded_mvm_host(clover_m4_sharded *h, const int8_t *xv_host, cons
         CLOVER_CUDA_CHECK(cudaMemcpyAsync(k.x, xv_host, xvb, cudaMemcpyHostToDevice, k.stream));
         CLOVER_CUDA_CHECK(cudaMemcpyAsync(k.x + xvb, xs_host, xsb, cudaMemcpyHostToDevice, k.stream));
         // the key is read at each block's GLOBAL position by every GPU and advanced once below, like the reference's stream
-        int rc = clover_m4_mvm_shard_fused_async(k.values, k.scales, k.rows_local, h->cols, k.row0, reinterpret_cast<const int8_t *>(k.x),
-                                           reinterpret_cast<const float *>(k.x + xvb), peer_yv, peer_ys, peer_flags,
-                                           reinterpret_cast<unsigned int *>(k.block + h->off_ticket), h->world, r, epoch, key_host, k.stream);
+        int rc = clover_m4_mvm_shard_stamped(k.values, k.scales, k.rows_local, h->cols, k.row0, reinterpret_cast<const int8_t *>(k.x),
+                                             reinterpret_cast<const float *>(k.x + xvb), reinterpret_cast<int8_t *>(k.block + h->off_yv[b]),
+                                             reinterpret_cast<float *>(k.block + h->off_ys[b]), peer_msg, peer_started, h->world, r, epoch,
+                                             key_host, k.stream);
         if (rc != CLOVER_OK) return rc;
     }
     if (key_host) host_key_skip(key_host, 2 * (h->rows / 64));
-    // pipelined exchange: no kernel waits for its peers at its end; GPU 0 waits for their flags in front of the read-back,
-    // the other GPUs in the prologue of their next call's kernel
+    // stamped exchange: no kernel waits for anything at its end; GPU 0 unpacks the other GPUs' messages in front of the read-back
     clover_m4_sharded::Rank &k0 = h->ranks[0];
     CLOVER_CUDA_CHECK(cudaSetDevice(k0.device));
     {
-        int rc = clover_m4_shard_fused_wait(peer_flags[0], h->world, 0, epoch, k0.stream);
+        int rc = clover_m4_shard_stamped_unpack(peer_msg[0], h->rows, k0.row0, k0.rows_local, epoch,
+                                                reinterpret_cast<int8_t *>(k0.block + h->off_yv[b]),
+                                                reinterpret_cast<float *>(k0.block + h->off_ys[b]), k0.stream);
         if (rc != CLOVER_OK) return rc;
     }
     CLOVER_CUDA_CHECK(cudaMemcpyAsync(yv_host, k0.block + h->off_yv[b], h->rows / 2, cudaMemcpyDeviceToHost, k0.stream));

@@ -15,19 +15,26 @@ bit-for-bit, because the fp32 row results do not depend on the sharding.
 
   * ``exchange="fused"``: no collective call at all. Re-quantization blocks are 64 rows and shards are whole
     blocks, so each rank's GEMV kernel re-quantizes its own blocks and its epilogue stores them (36 bytes per
-    block) directly into every peer's result vector over NVLink (peer memory mapped with CUDA IPC), then
-    signals per-rank flags (``clover_m4_mvm_shard_fused_async``). One kernel per step and rank; the same bytes
-    as the single-GPU call. ``mvm(x, wait=True)`` (default): the kernel itself waits for the peers' flags at its
-    end (``clover_m4_mvm_shard_fused``). ``mvm(x, wait=False)``: pipelined - the kernel ends after its flag stores
-    and the wait happens in the prologue of the next step's kernel, or in ``wait()``
-    (``clover_m4_shard_fused_wait``) in front of any other consumer (``clover_m4_mvm_shard_fused_async``).
-    Measured on B200s (tools/exchange_probe.py, C3 sharded, us per step synchronous / pipelined): 2 GPUs
-    193.4 / 197.0, 4 GPUs 108.0 / 108.0, 8 GPUs 65.1 / 63.1 - the pipelined form is therefore used from 8 ranks on.
-  * ``exchange="stamped"``: the fused epilogue without ANY ordering between stores - every 32-bit word of a finished
-    block travels to every peer in one 8-byte store {word, epoch} into a message area (``clover_m4_mvm_shard_stamped``),
-    no per-CTA system fence, no flags; the consumer side (``wait()`` = ``clover_m4_shard_stamped_unpack``) polls the
-    stamps and writes the words into the reference layout. ``mvm(x, wait=True)`` = kernel + unpack;
-    ``mvm(x, wait=False)`` = kernel only, ``wait()`` in front of whatever reads the result.
+    block) directly into every peer's memory over NVLink (peer memory mapped with CUDA IPC). One kernel per step
+    and rank; the same bytes as the single-GPU call. Two protocols, chosen per call by what was measured
+    (tools/exchange_probe.py, C3 sharded, us per step on one HGX box):
+
+      - *stamped* (``clover_m4_mvm_shard_stamped``): every 32-bit word of a finished block travels to every peer
+        in ONE 8-byte store {word, epoch} into a message area - no ordering between stores, so no system-scope
+        fence per CTA, no flags; the kernel just ends. ``wait()`` (``clover_m4_shard_stamped_unpack``) polls the
+        stamps and writes the words into the reference layout in front of whatever reads the result.
+      - *flags* (``clover_m4_mvm_shard_fused``): plain stores into the peers' result vectors, a system-scope fence
+        per CTA, one flag word per peer, and the kernel waits for the peers' flags at its end.
+
+                                    2 GPUs    4 GPUs    8 GPUs
+        flags                        180.8     101.5      63.6
+        stamped, wait=False          178.7      95.0      50.8     (one unpack at the end)
+        stamped + unpack per step    184.5     101.5      55.8
+        shard kernel alone           170       89.5       45.7
+
+    ``mvm(x, wait=False)`` therefore always uses the stamped kernel (call ``wait()`` before the result is read);
+    ``mvm(x)`` (complete when it returns in stream order) uses stamped + unpack from 4 ranks on, flags below.
+    ``exchange="stamped"`` / ``"fused_sync"`` force either.
 """
 from __future__ import annotations
 
@@ -93,8 +100,8 @@ class ShardedCloverMatrix4:
         self._sizes = sizes
         self.key = None
         self._peer = None
-        self._pending_wait = False                     # the last step was pipelined and nobody has waited for it yet
-        if exchange in ("fused", "fused_sync", "fused_pipelined", "stamped"):   # _sync / _pipelined force either form of the wait
+        self._pending_wait = False                     # the last step was stamped and its messages are not unpacked yet
+        if exchange in ("fused", "fused_sync", "stamped"):           # fused = by measurement; the other two force a protocol
             self._setup_peer_memory()
 
     # ---- fused exchange: one IPC-shared block per rank = [values x2 | scales x2 | flags | ticket] ------------------
@@ -179,41 +186,31 @@ class ShardedCloverMatrix4:
         self._peer = None
 
     def wait(self) -> None:
-        """Fused exchange: enqueue the wait for the peers' flags of the LAST step on the current stream. When it has
-        completed in stream order, the whole result of that step is present on this rank (no-op for the NCCL modes,
-        whose collectives are stream-ordered already)."""
+        """Fused exchange, after ``mvm(x, wait=False)``: enqueue the unpack of the LAST step's messages on the current
+        stream. When it has completed in stream order, the whole result of that step is present on this rank in the
+        reference layout (no-op otherwise; the NCCL modes' collectives are stream-ordered already)."""
         pr = self._peer
         if pr is None or self.world == 1 or pr["epoch"] == 0 or not self._pending_wait:
             return
         self._pending_wait = False
-        if self.exchange == "stamped":
-            k = pr["epoch"] & 1
-            call("clover_m4_shard_stamped_unpack", C.c_void_p(pr["base"] + pr["lay"]["msg"][k]), C.c_uint64(self.rows),
-                 C.c_uint64(self.row0), C.c_uint64(self.rows_local), C.c_uint32(pr["epoch"]),
-                 C.c_void_p(pr["base"] + pr["lay"]["yv"][k]), C.c_void_p(pr["base"] + pr["lay"]["ys"][k]), _stream())
-            return
-        call("clover_m4_shard_fused_wait", C.c_void_p(pr["base"] + pr["lay"]["flags"]), self.world, self.rank,
-             C.c_uint32(pr["epoch"]), _stream())
+        k = pr["epoch"] & 1
+        call("clover_m4_shard_stamped_unpack", C.c_void_p(pr["base"] + pr["lay"]["msg"][k]), C.c_uint64(self.rows),
+             C.c_uint64(self.row0), C.c_uint64(self.rows_local), C.c_uint32(pr["epoch"]),
+             C.c_void_p(pr["base"] + pr["lay"]["yv"][k]), C.c_void_p(pr["base"] + pr["lay"]["ys"][k]), _stream())
 
     def _mvm_fused(self, x: CloverVector4, y, key_ptr, wait: bool):
         """y = None: returns a CloverVector4 VIEW of the shared result buffer of this step - no copy at all. The view is
         valid until this rank issues its NEXT mvm (a faster peer may then already be storing the step after that into the
-        same buffer); otherwise the result is copied into the caller's vector. wait = False (pipelined): the step's
-        kernel does not wait for the peers - the next step's kernel does, before it reads its x (which may be this
-        view), and ``wait()`` does for every other consumer."""
+        same buffer); otherwise the result is copied into the caller's vector. wait = False: the result is complete only
+        after ``wait()``."""
         pr = self._peer
-        if self.exchange == "stamped":
+        stamped = self.exchange == "stamped" or (self.exchange == "fused" and (not wait or self.world >= 4))
+        if stamped:
             return self._mvm_stamped(x, y, key_ptr, wait)
-        # pipelined only where it pays (see the module docstring); a step that must be complete when it ends uses the
-        # synchronous kernel - after a pipelined step that nobody waited for, the wait kernel first (the synchronous kernel
-        # has no prologue wait, and it may not store into a peer's buffer before that peer has finished the step before)
-        piped = (not wait and y is None) and (self.exchange == "fused_pipelined" or (self.exchange == "fused" and self.world >= 8))
-        if not piped:
-            self.wait()                      # for the PREVIOUS epoch: before this step's epoch is counted
-        self._pending_wait = piped
+        self._pending_wait = False           # a stamped step nobody waited for is dropped: its buffers are simply re-used
         pr["epoch"] += 1
         k = pr["epoch"] & 1
-        call("clover_m4_mvm_shard_fused_async" if piped else "clover_m4_mvm_shard_fused", _ptr(self.local.values), _ptr(self.local.scales), C.c_uint64(self.rows_local),
+        call("clover_m4_mvm_shard_fused", _ptr(self.local.values), _ptr(self.local.scales), C.c_uint64(self.rows_local),
              C.c_uint64(self.cols), C.c_uint64(self.row0), _ptr(x.values), _ptr(x.scales), pr["yv"][k], pr["ys"][k],
              pr["flags"], pr["ticket"], self.world, self.rank, C.c_uint32(pr["epoch"]), key_ptr, _stream())
         lay = pr["lay"]
@@ -258,10 +255,11 @@ class ShardedCloverMatrix4:
     def mvm(self, x: CloverVector4, y: CloverVector4 = None, wait: bool = True):
         if x.size() != self.cols or (y is not None and y.size_pad() != self.rows):
             raise CloverSizeError("MVM can not be performed.")
-        if y is None and not self.exchange.startswith("fused"):
+        fused = self.exchange.startswith("fused") or self.exchange == "stamped"
+        if y is None and not fused:
             y = CloverVector4(self.rows, device=self.device)
         key_ptr = None if self.key is None else self.key.ctypes.data_as(C.c_void_p)
-        if self.exchange.startswith("fused"):
+        if fused:
             return self._mvm_fused(x, y, key_ptr, wait)
         if self.exchange == "allreduce":
             self.y32.zero_()

@@ -181,20 +181,6 @@ int clover_m4_mvm_shard_fused(const int8_t *values_local, const float *scales_lo
                               uint64_t row0, const int8_t *xv, const float *xs, int8_t *const *peer_yv_host,
                               float *const *peer_ys_host, uint32_t *const *peer_flags_host, unsigned int *ticket,
                               int world, int rank, uint32_t epoch, uint64_t *key_host, void *stream);
-/* The same exchange, pipelined: the kernel ends right after its flag stores instead of waiting for the peers' flags, and
- * the wait moves to where the result is consumed -
- *   - the NEXT clover_m4_mvm_shard_fused[_async] call of this rank: its kernel waits in its prologue, before it reads x
- *     and before its first peer store, until every peer has raised flags >= epoch - 1. So x may be the previous call's
- *     result, and the result buffer of two calls ago may be overwritten (use two buffers alternately, as above);
- *   - any other consumer (a copy, another kernel): enqueue clover_m4_shard_fused_wait(flags_local, world, rank, epoch, stream)
- *     in front of it; when that has completed in stream order, the full result of call `epoch` is present on this rank.
- * The flag flight, the spin and the spread of the ranks' finishing times then overlap the next kernel's launch and ring
- * fill instead of idling all GPUs at the end of every call. Same arguments, same bytes. */
-int clover_m4_mvm_shard_fused_async(const int8_t *values_local, const float *scales_local, uint64_t rows_local, uint64_t cols,
-                                    uint64_t row0, const int8_t *xv, const float *xs, int8_t *const *peer_yv_host,
-                                    float *const *peer_ys_host, uint32_t *const *peer_flags_host, unsigned int *ticket,
-                                    int world, int rank, uint32_t epoch, uint64_t *key_host, void *stream);
-int clover_m4_shard_fused_wait(uint32_t *flags_local, int world, int rank, uint32_t epoch, void *stream);
 /* Stamped exchange: the same fused epilogue without any ordering between stores. Every 32-bit word of a finished block (8
  * words of nibbles + the scale) travels to every peer in ONE naturally aligned 8-byte store {word, epoch} into that peer's
  * message area (9 x 8 bytes per 64-row block of the WHOLE vector, i.e. rows / 64 * 72 bytes; use two areas alternately,

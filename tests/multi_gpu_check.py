@@ -38,14 +38,15 @@ def main():
         want = []
         for q in xs:
             y = cb.CloverVector4(rows); full.mvm(q, y); want.append((y.values.clone(), y.scales.clone()))
-        for mode in ("fused", "allgather", "allreduce"):
+        for mode in ("fused", "fused_sync", "stamped", "allgather", "allreduce"):
             A = ShardedCloverMatrix4(rows, cols, exchange=mode)
             hb = cols // 64
             A.load_shard(full.values[A.row0 * cols // 2:(A.row0 + A.rows_local) * cols // 2],
                          full.scales[(A.row0 // 64) * hb:((A.row0 + A.rows_local) // 64) * hb])
             for step, (q, (wv, ws)) in enumerate(zip(xs, want)):
-                if mode == "fused" and step % 2:          # zero-copy form: a view of the shared result vector
-                    y = A.mvm(q)
+                if mode in ("fused", "fused_sync", "stamped") and step % 2:          # zero-copy form: a view of the shared result vector
+                    y = A.mvm(q) if step % 4 == 1 else A.mvm(q, wait=False)
+                    A.wait()
                 else:
                     y = cb.CloverVector4(rows)
                     A.mvm(q, y)
@@ -56,9 +57,9 @@ def main():
             if rank == 0:
                 print(f"multi-gpu check: {rows} x {cols}, exchange={mode}: 5 steps identical to the single-GPU mvm on every rank ({world} ranks)", flush=True)
         dist.barrier()
-    # pipelined fused exchange: a chain y_{e+1} = A y_e on a square matrix, every step consuming the previous step's result
-    # VIEW (written by the peers over NVLink) with no host synchronisation and no wait kernel in between - the next kernel's
-    # prologue is the only wait. Compared with the same chain on one GPU; 3 rounds so that both result buffers are re-used.
+    # a chain y_{e+1} = A y_e on a square matrix, every step consuming the previous step's result VIEW (assembled from the
+    # peers' stamped messages) with no host synchronisation in between; compared with the same chain on one GPU; 3 rounds so
+    # that both result buffers and both message areas are re-used, round 2 with explicit wait() calls.
     for n in (2048, 16384 + 128):
         n += (-n) % 128
         g = torch.Generator(device=dev).manual_seed(11)
@@ -71,24 +72,28 @@ def main():
         want, cur = [], x0
         for _ in range(steps):
             y = cb.CloverVector4(n); full.mvm(cur, y); want.append(y); cur = y
-        A = ShardedCloverMatrix4(n, n, exchange="fused_pipelined")
+        A = ShardedCloverMatrix4(n, n, exchange="fused")
         hb = n // 64
         A.load_shard(full.values[A.row0 * n // 2:(A.row0 + A.rows_local) * n // 2],
                      full.scales[(A.row0 // 64) * hb:((A.row0 + A.rows_local) // 64) * hb])
         for rnd in range(3):
             cur = x0
             for e in range(steps):
-                cur = A.mvm(cur, wait=(rnd == 2 and e % 3 == 1))      # round 2 mixes synchronous steps into the pipelined chain
+                if rnd == 2 and e % 3 == 1:
+                    cur = A.mvm(cur, wait=False)
+                    A.wait()                                # the next step reads this result: unpack first
+                else:
+                    cur = A.mvm(cur)
             A.wait()
             torch.cuda.synchronize()
-            assert torch.equal(cur.values, want[-1].values), ("pipelined chain", n, rank, "values")
-            assert torch.equal(cur.scales.view(torch.int32)[: n // 64], want[-1].scales.view(torch.int32)[: n // 64]), ("pipelined chain", n, rank, "scales")
+            assert torch.equal(cur.values, want[-1].values), ("chain", n, rank, "values")
+            assert torch.equal(cur.scales.view(torch.int32)[: n // 64], want[-1].scales.view(torch.int32)[: n // 64]), ("chain", n, rank, "scales")
             dist.barrier()
         A.close()
         if rank == 0:
-            print(f"multi-gpu check: {n} x {n}, pipelined fused chain of {steps} steps x 3 identical to the single-GPU chain on every rank ({world} ranks)", flush=True)
+            print(f"multi-gpu check: {n} x {n}, fused chain of {steps} steps x 3 identical to the single-GPU chain on every rank ({world} ranks)", flush=True)
     if rank == 0:
-        print("multi-gpu ok: fused / allgather / allreduce == single-GPU mvm on", world, "ranks")
+        print("multi-gpu ok: fused (stamped / flags) / allgather / allreduce == single-GPU mvm on", world, "ranks")
     dist.destroy_process_group()
 
 

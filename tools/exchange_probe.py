@@ -1,5 +1,6 @@
-"""Multi-GPU exchange probe (torchrun, one rank per GPU): per-rank step time of the sharded C3 mvm with the synchronous fused
-exchange, the pipelined one (with and without a wait kernel per step) and the bare shard kernel, all in one process.
+"""Multi-GPU exchange probe (torchrun, one rank per GPU): per-rank step time of the sharded C3 mvm with the flag-synchronised
+fused exchange, the stamped one (with one unpack at the end and with an unpack per step) and the bare shard kernel, all in
+one process.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/exchange_probe.py [steps=200]
 """
@@ -26,7 +27,7 @@ def main():
     x.scales.uniform_(0.25, 1.0, generator=torch.Generator(device=dev).manual_seed(6))
     res = {}
     mats = {}
-    for mode in ("fused_sync", "fused_pipelined", "stamped"):
+    for mode in ("fused_sync", "stamped"):
         A = ShardedCloverMatrix4(rows, cols, exchange=mode)
         if mode == "fused_sync":
             A.local.values[: A.rows_local * cols // 2].copy_(random_nibbles(torch, A.rows_local * cols // 2, g, dev))
@@ -49,12 +50,10 @@ def main():
         torch.cuda.synchronize(); dist.barrier()
         res[name] = e0.elapsed_time(e1) / steps * 1e3
 
-    S, P, T = mats["fused_sync"], mats["fused_pipelined"], mats["stamped"]
+    S, T = mats["fused_sync"], mats["stamped"]
     y = cb.CloverVector4(rows)
     for rep in range(1):
-        timed(f"sync_{rep}", lambda: S.mvm(x, wait=False))
-        timed(f"pipelined_{rep}", lambda: P.mvm(x, wait=False), P.wait)
-        timed(f"pipelined_wait_each_{rep}", lambda: P.mvm(x, wait=True))
+        timed(f"flags_{rep}", lambda: S.mvm(x))
         timed(f"stamped_{rep}", lambda: T.mvm(x, wait=False), T.wait)
         timed(f"stamped_unpack_each_{rep}", lambda: T.mvm(x, wait=True))
         ys_, yt_ = S.mvm(x, wait=True), T.mvm(x, wait=True)
@@ -73,7 +72,7 @@ def main():
     if rank == 0:
         for k in res:
             print(k, "us per step by rank:", [round(r[k], 1) for r in allres], flush=True)
-    S.close(); P.close(); T.close()
+    S.close(); T.close()
     dist.destroy_process_group()
 
 
