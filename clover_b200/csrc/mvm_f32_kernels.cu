@@ -127,6 +127,11 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
@@ -292,6 +297,164 @@ k_mvm_f32_ring(const __grid_constant__ CUtensorMap tmap, const float *__restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same arithmetic with 8-row work items: thread = (row, ONE accumulator k: elements 8k..8k+7 of each half block, four
+// packed f32x2 accumulators), 28 warps per CTA, and TWO 128-byte chunks per ring stage. What the 16-row kernel lacks is
+// warps: 2048 items at 32768 rows are 14 per SM, 3.5 per scheduler, 1.5 of them eligible (ncu r02t), so the loop issues in
+// 69 % of the cycles. Halving the item doubles the warps; a first cut with one chunk per stage lost more than that gained
+// (228 vs 198 us: the per-stage work of a warp - barrier wait, scale shuffles, refill by lane 0 - was paid twice as often),
+// so a stage now holds two chunks and the per-element overhead is that of the 16-row kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kR8Rows = 8, kR8Warps = 28, kR8Stages = 2, kR8Chunks = 2;
+constexpr int kR8StageBytes = kR8Chunks * kR8Rows * 128 + kR8Chunks * 1024;     // 2 x (8 rows x 128 B) + up to 512 floats of x = 4096
+constexpr int kR8SmemBytes = kR8Warps * kR8Stages * kR8StageBytes + kR8Warps * kR8Stages * 8 + 1024 /* alignment slack */;
+
+template <int MBITS>
+__global__ void __launch_bounds__(kR8Warps * 32, 1)
+k_mvm_f32_ring8(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ scales, uint64_t rows, uint64_t cols,
+                const float *__restrict__ x, float *__restrict__ y, uint32_t zero) {
+    extern __shared__ uint8_t smem_raw_f32[];
+    constexpr int kBPC = MBITS == 4 ? 4 : 2;                          // blocks of 64 columns per 128-byte chunk
+    constexpr int kBPS = kR8Chunks * kBPC;                            // blocks per stage
+    constexpr float kQ = MBITS == 4 ? 7.0f : 127.0f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // lane -> (row r, accumulator k). 4-bit: a warp-wide 4-byte load covers 8 rows x one 16-byte chunk; 8-bit: a half warp's
+    // 8-byte loads cover 8 rows x one 16-byte chunk (k >> 1 fixed per half warp) - conflict-free under the 128-byte swizzle.
+    const int r = MBITS == 4 ? lane >> 2 : (lane >> 1) & 7, k = MBITS == 4 ? lane & 3 : 2 * (lane >> 4) + (lane & 1);
+    const uint32_t hb = (uint32_t)(cols >> 6), nitems = (uint32_t)(rows / kR8Rows);
+    const uint32_t nchunks = (hb + kBPC - 1) / kBPC, nst = (nchunks + kR8Chunks - 1) / kR8Chunks;      // stages per item
+    const uint32_t wstride = gridDim.x * kR8Warps;
+    const uint32_t first = (uint32_t)warp * gridDim.x + blockIdx.x;      // warp-major: every SM gets the same number of busy warps
+    if (first >= nitems) return;
+
+    const uint32_t smem0 = (smem_u32(smem_raw_f32) + 1023u) & ~1023u;
+    const uint32_t ring = smem0 + (uint32_t)warp * (kR8Stages * kR8StageBytes);
+    const uint32_t bars = smem0 + kR8Warps * kR8Stages * kR8StageBytes + (uint32_t)warp * (8 * kR8Stages);
+    if (lane == 0) {
+        for (int s = 0; s < kR8Stages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8 * s), "r"(1) : "memory");
+        mbar_fence_init();
+        tma_prefetch_descriptor(&tmap);
+    }
+    __syncwarp();
+
+    // producer state (lane 0): the next (item, stage-of-item) to request and its ring slot
+    uint32_t p_item = first, p_t = 0, p_s = 0;
+    auto issue = [&]() {                                               // lane 0 only; no-op when the warp's work is exhausted
+        if (p_item >= nitems) return;
+        const uint32_t c0 = p_t * kR8Chunks;
+        const uint32_t nblk = min((uint32_t)kBPS, hb - c0 * kBPC);                  // blocks of this stage (x floats = 64 nblk)
+        const bool two = c0 + 1 < nchunks;
+        const uint32_t dst = ring + p_s * kR8StageBytes, bar = bars + 8 * p_s;
+        mbar_arrive_expect_tx_a(bar, kR8Rows * 128 * (two ? 2u : 1u) + nblk * 256);
+        tma_load_2d_a(dst, &tmap, (int)(c0 * 128), (int)(p_item * kR8Rows), bar);
+        if (two) tma_load_2d_a(dst + kR8Rows * 128, &tmap, (int)((c0 + 1) * 128), (int)(p_item * kR8Rows), bar);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst + kR8Chunks * kR8Rows * 128u), "l"(x + (uint64_t)c0 * kBPC * 64), "r"(nblk * 256u), "r"(bar) : "memory");
+        p_s ^= 1u;
+        if (++p_t == nst) { p_t = 0; p_item += wstride; }
+    };
+    if (lane == 0) { issue(); issue(); }
+
+    // block scales: lane L holds s = su[b] / Q of block 32g + L of the current row block; a group of 32 blocks = kSPG stages
+    constexpr uint32_t kSPG = 32 / kBPS;
+    auto load_scale = [&](uint32_t item, uint32_t g) -> float {
+        if (item >= nitems) return 1.0f;
+        const uint32_t b = min(g * 32u + (uint32_t)lane, hb - 1);
+        return __ldg(scales + (uint64_t)(item / (64 / kR8Rows)) * hb + b);
+    };
+
+    const uint64_t neg = MBITS == 4 ? pack2f(-12582920.0f, -12582920.0f) : pack2f(-12583040.0f, -12583040.0f);   // -(magic + bias)
+    const RegConsts rc = reg_consts(zero);
+    const uint32_t rsw = (uint32_t)(r & 7), rowoff = (uint32_t)r * 128u;
+    uint32_t s = 0, phase = 0;
+    float sraw = load_scale(first, 0);
+    for (uint32_t item = first; item < nitems; item += wstride) {
+        uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};                    // accumulator k; pair p = AVX lanes 2p, 2p+1
+        float sdiv = 0.f;
+        for (uint32_t t = 0; t < nst; ++t) {
+            if (t % kSPG == 0) {
+                sdiv = __fdiv_rn(sraw, kQ);
+                sraw = (t + kSPG) * kBPS < hb ? load_scale(item, t / kSPG + 1) : load_scale(item + wstride, 0);
+            }
+            mbar_wait_a(bars + 8 * s, phase);
+            const uint32_t st = ring + s * kR8StageBytes, xbase = st + kR8Chunks * kR8Rows * 128u;
+            const int nblk = (int)min((uint32_t)kBPS, hb - t * kBPS);
+            float sjs[kBPS];
+#pragma unroll
+            for (int j = 0; j < kBPS; ++j) sjs[j] = __shfl_sync(0xFFFFFFFFu, sdiv, (int)(t % kSPG) * kBPS + j);
+            if (MBITS == 8) {
+                // t = x * s (CloverMatrix8.h:632-639) for the stage's 4 blocks = 256 floats, in place: lane L owns floats 8L .. 8L+7
+                const uint32_t ta = xbase + 32u * (uint32_t)lane;
+                const float sj = __shfl_sync(0xFFFFFFFFu, sdiv, (int)(t % kSPG) * kBPS + ((lane >> 3) & (kBPS - 1)));
+                const uint64_t s2 = pack2f(sj, sj);
+                uint64_t a, b, c, d;
+                asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(ta));
+                asm volatile("ld.shared.v2.b64 {%0,%1}, [%2+16];" : "=l"(c), "=l"(d) : "r"(ta));
+                a = mul2(a, s2); b = mul2(b, s2); c = mul2(c, s2); d = mul2(d, s2);
+                asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(ta), "l"(a), "l"(b) : "memory");
+                asm volatile("st.shared.v2.b64 [%0+16], {%1,%2};" ::"r"(ta), "l"(c), "l"(d) : "memory");
+                __syncwarp();
+            }
+            // block jj of the stage = chunk jj / kBPC, block jj % kBPC of the chunk; its x (or t) starts 256 jj bytes into the x area
+            auto block_step = [&](auto JJ) {
+                constexpr int jj = decltype(JJ)::value;
+                if (jj < kBPS) {
+                    constexpr int h = jj / kBPC, j = jj % kBPC;
+                    const uint64_t ss = pack2f(sjs[jj], sjs[jj]);
+                    const uint32_t rowp = st + (uint32_t)h * (kR8Rows * 128u) + rowoff, xs = xbase + 32u * (uint32_t)k;
+                    if (MBITS == 4) {
+                        const uint32_t w0 = lds32(rowp + ((((uint32_t)(2 * j)) ^ rsw) << 4) + 4u * (uint32_t)k);        // elements 8k .. 8k+7
+                        const uint32_t w1 = lds32(rowp + ((((uint32_t)(2 * j + 1)) ^ rsw) << 4) + 4u * (uint32_t)k);    // elements 32+8k ..
+                        word4<256 * jj>(w0, xs, ss, neg, rc, acc);
+                        word4<256 * jj + 128>(w1, xs, ss, neg, rc, acc);
+                    } else {
+                        const uint2 w0 = lds64(rowp + ((((uint32_t)(4 * j) + (uint32_t)(k >> 1)) ^ rsw) << 4) + 8u * (uint32_t)(k & 1));
+                        const uint2 w1 = lds64(rowp + ((((uint32_t)(4 * j + 2) + (uint32_t)(k >> 1)) ^ rsw) << 4) + 8u * (uint32_t)(k & 1));
+                        word8<256 * jj>(w0.x, xs, neg, rc, &acc[0]);
+                        word8<256 * jj + 16>(w0.y, xs, neg, rc, &acc[2]);
+                        word8<256 * jj + 128>(w1.x, xs, neg, rc, &acc[0]);
+                        word8<256 * jj + 144>(w1.y, xs, neg, rc, &acc[2]);
+                    }
+                }
+            };
+            if (nblk == kBPS) {                                      // full stage: no guards, the accumulators stay in place
+                block_step(std::integral_constant<int, 0>{}); block_step(std::integral_constant<int, 1>{});
+                block_step(std::integral_constant<int, 2>{}); block_step(std::integral_constant<int, 3>{});
+                block_step(std::integral_constant<int, 4>{}); block_step(std::integral_constant<int, 5>{});
+                block_step(std::integral_constant<int, 6>{}); block_step(std::integral_constant<int, 7>{});
+            } else {
+                if (nblk > 0) block_step(std::integral_constant<int, 0>{});
+                if (nblk > 1) block_step(std::integral_constant<int, 1>{});
+                if (nblk > 2) block_step(std::integral_constant<int, 2>{});
+                if (nblk > 3) block_step(std::integral_constant<int, 3>{});
+                if (nblk > 4) block_step(std::integral_constant<int, 4>{});
+                if (nblk > 5) block_step(std::integral_constant<int, 5>{});
+                if (nblk > 6) block_step(std::integral_constant<int, 6>{});
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (MBITS == 8) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this warp WROTE the stage (t = x * s) before the async-proxy refill
+                issue();
+            }
+            s ^= 1u;
+            if (s == 0) phase ^= 1u;
+        }
+        // the four accumulators of a row live in four threads: (acc_1 + acc_2) and (acc_3 + acc_4) across the pair that differs
+        // in the low bit of k, their sum across the other pair, then the hadd tree (CloverBase.h:149-157); fp32 add commutes
+        float tt[8];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) { tt[2 * p] = lo_f(acc[p]); tt[2 * p + 1] = hi_f(acc[p]); }
+#pragma unroll
+        for (int l = 0; l < 8; ++l) tt[l] = __fadd_rn(tt[l], __shfl_xor_sync(0xFFFFFFFFu, tt[l], 1));
+#pragma unroll
+        for (int l = 0; l < 8; ++l) tt[l] = __fadd_rn(tt[l], __shfl_xor_sync(0xFFFFFFFFu, tt[l], MBITS == 4 ? 2 : 16));
+        if (k == 0)
+            y[(uint64_t)item * kR8Rows + r] = __fadd_rn(__fadd_rn(__fadd_rn(tt[4], tt[0]), __fadd_rn(tt[6], tt[2])),
+                                                        __fadd_rn(__fadd_rn(tt[5], tt[1]), __fadd_rn(tt[7], tt[3])));
+    }
+}
+
 // One warp per row, lane 8k+l = the reference's chain (accumulator k, AVX lane l); plain loads. Same bits as the ring kernel.
 template <int MBITS>
 __global__ void __launch_bounds__(256)
@@ -341,17 +504,29 @@ static int launch_mvm_f32(const int8_t *values, const float *scales, uint64_t ro
         k_mvm_f32_simple<MBITS><<<(unsigned)(want > cap ? cap : want), 256, 0, stream>>>(
             reinterpret_cast<const uint8_t *>(values), scales, rows, cols, x32, y32);
     } else {
+        // 8-row items (k_mvm_f32_ring8, 28 warps per SM) unless the matrix is tall enough to fill the 16-row kernel's warp slots
+        // (8-bit) / to fill them twice over (4-bit). Measured on B200 (tools/f32_sweep.py, us 16-row / 8-row items): 4-bit
+        // 32768^2 198.7 / 182.6, 8192 x 32768 86.3 / 72.0, 32768 x 8192 55.0 / 51.6, 65536 x 16384 181.7 / 182.8; 8-bit 32768^2
+        // 221.2 / 216.8, 8192 x 32768 131.1 / 100.8, 65536 x 16384 203.8 / 219.4. CLOVER_GEMV_IMPL=rows16 / rows8 force either.
+        const bool rows8 = impl && !strcmp(impl, "rows8") ? true : impl && !strcmp(impl, "rows16") ? false
+                                                          : rows / 16 <= (uint64_t)sm_count() * kF32Warps * (MBITS == 4 ? 2 : 1);
         CUtensorMap tmap;
-        int rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows, MBITS == 4 ? cols >> 1 : cols, kF32Rows);
+        int rc = make_tensor_map_u8_2d_sw128(&tmap, values, rows, MBITS == 4 ? cols >> 1 : cols, rows8 ? kR8Rows : kF32Rows);
         if (rc != CLOVER_OK) return rc;
-        const int smem = kF32SmemBytes;
-        auto kern = k_mvm_f32_ring<MBITS>;
-        CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   // per device and call: cheap
         // one CTA per SM as soon as there are that many work items: the warp-major item order then spreads the busy warps
         // evenly over all SMs (round 2a launched ceil(items / warps) CTAs and left 20 SMs idle at 32768 rows)
-        const uint64_t nitems = rows / kF32Rows;
+        const uint64_t nitems = rows / (rows8 ? kR8Rows : kF32Rows);
         const unsigned grid = (unsigned)(nitems < (uint64_t)sm_count() ? nitems : (uint64_t)sm_count());
-        kern<<<grid, kF32Warps * 32, smem, stream>>>(tmap, scales, rows, cols, x32, y32, 0u);
+        if (rows8) {
+            auto kern = k_mvm_f32_ring8<MBITS>;
+            CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kR8SmemBytes));   // per device and call: cheap
+            kern<<<grid, kR8Warps * 32, kR8SmemBytes, stream>>>(tmap, scales, rows, cols, x32, y32, 0u);
+        } else {
+            const int smem = kF32SmemBytes;
+            auto kern = k_mvm_f32_ring<MBITS>;
+            CLOVER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            kern<<<grid, kF32Warps * 32, smem, stream>>>(tmap, scales, rows, cols, x32, y32, 0u);
+        }
     }
     count_launch();
     return launch_status("k_mvm_f32");

@@ -43,14 +43,19 @@ F32_SHAPES = [(128, 128), (256, 384), (640, 1152), (128, 4224), (384, 2048), (20
               (148 * 8 * 32 + 256, 640)]
 
 
+@pytest.mark.parametrize("impl", [None, "rows8", "rows16"])
 @pytest.mark.parametrize("bits_", [4, 8])
 @pytest.mark.parametrize("kind", ["floats", "ints"])
 @pytest.mark.parametrize("shape", F32_SHAPES)
-def test_matrix_mvm_f32_ring_vs_oracle(cb, oracle, shape, kind, bits_, monkeypatch):
-    """mvm(V32,V32) (CloverMatrix4.h:1451-1547, CloverMatrix8.h:558-661) through the per-warp TMA-ring kernel: partial
-    chunks at the row end (cols = 64 / 128 / 192 mod 256), more work items than warps (several items per warp, ring wrap
+def test_matrix_mvm_f32_ring_vs_oracle(cb, oracle, shape, kind, bits_, impl, monkeypatch):
+    """mvm(V32,V32) (CloverMatrix4.h:1451-1547, CloverMatrix8.h:558-661) through the per-warp TMA-ring kernels (default
+    dispatch; 8-row items with two chunks per stage and 16-row items forced): partial chunks and partial stages at the row
+    end (cols = 64 / 128 / 192 mod 256, odd chunk counts), more work items than warps (several items per warp, ring wrap
     across items), one block per row - every fp32 result bit-for-bit."""
-    monkeypatch.delenv("CLOVER_GEMV_IMPL", raising=False)
+    if impl is None:
+        monkeypatch.delenv("CLOVER_GEMV_IMPL", raising=False)
+    else:
+        monkeypatch.setenv("CLOVER_GEMV_IMPL", impl)          # read per call by the launcher
     qa, mv, ms, x, (R, Cc) = _quantized(cb, oracle, bits_, *shape, kind)
     y = cb.CloverVector32(R)
     qa.mvm(cb.CloverVector32(Cc, x), y)
