@@ -114,6 +114,25 @@ int clover_host_m4_mvm(const int8_t *values_dev, const float *scales_dev, uint64
         CLOVER_CUDA_CHECK(cudaMemcpyAsync(dx, xv_host, xvb, cudaMemcpyHostToDevice, s));
         CLOVER_CUDA_CHECK(cudaMemcpyAsync(dx + xv_al, xs_host, xsb, cudaMemcpyHostToDevice, s));
     }
+    // Result buffers in PINNED host memory (clover_malloc_host / cudaHostAlloc: mapped into the device's address space) are
+    // written by the kernel's re-quantizer itself - 36 bytes per 64-row block straight over PCIe / C2C - and the device->host
+    // copy and its launch latency disappear from every call; pageable buffers take the staged copy below.
+    int8_t *yv_map = nullptr;
+    float *ys_map = nullptr;
+    {
+        cudaPointerAttributes av{}, as{};
+        if (cudaPointerGetAttributes(&av, yv_host) == cudaSuccess && cudaPointerGetAttributes(&as, ys_host) == cudaSuccess &&
+            av.type == cudaMemoryTypeHost && as.type == cudaMemoryTypeHost && av.devicePointer && as.devicePointer) {
+            yv_map = static_cast<int8_t *>(av.devicePointer); ys_map = static_cast<float *>(as.devicePointer);
+        }
+        cudaGetLastError();                                                // a pageable pointer may leave cudaErrorInvalidValue behind
+    }
+    if (yv_map && ys_map) {
+        CLOVER_TRY(clover_m4_mvm(values_dev, scales_dev, rows, cols, (const int8_t *)dx, (const float *)(dx + xv_al),
+                                 yv_map, ys_map, nullptr, key_host, s));
+        CLOVER_CUDA_CHECK(cudaStreamSynchronize(s));
+        return CLOVER_OK;
+    }
     CLOVER_TRY(clover_m4_mvm(values_dev, scales_dev, rows, cols, (const int8_t *)dx, (const float *)(dx + xv_al),
                              (int8_t *)dy, (float *)(dy + yv_al), nullptr, key_host, s));
     if ((char *)ys_host == (char *)yv_host + yvb && yv_al == yvb) {

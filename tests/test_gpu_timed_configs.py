@@ -232,3 +232,44 @@ def test_host_api_v4_quantize_and_dot(cb, oracle, n):
                      zv.ctypes.data_as(C.c_void_p), zs.ctypes.data_as(C.c_void_p), C.c_uint64(npad),
                      res.ctypes.data_as(C.c_void_p), C.c_int(clover_b200.DOT_EXACT))
     assert bits(res)[0] == bits(oracle.v4_dot(xv, xs, zv, zs, n))
+
+
+@pytest.mark.parametrize("shape", [(256, 384), (4992, 16384 + 128)])
+def test_host_api_m4_mvm_pageable_and_pinned(cb, oracle, shape):
+    """clover_host_m4_mvm (matrix resident, vectors in host memory): pageable result buffers take the staged copy, pinned ones
+    (clover_malloc_host) are written by the kernel's re-quantizer itself over the mapped pointer - both return the oracle's
+    bytes, rounding disabled and keyed (the key advances like the reference's)."""
+    import clover_b200
+    rows, cols = shape
+    A = _random_m4(cb, rows, cols, 91)
+    x = _random_v4(cb, cols, 92)
+    av, as_ = A.values.cpu().numpy(), A.scales.cpu().numpy()
+    xv, xs = x.values.cpu().numpy().copy(), x.scales.cpu().numpy().copy()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for keyed in (False, True):
+        st = oracle.xs_init(5, 6) if keyed else None
+        wv, ws = oracle.m4_mvm(av, as_, rows, cols, xv, xs, state=st)
+        # pageable
+        key = oracle.xs_init(5, 6) if keyed else None
+        yv, ys = np.zeros(rows // 2, np.int8), np.zeros(rows // 64, np.float32)
+        clover_b200.call("clover_host_m4_mvm", C.c_void_p(A.values.data_ptr()), C.c_void_p(A.scales.data_ptr()), C.c_uint64(rows),
+                         C.c_uint64(cols), p(xv), p(xs), p(yv), p(ys), None if key is None else p(key))
+        assert np.array_equal(yv, wv) and np.array_equal(bits(ys), bits(ws[: rows // 64]))
+        if keyed:
+            assert np.array_equal(key, st)
+        # pinned: one allocation [values | scales], like the containers
+        key = oracle.xs_init(5, 6) if keyed else None
+        nb = rows // 2 + rows // 64 * 4
+        hp = C.c_void_p()
+        clover_b200.call("clover_malloc_host", C.byref(hp), C.c_size_t(nb))
+        try:
+            C.memset(hp, 0, nb)
+            clover_b200.call("clover_host_m4_mvm", C.c_void_p(A.values.data_ptr()), C.c_void_p(A.scales.data_ptr()), C.c_uint64(rows),
+                             C.c_uint64(cols), p(xv), p(xs), hp, C.c_void_p(hp.value + rows // 2), None if key is None else p(key))
+            got = np.frombuffer(C.string_at(hp.value, nb), dtype=np.uint8)
+            assert np.array_equal(got[: rows // 2].view(np.int8), wv)
+            assert np.array_equal(got[rows // 2:].view(np.uint32), bits(ws[: rows // 64]))
+            if keyed:
+                assert np.array_equal(key, st)
+        finally:
+            clover_b200.call("clover_free_host", hp)
