@@ -224,8 +224,8 @@ class ShardedCloverMatrix4:
 
     def _mvm_stamped(self, x: CloverVector4, y, key_ptr, wait: bool):
         """The stamped exchange: kernel (messages to every peer, own blocks in place), then - unless wait is False - the
-        unpack pass. The unpack of call e must precede call e + 2 in this stream (same message area): a pending one is
-        issued here before the epoch advances past it."""
+        unpack pass. ``wait()`` always unpacks the LAST call; a call whose messages were never unpacked is simply
+        dropped (its message area is re-used two calls later, after every peer has started that call)."""
         pr = self._peer
         lay = pr["lay"]
         pr["epoch"] += 1
