@@ -75,3 +75,26 @@ def test_sharded_mvm_over_gloo(tmp_path, world, mode):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, mode, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_peer_block_layout_is_aligned_and_disjoint():
+    """The IPC-shared block of the fused exchange: two result vectors, flags, ticket, two message areas of the stamped
+    exchange (9 x 8 bytes per 64-row block of the WHOLE vector), started words - 256-byte aligned, non-overlapping."""
+    from clover_b200.sharded import ShardedCloverMatrix4, shard_rows
+    for rows in (128, 1152, 65536):
+        for world in (1, 2, 3, 8):
+            lay = ShardedCloverMatrix4.peer_block_layout(rows, world)
+            spans = [(lay["yv"][0], rows // 2), (lay["yv"][1], rows // 2), (lay["ys"][0], rows // 64 * 4), (lay["ys"][1], rows // 64 * 4),
+                     (lay["flags"], 4 * world), (lay["ticket"], 12), (lay["msg"][0], rows // 64 * 72), (lay["msg"][1], rows // 64 * 72),
+                     (lay["started"], 4 * world)]
+            assert all(off % 256 == 0 for off, _ in spans)
+            spans.sort()
+            assert all(a + n <= b for (a, n), (b, _) in zip(spans, spans[1:]))
+            assert spans[-1][0] + spans[-1][1] <= lay["bytes"]
+            # shards: whole 64-row blocks, contiguous, covering every block exactly once
+            pos = 0
+            for r in range(world):
+                row0, n = shard_rows(rows, world, r)
+                assert row0 == pos and n % 64 == 0
+                pos += n
+            assert pos == rows
