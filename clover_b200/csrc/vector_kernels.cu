@@ -231,6 +231,9 @@ k_vdot_fast(const uint4 *__restrict__ u, const float *__restrict__ su, const uin
     // UNROLL chunks per operand and thread are requested before the first is consumed.
     const uint64_t first = (uint64_t)blockIdx.x * kDotThreads + threadIdx.x;
     const uint64_t warp_first = first - (threadIdx.x & 31);
+    // launched with programmatic stream serialization: the grid may be set up while its predecessor in the stream drains;
+    // nothing of the predecessor's output (operands, the ticket, the result word) is touched before this returns
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (uint64_t base = warp_first; base < nchunks; base += stride * UNROLL) {
         uint4 a[UNROLL], b[UNROLL];
 #pragma unroll
@@ -263,6 +266,7 @@ k_vdot_fast(const uint4 *__restrict__ u, const float *__restrict__ su, const uin
             }
         }
     }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // a dependent grid may be scheduled from here on (it waits at its top)
     // fixed reduction tree
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
@@ -334,9 +338,16 @@ static int launch_vdot(const int8_t *u, const float *su, const int8_t *v, const 
     DotWorkspace ws;
     int rc = dot_workspace(stream, (int)cap, &ws);
     if (rc != CLOVER_OK) return rc;
-    k_vdot_fast<BITS, 2><<<grid, kDotThreads, 0, stream>>>(reinterpret_cast<const uint4 *>(u), su,
-                                                           reinterpret_cast<const uint4 *>(v), sv, nchunks,
-                                                           ws.partials, ws.ticket, result);
+    // programmatic dependent launch: of the 16.4 us a 2^26-element 4-bit dot takes, ~5 are launch ramp and the last-CTA
+    // finish; back-to-back dots overlap the next grid's set-up with the finish of the previous one
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kDotThreads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CLOVER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vdot_fast<BITS, 2>, reinterpret_cast<const uint4 *>(u), su,
+                                         reinterpret_cast<const uint4 *>(v), sv, nchunks, ws.partials, ws.ticket, result));
     count_launch();
     return launch_status("k_vdot_fast");
 }
